@@ -1,0 +1,214 @@
+/* libtmae_sm100.so -- C ABI of the B200-native (sm_100a) T-MAE sparse-window voxel-encoder hot path.
+ *
+ * Drop-in boundary.  The reference reaches this path through
+ *   - its pybind module `sst_ops_cuda` (pcdet/ops/sst_ops/src/sst_ops_api.cpp:6-8), and
+ *   - library calls (torch_scatter, spconv, pytorch3d, ATen/cuBLAS) made from the pcdet modules
+ *     vfe (temporal_dyn_vfe.py / dyn_vfe.py) and backbone_3d (SiamWCA.py / SiamWCA_MAE.py).
+ * Every entry point below names the reference interface it replaces (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes stub a pcdet maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is DEVICE memory unless marked HOST;
+ *   - the caller owns every buffer, including the workspace (query *_workspace_bytes first);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises;
+ *   - returns 0 on success, a negative TMAE_ERR_* otherwise (never exits the process, unlike
+ *     pcdet/ops/sst_ops/src/sst_ops.cpp:7-19); tmae_last_error_string() describes the failure;
+ *   - re-entrant, no globals besides the thread-local error string: one process per GPU is safe;
+ *   - element counts are int64_t; index tensors use the reference's dtypes where they cross the
+ *     module API (int64 coords / inverse indices) and int32 internally.
+ *   - features are fp32 row-major (rows, channels).
+ */
+#ifndef TMAE_SM100_H_
+#define TMAE_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TMAE_API __attribute__((visibility("default")))
+#else
+#define TMAE_API
+#endif
+
+#define TMAE_ABI_VERSION 1
+
+#define TMAE_ERR_INVALID_ARG (-1)
+#define TMAE_ERR_CUDA (-2)
+#define TMAE_ERR_UNSUPPORTED (-3)
+
+/* GEMM arithmetic selector for the ops that take `precision`. */
+#define TMAE_PREC_FP32 0 /* fp32 FFMA, parity mode (rtol 1e-5 vs the fp32 oracle) */
+#define TMAE_PREC_BF16 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM */
+
+#define TMAE_ACT_NONE 0
+#define TMAE_ACT_GELU 1 /* exact erf GELU (torch default, sst_basic_block.py:121-122) */
+#define TMAE_ACT_RELU 2
+
+#define TMAE_MAX_LEVELS 8
+#define TMAE_WIN_TOKENS 64 /* 8 x 8 x 1 windows (t_mae_ssl.yaml:61) */
+
+/* ---- library ------------------------------------------------------------------------------- */
+TMAE_API const char* tmae_last_error_string(void);
+TMAE_API int tmae_version(void);
+TMAE_API int tmae_device_check(void); /* 0 iff the current device is sm_100 */
+TMAE_API int64_t tmae_scan_scratch_elems(int64_t n);
+TMAE_API int tmae_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* total, int32_t* scratch, void* stream);
+
+/* ---- A1-A2 dynamic voxelisation -------------------------------------------------------------
+ * Replaces common_utils.get_in_range_mask (pcdet/utils/common_utils.py:66-76), points[keep],
+ * coords.unique(dim=0, return_inverse=True) and torch_scatter.scatter(reduce='mean')
+ * (pcdet/models/backbones_3d/vfe/temporal_dyn_vfe.py:69-85, dyn_vfe.py:66-82).
+ *   points        (n_points, point_stride) f32  [b, x, y, z, feat...]
+ *   range_lo, voxel  HOST float[3];  grid HOST int32[3] = [gx, gy, gz]
+ * Outputs are allocated by the caller at capacity n_points rows (mcap = min(n_points, cells) voxel
+ * rows); the first counts[0] / counts[1] rows are valid:
+ *   points_out    (n_points, point_stride) f32   kept points, original order
+ *   point_coords  (n_points, 4) i64  [b, z, y, x]
+ *   inverse       (n_points,)  i64   voxel row of every kept point
+ *   voxel_coords  (mcap, 4) i64      lexicographic (b,z,y,x) = torch.unique(dim=0) order
+ *   voxel_mean    (mcap, point_stride-1) f32
+ *   voxel_npts    (mcap,) i32 ; voxel_offset (mcap+1,) i32 ; pt_order (n_points,) i32
+ *                 CSR of kept-point rows per voxel, ascending inside a voxel (canonical slot order)
+ *   counts        (2 + batch,) i64: [n_kept, n_voxels, first voxel row of sample 0..batch-1]
+ */
+TMAE_API size_t tmae_voxelize_workspace_bytes(int64_t n_points, int32_t batch, const int32_t* grid);
+TMAE_API int tmae_voxelize(const float* points, int64_t n_points, int32_t point_stride, const float* range_lo, const float* voxel,
+                  const int32_t* grid, int32_t batch, float* points_out, int64_t* point_coords, int64_t* inverse,
+                  int64_t* voxel_coords, float* voxel_mean, int32_t* voxel_npts, int32_t* voxel_offset, int32_t* pt_order,
+                  int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* A3 (first half): per-point VFE input  [f_center(3), x,y,z,feat..., f_cluster(3)]
+ * (temporal_dyn_vfe.py:89-110); features is (n_kept, point_stride - 1 + 6) f32. */
+TMAE_API int tmae_vfe_point_features(const float* points_kept, int64_t n_kept, int32_t point_stride, const int64_t* point_coords,
+                            const int64_t* inverse, const float* voxel_mean, const float* range_lo, const float* voxel,
+                            float* features, void* stream);
+
+/* ---- A4-A6 window partition -------------------------------------------------------------------
+ * Replaces get_window_coors (pcdet/models/model_utils/sst_utils.py:6-58), drop_single_shift / drop_voxel
+ * (pcdet/models/backbones_3d/spt_backbone.py:47-135), the temporal form drop_single_shift_ref_to_prv
+ * (pcdet/models/backbones_3d/SiamWCA.py:65-199), get_inner_win_inds (pcdet/ops/sst_ops/sst_ops_utils.py:5-12
+ * -> src/sst_ops_gpu.cu:14-20) and make_continuous_inds / get_flat2win_inds (sst_utils.py:61-115), for BOTH
+ * shifts in one call.  coords_* are (m,3) i32 [b,y,x] in ascending lexicographic order (what the voxeliser
+ * and the strided-conv table emit).  coords_b == NULL: single frame (SSTInputLayer); otherwise temporal
+ * (frame a = current, b = previous): level from max(count_a, count_b), windows empty in either frame are
+ * dropped.  wcap = tmae_partition_window_capacity().  Outputs, leading dimension 2 = shift:
+ *   win_*   [2][m]  compact window id (level-major order) or -1 if the voxel is dropped
+ *   slot_*  [2][m]  canonical inner-window slot (stable rank by element index)
+ *   posidx_*[2][m]  u8  ly*8+lx  (row of the 64-entry position-embedding table)
+ *   tok_*   [2][wcap*64] voxel row per (window, slot);  cnt_* [2][wcap] tokens per window
+ *   win_level [2][wcap] ; n_win [2] ; level_base [2][n_levels+1] first compact id of each level
+ *   status  [1]  bit0 coords not ascending, bit1 out-of-grid coordinate, bit2 count in no level,
+ *                bit3 a window exceeds its level's max_tokens (voxel dropping is unsupported)
+ *   ref_*   optional (NULL to skip) reference-format tables: batch_win_inds, voxel_drop_level,
+ *           flat2win index (= compact id inside the level * max_tokens + slot), all [2][m] i64
+ */
+TMAE_API int64_t tmae_partition_window_capacity(int32_t batch, int32_t grid_x, int32_t grid_y);
+TMAE_API size_t tmae_window_partition_workspace_bytes(int32_t batch, int32_t grid_x, int32_t grid_y, int32_t n_levels);
+TMAE_API int tmae_window_partition(const int32_t* coords_a, int64_t m_a, const int32_t* coords_b, int64_t m_b, int32_t batch,
+                          int32_t grid_x, int32_t grid_y, int32_t n_levels, const int32_t* lvl_lo, const int32_t* lvl_hi,
+                          const int32_t* lvl_tokens,
+                          int32_t* win_a, int32_t* slot_a, uint8_t* posidx_a, int32_t* tok_a, int32_t* cnt_a,
+                          int32_t* win_b, int32_t* slot_b, uint8_t* posidx_b, int32_t* tok_b, int32_t* cnt_b,
+                          int32_t* win_level, int32_t* n_win, int32_t* level_base, int32_t* status,
+                          int64_t* ref_bwi_a, int64_t* ref_lvl_a, int64_t* ref_f2w_a,
+                          int64_t* ref_bwi_b, int64_t* ref_lvl_b, int64_t* ref_f2w_b,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- dense contractions (fp32 parity mode) ------------------------------------------------------
+ * Replace torch.nn.functional.linear at cosine_msa.py:57-62,431, sst_basic_block.py:81, wca_block.py:99,
+ * network_utils.py:30, SiamWCA_MAE.py:117-119 and their autograd backward.  w is (n, k) row-major
+ * (torch Linear layout).  y = act(x w^T + bias) + residual ; preact (nullable) receives x w^T + bias. */
+TMAE_API int tmae_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact,
+                    int64_t m, int64_t n, int64_t k, int32_t act, int32_t precision, void* stream);
+TMAE_API int tmae_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int32_t accumulate,
+                         int32_t precision, void* stream);
+TMAE_API int tmae_linear_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int64_t m, int64_t n, int64_t k,
+                           int32_t precision, void* stream);
+TMAE_API int tmae_colsum(const float* x, float* out, int64_t rows, int32_t cols, void* stream);
+TMAE_API int tmae_gelu_bwd(const float* dy, const float* preact, float* dx, int64_t n, void* stream);
+
+/* ---- A9 sparse 2-D convolution ------------------------------------------------------------------
+ * Replaces spconv SubMConv2d / SparseConv2d inside post_act_block (pcdet/utils/spconv_utils.py:37-56).
+ * Tables: (rows, 9) i32 input row per tap (ky*3+kx) or -1.  Weights (cout, 3, 3, cin) = (cout, taps, cin). */
+TMAE_API size_t tmae_subm_table_workspace_bytes(int32_t batch, int32_t y, int32_t x);
+TMAE_API int tmae_subm_table(const int32_t* indices, int64_t rows_cap, const int32_t* rows_dev, int32_t batch, int32_t y, int32_t x,
+                    int32_t* table, void* workspace, size_t workspace_bytes, void* stream);
+TMAE_API size_t tmae_strided_table_workspace_bytes(int32_t batch, int32_t y_in, int32_t x_in);
+TMAE_API int tmae_strided_table(const int32_t* indices, int64_t rows_cap, const int32_t* rows_dev, int32_t batch, int32_t y_in, int32_t x_in,
+                       int32_t* indices_out, int64_t out_cap, int32_t* n_out, int32_t* table, int32_t* table_t, void* workspace,
+                       size_t workspace_bytes, void* stream);
+TMAE_API int tmae_sparse_conv_fwd(const float* x, const int32_t* table, const float* w, float* y, int64_t rows_out, int32_t taps,
+                         int32_t cin, int32_t cout, int32_t accumulate, int32_t precision, void* stream);
+TMAE_API int tmae_sparse_conv_bwd_weight(const float* dy, const float* x, const int32_t* table, float* dw, int64_t rows_out, int32_t taps,
+                                int32_t cin, int32_t cout, int32_t precision, void* stream);
+TMAE_API int tmae_transpose_taps(const float* w, float* wt, int32_t cout, int32_t taps, int32_t cin, int32_t flip, void* stream);
+
+/* ---- row-wise kernels ---------------------------------------------------------------------------- */
+/* y = x + lut[posidx]  : position embedding (spt_backbone.py:186-231) as a 64-row table lookup */
+TMAE_API int tmae_add_pos(const float* x, const uint8_t* posidx, const float* lut, float* y, int64_t rows, int32_t c, void* stream);
+/* y = LayerNorm(x + res) ; rows with rowmask == 0 ignore res (wca_block.py:96-98).  (sst_basic_block.py:78-83)
+ * backward: dv = grad wrt (x + res) ; dres (nullable) = dv on rows whose res was used, else 0 */
+TMAE_API int tmae_add_layernorm_fwd(const float* x, const float* res, const uint8_t* rowmask, const float* gamma, const float* beta, float* y,
+                           float* mean, float* rstd, int64_t rows, int32_t c, float eps, void* stream);
+TMAE_API int tmae_add_layernorm_bwd(const float* dy, const float* x, const float* res, const uint8_t* rowmask, const float* gamma,
+                           const float* mean, const float* rstd, float* dv, float* dres, float* dgamma, float* dbeta, int64_t rows,
+                           int32_t c, void* stream);
+/* BatchNorm1d (+ReLU) over rows: network_utils.py:31 (VFE), spconv_utils.py:50-54 (after sparse convs) */
+TMAE_API size_t tmae_bn_workspace_bytes(int32_t c);
+TMAE_API int tmae_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
+                      float eps, float* y, float* save_mean, float* save_rstd, int64_t rows, int32_t c, int32_t relu,
+                      void* workspace, size_t workspace_bytes, void* stream);
+TMAE_API int tmae_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y, int64_t rows,
+                  int32_t c, int32_t relu, void* stream);
+TMAE_API int tmae_bn_bwd(const float* dy, const float* x, const float* y, const float* mean, const float* rstd, const float* gamma, float* dx,
+                float* dgamma, float* dbeta, int64_t rows, int32_t c, int32_t relu, int32_t training, void* workspace,
+                size_t workspace_bytes, void* stream);
+/* per-voxel max over its points: torch_scatter.scatter_max (temporal_dyn_vfe.py:113) through the CSR */
+TMAE_API int tmae_segment_max_fwd(const float* x, const int32_t* voxel_offset, const int32_t* pt_order, int64_t n_voxels, int32_t c, float* out,
+                         int32_t* argmax, void* stream);
+TMAE_API int tmae_segment_max_bwd(const float* dout, const int32_t* argmax, int64_t n_voxels, int32_t c, float* dx, int64_t n_points,
+                         void* stream);
+/* SparseConvTensor.dense() as a channels-last (B,Y,X,C) map (SiamWCA_MAE.py:235) and its inverse gather
+ * (also spatial_features[b,y,x] at SiamWCA_MAE.py:311-312) */
+TMAE_API int tmae_densify_nhwc(const float* rows, const int32_t* indices, int64_t m, int32_t c, int32_t batch, int32_t y, int32_t x,
+                      float* dense, int32_t zero_fill, void* stream);
+TMAE_API int tmae_gather_nhwc(const float* dense, const int32_t* indices, int64_t m, int32_t c, int32_t y, int32_t x, float* rows, void* stream);
+TMAE_API int tmae_gather_rows(const float* src, const int32_t* sel, int64_t m, int32_t c, float* out, void* stream);
+TMAE_API int tmae_scatter_rows(const float* rows, const int32_t* sel, int64_t m, int32_t c, float* dst, void* stream);
+
+/* ---- A7-A8 windowed cosine attention core -------------------------------------------------------
+ * Replaces flat2window + _scaled_cosine_attention + window2flat (cosine_msa.py:114-176, sst_basic_block.py:22-54,
+ * wca_block.py:26-67).  q/k/v are the PROJECTED rows (rows, C) in flat voxel order; tok/cnt tables come from
+ * tmae_window_partition (self: q and k tables are the same; cross: q = current frame, k = previous frame).
+ * max_windows bounds the grid; the live count is read from n_win on the device. */
+TMAE_API int tmae_window_attention_fwd(const float* q, const float* k, const float* v, float* o, float* lse, const int32_t* qtok,
+                              const int32_t* qcnt, const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win,
+                              int64_t max_windows, const float* tau, float tau_min, int32_t channels, int32_t heads, void* stream);
+TMAE_API int tmae_window_attention_bwd(const float* dout, const float* q, const float* k, const float* v, const float* o, const float* lse,
+                              float* dq, float* dk, float* dv, float* dtau, const int32_t* qtok, const int32_t* qcnt,
+                              const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win, int64_t max_windows, const float* tau,
+                              float tau_min, int32_t channels, int32_t heads, void* stream);
+
+/* ---- A10-A11 reconstruction target + Chamfer loss ------------------------------------------------
+ * Replaces sst_ops_cuda.group_inner_inds_wrapper (pcdet/ops/sst_ops/src/sst_ops_api.cpp:8, sst_ops_gpu.cu:22-39),
+ * the GT gather / centre subtraction (SiamWCA_MAE.py:132-139) and pytorch3d chamfer_distance (SiamWCA_MAE.py:163). */
+TMAE_API int tmae_gt_group(const float* points_kept, int32_t point_stride, const int32_t* voxel_offset, const int32_t* pt_order,
+                  const int64_t* voxel_coords, const float* range_lo, const float* voxel, int64_t n_voxels, int32_t k, float* gt,
+                  int64_t* group_inds, void* stream);
+TMAE_API size_t tmae_chamfer_workspace_bytes(void);
+TMAE_API int tmae_chamfer_fwd(const float* pred, const float* gt, const float* w, int64_t n_voxels, int32_t p1, int32_t p2,
+                     const float* points_kept, int32_t point_stride, const int32_t* voxel_offset, const int32_t* pt_order,
+                     const int64_t* voxel_coords, const float* range_lo, const float* voxel, float* loss, void* state, void* stream);
+TMAE_API int tmae_chamfer_bwd(const float* grad_loss, const float* pred, const float* gt, const float* w, int64_t n_voxels, int32_t p1,
+                     int32_t p2, const float* points_kept, int32_t point_stride, const int32_t* voxel_offset,
+                     const int32_t* pt_order, const int64_t* voxel_coords, const float* range_lo, const float* voxel,
+                     const void* state, float* dpred, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMAE_SM100_H_ */

@@ -1,0 +1,506 @@
+"""Drop-in backbone_3d modules (pcdet API): `SiamWCA` (finetune encoder) and `SiamWCA_MAE` (pretraining).
+
+Mirrors pcdet/models/backbones_3d/{spt_backbone.py, SiamWCA.py, SiamWCA_MAE.py} and
+pcdet/models/model_utils/{sst_basic_block.py, wca_block.py, cosine_msa.py}: same constructor signature,
+`forward(batch_dict)` keys, `get_loss()`, `num_point_features`, and the same parameter names
+(`sst_blocks.{s}.encoder_blocks.{b}.encoder_list.{k}.win_attn.self_attn.in_proj_weight`, ...), so pcdet's
+`backbones_3d.__all__` registry and released checkpoints work unchanged.
+
+What differs is how it runs.  All coordinate-only work is done once per forward by `plan.build_plans`
+(one host read), features stay in the flat voxel-major layout for the whole encoder (the padded
+(windows, tokens, C) tensors of flat2window are never materialised), and every encoder layer is one
+autograd node that launches the library kernels in sequence.  The dense decoder (ConvTranspose2d /
+Conv2d + BatchNorm2d, SiamWCA_MAE.py:79-115) stays on cuDNN in channels-last layout.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .plan import build_plans
+from .sparse import ConvBNReLU, SparseConvTensor, gather_bev
+from .vfe import _LinearFn  # noqa: F401
+
+
+def _get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def pos_embed_table(C, temperature, win=(8, 8), normalize=False):
+    """64-row table of the window position embedding, row = ly*8 + lx  (spt_backbone.py:186-222:
+    the embedding depends only on the in-window cell, so it is built once with the reference's own op
+    sequence and looked up in-kernel)."""
+    wx, wy = win
+    ly, lx = torch.meshgrid(torch.arange(wy), torch.arange(wx), indexing="ij")
+    y, x = ly.reshape(-1) - wy / 2, lx.reshape(-1) - wx / 2
+    if normalize:
+        x, y = x / wx * 2 * 3.1415, y / wy * 2 * 3.1415
+    L = C // 2
+    inv_freq = torch.arange(L, dtype=torch.float32)
+    inv_freq = temperature ** (2 * torch.div(inv_freq, 2, rounding_mode="floor") / L)
+    ex, ey = x[:, None] / inv_freq[None, :], y[:, None] / inv_freq[None, :]
+    ex = torch.stack([ex[:, ::2].sin(), ex[:, 1::2].cos()], dim=-1).flatten(1)
+    ey = torch.stack([ey[:, ::2].sin(), ey[:, 1::2].cos()], dim=-1).flatten(1)
+    return torch.cat([ex, ey], dim=-1).float().contiguous()
+
+
+# ============================================================================ encoder layers
+class CosineMHAParams(nn.Module):
+    """Parameters of CosineMultiheadAttention (cosine_msa.py:441-458): packed in_proj (3C, C), out_proj, tau."""
+
+    def __init__(self, C, H, tau_min=0.01):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.tau_min = C, H, tau_min
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * C, C))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * C))
+        self.out_proj = nn.Linear(C, C)
+        self.tau = nn.Parameter(torch.ones(1, 1, 1))
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.zeros_(self.out_proj.bias)
+
+
+class _AttnHolder(nn.Module):
+    def __init__(self, name, C, H, tau_min):
+        super().__init__()
+        setattr(self, name, CosineMHAParams(C, H, tau_min))
+
+
+def _ffn_fwd(x_in, a, rowmask, p, eps):
+    """LN1(x_in + a) -> Linear/GELU/Linear -> LN2 ; returns output and what backward needs."""
+    g1, b1, W1, bb1, W2, bb2, g2, b2 = p
+    x1, m1, r1 = ops.add_layernorm_fwd(x_in, a, rowmask, g1, b1, eps)
+    h, hpre = ops.linear_fwd(x1, W1, bb1, act=ops.ACT_GELU, want_preact=True)
+    f = ops.linear_fwd(h, W2, bb2)
+    x2, m2, r2 = ops.add_layernorm_fwd(x1, f, None, g2, b2, eps)
+    return x2, (x1, m1, r1, h, hpre, f, m2, r2)
+
+
+def _ffn_bwd(dx2, x_in, a, rowmask, p, saved):
+    """-> (d x_in, d a, grads of the 8 FFN/LN parameters)."""
+    g1, b1, W1, bb1, W2, bb2, g2, b2 = p
+    x1, m1, r1, h, hpre, f, m2, r2 = saved
+    dg2, db2 = torch.empty_like(g2), torch.empty_like(b2)
+    dv2, _ = ops.add_layernorm_bwd(dx2, x1, f, None, g2, m2, r2, dg2, db2)
+    dW2, dbb2 = torch.empty_like(W2), torch.empty_like(bb2)
+    ops.linear_bwd_weight(dv2, h, dW2, dbb2)
+    dh = ops.linear_bwd_data(dv2, W2)
+    dhpre = ops.gelu_bwd(dh, hpre)
+    dW1, dbb1 = torch.empty_like(W1), torch.empty_like(bb1)
+    ops.linear_bwd_weight(dhpre, x1, dW1, dbb1)
+    ops.linear_bwd_data(dhpre, W1, dx=dv2, accumulate=True)  # dv2 now holds d x1
+    dg1, db1 = torch.empty_like(g1), torch.empty_like(b1)
+    dv1, da = ops.add_layernorm_bwd(dv2, x_in, a, rowmask, g1, m1, r1, dg1, db1, want_dres=rowmask is not None)
+    if da is None:
+        da = dv1
+    return dv1, da, (dg1, db1, dW1, dbb1, dW2, dbb2, dg2, db2)
+
+
+class _SelfLayerFn(torch.autograd.Function):
+    """One SST encoder layer (sst_basic_block.py:58-84 with WindowAttention :22-54) on flat voxel rows."""
+
+    @staticmethod
+    def forward(ctx, x, Win, bin_, Wo, bo, tau, g1, b1, W1, bb1, W2, bb2, g2, b2, part, shift, lut, heads, tau_min, eps):
+        x = x.contiguous()
+        M, C = x.shape
+        tok, cnt, nwin = part.tok_a[shift], part.cnt_a[shift], part.n_win[shift:shift + 1]
+        maxw = min(part.wcap, M)
+        xp = ops.add_pos(x, part.posidx_a[shift], lut)
+        q = ops.linear_fwd(xp, Win, bin_, w_offset_rows=0, n=C)
+        k = ops.linear_fwd(xp, Win, bin_, w_offset_rows=C, n=C)
+        v = ops.linear_fwd(x, Win, bin_, w_offset_rows=2 * C, n=C)
+        o, lse = ops.window_attention_fwd(q, k, v, tok, cnt, tok, cnt, nwin, maxw, tau, tau_min, heads, zero_out=False)
+        a = ops.linear_fwd(o, Wo, bo)
+        ffn_p = (g1, b1, W1, bb1, W2, bb2, g2, b2)
+        x2, saved = _ffn_fwd(x, a, None, ffn_p, eps)
+        ctx.save_for_backward(x, xp, q, k, v, o, lse, a, Win, Wo, tau, *ffn_p, *saved)
+        ctx.misc = (part, shift, heads, tau_min, maxw)
+        return x2
+
+    @staticmethod
+    def backward(ctx, dx2):
+        t = ctx.saved_tensors
+        x, xp, q, k, v, o, lse, a, Win, Wo, tau = t[:11]
+        ffn_p, saved = t[11:19], t[19:]
+        part, shift, heads, tau_min, maxw = ctx.misc
+        C = x.shape[1]
+        tok, cnt, nwin = part.tok_a[shift], part.cnt_a[shift], part.n_win[shift:shift + 1]
+        dx, da, ffn_g = _ffn_bwd(dx2.contiguous(), x, a, None, ffn_p, saved)
+        dWo, dbo = torch.empty_like(Wo), torch.empty(C, dtype=torch.float32, device=x.device)
+        ops.linear_bwd_weight(da, o, dWo, dbo)
+        do = ops.linear_bwd_data(da, Wo)
+        dtau = torch.zeros_like(tau)
+        dq, dk, dv = ops.window_attention_bwd(do, q, k, v, o, lse, tok, cnt, tok, cnt, nwin, maxw, tau, tau_min, heads, dtau, zero=False)
+        dWin, dbin = torch.empty_like(Win), torch.empty(3 * C, dtype=torch.float32, device=x.device)
+        ops.linear_bwd_weight(dq, xp, dWin, dbin, w_offset_rows=0)
+        ops.linear_bwd_weight(dk, xp, dWin, dbin, w_offset_rows=C)
+        ops.linear_bwd_weight(dv, x, dWin, dbin, w_offset_rows=2 * C)
+        ops.linear_bwd_data(dq, Win, dx=dx, accumulate=True, w_offset_rows=0)
+        ops.linear_bwd_data(dk, Win, dx=dx, accumulate=True, w_offset_rows=C)
+        ops.linear_bwd_data(dv, Win, dx=dx, accumulate=True, w_offset_rows=2 * C)
+        return (dx, dWin, dbin, dWo, dbo, dtau, *ffn_g, None, None, None, None, None, None)
+
+
+class _CrossLayerFn(torch.autograd.Function):
+    """One WCA encoder layer (wca_block.py:70-103 with WindowCrossAttention :26-67): queries from the current
+    frame, keys/values from the previous frame, attention only inside windows occupied in both frames; rows
+    outside those windows skip the attention term but still take LN/FFN/LN."""
+
+    @staticmethod
+    def forward(ctx, x, xprev, Win, bin_, Wo, bo, tau, g1, b1, W1, bb1, W2, bb2, g2, b2, tp, shift, lut, heads, tau_min, eps):
+        x, xprev = x.contiguous(), xprev.contiguous()
+        M, C = x.shape
+        maxw = min(tp.wcap, M, xprev.shape[0])
+        nwin = tp.n_win[shift:shift + 1]
+        xq = ops.add_pos(x, tp.posidx_a[shift], lut)
+        xk = ops.add_pos(xprev, tp.posidx_b[shift], lut)
+        q = ops.linear_fwd(xq, Win, bin_, w_offset_rows=0, n=C)
+        k = ops.linear_fwd(xk, Win, bin_, w_offset_rows=C, n=C)
+        v = ops.linear_fwd(xprev, Win, bin_, w_offset_rows=2 * C, n=C)
+        o, lse = ops.window_attention_fwd(q, k, v, tp.tok_a[shift], tp.cnt_a[shift], tp.tok_b[shift], tp.cnt_b[shift], nwin, maxw, tau,
+                                          tau_min, heads, zero_out=True)
+        a = ops.linear_fwd(o, Wo, bo)
+        ffn_p = (g1, b1, W1, bb1, W2, bb2, g2, b2)
+        x2, saved = _ffn_fwd(x, a, tp.keep_a[shift], ffn_p, eps)
+        ctx.save_for_backward(x, xprev, xq, xk, q, k, v, o, lse, a, Win, Wo, tau, *ffn_p, *saved)
+        ctx.misc = (tp, shift, heads, tau_min, maxw)
+        return x2
+
+    @staticmethod
+    def backward(ctx, dx2):
+        t = ctx.saved_tensors
+        x, xprev, xq, xk, q, k, v, o, lse, a, Win, Wo, tau = t[:13]
+        ffn_p, saved = t[13:21], t[21:]
+        tp, shift, heads, tau_min, maxw = ctx.misc
+        C = x.shape[1]
+        nwin = tp.n_win[shift:shift + 1]
+        dx, da, ffn_g = _ffn_bwd(dx2.contiguous(), x, a, tp.keep_a[shift], ffn_p, saved)
+        dWo, dbo = torch.empty_like(Wo), torch.empty(C, dtype=torch.float32, device=x.device)
+        ops.linear_bwd_weight(da, o, dWo, dbo)
+        do = ops.linear_bwd_data(da, Wo)
+        dtau = torch.zeros_like(tau)
+        dq, dk, dv = ops.window_attention_bwd(do, q, k, v, o, lse, tp.tok_a[shift], tp.cnt_a[shift], tp.tok_b[shift], tp.cnt_b[shift],
+                                              nwin, maxw, tau, tau_min, heads, dtau, zero=True)
+        dWin, dbin = torch.empty_like(Win), torch.empty(3 * C, dtype=torch.float32, device=x.device)
+        ops.linear_bwd_weight(dq, xq, dWin, dbin, w_offset_rows=0)
+        ops.linear_bwd_weight(dk, xk, dWin, dbin, w_offset_rows=C)
+        ops.linear_bwd_weight(dv, xprev, dWin, dbin, w_offset_rows=2 * C)
+        ops.linear_bwd_data(dq, Win, dx=dx, accumulate=True, w_offset_rows=0)
+        dprev = None
+        if ctx.needs_input_grad[1]:
+            dprev = ops.linear_bwd_data(dk, Win, w_offset_rows=C)
+            ops.linear_bwd_data(dv, Win, dx=dprev, accumulate=True, w_offset_rows=2 * C)
+        return (dx, dprev, dWin, dbin, dWo, dbo, dtau, *ffn_g, None, None, None, None, None, None)
+
+
+class EncoderLayer(nn.Module):
+    def __init__(self, C, H, FF, layer_cfg, cross):
+        super().__init__()
+        self.cross, self.nhead = cross, H
+        if not _get(layer_cfg, "cosine", False):
+            raise NotImplementedError("only cosine attention is on the T-MAE path (t_mae_ssl.yaml:86-89)")
+        if _get(layer_cfg, "non_shared_tau", False):
+            raise NotImplementedError("non_shared_tau is not used by the T-MAE configs")
+        self.tau_min = float(_get(layer_cfg, "tau_min", 0.01))
+        self.win_attn = _AttnHolder("cross_attn" if cross else "self_attn", C, H, self.tau_min)
+        self.linear1, self.linear2 = nn.Linear(C, FF), nn.Linear(FF, C)
+        self.norm1, self.norm2 = nn.LayerNorm(C), nn.LayerNorm(C)
+
+    def _params(self):
+        at = self.win_attn.cross_attn if self.cross else self.win_attn.self_attn
+        return (at.in_proj_weight, at.in_proj_bias, at.out_proj.weight, at.out_proj.bias, at.tau, self.norm1.weight, self.norm1.bias,
+                self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias, self.norm2.weight, self.norm2.bias)
+
+    def forward_self(self, x, part, shift, lut):
+        return _SelfLayerFn.apply(x, *self._params(), part, shift, lut, self.nhead, self.tau_min, self.norm1.eps)
+
+    def forward_cross(self, x, xprev, tp, shift, lut):
+        return _CrossLayerFn.apply(x, xprev, *self._params(), tp, shift, lut, self.nhead, self.tau_min, self.norm1.eps)
+
+
+class ShiftBlock(nn.Module):
+    """BasicShiftBlockV2 (sst_basic_block.py:87-114) / BasicShiftBlock_WCA (wca_block.py:106-145)."""
+
+    def __init__(self, C, H, FF, layer_cfg, cross):
+        super().__init__()
+        self.encoder_list = nn.ModuleList([EncoderLayer(C, H, FF, layer_cfg, cross) for _ in range(2)])
+
+
+class _EncBlockBase(nn.Module):
+    def _common(self, cfg):
+        enc, pre = cfg["ENCODER"], cfg["PREPROCESS"]
+        if list(pre["WINDOW_SHAPE"]) != [8, 8, 1]:
+            raise NotImplementedError("the kernels are specialised to 8x8x1 windows (t_mae_ssl.yaml:61)")
+        if pre["SHUFFLE_VOXELS"]:
+            raise NotImplementedError("SHUFFLE_VOXELS is False in both T-MAE configs (t_mae_ssl.yaml:74)")
+        if enc["ACTIVATION"] != "gelu" or enc["DROPOUT"] != 0.0:
+            raise NotImplementedError("encoder uses GELU and no dropout on the T-MAE path")
+        self.d_model = enc["D_MODEL"]
+        self.register_buffer("pos_lut", pos_embed_table(self.d_model, pre["POS_TEMPERATURE"], normalize=pre["NORMALIZE_POS"]),
+                             persistent=False)
+        return enc
+
+
+class SSTBlockV1(_EncBlockBase):
+    """spt_backbone.py:267-353: [conv_down] -> 2 x (shift-0 layer, shift-1 layer) -> conv_out(x + enc(x))."""
+
+    def __init__(self, cfg, cin, indice_key=None, **kw):
+        super().__init__()
+        enc = self._common(cfg)
+        C = self.d_model
+        self.conv_down = ConvBNReLU(cin, C) if enc["STRIDE"] > 1 else None
+        self.encoder_blocks = nn.ModuleList(
+            [ShiftBlock(C, enc["NHEAD"], enc["DIM_FEEDFORWARD"], enc["LAYER_CFG"], False) for _ in range(enc["NUM_BLOCKS"])])
+        self.conv_out = ConvBNReLU(C, C)
+
+    def forward(self, feats, stage):
+        if self.conv_down is not None:
+            feats = self.conv_down(feats, stage.down, stage.down_t, False, stage.m)
+        x = feats
+        for blk in self.encoder_blocks:
+            for s, layer in enumerate(blk.encoder_list):
+                x = layer.forward_self(x, stage.part, s, self.pos_lut)
+        return self.conv_out(feats + x, stage.subm, stage.subm, True, stage.m)
+
+
+class WCABlock(_EncBlockBase):
+    """SiamWCA.py:272-447: one BasicShiftBlock_WCA (NUM_BLOCKS forced to 1, :294-296) -> conv_out(x + enc(x))."""
+
+    def __init__(self, cfg, cin, indice_key=None, **kw):
+        super().__init__()
+        enc = self._common(cfg)
+        C = self.d_model
+        n = 1 if enc["NUM_BLOCKS"] == 2 else enc["NUM_BLOCKS"]
+        self.encoder_blocks = nn.ModuleList([ShiftBlock(C, enc["NHEAD"], enc["DIM_FEEDFORWARD"], enc["LAYER_CFG"], True) for _ in range(n)])
+        self.conv_out = ConvBNReLU(C, C)
+
+    def forward(self, feats, feats_prev, stage, tp):
+        x = feats
+        for s, layer in enumerate(self.encoder_blocks[0].encoder_list):
+            x = layer.forward_cross(x, feats_prev, tp, s, self.pos_lut)
+        return self.conv_out(feats + x, stage.subm, stage.subm, True, stage.m)
+
+
+def _deblocks(cfg):
+    blocks, cin = nn.ModuleList(), 0
+    for src in cfg["FEATURES_SOURCE"]:
+        c = cfg["FUSE_LAYER"][src]
+        blocks.append(nn.Sequential(
+            nn.ConvTranspose2d(c["NUM_FILTER"], c["NUM_UPSAMPLE_FILTER"], c["UPSAMPLE_STRIDE"], stride=c["UPSAMPLE_STRIDE"], bias=False),
+            nn.BatchNorm2d(c["NUM_UPSAMPLE_FILTER"], eps=1e-3, momentum=0.01), nn.ReLU(inplace=True)))
+        cin += c["NUM_UPSAMPLE_FILTER"]
+    out = nn.Sequential(nn.Conv2d(cin, cin // len(blocks), 3, padding=1, bias=False),
+                        nn.BatchNorm2d(cin // len(blocks), eps=1e-3, momentum=0.01), nn.ReLU(inplace=True))
+    return blocks, out, cin // len(blocks)
+
+
+class SiamWCA(nn.Module):
+    """pcdet `SiamWCA` (SiamWCA.py:450-667), finetune-mode encoder: encode prev, encode cur, WCA x3, dense fuse."""
+    _deblocks_name, _conv_out_name = "deblocks", "conv_out"
+
+    def __init__(self, model_cfg, input_channels, grid_size, voxel_size, point_cloud_range, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+        self.grid_size = np.asarray(grid_size)
+        self.voxel_size = [float(v) for v in voxel_size]
+        self.point_cloud_range = [float(v) for v in point_cloud_range]
+        self.sparse_shape = [int(grid_size[1]), int(grid_size[0])]
+        asym = _get(model_cfg, "ASYMMETRIC", False)
+        if asym and asym["ENABLED"]:
+            raise NotImplementedError("ASYMMETRIC encoders are not enabled in either T-MAE config")
+        self.block_cfgs = list(model_cfg["SST_BLOCK_LIST"])
+        cin = input_channels
+        self.sst_blocks = nn.ModuleList()
+        for c in self.block_cfgs:
+            self.sst_blocks.append(SSTBlockV1(c, cin, c["NAME"]))
+            cin = c["ENCODER"]["D_MODEL"]
+        self.wca_blocks = nn.ModuleList([WCABlock(c, c["ENCODER"]["D_MODEL"], c["NAME"]) for c in self.block_cfgs])
+        de, out, self.num_point_features = _deblocks(model_cfg)
+        setattr(self, self._deblocks_name, de)
+        setattr(self, self._conv_out_name, out)
+        self.decoder_autocast = None  # e.g. torch.bfloat16 for the cuDNN decoder in throughput runs
+        self.debug_refs = False       # emit reference-format partition tables and check the status word
+        self.last_plan = None
+
+    # ---- pieces -------------------------------------------------------------------------------
+    @staticmethod
+    def _indices(coords):
+        return coords[:, [0, 2, 3]].contiguous().int()  # (bs_idx, y_idx, x_idx), SiamWCA.py:553-557
+
+    def _encode(self, feats, fp):
+        hidden = []
+        x = feats
+        for blk, st in zip(self.sst_blocks, fp.stages):
+            x = blk(x, st)
+            hidden.append(x)
+        return hidden
+
+    def _cross(self, hid, hid_prev, fp, tparts):
+        return [blk(hid[i], hid_prev[i], fp.stages[i], tparts[i]) for i, blk in enumerate(self.wca_blocks)]
+
+    def _sp(self, feats, st, B):
+        return SparseConvTensor(feats, st.indices, [st.Y, st.X], B)
+
+    def _dense(self, sps):
+        de, out = getattr(self, self._deblocks_name), getattr(self, self._conv_out_name)
+        maps = [sps[src].dense() for src in self.model_cfg["FEATURES_SOURCE"]]
+        if self.decoder_autocast is not None:
+            with torch.autocast("cuda", dtype=self.decoder_autocast):
+                y = out(torch.cat([de[i](m) for i, m in enumerate(maps)], 1))
+            return y.float()
+        return out(torch.cat([de[i](m) for i, m in enumerate(maps)], 1))
+
+    def _strides(self, sps):
+        return {k: 2 ** (i + 1) for i, k in enumerate(sps)}  # SiamWCA.py:581
+
+    def _stride_out(self, strides):
+        src = self.model_cfg["FEATURES_SOURCE"][0]
+        return strides[src] // self.model_cfg["FUSE_LAYER"][src]["UPSAMPLE_STRIDE"]
+
+    def _check_z(self, bd):
+        # reference asserts voxel_coords[:, 1] == 0 (SiamWCA.py:620-621) with two host syncs per step; the grid
+        # has a single z slab by construction, checked here once on the host
+        if int(self.grid_size[2]) != 1:
+            raise RuntimeError("the backbone needs a single z slab (pillars)")
+
+    def _run(self, bd, feats, coords, feats_prev, coords_prev):
+        B = int(bd["batch_size"])
+        plans, tparts = build_plans([self._indices(coords), self._indices(coords_prev)], B, self.sparse_shape, self.block_cfgs,
+                                    temporal_pair=(0, 1), want_ref=self.debug_refs, check=self.debug_refs)
+        self.last_plan = (plans, tparts)
+        hid_prev = self._encode(feats_prev, plans[1])
+        hid = self._encode(feats, plans[0])
+        hid = self._cross(hid, hid_prev, plans[0], tparts)
+        sps = {f"x_conv{i + 1}": self._sp(h, plans[0].stages[i], B) for i, h in enumerate(hid)}
+        strides = self._strides(sps)
+        sf = self._dense(sps)
+        bd["multi_scale_3d_features"], bd["multi_scale_3d_strides"] = sps, strides
+        bd["spatial_features"], bd["spatial_features_stride"] = sf, self._stride_out(strides)
+        return sf
+
+    def forward(self, batch_dict):
+        self._check_z(batch_dict)
+        self._run(batch_dict, batch_dict["voxel_features"], batch_dict["voxel_coords"], batch_dict["voxel_features_prev"],
+                  batch_dict["voxel_coords_prev"])
+        return batch_dict
+
+
+class _GatherRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, sel):
+        ctx.save_for_backward(sel)
+        ctx.rows = src.shape[0]
+        out = torch.empty(sel.shape[0], src.shape[1], dtype=src.dtype, device=src.device)
+        ops._call("gather_rows", ops._p(src.contiguous()), ops._p(sel), sel.shape[0], src.shape[1], ops._p(out), ops._stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        (sel,) = ctx.saved_tensors
+        g = torch.zeros(ctx.rows, d.shape[1], dtype=d.dtype, device=d.device)
+        ops._call("scatter_rows", ops._p(d.contiguous()), ops._p(sel), sel.shape[0], d.shape[1], ops._p(g), ops._stream())
+        return g, None
+
+
+class _LinearBiasFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return ops.linear_fwd(x.contiguous(), w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dw, db = torch.empty_like(w), torch.empty(w.shape[0], dtype=w.dtype, device=w.device)
+        ops.linear_bwd_weight(dy, x.contiguous(), dw, db)
+        return (ops.linear_bwd_data(dy, w) if ctx.needs_input_grad[0] else None), dw, db
+
+
+class _ChamferFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, w, gtctx):
+        loss, state = ops.chamfer_fwd(pred, None, w, gtctx)
+        ctx.save_for_backward(pred, w, state)
+        ctx.gtctx = gtctx
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, w, state = ctx.saved_tensors
+        return ops.chamfer_bwd(g.contiguous(), pred, None, w, state, ctx.gtctx), None, None
+
+
+class SiamWCA_MAE(SiamWCA):
+    """pcdet `SiamWCA_MAE` (SiamWCA_MAE.py): 75 % voxel masking, encode prev + visible cur, WCA, dense decode,
+    16 predicted points per pillar, Chamfer loss against <= 64 grouped ground-truth points."""
+    _deblocks_name, _conv_out_name = "decoder_deblocks", "decoder_conv_out"
+
+    def __init__(self, model_cfg, input_channels, grid_size, voxel_size, point_cloud_range, **kwargs):
+        super().__init__(model_cfg, input_channels, grid_size, voxel_size, point_cloud_range)
+        self.mask_cfg = model_cfg["MASK_CONFIG"]
+        self.mask_ratio = float(self.mask_cfg["RATIO"])
+        self.decoder_pred = nn.Linear(self.num_point_features, int(self.mask_cfg["NUM_PRD_POINTS"]) * 3, bias=True)
+        self.forward_ret_dict = {}
+        self.mask_generator = None  # optional torch.Generator on the device
+
+    def _strides(self, sps):
+        return {k: self.sparse_shape[0] // v.spatial_shape[0] for k, v in sps.items()}  # SiamWCA_MAE.py:214-216
+
+    def mask_voxels(self, coords, voxels_per_sample):
+        """SiamWCA_MAE.py:166-182 / common_utils.random_masking: per sample keep the int(L*(1-ratio)) voxels with
+        the smallest uniform noise.  One batched draw + one sort, no per-sample .item(); returns mask (1 = removed)
+        and the number of visible voxels (known on the host from the per-sample counts)."""
+        M, dev = coords.shape[0], coords.device
+        noise = torch.rand(M, device=dev, generator=self.mask_generator)
+        sample = coords[:, 0].double()
+        order = torch.argsort(sample + noise.double())  # samples are contiguous row blocks; noise orders inside
+        starts = np.concatenate([[0], np.cumsum(voxels_per_sample)])
+        keep_n = [int(L * (1 - self.mask_ratio)) for L in voxels_per_sample]
+        pos = torch.arange(M, device=dev)
+        lim = torch.repeat_interleave(torch.tensor([s + k for s, k in zip(starts[:-1], keep_n)], device=dev),
+                                      torch.tensor(voxels_per_sample, device=dev), output_size=M)
+        mask = torch.ones(M, device=dev)
+        mask[order] = (pos >= lim).float()
+        return mask, int(sum(keep_n))
+
+    def forward(self, batch_dict):
+        self._check_z(batch_dict)
+        bd = batch_dict
+        feats, coords = bd["voxel_features"], bd["voxel_coords"]
+        if "voxel_mae_mask_in" in bd:  # caller-supplied mask (tests, reproducible runs)
+            mask = bd["voxel_mae_mask_in"].float()
+            n_vis = int((mask == 0).sum())
+        else:
+            vps = bd.get("voxels_per_sample")
+            if vps is None:
+                vps = torch.bincount(coords[:, 0], minlength=int(bd["batch_size"])).tolist()
+            mask, n_vis = self.mask_voxels(coords, vps)
+        bd["voxel_mae_mask"] = mask
+        vis = torch.nonzero_static(mask == 0, size=n_vis).view(-1).int()
+        vis_feats = _GatherRowsFn.apply(feats, vis)
+        vis_coords = coords[vis.long()]
+        sf = self._run(bd, vis_feats, vis_coords, bd["voxel_features_prev"], bd["voxel_coords_prev"])
+        all_idx = self._indices(coords)
+        vf = gather_bev(sf, all_idx)
+        bd["voxel_features"], bd["voxel_coords"] = vf, coords
+        bd["voxel_shuffle_inds"] = torch.arange(coords.shape[0], device=coords.device)
+        pred = _LinearBiasFn.apply(vf, self.decoder_pred.weight, self.decoder_pred.bias).view(vf.shape[0], -1, 3)
+        off, order, _ = bd["voxel_point_csr"]
+        self._gtctx = (bd["points"], off, order, coords.contiguous(), self.point_cloud_range, self.voxel_size,
+                       int(self.mask_cfg["NUM_GT_POINTS"]))
+        self.forward_ret_dict = {"pred_points": pred, "mask": mask}
+        return bd
+
+    def gt_points(self):
+        """(M, 64, 3) normalised ground-truth points (the reference's forward_ret_dict['gt_points'],
+        SiamWCA_MAE.py:132-139); materialised only on request -- the loss kernel reads the CSR directly."""
+        pk, off, order, vc, rng, vs, k = self._gtctx
+        return ops.gt_group(pk, off, order, vc, rng, vs, vc.shape[0], k)
+
+    def get_loss(self, tb_dict=None):
+        tb_dict = {} if tb_dict is None else tb_dict
+        r = self.forward_ret_dict
+        loss = _ChamferFn.apply(r["pred_points"].float().contiguous(), r["mask"].contiguous(), self._gtctx)
+        return loss, tb_dict

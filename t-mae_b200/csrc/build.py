@@ -1,0 +1,61 @@
+"""Builds csrc/libtmae_sm100.so with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python t-mae_b200/csrc/build.py [--force] [--verbose]
+
+Objects are rebuilt only when a source or header is newer; the .so stays in-tree (git-ignored)
+so it travels to the GPU box with the snapshot.
+"""
+import glob
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LIB = os.path.join(HERE, "libtmae_sm100.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+         "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    srcs = sorted(glob.glob(os.path.join(HERE, "*.cu")))
+    hdrs = glob.glob(os.path.join(HERE, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    objs, jobs = [], []
+    for s in srcs:
+        o = os.path.join(HERE, "build", os.path.basename(s)[:-3] + ".o")
+        objs.append(o)
+        if force or _newer(o, [s] + hdrs):
+            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            jobs.append(cmd)
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return cmd, r
+
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        for cmd, r in ex.map(run, jobs):
+            if verbose or r.returncode:
+                sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            if r.returncode:
+                raise RuntimeError("nvcc failed for " + cmd[-3])
+    if jobs or force or _newer(LIB, objs):
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build("--force" in sys.argv, "--verbose" in sys.argv))

@@ -1,0 +1,330 @@
+// fp32 SIMT GEMM family (TMAE_PREC_FP32, the parity mode) for every dense contraction on the path:
+// linear layers (cosine_msa.py:57-62,431; sst_basic_block.py:81; network_utils.py:30;
+// SiamWCA_MAE.py:117-119), their backward passes, and the gather-GEMM form of the 2-D sparse
+// convolutions (utils/spconv_utils.py:37-56).  The bf16 tcgen05 path lives in gemm_tc.cu and is
+// validated against this one.
+//
+// One kernel template computes C[m,n] = sum_k A(m,k) * B(k,n) over 64x64x16 tiles (256 threads,
+// 4x4 register micro-tiles, operands staged k-major in shared memory); the operand accessors are
+// template modes so forward (NT), backward-data (NN), backward-weight (TN, split over the long
+// reduction with fp32 atomics) and the neighbour-table gathers share the inner loop.
+#include "common.cuh"
+
+namespace tmae {
+
+constexpr int BM = 64, BN = 64, BK = 16, GT = 256;
+
+enum AMode { A_KCONTIG = 0, A_MCONTIG = 1, A_GATHER = 2 };
+enum BMode { B_KCONTIG = 0, B_NCONTIG = 1, B_GATHER = 2 };
+
+struct GemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  int64_t M, N, K;
+  int64_t lda, ldb, ldc;
+  const float* bias;      // per n
+  const float* residual;  // same layout as C
+  float* preact;          // optional copy of the pre-activation (for GELU backward)
+  const int* tab;         // neighbour table (rows, taps), -1 = absent
+  int taps, cin;          // gather decomposition: k (or n) = tap * cin + c
+  const int* row_count;   // optional device row count overriding M (rows beyond are skipped)
+  int act;
+  int accumulate;         // C += result
+  int atomic;             // split-K: atomicAdd into C
+  int64_t k_chunk;        // K range per blockIdx.z
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+template <int AM, int BMD>
+__global__ void __launch_bounds__(GT) gemm_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  int64_t M = g.M;
+  if (g.row_count) {
+    int64_t rc = *g.row_count;
+    if (AM != A_MCONTIG) { M = rc < M ? rc : M; }
+  }
+  int64_t kbeg = (int64_t)blockIdx.z * g.k_chunk;
+  int64_t kend = kbeg + g.k_chunk < g.K ? kbeg + g.k_chunk : g.K;
+  if (g.row_count && AM == A_MCONTIG) {  // TN: the reduction runs over rows
+    int64_t rc = *g.row_count;
+    if (kend > rc) kend = rc;
+  }
+  if (m0 >= M && AM != A_MCONTIG) return;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+    // ---- stage A tile (BM x BK) into As[k][m]
+    if (AM == A_MCONTIG) {
+      int k = tid >> 4, m4 = (tid & 15) * 4;
+      int64_t kk = k0 + k;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int64_t mm = m0 + m4 + j;
+        As[k][m4 + j] = (kk < kend && mm < g.M) ? g.A[kk * g.lda + mm] : 0.f;
+      }
+    } else {
+      int m = tid >> 2, k4 = (tid & 3) * 4;
+      int64_t mm = m0 + m;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int64_t kk = k0 + k4 + j;
+        float v = 0.f;
+        if (mm < M && kk < kend) {
+          if (AM == A_KCONTIG) {
+            v = g.A[mm * g.lda + kk];
+          } else {
+            int tap = (int)(kk / g.cin);
+            int c = (int)(kk - (int64_t)tap * g.cin);
+            int row = g.tab[mm * g.taps + tap];
+            v = row >= 0 ? g.A[(int64_t)row * g.lda + c] : 0.f;
+          }
+        }
+        As[k4 + j][m] = v;
+      }
+    }
+    // ---- stage B tile (BK x BN) into Bs[k][n]
+    if (BMD == B_KCONTIG) {
+      int n = tid >> 2, k4 = (tid & 3) * 4;
+      int64_t nn = n0 + n;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int64_t kk = k0 + k4 + j;
+        Bs[k4 + j][n] = (nn < g.N && kk < kend) ? g.B[nn * g.ldb + kk] : 0.f;
+      }
+    } else {
+      int k = tid >> 4, n4 = (tid & 15) * 4;
+      int64_t kk = k0 + k;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int64_t nn = n0 + n4 + j;
+        float v = 0.f;
+        if (kk < kend && nn < g.N) {
+          if (BMD == B_NCONTIG) {
+            v = g.B[kk * g.ldb + nn];
+          } else {
+            int tap = (int)(nn / g.cin);
+            int c = (int)(nn - (int64_t)tap * g.cin);
+            int row = g.tab[kk * g.taps + tap];
+            v = row >= 0 ? g.B[(int64_t)row * g.ldb + c] : 0.f;
+          }
+        }
+        Bs[k][n4 + j] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  int64_t Mout = (AM == A_MCONTIG) ? g.M : M;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t mm = m0 + ty * 4 + i;
+    if (mm >= Mout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t nn = n0 + tx * 4 + j;
+      if (nn >= g.N) continue;
+      float v = acc[i][j];
+      int64_t o = mm * g.ldc + nn;
+      if (g.atomic) {
+        atomicAdd(g.C + o, v);
+        continue;
+      }
+      if (g.bias) v += g.bias[nn];
+      if (g.preact) g.preact[o] = v;
+      if (g.act == TMAE_ACT_GELU) v = gelu_erf(v);
+      else if (g.act == TMAE_ACT_RELU) v = fmaxf(v, 0.f);
+      if (g.residual) v += g.residual[o];
+      if (g.accumulate) v += g.C[o];
+      g.C[o] = v;
+    }
+  }
+}
+
+template <int AM, int BMD>
+static int launch(GemmArgs& g, int splits, cudaStream_t s) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  if (splits < 1) splits = 1;
+  g.k_chunk = align_up((g.K + splits - 1) / splits, BK);
+  int z = (int)((g.K + g.k_chunk - 1) / g.k_chunk);
+  if (z < 1) z = 1;
+  g.atomic = z > 1;
+  dim3 grid((unsigned)cdiv(g.N, BN), (unsigned)cdiv(g.M, BM), (unsigned)z);
+  gemm_kernel<AM, BMD><<<grid, GT, 0, s>>>(g);
+  return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
+}
+
+__global__ void colsum_kernel(const float* __restrict__ x, int64_t rows, int cols, const int* __restrict__ row_count,
+                              float* __restrict__ out, int rows_per_block) {
+  // block: 256 threads = 8 row-lanes x 32 column-lanes; grid.x over column groups of 32, grid.y over row chunks
+  __shared__ float sm[8][33];
+  if (row_count && *row_count < rows) rows = *row_count;
+  int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  int rl = threadIdx.x >> 5;
+  int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s = 0.f;
+  if (c < cols)
+    for (int64_t r = r0 + rl; r < r1; r += 8) s += x[r * cols + c];
+  sm[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
+    atomicAdd(out + c, t);
+  }
+}
+
+__global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, float* __restrict__ dx, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x = pre[i];
+  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  dx[i] = dy[i] * (cdf + x * pdf);
+}
+
+__global__ void transpose_taps_kernel(const float* __restrict__ w, float* __restrict__ wt, int cout, int taps, int cin, int flip) {
+  // w (cout, taps, cin) -> wt (cin, taps, cout); flip reverses the tap order
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n = (int64_t)cout * taps * cin;
+  if (i >= n) return;
+  int c = (int)(i % cin);
+  int t = (int)((i / cin) % taps);
+  int o = (int)(i / ((int64_t)cin * taps));
+  int tt = flip ? taps - 1 - t : t;
+  wt[((int64_t)c * taps + tt) * cout + o] = w[i];
+}
+
+}  // namespace tmae
+
+using namespace tmae;
+
+extern "C" {
+
+int tmae_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact,
+                    int64_t m, int64_t n, int64_t k, int32_t act, int32_t precision, void* stream) {
+  TMAE_CHECK_ARG(precision == TMAE_PREC_FP32, "tmae_linear_fwd: fp32 entry; use tmae_linear_fwd_bf16 for tensor cores");
+  GemmArgs g{};
+  g.A = x; g.B = w; g.C = y; g.M = m; g.N = n; g.K = k; g.lda = k; g.ldb = k; g.ldc = n;
+  g.bias = bias; g.residual = residual; g.preact = preact; g.act = act;
+  if (launch<A_KCONTIG, B_KCONTIG>(g, 1, (cudaStream_t)stream)) { set_error("tmae_linear_fwd: launch failed"); return TMAE_ERR_CUDA; }
+  return 0;
+}
+
+int tmae_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int32_t accumulate,
+                         int32_t precision, void* stream) {
+  TMAE_CHECK_ARG(precision == TMAE_PREC_FP32, "fp32 entry");
+  // dx[m,k] = sum_n dy[m,n] * w[n,k]
+  GemmArgs g{};
+  g.A = dy; g.B = w; g.C = dx; g.M = m; g.N = k; g.K = n; g.lda = n; g.ldb = k; g.ldc = k; g.accumulate = accumulate;
+  if (launch<A_KCONTIG, B_NCONTIG>(g, 1, (cudaStream_t)stream)) { set_error("tmae_linear_bwd_data: launch failed"); return TMAE_ERR_CUDA; }
+  return 0;
+}
+
+static int pick_splits(int64_t out_tiles, int64_t k) {
+  int64_t want = (2 * kNumSMs + out_tiles - 1) / out_tiles;
+  int64_t maxs = (k + 4 * BK - 1) / (4 * BK);
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+int tmae_linear_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int64_t m, int64_t n, int64_t k,
+                           int32_t precision, void* stream) {
+  TMAE_CHECK_ARG(precision == TMAE_PREC_FP32, "fp32 entry");
+  cudaStream_t s = (cudaStream_t)stream;
+  // dw[n,k] = sum_m dy[m,n] * x[m,k]   (overwrites dw; reduction over m split across CTAs)
+  TMAE_CUDA(cudaMemsetAsync(dw, 0, (size_t)n * k * sizeof(float), s));
+  GemmArgs g{};
+  g.A = dy; g.B = x; g.C = dw; g.M = n; g.N = k; g.K = m; g.lda = n; g.ldb = k; g.ldc = k;
+  int splits = pick_splits((int64_t)cdiv(n, BM) * cdiv(k, BN), m);
+  if (m > 0 && launch<A_MCONTIG, B_NCONTIG>(g, splits, s)) { set_error("tmae_linear_bwd_weight: launch failed"); return TMAE_ERR_CUDA; }
+  if (dbias) {
+    TMAE_CUDA(cudaMemsetAsync(dbias, 0, (size_t)n * sizeof(float), s));
+    if (m > 0) {
+      int rpb = 512;
+      dim3 grid((unsigned)cdiv(n, 32), (unsigned)cdiv(m, rpb));
+      colsum_kernel<<<grid, 256, 0, s>>>(dy, m, (int)n, nullptr, dbias, rpb);
+      TMAE_CHECK_LAUNCH();
+    }
+  }
+  return 0;
+}
+
+int tmae_colsum(const float* x, float* out, int64_t rows, int32_t cols, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  TMAE_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), s));
+  if (rows > 0) {
+    int rpb = 512;
+    dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, rpb));
+    colsum_kernel<<<grid, 256, 0, s>>>(x, rows, cols, nullptr, out, rpb);
+    TMAE_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+int tmae_gelu_bwd(const float* dy, const float* preact, float* dx, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  gelu_bwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, preact, dx, n);
+  TMAE_CHECK_LAUNCH();
+  return 0;
+}
+
+/* y[o,:] = sum_tap x[table[o,tap], :] . w[:, tap, :]^T      w is (cout, taps, cin) */
+int tmae_sparse_conv_fwd(const float* x, const int32_t* table, const float* w, float* y, int64_t rows_out, int32_t taps,
+                         int32_t cin, int32_t cout, int32_t accumulate, int32_t precision, void* stream) {
+  TMAE_CHECK_ARG(precision == TMAE_PREC_FP32, "fp32 entry");
+  GemmArgs g{};
+  g.A = x; g.B = w; g.C = y; g.M = rows_out; g.N = cout; g.K = (int64_t)taps * cin; g.lda = cin; g.ldb = g.K; g.ldc = cout;
+  g.tab = table; g.taps = taps; g.cin = cin; g.accumulate = accumulate;
+  if (launch<A_GATHER, B_KCONTIG>(g, 1, (cudaStream_t)stream)) { set_error("tmae_sparse_conv_fwd: launch failed"); return TMAE_ERR_CUDA; }
+  return 0;
+}
+
+/* dw[n, tap, c] = sum_o dy[o, n] * x[table[o, tap], c]   (overwrites dw) */
+int tmae_sparse_conv_bwd_weight(const float* dy, const float* x, const int32_t* table, float* dw, int64_t rows_out, int32_t taps,
+                                int32_t cin, int32_t cout, int32_t precision, void* stream) {
+  TMAE_CHECK_ARG(precision == TMAE_PREC_FP32, "fp32 entry");
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t kk = (int64_t)taps * cin;
+  TMAE_CUDA(cudaMemsetAsync(dw, 0, (size_t)cout * kk * sizeof(float), s));
+  if (rows_out <= 0) return 0;
+  GemmArgs g{};
+  g.A = dy; g.B = x; g.C = dw; g.M = cout; g.N = kk; g.K = rows_out; g.lda = cout; g.ldb = cin; g.ldc = kk;
+  g.tab = table; g.taps = taps; g.cin = cin;
+  int splits = pick_splits((int64_t)cdiv(cout, BM) * cdiv(kk, BN), rows_out);
+  if (launch<A_MCONTIG, B_GATHER>(g, splits, s)) { set_error("tmae_sparse_conv_bwd_weight: launch failed"); return TMAE_ERR_CUDA; }
+  return 0;
+}
+
+/* w (cout, taps, cin) -> wt (cin, taps, cout): the weight of the backward-data gather GEMM */
+int tmae_transpose_taps(const float* w, float* wt, int32_t cout, int32_t taps, int32_t cin, int32_t flip, void* stream) {
+  int64_t n = (int64_t)cout * taps * cin;
+  if (n <= 0) return 0;
+  transpose_taps_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, wt, cout, taps, cin, flip);
+  TMAE_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,391 @@
+"""Thin tensor-level wrappers over the C ABI (include/tmae_sm100.h): pointer passing only.
+
+Every function takes CUDA tensors, allocates the outputs/workspace with torch (device memory
+plumbing) and enqueues the kernels on torch's current stream.  No arithmetic happens here and
+there is no fallback path: a tensor that is not on a CUDA device raises.
+"""
+import ctypes
+
+import torch
+
+from ._lib import lib
+
+PREC_FP32, PREC_BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+_state = {"precision": PREC_FP32, "launches": 0}
+
+
+def set_precision(p):
+    """'fp32' (parity mode, FFMA) or 'bf16' (tcgen05 tensor cores, fp32 accumulate)."""
+    _state["precision"] = {"fp32": PREC_FP32, "bf16": PREC_BF16}[p]
+
+
+def precision():
+    return _state["precision"]
+
+
+def launch_count():
+    """ABI calls made so far (each enqueues >= 1 kernel of this library)."""
+    return _state["launches"]
+
+
+def _p(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("tmae_b200 ops need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("tmae_b200 ops need contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"expected {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f3(v):
+    return (ctypes.c_float * 3)(*[float(x) for x in v[:3]])
+
+
+def _i32(v):
+    return (ctypes.c_int32 * len(v))(*[int(x) for x in v])
+
+
+def _call(name, *a):
+    _state["launches"] += 1
+    getattr(lib(), name)(*a)
+
+
+def _ws(nbytes, device):
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+F32, I32, I64, U8 = torch.float32, torch.int32, torch.int64, torch.uint8
+
+
+# ------------------------------------------------------------------------------------ voxelise
+def voxelize(points, pc_range, voxel_size, grid_size, batch_size):
+    """-> dict with capacity-sized device buffers and `counts` (2+B,) i64 on the device."""
+    L = lib()
+    n, stride = points.shape
+    dev = points.device
+    grid = _i32(grid_size)
+    cells = batch_size * int(grid_size[0]) * int(grid_size[1]) * int(grid_size[2])
+    mcap = max(1, min(n, cells))
+    ncap = max(1, n)
+    out = dict(
+        points=torch.empty(ncap, stride, dtype=F32, device=dev),
+        point_coords=torch.empty(ncap, 4, dtype=I64, device=dev),
+        inverse=torch.empty(ncap, dtype=I64, device=dev),
+        voxel_coords=torch.empty(mcap, 4, dtype=I64, device=dev),
+        voxel_mean=torch.empty(mcap, stride - 1, dtype=F32, device=dev),
+        voxel_npts=torch.empty(mcap, dtype=I32, device=dev),
+        voxel_offset=torch.empty(mcap + 1, dtype=I32, device=dev),
+        pt_order=torch.empty(ncap, dtype=I32, device=dev),
+        counts=torch.empty(2 + batch_size, dtype=I64, device=dev),
+    )
+    wsb = L.voxelize_workspace_bytes(n, batch_size, grid)
+    ws = _ws(wsb, dev)
+    _call("voxelize", _p(points, F32), n, stride, _f3(pc_range), _f3(voxel_size), grid, batch_size, _p(out["points"]),
+          _p(out["point_coords"]), _p(out["inverse"]), _p(out["voxel_coords"]), _p(out["voxel_mean"]), _p(out["voxel_npts"]),
+          _p(out["voxel_offset"]), _p(out["pt_order"]), _p(out["counts"]), _p(ws), wsb, _stream())
+    return out
+
+
+def vfe_point_features(points_kept, point_coords, inverse, voxel_mean, pc_range, voxel_size):
+    n, stride = points_kept.shape
+    x = torch.empty(n, stride - 1 + 6, dtype=F32, device=points_kept.device)
+    _call("vfe_point_features", _p(points_kept, F32), n, stride, _p(point_coords, I64), _p(inverse, I64), _p(voxel_mean, F32),
+          _f3(pc_range), _f3(voxel_size), _p(x), _stream())
+    return x
+
+
+# ------------------------------------------------------------------------------------ partition
+class Partition:
+    """Device tables of one window partition (both shifts); see tmae_window_partition."""
+    __slots__ = ("m_a", "m_b", "wcap", "n_levels", "tokens", "win_a", "slot_a", "posidx_a", "tok_a", "cnt_a", "win_b", "slot_b",
+                 "posidx_b", "tok_b", "cnt_b", "win_level", "n_win", "level_base", "status", "ref_a", "ref_b", "temporal",
+                 "keep_a", "keep_b")
+
+
+def window_partition(coords_a, batch, grid_x, grid_y, levels, coords_b=None, want_ref=False):
+    """coords_* (m,3) i32 ascending [b,y,x]; levels = [(max_tokens, lo, hi), ...]."""
+    L = lib()
+    dev = coords_a.device
+    P = Partition()
+    P.temporal = coords_b is not None
+    P.m_a, P.m_b = coords_a.shape[0], (coords_b.shape[0] if P.temporal else 0)
+    P.n_levels, P.tokens = len(levels), [int(l[0]) for l in levels]
+    wcap = P.wcap = int(L.partition_window_capacity(batch, grid_x, grid_y))
+
+    def per_voxel(m):
+        m = max(1, m)
+        return (torch.empty(2, m, dtype=I32, device=dev), torch.empty(2, m, dtype=I32, device=dev),
+                torch.empty(2, m, dtype=U8, device=dev))
+
+    P.win_a, P.slot_a, P.posidx_a = per_voxel(P.m_a)
+    P.tok_a = torch.empty(2, wcap * 64, dtype=I32, device=dev)
+    P.cnt_a = torch.empty(2, wcap, dtype=I32, device=dev)
+    if P.temporal:
+        P.win_b, P.slot_b, P.posidx_b = per_voxel(P.m_b)
+        P.tok_b = torch.empty(2, wcap * 64, dtype=I32, device=dev)
+        P.cnt_b = torch.empty(2, wcap, dtype=I32, device=dev)
+    else:
+        P.win_b = P.slot_b = P.posidx_b = P.tok_b = P.cnt_b = None
+    P.win_level = torch.empty(2, wcap, dtype=I32, device=dev)
+    P.n_win = torch.empty(2, dtype=I32, device=dev)
+    P.level_base = torch.empty(2, P.n_levels + 1, dtype=I32, device=dev)
+    P.status = torch.empty(1, dtype=I32, device=dev)
+    P.ref_a = P.ref_b = None
+    if want_ref:
+        P.ref_a = [torch.empty(2, max(1, P.m_a), dtype=I64, device=dev) for _ in range(3)]
+        if P.temporal:
+            P.ref_b = [torch.empty(2, max(1, P.m_b), dtype=I64, device=dev) for _ in range(3)]
+    ra = [_p(t) for t in P.ref_a] if P.ref_a else [None] * 3
+    rb = [_p(t) for t in P.ref_b] if P.ref_b else [None] * 3
+    wsb = L.window_partition_workspace_bytes(batch, grid_x, grid_y, P.n_levels)
+    ws = _ws(wsb, dev)
+    _call("window_partition", _p(coords_a, I32), P.m_a, _p(coords_b, I32) if P.temporal else None, P.m_b, batch, grid_x, grid_y,
+          P.n_levels, _i32([l[1] for l in levels]), _i32([l[2] for l in levels]), _i32(P.tokens),
+          _p(P.win_a), _p(P.slot_a), _p(P.posidx_a), _p(P.tok_a), _p(P.cnt_a),
+          _p(P.win_b), _p(P.slot_b), _p(P.posidx_b), _p(P.tok_b), _p(P.cnt_b),
+          _p(P.win_level), _p(P.n_win), _p(P.level_base), _p(P.status), *ra, *rb, _p(ws), wsb, _stream())
+    P.keep_a = P.keep_b = None
+    return P
+
+
+# ------------------------------------------------------------------------------------ GEMMs
+def linear_fwd(x, w, bias=None, residual=None, act=ACT_NONE, want_preact=False, w_offset_rows=0, n=None):
+    """y = act(x @ w[w_offset_rows : w_offset_rows + n].T + bias) + residual."""
+    m, k = x.shape
+    n = w.shape[0] if n is None else n
+    y = torch.empty(m, n, dtype=F32, device=x.device)
+    pre = torch.empty(m, n, dtype=F32, device=x.device) if want_preact else None
+    wp = _p(w, F32) + w_offset_rows * k * 4
+    bp = None if bias is None else _p(bias, F32) + w_offset_rows * 4
+    _call("linear_fwd", _p(x, F32), wp, bp, _p(residual), _p(y), _p(pre), m, n, k, act, PREC_FP32, _stream())
+    return (y, pre) if want_preact else y
+
+
+def linear_bwd_data(dy, w, dx=None, accumulate=False, w_offset_rows=0):
+    m, n = dy.shape
+    k = w.shape[1]
+    if dx is None:
+        dx = torch.empty(m, k, dtype=F32, device=dy.device)
+        accumulate = False
+    _call("linear_bwd_data", _p(dy, F32), _p(w, F32) + w_offset_rows * k * 4, _p(dx), m, n, k, int(accumulate), PREC_FP32, _stream())
+    return dx
+
+
+def linear_bwd_weight(dy, x, dw, dbias=None, w_offset_rows=0):
+    """dw[w_offset_rows : +n] = dy.T @ x (overwrites that slice); dbias slice likewise."""
+    m, n = dy.shape
+    k = x.shape[1]
+    dbp = None if dbias is None else _p(dbias, F32) + w_offset_rows * 4
+    _call("linear_bwd_weight", _p(dy, F32), _p(x, F32), _p(dw, F32) + w_offset_rows * k * 4, dbp, m, n, k, PREC_FP32, _stream())
+
+
+def gelu_bwd(dy, preact):
+    dx = torch.empty_like(dy)
+    _call("gelu_bwd", _p(dy, F32), _p(preact, F32), _p(dx), dy.numel(), _stream())
+    return dx
+
+
+# ------------------------------------------------------------------------------------ sparse conv
+def subm_table(indices, batch, Y, X, rows_dev=None):
+    L = lib()
+    m = indices.shape[0]
+    table = torch.empty(max(1, m), 9, dtype=I32, device=indices.device)
+    wsb = L.subm_table_workspace_bytes(batch, Y, X)
+    ws = _ws(wsb, indices.device)
+    _call("subm_table", _p(indices, I32), m, _p(rows_dev), batch, Y, X, _p(table), _p(ws), wsb, _stream())
+    return table
+
+
+def strided_table(indices, batch, Y, X, rows_dev=None):
+    """-> indices_out (cap,3), n_out (device i32[1]), table (cap,9), table_t (m,9), (Yo, Xo)."""
+    L = lib()
+    m = indices.shape[0]
+    Yo, Xo = (Y + 2 - 3) // 2 + 1, (X + 2 - 3) // 2 + 1
+    cap = max(1, min(4 * m, batch * Yo * Xo))
+    dev = indices.device
+    idx_out = torch.empty(cap, 3, dtype=I32, device=dev)
+    n_out = torch.empty(1, dtype=I32, device=dev)
+    table = torch.empty(cap, 9, dtype=I32, device=dev)
+    table_t = torch.empty(max(1, m), 9, dtype=I32, device=dev)
+    wsb = L.strided_table_workspace_bytes(batch, Y, X)
+    ws = _ws(wsb, dev)
+    _call("strided_table", _p(indices, I32), m, _p(rows_dev), batch, Y, X, _p(idx_out), cap, _p(n_out), _p(table), _p(table_t),
+          _p(ws), wsb, _stream())
+    return idx_out, n_out, table, table_t, (Yo, Xo)
+
+
+def sparse_conv_fwd(x, table, w, rows_out):
+    cout, taps, cin = w.shape[0], w.shape[1] * w.shape[2] if w.dim() == 4 else w.shape[1], w.shape[-1]
+    y = torch.empty(rows_out, cout, dtype=F32, device=x.device)
+    _call("sparse_conv_fwd", _p(x, F32), _p(table, I32), _p(w, F32), _p(y), rows_out, taps, cin, cout, 0, PREC_FP32, _stream())
+    return y
+
+
+def sparse_conv_bwd_weight(dy, x, table, w_shape):
+    cout, taps, cin = w_shape[0], w_shape[1] * w_shape[2], w_shape[3]
+    dw = torch.empty(w_shape, dtype=F32, device=x.device)
+    _call("sparse_conv_bwd_weight", _p(dy, F32), _p(x, F32), _p(table, I32), _p(dw), dy.shape[0], taps, cin, cout, PREC_FP32, _stream())
+    return dw
+
+
+def transpose_taps(w, flip):
+    cout, taps, cin = w.shape[0], w.shape[1] * w.shape[2], w.shape[3]
+    wt = torch.empty(cin, taps, cout, dtype=F32, device=w.device)
+    _call("transpose_taps", _p(w, F32), _p(wt), cout, taps, cin, int(flip), _stream())
+    return wt
+
+
+# ------------------------------------------------------------------------------------ row ops
+def add_pos(x, posidx, lut):
+    y = torch.empty_like(x)
+    _call("add_pos", _p(x, F32), _p(posidx, U8), _p(lut, F32), _p(y), x.shape[0], x.shape[1], _stream())
+    return y
+
+
+def add_layernorm_fwd(x, res, rowmask, gamma, beta, eps):
+    rows, c = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(max(1, rows), dtype=F32, device=x.device)
+    rstd = torch.empty(max(1, rows), dtype=F32, device=x.device)
+    _call("add_layernorm_fwd", _p(x, F32), _p(res), _p(rowmask), _p(gamma, F32), _p(beta, F32), _p(y), _p(mean), _p(rstd), rows, c,
+          float(eps), _stream())
+    return y, mean, rstd
+
+
+def add_layernorm_bwd(dy, x, res, rowmask, gamma, mean, rstd, dgamma, dbeta, want_dres=False):
+    rows, c = x.shape
+    dv = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    _call("add_layernorm_bwd", _p(dy, F32), _p(x, F32), _p(res), _p(rowmask), _p(gamma, F32), _p(mean), _p(rstd), _p(dv), _p(dres),
+          _p(dgamma, F32), _p(dbeta, F32), rows, c, _stream())
+    return dv, dres
+
+
+def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, relu):
+    L = lib()
+    rows, c = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(c, dtype=F32, device=x.device)
+    rstd = torch.empty(c, dtype=F32, device=x.device)
+    wsb = L.bn_workspace_bytes(c)
+    ws = _ws(wsb, x.device)
+    _call("bn_train_fwd", _p(x, F32), _p(gamma, F32), _p(beta, F32), _p(running_mean), _p(running_var), float(momentum), float(eps),
+          _p(y), _p(mean), _p(rstd), rows, c, int(relu), _p(ws), wsb, _stream())
+    return y, mean, rstd
+
+
+def bn_apply(x, mean, rstd, gamma, beta, relu):
+    y = torch.empty_like(x)
+    _call("bn_apply", _p(x, F32), _p(mean, F32), _p(rstd, F32), _p(gamma, F32), _p(beta, F32), _p(y), x.shape[0], x.shape[1], int(relu),
+          _stream())
+    return y
+
+
+def bn_bwd(dy, x, y, mean, rstd, gamma, relu, training):
+    L = lib()
+    rows, c = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(c, dtype=F32, device=x.device)
+    dbeta = torch.empty(c, dtype=F32, device=x.device)
+    wsb = L.bn_workspace_bytes(c)
+    ws = _ws(wsb, x.device)
+    _call("bn_bwd", _p(dy, F32), _p(x, F32), _p(y, F32), _p(mean), _p(rstd), _p(gamma, F32), _p(dx), _p(dgamma), _p(dbeta), rows, c,
+          int(relu), int(training), _p(ws), wsb, _stream())
+    return dx, dgamma, dbeta
+
+
+def segment_max_fwd(x, voxel_offset, pt_order, n_voxels):
+    c = x.shape[1]
+    out = torch.empty(n_voxels, c, dtype=F32, device=x.device)
+    arg = torch.empty(n_voxels, c, dtype=I32, device=x.device)
+    _call("segment_max_fwd", _p(x, F32), _p(voxel_offset, I32), _p(pt_order, I32), n_voxels, c, _p(out), _p(arg), _stream())
+    return out, arg
+
+
+def segment_max_bwd(dout, arg, n_points):
+    n_voxels, c = dout.shape
+    dx = torch.empty(n_points, c, dtype=F32, device=dout.device)
+    _call("segment_max_bwd", _p(dout, F32), _p(arg, I32), n_voxels, c, _p(dx), n_points, _stream())
+    return dx
+
+
+def densify_nhwc(rows, indices, batch, Y, X):
+    m, c = rows.shape
+    dense = torch.empty(batch, Y, X, c, dtype=F32, device=rows.device)
+    _call("densify_nhwc", _p(rows, F32), _p(indices, I32), m, c, batch, Y, X, _p(dense), 1, _stream())
+    return dense
+
+
+def gather_nhwc(dense, indices):
+    _, Y, X, c = dense.shape
+    m = indices.shape[0]
+    rows = torch.empty(m, c, dtype=F32, device=dense.device)
+    _call("gather_nhwc", _p(dense, F32), _p(indices, I32), m, c, Y, X, _p(rows), _stream())
+    return rows
+
+
+# ------------------------------------------------------------------------------------ attention
+def window_attention_fwd(q, k, v, qtok, qcnt, ktok, kcnt, n_win, max_windows, tau, tau_min, heads, zero_out):
+    mq, c = q.shape
+    o = torch.zeros_like(q) if zero_out else torch.empty_like(q)
+    lse = torch.empty(max(1, mq), heads, dtype=F32, device=q.device)
+    _call("window_attention_fwd", _p(q, F32), _p(k, F32), _p(v, F32), _p(o), _p(lse), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win),
+          max_windows, _p(tau, F32), float(tau_min), c, heads, _stream())
+    return o, lse
+
+
+def window_attention_bwd(dout, q, k, v, o, lse, qtok, qcnt, ktok, kcnt, n_win, max_windows, tau, tau_min, heads, dtau, zero):
+    alloc = torch.zeros_like if zero else torch.empty_like
+    dq, dk, dv = alloc(q), alloc(k), alloc(v)
+    _call("window_attention_bwd", _p(dout, F32), _p(q, F32), _p(k, F32), _p(v, F32), _p(o, F32), _p(lse, F32), _p(dq), _p(dk), _p(dv),
+          _p(dtau, F32), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win), max_windows, _p(tau, F32), float(tau_min), q.shape[1],
+          heads, _stream())
+    return dq, dk, dv
+
+
+# ------------------------------------------------------------------------------------ loss
+def gt_group(points_kept, voxel_offset, pt_order, voxel_coords, pc_range, voxel_size, n_voxels, k, want_inds=False):
+    dev = points_kept.device
+    gt = torch.empty(n_voxels, k, 3, dtype=F32, device=dev)
+    inds = torch.empty(n_voxels, k, dtype=I64, device=dev) if want_inds else None
+    _call("gt_group", _p(points_kept, F32), points_kept.shape[1], _p(voxel_offset, I32), _p(pt_order, I32), _p(voxel_coords, I64),
+          _f3(pc_range), _f3(voxel_size), n_voxels, k, _p(gt), _p(inds), _stream())
+    return (gt, inds) if want_inds else gt
+
+
+def chamfer_fwd(pred, gt, w, gtctx=None):
+    """gt (M,P2,3) or None with gtctx = (points_kept, voxel_offset, pt_order, voxel_coords, pc_range, voxel_size, P2)."""
+    m, p1, _ = pred.shape
+    dev = pred.device
+    loss = torch.empty((), dtype=F32, device=dev)
+    state = torch.empty(4, dtype=torch.float64, device=dev)
+    if gt is not None:
+        p2 = gt.shape[1]
+        ctx = (None, 0, None, None, None, None, None)
+    else:
+        pk, off, order, vc, rng, vs, p2 = gtctx
+        ctx = (_p(pk, F32), pk.shape[1], _p(off, I32), _p(order, I32), _p(vc, I64), _f3(rng), _f3(vs))
+    _call("chamfer_fwd", _p(pred, F32), _p(gt), _p(w, F32), m, p1, p2, *ctx, _p(loss), _p(state), _stream())
+    return loss, state
+
+
+def chamfer_bwd(grad_loss, pred, gt, w, state, gtctx=None):
+    m, p1, _ = pred.shape
+    dpred = torch.empty_like(pred)
+    if gt is not None:
+        p2 = gt.shape[1]
+        ctx = (None, 0, None, None, None, None, None)
+    else:
+        pk, off, order, vc, rng, vs, p2 = gtctx
+        ctx = (_p(pk, F32), pk.shape[1], _p(off, I32), _p(order, I32), _p(vc, I64), _f3(rng), _f3(vs))
+    _call("chamfer_bwd", _p(grad_loss, F32), _p(pred, F32), _p(gt), _p(w, F32), m, p1, p2, *ctx, _p(state), _p(dpred), _stream())
+    return dpred
