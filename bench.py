@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the T-MAE sparse-window voxel-encoder hot path on B200 (driver contract: see DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pretrain|finetune] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of the hot path over one batch of synthetic ONCE-shaped scan pairs:
+  pretrain (default, BASELINE.json configs[1]): TemporalDynVFE -> SiamWCA_MAE.forward -> Chamfer loss -> backward
+            -> AdamW step, batch 4 scan pairs per GPU, 75 % voxel mask;
+  finetune (configs[3]): TemporalDynVFE -> SiamWCA.forward, batch 8, 120k-point scans, no gradient.
+Prints ONE JSON line.  `value` = scan pairs per second with the inputs resident in HBM; `e2e` = the same through
+the public module API from pinned HOST buffers (H2D copies and the loss read-back inside the timed region).
+`--impl reference` times the reference's algorithm on the host cores (the tier-2 oracle port; /root/reference does
+not exist on the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "pretrain": dict(kind="pretrain", batch=4, n_points=60000, train=True,
+                     name="T-MAE pretraining forward+backward+AdamW, synthetic ONCE scan pairs (60k pts/frame, 0.32 m pillars, "
+                          "468x468 grid), 75% voxel mask, Chamfer loss, batch 4 scan pairs per GPU"),
+    "finetune": dict(kind="finetune", batch=8, n_points=120000, train=False,
+                     name="finetune-mode encoder forward (no masking, temporal cross-attention), synthetic ONCE scans "
+                          "(120k pts/frame, 0.32 m pillars), batch 8 scan pairs per GPU"),
+}
+
+
+def dist_env():
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    return rank, world, int(os.environ.get("LOCAL_RANK", 0))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(hbm=6650.0, tensor=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            sm.append(int(f[0]))
+            mx = max(mx, int(f[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batches(w, n_batches, rank):
+    from tmae_b200 import synth
+    out = []
+    for i in range(n_batches):
+        pts, ptsp = synth.batch(1000 + (rank * n_batches + i) * w["batch"], w["batch"], w["n_points"])
+        out.append((torch.from_numpy(pts).pin_memory(), torch.from_numpy(ptsp).pin_memory()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import tmae_b200
+    from tmae_b200 import ops, synth
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    shape = synth.ONCE
+    grid = synth.grid_size(shape).tolist()
+    torch.manual_seed(0)
+    vfe, bb = tmae_b200.build_model(w["kind"], grid, shape["voxel"], shape["range"])
+    ops.set_precision(args.precision)
+    bb.decoder_autocast = torch.bfloat16 if args.decoder == "bf16" else None
+    torch.backends.cudnn.benchmark = True
+
+    class Step(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.vfe, self.backbone_3d = vfe, bb
+
+        def forward(self, pts, ptsp):
+            bd = self.vfe(dict(points=pts, points_prev=ptsp, batch_size=w["batch"]))
+            bd = self.backbone_3d(bd)
+            if w["train"]:
+                return self.backbone_3d.get_loss()[0]
+            return bd["spatial_features"]
+
+    model = Step().to(dev)
+    model.train(w["train"])
+    net = model
+    opt = None
+    if w["train"]:
+        if world > 1:
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
+    bb.mask_generator = torch.Generator(device=dev).manual_seed(2000 + rank)
+
+    host = make_batches(w, args.batches, rank)
+    resident = [(a.to(dev), b.to(dev)) for a, b in host]
+    h2d = sum(t.numel() * 4 for t in host[0])
+
+    def step(pts, ptsp):
+        if w["train"]:
+            loss = net(pts, ptsp)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+        with torch.no_grad():
+            return net(pts, ptsp)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(from_host):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        d2h = 0
+        barrier()
+        c0 = ops.launch_count()
+        ev[0].record()
+        for i in range(args.steps):
+            if from_host:
+                a, b = host[i % len(host)]
+                out = step(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True))
+                if w["train"]:
+                    out.item()  # loss read-back
+                    d2h = 4
+                else:
+                    out.mean().item()
+                    d2h = 4
+            else:
+                out = step(*resident[i % len(resident)])
+            ev[i + 1].record()
+        barrier()
+        per = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+        total = ev[0].elapsed_time(ev[-1])
+        return total, per, ops.launch_count() - c0, d2h
+
+    for i in range(args.warmup):
+        step(*resident[i % len(resident)])
+    with ClockSampler(local) as cs:
+        total, per, launches, _ = timed(False)
+    clocks = cs.summary()
+    e_total, e_per, _, d2h = timed(True)
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t)
+
+    total, e_total = maxr(total), maxr(e_total)
+    units = w["batch"] * args.steps * world
+    value, e_value = units / (total / 1e3), units / (e_total / 1e3)
+
+    roof, prof_table = None, None
+    if rank == 0:
+        roof, prof_table = roofline(ops, step, resident, args)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(w, args)
+
+    if rank == 0:
+        line = {
+            "metric": "encoder scans/sec (scan pairs through vfe -> backbone_3d -> loss)", "value": round(value, 3), "unit": "scans/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total / args.steps, 3),
+            "p50_ms_per_scan": round(float(np.median(per)) / w["batch"], 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": w["name"], "precision": f"encoder kernels {args.precision}; cuDNN decoder {args.decoder}",
+                       "parallelism": f"dp{world} (scan-pair sharding" + (", DDP NCCL gradient all-reduce)" if w["train"] else ", no collective)"),
+                       "l2": f"inputs cycle over {args.batches} distinct batches; per-step activation working set >> 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": round(e_value, 3), "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e_total / args.steps, 3)},
+            "gpu_launches": launches,
+            "roofline": roof, "cpu_baseline": cpu, "kernel_time_table": prof_table,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def roofline(ops, step, resident, args):
+    """Per-ABI-call CUDA-event timing over extra (untimed) steps on the launching stream; the dominant kernel family
+    is reported against its roofline with ALGORITHMIC flops / bytes."""
+    pk = peaks()
+    ops.profile_begin()
+    n = 2
+    for i in range(n):
+        step(*resident[i % len(resident)])
+    table = ops.profile_end()
+    if not table:
+        return None, None
+    tot = sum(r["ms"] for r in table.values())
+    rows = sorted(table.items(), key=lambda kv: -kv[1]["ms"])
+    name, r = rows[0]
+    launches = r["calls"]
+    if r["flops"] > 0 and name in ops.TENSOR_BOUND:
+        ach = r["flops"] / (r["ms"] / 1e3) / 1e12
+        roof = {"kernel": name, "bound": "tensor", "achieved": round(ach, 3), "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": round(ach / pk["tensor"], 5), "traffic": None}
+    else:
+        ach = r["bytes"] / (r["ms"] / 1e3) / 1e9
+        roof = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
+                "frac": round(ach / pk["hbm"], 5), "traffic": None}
+    roof.update(peak_source=pk["src"], avg_launch_us=round(r["ms"] * 1e3 / launches, 2), launches_per_step=launches // n,
+                share_of_step=round(r["ms"] / tot, 4))
+    short = {k: {"ms_per_step": round(v["ms"] / n, 3), "calls_per_step": v["calls"] // n,
+                 "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 2) if v["flops"] else None,
+                 "gbs": round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1) if v["bytes"] else None} for k, v in rows[:12]}
+    return roof, short
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_step_fn(w):
+    """The reference's algorithm on the host (tier-2 oracle port): one B=1 scan pair of the same workload."""
+    from oracle import restated
+    from tmae_b200 import synth
+    shape = synth.ONCE
+    grid = synth.grid_size(shape).tolist()
+    torch.manual_seed(0)
+    vfe, bb = restated.build(w["kind"], grid, shape["voxel"], shape["range"])
+    vfe.train(w["train"]), bb.train(w["train"])
+    pts, ptsp = synth.batch(1000, 1, w["n_points"])
+    pts, ptsp = torch.from_numpy(pts), torch.from_numpy(ptsp)
+
+    def step():
+        if w["train"]:
+            bd = bb(vfe(dict(points=pts, points_prev=ptsp, batch_size=1)))
+            loss = bb.get_loss()[0]
+            loss.backward()
+            for p in list(vfe.parameters()) + list(bb.parameters()):
+                p.grad = None
+        else:
+            with torch.no_grad():
+                bb(vfe(dict(points=pts, points_prev=ptsp, batch_size=1)))
+    return step
+
+
+def cpu_baseline(w, args, steps=2):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(w)
+    step()
+    t = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t) / steps
+    return {"value": round(1.0 / dt, 4), "unit": "scans/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} steps of ONE scan pair (batch 1) of the same workload, fp32, torch CPU ops, {cores} threads; "
+                      "sparse convs dense-emulated"}
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(w)
+    for _ in range(args.warmup):
+        step()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t
+    v = round(args.steps / dt, 4)
+    sample = f"each step = ONE scan pair (batch 1) of the workload, fp32 torch CPU ops, {cores} threads; sparse convs dense-emulated"
+    print(json.dumps({
+        "impl": "reference", "metric": "encoder scans/sec (scan pairs through vfe -> backbone_3d -> loss)", "value": v, "unit": "scans/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pretrain", choices=list(WORKLOADS))
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--decoder", default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--batches", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

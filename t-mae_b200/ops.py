@@ -54,9 +54,40 @@ def _i32(v):
     return (ctypes.c_int32 * len(v))(*[int(x) for x in v])
 
 
-def _call(name, *a):
+TENSOR_BOUND = {"linear_fwd", "linear_bwd_data", "linear_bwd_weight", "sparse_conv_fwd", "sparse_conv_bwd_weight"}
+
+
+def _call(name, *a, flops=0, nbytes=0):
     _state["launches"] += 1
+    prof = _state.get("prof")
+    if prof is None:
+        getattr(lib(), name)(*a)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     getattr(lib(), name)(*a)
+    e1.record()
+    prof.append((name, e0, e1, flops, nbytes))
+
+
+def profile_begin():
+    """Time every ABI call with CUDA events on the launching stream (diagnostic pass, not the timed region)."""
+    torch.cuda.synchronize()
+    _state["prof"] = []
+
+
+def profile_end():
+    """-> {abi name: {ms, calls, flops, bytes}} (algorithmic work as stated in DESIGN.md)."""
+    torch.cuda.synchronize()
+    rec, _state["prof"] = _state.get("prof") or [], None
+    out = {}
+    for name, e0, e1, fl, nb in rec:
+        r = out.setdefault(name, {"ms": 0.0, "calls": 0, "flops": 0, "bytes": 0})
+        r["ms"] += e0.elapsed_time(e1)
+        r["calls"] += 1
+        r["flops"] += fl
+        r["bytes"] += nb
+    return out
 
 
 def _ws(nbytes, device):
@@ -166,7 +197,8 @@ def linear_fwd(x, w, bias=None, residual=None, act=ACT_NONE, want_preact=False, 
     pre = torch.empty(m, n, dtype=F32, device=x.device) if want_preact else None
     wp = _p(w, F32) + w_offset_rows * k * 4
     bp = None if bias is None else _p(bias, F32) + w_offset_rows * 4
-    _call("linear_fwd", _p(x, F32), wp, bp, _p(residual), _p(y), _p(pre), m, n, k, act, PREC_FP32, _stream())
+    _call("linear_fwd", _p(x, F32), wp, bp, _p(residual), _p(y), _p(pre), m, n, k, act, PREC_FP32, _stream(),
+          flops=2 * m * n * k, nbytes=4 * (m * k + n * k + m * n))
     return (y, pre) if want_preact else y
 
 
@@ -176,7 +208,8 @@ def linear_bwd_data(dy, w, dx=None, accumulate=False, w_offset_rows=0):
     if dx is None:
         dx = torch.empty(m, k, dtype=F32, device=dy.device)
         accumulate = False
-    _call("linear_bwd_data", _p(dy, F32), _p(w, F32) + w_offset_rows * k * 4, _p(dx), m, n, k, int(accumulate), PREC_FP32, _stream())
+    _call("linear_bwd_data", _p(dy, F32), _p(w, F32) + w_offset_rows * k * 4, _p(dx), m, n, k, int(accumulate), PREC_FP32, _stream(),
+          flops=2 * m * n * k, nbytes=4 * (m * k + n * k + m * n))
     return dx
 
 
@@ -185,7 +218,8 @@ def linear_bwd_weight(dy, x, dw, dbias=None, w_offset_rows=0):
     m, n = dy.shape
     k = x.shape[1]
     dbp = None if dbias is None else _p(dbias, F32) + w_offset_rows * 4
-    _call("linear_bwd_weight", _p(dy, F32), _p(x, F32), _p(dw, F32) + w_offset_rows * k * 4, dbp, m, n, k, PREC_FP32, _stream())
+    _call("linear_bwd_weight", _p(dy, F32), _p(x, F32), _p(dw, F32) + w_offset_rows * k * 4, dbp, m, n, k, PREC_FP32, _stream(),
+          flops=2 * m * n * k, nbytes=4 * (m * k + n * k + m * n))
 
 
 def gelu_bwd(dy, preact):
@@ -226,14 +260,16 @@ def strided_table(indices, batch, Y, X, rows_dev=None):
 def sparse_conv_fwd(x, table, w, rows_out):
     cout, taps, cin = w.shape[0], w.shape[1] * w.shape[2] if w.dim() == 4 else w.shape[1], w.shape[-1]
     y = torch.empty(rows_out, cout, dtype=F32, device=x.device)
-    _call("sparse_conv_fwd", _p(x, F32), _p(table, I32), _p(w, F32), _p(y), rows_out, taps, cin, cout, 0, PREC_FP32, _stream())
+    _call("sparse_conv_fwd", _p(x, F32), _p(table, I32), _p(w, F32), _p(y), rows_out, taps, cin, cout, 0, PREC_FP32, _stream(),
+          flops=2 * rows_out * taps * cin * cout, nbytes=4 * (x.numel() + w.numel() + rows_out * cout) + 4 * rows_out * taps)
     return y
 
 
 def sparse_conv_bwd_weight(dy, x, table, w_shape):
     cout, taps, cin = w_shape[0], w_shape[1] * w_shape[2], w_shape[3]
     dw = torch.empty(w_shape, dtype=F32, device=x.device)
-    _call("sparse_conv_bwd_weight", _p(dy, F32), _p(x, F32), _p(table, I32), _p(dw), dy.shape[0], taps, cin, cout, PREC_FP32, _stream())
+    _call("sparse_conv_bwd_weight", _p(dy, F32), _p(x, F32), _p(table, I32), _p(dw), dy.shape[0], taps, cin, cout, PREC_FP32, _stream(),
+          flops=2 * dy.shape[0] * taps * cin * cout, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
     return dw
 
 
@@ -339,7 +375,7 @@ def window_attention_fwd(q, k, v, qtok, qcnt, ktok, kcnt, n_win, max_windows, ta
     o = torch.zeros_like(q) if zero_out else torch.empty_like(q)
     lse = torch.empty(max(1, mq), heads, dtype=F32, device=q.device)
     _call("window_attention_fwd", _p(q, F32), _p(k, F32), _p(v, F32), _p(o), _p(lse), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win),
-          max_windows, _p(tau, F32), float(tau_min), c, heads, _stream())
+          max_windows, _p(tau, F32), float(tau_min), c, heads, _stream(), nbytes=4 * (q.numel() * 2 + k.numel() * 2))
     return o, lse
 
 
@@ -348,7 +384,7 @@ def window_attention_bwd(dout, q, k, v, o, lse, qtok, qcnt, ktok, kcnt, n_win, m
     dq, dk, dv = alloc(q), alloc(k), alloc(v)
     _call("window_attention_bwd", _p(dout, F32), _p(q, F32), _p(k, F32), _p(v, F32), _p(o, F32), _p(lse, F32), _p(dq), _p(dk), _p(dv),
           _p(dtau, F32), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win), max_windows, _p(tau, F32), float(tau_min), q.shape[1],
-          heads, _stream())
+          heads, _stream(), nbytes=4 * (q.numel() * 4 + k.numel() * 4))
     return dq, dk, dv
 
 
