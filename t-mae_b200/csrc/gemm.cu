@@ -216,15 +216,35 @@ __global__ void transpose_taps_kernel(const float* __restrict__ w, float* __rest
   wt[((int64_t)c * taps + tt) * cout + o] = w[i];
 }
 
+// tensor-core path (gemm_tc.cu)
+bool tc_linear_fwd_ok(int64_t m, int64_t n, int64_t k);
+int tc_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact, int64_t m,
+                  int64_t n, int64_t k, int act, cudaStream_t s);
+bool tc_linear_bwd_data_ok(int64_t m, int64_t n, int64_t k);
+int tc_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int accumulate, cudaStream_t s);
+bool tc_linear_bwd_weight_ok(int64_t m, int64_t n, int64_t k);
+int tc_linear_bwd_weight(const float* dy, const float* x, float* dw, int64_t m, int64_t n, int64_t k, cudaStream_t s);
+bool tc_sparse_conv_ok(int cin, int cout);
+int tc_sparse_conv_fwd(const float* x, const int* table, const float* w, float* y, int64_t rows_out, int taps, int cin, int cout,
+                       int accumulate, cudaStream_t s);
+int tc_sparse_conv_bwd_weight(const float* dy, const float* x, const int* table, float* dw, int64_t rows_out, int taps, int cin,
+                              int cout, cudaStream_t s);
+
 }  // namespace tmae
 
 using namespace tmae;
+
+#define TMAE_CHECK_PREC(p) TMAE_CHECK_ARG((p) == TMAE_PREC_FP32 || (p) == TMAE_PREC_BF16, "precision must be TMAE_PREC_FP32 or TMAE_PREC_BF16")
 
 extern "C" {
 
 int tmae_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact,
                     int64_t m, int64_t n, int64_t k, int32_t act, int32_t precision, void* stream) {
-  TMAE_CHECK_ARG(precision == TMAE_PREC_FP32, "tmae_linear_fwd: fp32 entry; use tmae_linear_fwd_bf16 for tensor cores");
+  TMAE_CHECK_PREC(precision);
+  if (precision == TMAE_PREC_BF16 && tc_linear_fwd_ok(m, n, k)) {
+    if (tc_linear_fwd(x, w, bias, residual, y, preact, m, n, k, act, (cudaStream_t)stream)) { set_error("tmae_linear_fwd: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
+    return 0;
+  }
   GemmArgs g{};
   g.A = x; g.B = w; g.C = y; g.M = m; g.N = n; g.K = k; g.lda = k; g.ldb = k; g.ldc = n;
   g.bias = bias; g.residual = residual; g.preact = preact; g.act = act;
@@ -234,7 +254,11 @@ int tmae_linear_fwd(const float* x, const float* w, const float* bias, const flo
 
 int tmae_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int32_t accumulate,
                          int32_t precision, void* stream) {
-  TMAE_CHECK_ARG(precision == TMAE_PREC_FP32, "fp32 entry");
+  TMAE_CHECK_PREC(precision);
+  if (precision == TMAE_PREC_BF16 && tc_linear_bwd_data_ok(m, n, k)) {
+    if (tc_linear_bwd_data(dy, w, dx, m, n, k, accumulate, (cudaStream_t)stream)) { set_error("tmae_linear_bwd_data: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
+    return 0;
+  }
   // dx[m,k] = sum_n dy[m,n] * w[n,k]
   GemmArgs g{};
   g.A = dy; g.B = w; g.C = dx; g.M = m; g.N = k; g.K = n; g.lda = n; g.ldb = k; g.ldc = k; g.accumulate = accumulate;
@@ -252,14 +276,18 @@ static int pick_splits(int64_t out_tiles, int64_t k) {
 
 int tmae_linear_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int64_t m, int64_t n, int64_t k,
                            int32_t precision, void* stream) {
-  TMAE_CHECK_ARG(precision == TMAE_PREC_FP32, "fp32 entry");
+  TMAE_CHECK_PREC(precision);
   cudaStream_t s = (cudaStream_t)stream;
   // dw[n,k] = sum_m dy[m,n] * x[m,k]   (overwrites dw; reduction over m split across CTAs)
   TMAE_CUDA(cudaMemsetAsync(dw, 0, (size_t)n * k * sizeof(float), s));
-  GemmArgs g{};
-  g.A = dy; g.B = x; g.C = dw; g.M = n; g.N = k; g.K = m; g.lda = n; g.ldb = k; g.ldc = k;
-  int splits = pick_splits((int64_t)cdiv(n, BM) * cdiv(k, BN), m);
-  if (m > 0 && launch<A_MCONTIG, B_NCONTIG>(g, splits, s)) { set_error("tmae_linear_bwd_weight: launch failed"); return TMAE_ERR_CUDA; }
+  if (precision == TMAE_PREC_BF16 && tc_linear_bwd_weight_ok(m, n, k)) {
+    if (tc_linear_bwd_weight(dy, x, dw, m, n, k, s)) { set_error("tmae_linear_bwd_weight: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
+  } else {
+    GemmArgs g{};
+    g.A = dy; g.B = x; g.C = dw; g.M = n; g.N = k; g.K = m; g.lda = n; g.ldb = k; g.ldc = k;
+    int splits = pick_splits((int64_t)cdiv(n, BM) * cdiv(k, BN), m);
+    if (m > 0 && launch<A_MCONTIG, B_NCONTIG>(g, splits, s)) { set_error("tmae_linear_bwd_weight: launch failed"); return TMAE_ERR_CUDA; }
+  }
   if (dbias) {
     TMAE_CUDA(cudaMemsetAsync(dbias, 0, (size_t)n * sizeof(float), s));
     if (m > 0) {
@@ -294,7 +322,11 @@ int tmae_gelu_bwd(const float* dy, const float* preact, float* dx, int64_t n, vo
 /* y[o,:] = sum_tap x[table[o,tap], :] . w[:, tap, :]^T      w is (cout, taps, cin) */
 int tmae_sparse_conv_fwd(const float* x, const int32_t* table, const float* w, float* y, int64_t rows_out, int32_t taps,
                          int32_t cin, int32_t cout, int32_t accumulate, int32_t precision, void* stream) {
-  TMAE_CHECK_ARG(precision == TMAE_PREC_FP32, "fp32 entry");
+  TMAE_CHECK_PREC(precision);
+  if (precision == TMAE_PREC_BF16 && tc_sparse_conv_ok(cin, cout)) {
+    if (tc_sparse_conv_fwd(x, table, w, y, rows_out, taps, cin, cout, accumulate, (cudaStream_t)stream)) { set_error("tmae_sparse_conv_fwd: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
+    return 0;
+  }
   GemmArgs g{};
   g.A = x; g.B = w; g.C = y; g.M = rows_out; g.N = cout; g.K = (int64_t)taps * cin; g.lda = cin; g.ldb = g.K; g.ldc = cout;
   g.tab = table; g.taps = taps; g.cin = cin; g.accumulate = accumulate;
@@ -305,11 +337,15 @@ int tmae_sparse_conv_fwd(const float* x, const int32_t* table, const float* w, f
 /* dw[n, tap, c] = sum_o dy[o, n] * x[table[o, tap], c]   (overwrites dw) */
 int tmae_sparse_conv_bwd_weight(const float* dy, const float* x, const int32_t* table, float* dw, int64_t rows_out, int32_t taps,
                                 int32_t cin, int32_t cout, int32_t precision, void* stream) {
-  TMAE_CHECK_ARG(precision == TMAE_PREC_FP32, "fp32 entry");
+  TMAE_CHECK_PREC(precision);
   cudaStream_t s = (cudaStream_t)stream;
   int64_t kk = (int64_t)taps * cin;
   TMAE_CUDA(cudaMemsetAsync(dw, 0, (size_t)cout * kk * sizeof(float), s));
   if (rows_out <= 0) return 0;
+  if (precision == TMAE_PREC_BF16 && tc_sparse_conv_ok(cin, cout) && cin % 8 == 0) {
+    if (tc_sparse_conv_bwd_weight(dy, x, table, dw, rows_out, taps, cin, cout, s)) { set_error("tmae_sparse_conv_bwd_weight: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
+    return 0;
+  }
   GemmArgs g{};
   g.A = dy; g.B = x; g.C = dw; g.M = cout; g.N = kk; g.K = rows_out; g.lda = cout; g.ldb = cin; g.ldc = kk;
   g.tab = table; g.taps = taps; g.cin = cin;

@@ -1,0 +1,359 @@
+// bf16 tensor-core GEMM family for sm_100a: tcgen05.mma with the accumulator in TMEM (TMAE_PREC_BF16).
+//
+// Same contractions as gemm.cu (linear forward / backward-data / backward-weight and the gather-GEMM form of
+// the sparse convolutions), with fp32 activations and weights in HBM converted to bf16 while they are staged
+// into shared memory, fp32 accumulation in tensor memory, and the bias / activation / residual epilogue
+// applied on the way out of TMEM.  The A operand is staged by the CTA's threads (not TMA) because its rows
+// are converted fp32 -> bf16 and, for the sparse convolutions, gathered through the neighbour table.
+//
+// Shared-memory operand layout: the no-swizzle canonical UMMA layouts (8 x 16-byte core matrices):
+//   K-major  (reduction index contiguous in HBM):  core(mn_group, k_chunk)  8 rows x 8 elements, row = 16 B
+//   MN-major (output index contiguous in HBM):     core(mn_group, k_group)  8 k-rows x 8 mn elements
+// both stored as [k][mn_group][128 B], so SBO (MN direction) = 128 B and LBO (K direction) = (tile_mn/8)*128 B.
+// One tcgen05.mma consumes K = 16 = two cores along K.
+//
+// Pipeline: STAGES-deep ring of {A,B} stages.  All 256 threads stage k-block kb (global -> regs -> bf16 ->
+// st.shared), fence.proxy.async + __syncthreads, then one thread issues BK/16 MMAs and a tcgen05.commit onto the
+// stage's mbarrier; staging of the next k-block overlaps the asynchronous MMAs.  Every mbarrier wait is bounded
+// and traps instead of hanging.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace tmae {
+
+constexpr int TBM = 128;     // UMMA M
+constexpr int TBK = 64;      // k-block per stage
+constexpr int TC_THREADS = 256;
+constexpr int TSTAGES = 3;
+
+enum TcMode { TC_NT = 0, TC_NN = 1, TC_TN = 2 };
+
+struct TcArgs {
+  const float* A; const float* B; float* C;
+  int64_t M, N, K;            // output M x N, reduction K
+  int64_t lda, ldb, ldc;
+  const float* bias; const float* residual; float* preact;
+  const int* tab; int taps, cin;   // gather (A rows for NT, B rows for TN)
+  int act, accumulate, atomic;
+  int64_t k_chunk;            // reduction range per blockIdx.z
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();  // protocol bug: fail loudly, never hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// no-swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start >> 4, LBO >> 4 at bit 16,
+// SBO >> 4 at bit 32, version 1 at bit 46, layout type 0 (SWIZZLE_NONE) at bit 61
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, majors, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t umma_idesc(int a_mn_major, int b_mn_major, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(TBM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint4 pack8(const float4& a, const float4& b) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+  uint4 r;
+  r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
+  r.z = *reinterpret_cast<uint32_t*>(&p2); r.w = *reinterpret_cast<uint32_t*>(&p3);
+  return r;
+}
+
+// Stage a (ROWS x 64) tile whose reduction index is contiguous in HBM (K-major): element (r, k) = src[row(r) * ld + k0 + k].
+// Thread mapping: 8 consecutive lanes take 8 consecutive rows of one 16-byte chunk (conflict-free 128 B stores,
+// 128 contiguous bytes per row per warp load).
+template <int ROWS, bool GATHER>
+__device__ __forceinline__ void stage_kmajor(uint8_t* dst, const float* __restrict__ src, int64_t ld, int64_t row0, int64_t row_end,
+                                             int64_t k0, int64_t k_end, const int* __restrict__ tab, int taps, int cin) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r8 = lane & 7, kcl = lane >> 3;
+  constexpr int COMBOS = (ROWS / 8) * 2;  // (row group, k half)
+#pragma unroll
+  for (int c = warp; c < COMBOS; c += TC_THREADS / 32) {
+    int rg = c >> 1, kc = (c & 1) * 4 + kcl;
+    int64_t row = row0 + rg * 8 + r8, k = k0 + kc * 8;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (row < row_end && k < k_end) {
+      const float* p;
+      bool ok = true;
+      if (GATHER) {
+        int tap = (int)(k / cin);
+        int srow = tab[row * taps + tap];
+        ok = srow >= 0;
+        p = src + (int64_t)srow * ld + (k - (int64_t)tap * cin);
+      } else {
+        p = src + row * ld + k;
+      }
+      if (ok) {
+        a = __ldg(reinterpret_cast<const float4*>(p));
+        b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      }
+    }
+    *reinterpret_cast<uint4*>(dst + ((kc * (ROWS / 8) + rg) * 128 + r8 * 16)) = pack8(a, b);
+  }
+}
+
+// Stage a (64 x COLS) tile whose output index is contiguous in HBM (MN-major): element (k, c) = src[row(k) * ld + c0 + c].
+// 8 consecutive lanes take the 8 k-rows of one core matrix (128 B contiguous store); a warp covers 4 adjacent
+// column groups = 128 contiguous bytes of each of 8 source rows.
+template <int COLS, bool GATHER>
+__device__ __forceinline__ void stage_mnmajor(uint8_t* dst, const float* __restrict__ src, int64_t ld, int64_t k0, int64_t k_end,
+                                              int64_t c0, int64_t c_end, const int* __restrict__ tab, int taps, int cin) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k8 = lane & 7, cgl = lane >> 3;
+  constexpr int COMBOS = 8 * (COLS / 32);  // (k group, 4-column-group block)
+#pragma unroll
+  for (int c = warp; c < COMBOS; c += TC_THREADS / 32) {
+    int kg = c / (COLS / 32), cg = (c % (COLS / 32)) * 4 + cgl;
+    int64_t k = k0 + kg * 8 + k8, col = c0 + cg * 8;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (k < k_end && col < c_end) {
+      const float* p;
+      bool ok = true;
+      if (GATHER) {
+        int tap = (int)(col / cin);
+        int srow = tab[k * taps + tap];
+        ok = srow >= 0;
+        p = src + (int64_t)srow * ld + (col - (int64_t)tap * cin);
+      } else {
+        p = src + k * ld + col;
+      }
+      if (ok) {
+        a = __ldg(reinterpret_cast<const float4*>(p));
+        b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      }
+    }
+    *reinterpret_cast<uint4*>(dst + ((kg * (COLS / 8) + cg) * 128 + k8 * 16)) = pack8(a, b);
+  }
+}
+
+__device__ __forceinline__ float gelu_erf_tc(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+// MODE NT: C[m,n] = sum_k A[m,k] W[n,k]      A K-major (optionally gathered), B K-major
+// MODE NN: C[m,n] = sum_k A[m,k] B[k,n]      A K-major, B MN-major
+// MODE TN: C[m,n] = sum_k A[k,m] B[k,n]      A MN-major, B MN-major (optionally gathered), split over k with atomics
+template <int MODE, int BN, bool GATHER>
+__global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int A_BYTES = TBM * TBK * 2, B_BYTES = BN * TBK * 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + TSTAGES * A_BYTES;
+  __shared__ uint64_t bar_free[TSTAGES];
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.y * TBM, n0 = (int64_t)blockIdx.x * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * g.k_chunk;
+  const int64_t kend = kbeg + g.k_chunk < g.K ? kbeg + g.k_chunk : g.K;
+  const int nkb = (int)((kend - kbeg + TBK - 1) / TBK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TSTAGES; ++s) mbar_init(&bar_free[s], 1);
+    mbar_init(&bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, BN < 32 ? 32 : BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+  const uint32_t idesc = umma_idesc(MODE == TC_TN, MODE != TC_NT, BN);
+  constexpr uint32_t A_LBO = (TBM / 8) * 128, B_LBO = (BN / 8) * 128, SBO = 128;
+
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb % TSTAGES, use = kb / TSTAGES;
+    if (use > 0) mbar_wait(&bar_free[s], (use - 1) & 1);  // MMAs that read this stage have retired
+    const int64_t k0 = kbeg + (int64_t)kb * TBK;
+    uint8_t* a = sA + s * A_BYTES;
+    uint8_t* b = sB + s * B_BYTES;
+    if (MODE == TC_TN) stage_mnmajor<TBM, false>(a, g.A, g.lda, k0, kend, m0, g.M, nullptr, 0, 1);
+    else stage_kmajor<TBM, GATHER && MODE == TC_NT>(a, g.A, g.lda, m0, g.M, k0, kend, g.tab, g.taps, g.cin);
+    if (MODE == TC_NT) stage_kmajor<BN, false>(b, g.B, g.ldb, n0, g.N, k0, kend, nullptr, 0, 1);
+    else stage_mnmajor<BN, GATHER && MODE == TC_TN>(b, g.B, g.ldb, k0, kend, n0, g.N, g.tab, g.taps, g.cin);
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(a), b_addr = smem_u32(b);
+#pragma unroll
+      for (int kk = 0; kk < TBK / 16; ++kk) {
+        uint64_t da = umma_desc(a_addr + kk * 2 * A_LBO, A_LBO, SBO);
+        uint64_t db = umma_desc(b_addr + kk * 2 * B_LBO, B_LBO, SBO);
+        umma_bf16(tmem_d, da, db, idesc, (kb | kk) ? 1u : 0u);
+      }
+      umma_commit(&bar_free[s]);
+      if (kb == nkb - 1) umma_commit(&bar_done);
+    }
+  }
+  if (nkb > 0) mbar_wait(&bar_done, 0);
+  tc_fence_after();
+
+  // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., column half w/4
+  const int64_t row = m0 + (warp & 3) * 32 + lane;
+  constexpr int CHUNKS = BN / 32;
+  for (int ch = (warp >> 2); ch < CHUNKS; ch += 2) {
+    uint32_t r[32];
+    if (nkb > 0) {
+      tmem_ld32(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + ch * 32, r);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = 0u;
+    }
+    if (row >= g.M) continue;
+    const int64_t cbase = n0 + ch * 32;
+    float* crow = g.C + row * g.ldc;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      int64_t col = cbase + j;
+      if (col >= g.N) break;
+      float v = __uint_as_float(r[j]);
+      if (g.atomic) { atomicAdd(crow + col, v); continue; }
+      if (g.bias) v += g.bias[col];
+      if (g.preact) g.preact[row * g.ldc + col] = v;
+      if (g.act == TMAE_ACT_GELU) v = gelu_erf_tc(v);
+      else if (g.act == TMAE_ACT_RELU) v = fmaxf(v, 0.f);
+      if (g.residual) v += g.residual[row * g.ldc + col];
+      if (g.accumulate) v += crow[col];
+      crow[col] = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, BN < 32 ? 32 : BN);
+}
+
+template <int MODE, int BN, bool GATHER>
+static int tc_launch(TcArgs& g, int splits, cudaStream_t s) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  if (splits < 1) splits = 1;
+  g.k_chunk = align_up((g.K + splits - 1) / splits, TBK);
+  int z = (int)((g.K + g.k_chunk - 1) / g.k_chunk);
+  if (z < 1) z = 1;
+  g.atomic = z > 1 || g.atomic;
+  size_t smem = (size_t)TSTAGES * (TBM * TBK * 2 + BN * TBK * 2);
+  auto kern = tc_gemm_kernel<MODE, BN, GATHER>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TMAE_ERR_CUDA;
+  dim3 grid((unsigned)cdiv(g.N, BN), (unsigned)cdiv(g.M, TBM), (unsigned)z);
+  kern<<<grid, TC_THREADS, smem, s>>>(g);
+  return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
+}
+
+template <int MODE, bool GATHER>
+static int tc_dispatch(TcArgs& g, int splits, cudaStream_t s) {
+  if (g.N > 128) return tc_launch<MODE, 256, GATHER>(g, splits, s);
+  if (g.N > 64) return tc_launch<MODE, 128, GATHER>(g, splits, s);
+  return tc_launch<MODE, 64, GATHER>(g, splits, s);
+}
+
+// ---- entry points used by gemm.cu's ABI functions when precision == TMAE_PREC_BF16
+bool tc_linear_fwd_ok(int64_t m, int64_t n, int64_t k) { return k % TBK == 0 && k >= TBK; }
+int tc_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact, int64_t m,
+                  int64_t n, int64_t k, int act, cudaStream_t s) {
+  TcArgs g{};
+  g.A = x; g.B = w; g.C = y; g.M = m; g.N = n; g.K = k; g.lda = k; g.ldb = k; g.ldc = n;
+  g.bias = bias; g.residual = residual; g.preact = preact; g.act = act;
+  return tc_dispatch<TC_NT, false>(g, 1, s);
+}
+
+bool tc_linear_bwd_data_ok(int64_t m, int64_t n, int64_t k) { return n % TBK == 0 && n >= TBK && k % 8 == 0; }
+int tc_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int accumulate, cudaStream_t s) {
+  TcArgs g{};
+  g.A = dy; g.B = w; g.C = dx; g.M = m; g.N = k; g.K = n; g.lda = n; g.ldb = k; g.ldc = k; g.accumulate = accumulate;
+  return tc_dispatch<TC_NN, false>(g, 1, s);
+}
+
+static int tn_splits(int64_t out_tiles, int64_t k) {
+  int64_t want = (kNumSMs + out_tiles - 1) / out_tiles;
+  int64_t maxs = (k + 4 * TBK - 1) / (4 * TBK);
+  if (want > maxs) want = maxs;
+  return (int)(want < 1 ? 1 : want);
+}
+
+bool tc_linear_bwd_weight_ok(int64_t m, int64_t n, int64_t k) { return n % 8 == 0 && k % 8 == 0 && m >= 1; }
+// dw must be zero-filled by the caller
+int tc_linear_bwd_weight(const float* dy, const float* x, float* dw, int64_t m, int64_t n, int64_t k, cudaStream_t s) {
+  TcArgs g{};
+  g.A = dy; g.B = x; g.C = dw; g.M = n; g.N = k; g.K = m; g.lda = n; g.ldb = k; g.ldc = k; g.atomic = 1;
+  int bn = k > 128 ? 256 : (k > 64 ? 128 : 64);
+  return tc_dispatch<TC_TN, false>(g, tn_splits((int64_t)cdiv(n, TBM) * cdiv(k, bn), m), s);
+}
+
+bool tc_sparse_conv_ok(int cin, int cout) { return cin % TBK == 0 && cout % 8 == 0; }
+int tc_sparse_conv_fwd(const float* x, const int* table, const float* w, float* y, int64_t rows_out, int taps, int cin, int cout,
+                       int accumulate, cudaStream_t s) {
+  TcArgs g{};
+  g.A = x; g.B = w; g.C = y; g.M = rows_out; g.N = cout; g.K = (int64_t)taps * cin; g.lda = cin; g.ldb = g.K; g.ldc = cout;
+  g.tab = table; g.taps = taps; g.cin = cin; g.accumulate = accumulate;
+  return tc_dispatch<TC_NT, true>(g, 1, s);
+}
+// dw (cout, taps*cin) must be zero-filled by the caller
+int tc_sparse_conv_bwd_weight(const float* dy, const float* x, const int* table, float* dw, int64_t rows_out, int taps, int cin,
+                              int cout, cudaStream_t s) {
+  TcArgs g{};
+  int64_t kk = (int64_t)taps * cin;
+  g.A = dy; g.B = x; g.C = dw; g.M = cout; g.N = kk; g.K = rows_out; g.lda = cout; g.ldb = cin; g.ldc = kk;
+  g.tab = table; g.taps = taps; g.cin = cin; g.atomic = 1;
+  return tc_dispatch<TC_TN, true>(g, tn_splits((int64_t)cdiv(cout, TBM) * cdiv(kk, 256), rows_out), s);
+}
+
+}  // namespace tmae

@@ -197,7 +197,7 @@ def linear_fwd(x, w, bias=None, residual=None, act=ACT_NONE, want_preact=False, 
     pre = torch.empty(m, n, dtype=F32, device=x.device) if want_preact else None
     wp = _p(w, F32) + w_offset_rows * k * 4
     bp = None if bias is None else _p(bias, F32) + w_offset_rows * 4
-    _call("linear_fwd", _p(x, F32), wp, bp, _p(residual), _p(y), _p(pre), m, n, k, act, PREC_FP32, _stream(),
+    _call("linear_fwd", _p(x, F32), wp, bp, _p(residual), _p(y), _p(pre), m, n, k, act, _state["precision"], _stream(),
           flops=2 * m * n * k, nbytes=4 * (m * k + n * k + m * n))
     return (y, pre) if want_preact else y
 
@@ -208,7 +208,7 @@ def linear_bwd_data(dy, w, dx=None, accumulate=False, w_offset_rows=0):
     if dx is None:
         dx = torch.empty(m, k, dtype=F32, device=dy.device)
         accumulate = False
-    _call("linear_bwd_data", _p(dy, F32), _p(w, F32) + w_offset_rows * k * 4, _p(dx), m, n, k, int(accumulate), PREC_FP32, _stream(),
+    _call("linear_bwd_data", _p(dy, F32), _p(w, F32) + w_offset_rows * k * 4, _p(dx), m, n, k, int(accumulate), _state["precision"], _stream(),
           flops=2 * m * n * k, nbytes=4 * (m * k + n * k + m * n))
     return dx
 
@@ -218,7 +218,7 @@ def linear_bwd_weight(dy, x, dw, dbias=None, w_offset_rows=0):
     m, n = dy.shape
     k = x.shape[1]
     dbp = None if dbias is None else _p(dbias, F32) + w_offset_rows * 4
-    _call("linear_bwd_weight", _p(dy, F32), _p(x, F32), _p(dw, F32) + w_offset_rows * k * 4, dbp, m, n, k, PREC_FP32, _stream(),
+    _call("linear_bwd_weight", _p(dy, F32), _p(x, F32), _p(dw, F32) + w_offset_rows * k * 4, dbp, m, n, k, _state["precision"], _stream(),
           flops=2 * m * n * k, nbytes=4 * (m * k + n * k + m * n))
 
 
@@ -260,7 +260,7 @@ def strided_table(indices, batch, Y, X, rows_dev=None):
 def sparse_conv_fwd(x, table, w, rows_out):
     cout, taps, cin = w.shape[0], w.shape[1] * w.shape[2] if w.dim() == 4 else w.shape[1], w.shape[-1]
     y = torch.empty(rows_out, cout, dtype=F32, device=x.device)
-    _call("sparse_conv_fwd", _p(x, F32), _p(table, I32), _p(w, F32), _p(y), rows_out, taps, cin, cout, 0, PREC_FP32, _stream(),
+    _call("sparse_conv_fwd", _p(x, F32), _p(table, I32), _p(w, F32), _p(y), rows_out, taps, cin, cout, 0, _state["precision"], _stream(),
           flops=2 * rows_out * taps * cin * cout, nbytes=4 * (x.numel() + w.numel() + rows_out * cout) + 4 * rows_out * taps)
     return y
 
@@ -268,7 +268,7 @@ def sparse_conv_fwd(x, table, w, rows_out):
 def sparse_conv_bwd_weight(dy, x, table, w_shape):
     cout, taps, cin = w_shape[0], w_shape[1] * w_shape[2], w_shape[3]
     dw = torch.empty(w_shape, dtype=F32, device=x.device)
-    _call("sparse_conv_bwd_weight", _p(dy, F32), _p(x, F32), _p(table, I32), _p(dw), dy.shape[0], taps, cin, cout, PREC_FP32, _stream(),
+    _call("sparse_conv_bwd_weight", _p(dy, F32), _p(x, F32), _p(table, I32), _p(dw), dy.shape[0], taps, cin, cout, _state["precision"], _stream(),
           flops=2 * dy.shape[0] * taps * cin * cout, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
     return dw
 

@@ -1,0 +1,98 @@
+"""GPU tests of the bf16 tcgen05 GEMM family (TMAE_PREC_BF16) against float64 references computed on the SAME
+bf16-rounded operands: products of bf16 values are exact in fp32, so only the accumulation order differs and the
+bound is rtol 1e-4 + atol 1e-4 (fp32 accumulate in TMEM); against the un-rounded fp32 operands the stated throughput
+tolerance is rtol 1e-2 + atol 1e-2 * |x| |w| sqrt(k) (bf16 has 8 mantissa bits)."""
+import numpy as np
+import pytest
+import torch
+
+from common import assert_close
+from oracle import restated
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import tmae_b200  # noqa: F401
+    from tmae_b200 import ops
+
+DEV = "cuda"
+
+
+def bf(t):
+    return t.to(torch.bfloat16).double()
+
+
+@pytest.fixture(autouse=True)
+def _bf16_mode():
+    ops.set_precision("bf16")
+    yield
+    ops.set_precision("fp32")
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (1, 128, 64), (1000, 128, 128), (333, 256, 128), (2049, 256, 512), (4100, 512, 256),
+                                   (65, 48, 128), (5000, 128, 256)])
+def test_tc_linear_fwd_bwd(m, n, k):
+    g = torch.Generator().manual_seed(m + n + k)
+    x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k ** .5, torch.randn(n, generator=g)
+    r = torch.randn(m, n, generator=g)
+    xd, wd, bd, rd = (t.to(DEV) for t in (x, w, b, r))
+    for act, f in ((ops.ACT_NONE, lambda t: t), (ops.ACT_GELU, torch.nn.functional.gelu)):
+        y, pre = ops.linear_fwd(xd, wd, bd, residual=rd, act=act, want_preact=True)
+        lin = bf(x) @ bf(w).T + b.double()
+        assert_close(pre, lin, 1e-4, 1e-4, f"tc linear preact m={m}")
+        assert_close(y, f(lin) + r.double(), 1e-4, 1e-4, f"tc linear act={act}")
+    dy = torch.randn(m, n, generator=g)
+    dx = ops.linear_bwd_data(dy.to(DEV), wd)
+    assert_close(dx, bf(dy) @ bf(w), 1e-4, 1e-4, "tc dx")
+    dx2 = ops.linear_bwd_data(dy.to(DEV), wd, dx=dx.clone(), accumulate=True)
+    assert_close(dx2, 2 * (bf(dy) @ bf(w)), 1e-4, 2e-4, "tc dx accumulate")
+    dw, db = torch.empty_like(wd), torch.empty_like(bd)
+    ops.linear_bwd_weight(dy.to(DEV), xd, dw, db)
+    assert_close(dw, bf(dy).T @ bf(x), 1e-4, 1e-4 * max(1, m) ** .5, "tc dw")
+    assert_close(db, dy.double().sum(0), 1e-5, 1e-4 * max(1, m) ** .5, "db")
+
+
+def test_tc_weight_slices():
+    """packed in_proj: q/k/v slices addressed by row offset, as the encoder layers do."""
+    g = torch.Generator().manual_seed(0)
+    C, m = 128, 900
+    x, w, b = torch.randn(m, C, generator=g), torch.randn(3 * C, C, generator=g) / C ** .5, torch.randn(3 * C, generator=g)
+    for i in range(3):
+        y = ops.linear_fwd(x.to(DEV), w.to(DEV), b.to(DEV), w_offset_rows=i * C, n=C)
+        assert_close(y, bf(x) @ bf(w[i * C:(i + 1) * C]).T + b[i * C:(i + 1) * C].double(), 1e-4, 1e-4, f"slice {i}")
+
+
+def _coords(seed, m, B, g):
+    rng = np.random.default_rng(seed)
+    cells = np.sort(rng.choice(B * g * g, size=min(m, B * g * g), replace=False))
+    return torch.tensor(np.stack([cells // (g * g), (cells % (g * g)) // g, cells % g], 1), dtype=torch.int32)
+
+
+@pytest.mark.parametrize("seed,m,B,g,cin,cout", [(0, 1500, 2, 96, 128, 128), (1, 700, 2, 47, 128, 256), (2, 3000, 1, 90, 256, 256)])
+def test_tc_sparse_conv(seed, m, B, g, cin, cout):
+    c = _coords(seed, m, B, g)
+    m = c.shape[0]
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(m, cin, generator=gen)
+    for subm in (True, False):
+        conv = restated.SparseConv(cin, cout, 3, 1 if subm else 2, 1, subm).double()
+        with torch.no_grad():
+            conv.weight.copy_(bf(conv.weight.float()))
+        xr = bf(x).requires_grad_()
+        ref = conv(restated.SparseTensor(xr, c, [g, g], B))
+        w = conv.weight.detach().float().to(DEV)
+        if subm:
+            table = ops.subm_table(c.to(DEV), B, g, g)
+            table_t, flip, rows_out = table, True, m
+        else:
+            idx_out, n_out, table, table_t, _ = ops.strided_table(c.to(DEV), B, g, g)
+            rows_out = int(n_out)
+            table, flip = table[:rows_out], False
+        y = ops.sparse_conv_fwd(x.to(DEV), table, w, rows_out)
+        assert_close(y, ref.features.detach(), 1e-4, 1e-4, f"tc sparse conv fwd subm={subm}")
+        dy = torch.randn(rows_out, cout, generator=gen)
+        ref.features.backward(bf(dy))
+        dx = ops.sparse_conv_fwd(dy.to(DEV), table_t, ops.transpose_taps(w, flip), m)
+        assert_close(dx, xr.grad, 1e-4, 1e-4, f"tc sparse conv dx subm={subm}")
+        dw = ops.sparse_conv_bwd_weight(dy.to(DEV), x.to(DEV), table, w.shape)
+        assert_close(dw, conv.weight.grad, 1e-4, 1e-4 * m ** .5, f"tc sparse conv dw subm={subm}")
