@@ -184,14 +184,17 @@ TMAE_API int tmae_scatter_rows(const float* rows, const int32_t* sel, int64_t m,
  * Replaces flat2window + _scaled_cosine_attention + window2flat (cosine_msa.py:114-176, sst_basic_block.py:22-54,
  * wca_block.py:26-67).  q/k/v are the PROJECTED rows (rows, C) in flat voxel order; tok/cnt tables come from
  * tmae_window_partition (self: q and k tables are the same; cross: q = current frame, k = previous frame).
- * max_windows bounds the grid; the live count is read from n_win on the device. */
+ * max_windows bounds the grid; the live count is read from n_win on the device.  small_end (device i32) = number of
+ * leading windows that hold <= 16 tokens on both sides (= level_base[first level with max_tokens > 16]; windows are
+ * level-sorted): those run one warp per window, the rest one CTA per window.  Backward: dsum (q rows, heads) scratch. */
 TMAE_API int tmae_window_attention_fwd(const float* q, const float* k, const float* v, float* o, float* lse, const int32_t* qtok,
                               const int32_t* qcnt, const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win,
-                              int64_t max_windows, const float* tau, float tau_min, int32_t channels, int32_t heads, void* stream);
+                              const int32_t* small_end, int64_t max_windows, const float* tau, float tau_min, int32_t channels,
+                              int32_t heads, void* stream);
 TMAE_API int tmae_window_attention_bwd(const float* dout, const float* q, const float* k, const float* v, const float* o, const float* lse,
-                              float* dq, float* dk, float* dv, float* dtau, const int32_t* qtok, const int32_t* qcnt,
-                              const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win, int64_t max_windows, const float* tau,
-                              float tau_min, int32_t channels, int32_t heads, void* stream);
+                              float* dsum, float* dq, float* dk, float* dv, float* dtau, const int32_t* qtok, const int32_t* qcnt,
+                              const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win, const int32_t* small_end,
+                              int64_t max_windows, const float* tau, float tau_min, int32_t channels, int32_t heads, void* stream);
 
 /* ---- A10-A11 reconstruction target + Chamfer loss ------------------------------------------------
  * Replaces sst_ops_cuda.group_inner_inds_wrapper (pcdet/ops/sst_ops/src/sst_ops_api.cpp:8, sst_ops_gpu.cu:22-39),

@@ -110,7 +110,7 @@ class _SelfLayerFn(torch.autograd.Function):
         q = ops.linear_fwd(xp, Win, bin_, w_offset_rows=0, n=C)
         k = ops.linear_fwd(xp, Win, bin_, w_offset_rows=C, n=C)
         v = ops.linear_fwd(x, Win, bin_, w_offset_rows=2 * C, n=C)
-        o, lse = ops.window_attention_fwd(q, k, v, tok, cnt, tok, cnt, nwin, maxw, tau, tau_min, heads, zero_out=False)
+        o, lse = ops.window_attention_fwd(q, k, v, tok, cnt, tok, cnt, nwin, ops.small_end(part, shift), maxw, tau, tau_min, heads, zero_out=False)
         a = ops.linear_fwd(o, Wo, bo)
         ffn_p = (g1, b1, W1, bb1, W2, bb2, g2, b2)
         x2, saved = _ffn_fwd(x, a, None, ffn_p, eps)
@@ -131,7 +131,8 @@ class _SelfLayerFn(torch.autograd.Function):
         ops.linear_bwd_weight(da, o, dWo, dbo)
         do = ops.linear_bwd_data(da, Wo)
         dtau = torch.zeros_like(tau)
-        dq, dk, dv = ops.window_attention_bwd(do, q, k, v, o, lse, tok, cnt, tok, cnt, nwin, maxw, tau, tau_min, heads, dtau, zero=False)
+        dq, dk, dv = ops.window_attention_bwd(do, q, k, v, o, lse, tok, cnt, tok, cnt, nwin, ops.small_end(part, shift), maxw, tau, tau_min, heads,
+                                              dtau, zero=False)
         dWin, dbin = torch.empty_like(Win), torch.empty(3 * C, dtype=torch.float32, device=x.device)
         ops.linear_bwd_weight(dq, xp, dWin, dbin, w_offset_rows=0)
         ops.linear_bwd_weight(dk, xp, dWin, dbin, w_offset_rows=C)
@@ -158,8 +159,8 @@ class _CrossLayerFn(torch.autograd.Function):
         q = ops.linear_fwd(xq, Win, bin_, w_offset_rows=0, n=C)
         k = ops.linear_fwd(xk, Win, bin_, w_offset_rows=C, n=C)
         v = ops.linear_fwd(xprev, Win, bin_, w_offset_rows=2 * C, n=C)
-        o, lse = ops.window_attention_fwd(q, k, v, tp.tok_a[shift], tp.cnt_a[shift], tp.tok_b[shift], tp.cnt_b[shift], nwin, maxw, tau,
-                                          tau_min, heads, zero_out=True)
+        o, lse = ops.window_attention_fwd(q, k, v, tp.tok_a[shift], tp.cnt_a[shift], tp.tok_b[shift], tp.cnt_b[shift], nwin,
+                                          ops.small_end(tp, shift), maxw, tau, tau_min, heads, zero_out=True)
         a = ops.linear_fwd(o, Wo, bo)
         ffn_p = (g1, b1, W1, bb1, W2, bb2, g2, b2)
         x2, saved = _ffn_fwd(x, a, tp.keep_a[shift], ffn_p, eps)
@@ -181,7 +182,7 @@ class _CrossLayerFn(torch.autograd.Function):
         do = ops.linear_bwd_data(da, Wo)
         dtau = torch.zeros_like(tau)
         dq, dk, dv = ops.window_attention_bwd(do, q, k, v, o, lse, tp.tok_a[shift], tp.cnt_a[shift], tp.tok_b[shift], tp.cnt_b[shift],
-                                              nwin, maxw, tau, tau_min, heads, dtau, zero=True)
+                                              nwin, ops.small_end(tp, shift), maxw, tau, tau_min, heads, dtau, zero=True)
         dWin, dbin = torch.empty_like(Win), torch.empty(3 * C, dtype=torch.float32, device=x.device)
         ops.linear_bwd_weight(dq, xq, dWin, dbin, w_offset_rows=0)
         ops.linear_bwd_weight(dk, xk, dWin, dbin, w_offset_rows=C)

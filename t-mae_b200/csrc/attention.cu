@@ -6,233 +6,305 @@
 //  wca_block.py:26-67; sst_utils.py:118-192).
 //
 // The reference pads every window to its level's token count and masks the padding; mathematically
-// the padded keys contribute exp(-inf) = 0 and padded queries are discarded, so the kernel works
-// on the ragged windows directly: a work item is (compact window, head group of 128 channels);
-// the window's <= 64 key rows are gathered through the partition's token table into shared
-// memory, normalised per head, and each lane owns one query row with an online softmax.  Results
-// are written straight to the flat (voxel-major) layout.  The averaged attention map that the
-// reference also computes (cosine_msa.py:433-436) is never consumed and is not produced.
+// the padded keys contribute exp(-inf) = 0 and padded queries are discarded, so the kernels work
+// on the ragged windows directly and write straight to the flat (voxel-major) layout.  The
+// averaged attention map the reference also computes (cosine_msa.py:433-436) is never consumed and
+// is not produced.
+//
+// Work decomposition.  An "item" is (row, head) where the row is a query (forward, dQ pass) or a
+// key (dK/dV pass); the other side of the window is the "stationary" side it loops over.
+//   * small windows (the partition sorts windows by level, so windows [0, small_end) hold <= 16
+//     tokens -- 87 % of the windows of a lidar scan): one WARP per window, lanes = items, the
+//     stationary rows are read through L1 (every row is re-read by all items of the warp).  No
+//     shared memory, no block barriers, full occupancy.
+//   * large windows: one CTA per (window, 128-channel group); the stationary rows are gathered
+//     once into shared memory (head slices padded to HD+4 floats so that the 8 heads of a quarter
+//     warp hit distinct banks with 128-bit loads), normalised there, and threads = items.
+// Three passes share the template: MODE 0 forward (saves logsumexp), MODE 1 dQ (+ dtau, saves
+// D = dO.O), MODE 2 dK/dV.  Online softmax in fp32; exp via __expf.
 #include "common.cuh"
 
 namespace tmae {
 
-constexpr int TW = 128;            // channels per work item
-constexpr int TWP = TW + 1;        // padded row stride (conflict-free column access)
 constexpr int MAXT = TMAE_WIN_TOKENS;
 constexpr int ATT_THREADS = 256;
+constexpr int TW = 128;  // channels per large-window work item
 
 struct AttnArgs {
-  const float* q; const float* k; const float* v;   // (rows, C)
+  const float* q; const float* k; const float* v;   // (rows, C) projected
   float* o;                                          // (q rows, C)
   float* lse;                                        // (q rows, H)
+  float* dsum;                                       // (q rows, H)  D = dO . O   (written by MODE 1, read by MODE 2)
   const int* qtok; const int* qcnt;                  // [n_win*64], [n_win]
   const int* ktok; const int* kcnt;
-  const int* n_win;                                  // device
+  const int* n_win;                                  // device: number of windows
+  const int* small_end;                              // device: windows [0, *small_end) hold <= 16 tokens on both sides
   const float* tau; float tau_min;
   int C, H;
-  // backward
   const float* dout; float* dq; float* dk; float* dv; float* dtau;
 };
 
-__device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ src, const int* __restrict__ tok, int cnt, int C,
-                                          int col0) {
-  // dst[j][c] for j < cnt, c < TW ; coalesced along c
-  for (int e = threadIdx.x; e < cnt * TW; e += ATT_THREADS) {
-    int j = e / TW, c = e - j * TW;
-    dst[j * TWP + c] = src[(int64_t)tok[j] * C + col0 + c];
-  }
-}
-
-// scale every (row, head) slice to unit L2 norm (F.normalize, eps 1e-12); optionally keep 1/norm
-__device__ __forceinline__ void normalize_tile(float* t, int cnt, int hd, int heads, float* inv_out) {
-  for (int e = threadIdx.x; e < cnt * heads; e += ATT_THREADS) {
-    int j = e / heads, h = e - j * heads;
-    float* p = t + j * TWP + h * hd;
-    float s = 0.f;
-    for (int d = 0; d < hd; ++d) s += p[d] * p[d];
-    float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);
-    for (int d = 0; d < hd; ++d) p[d] *= inv;
-    if (inv_out) inv_out[j * 8 + h] = inv;
-  }
-}
-
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(AttnArgs a) {
-  extern __shared__ float sm[];
-  float* Ks = sm;                    // [64][TWP]
-  float* Vs = sm + MAXT * TWP;       // [64][TWP]
-  __shared__ int qt[MAXT], kt[MAXT];
-  constexpr int HEADS = TW / HD;     // heads per work item: 8 (hd 16) or 4 (hd 32)
-  constexpr int NSUB = 8 / HEADS;    // warps per head
-  const int groups = a.C / TW;
-  const int n_items = *a.n_win * groups;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hl = warp / NSUB, sub = warp % NSUB;
-  const float inv_tau = 1.f / fmaxf(*a.tau, a.tau_min);
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    int g = item / groups, col0 = (item - g * groups) * TW;
-    int nq = a.qcnt[g], nk = a.kcnt[g];
-    __syncthreads();
-    if (threadIdx.x < MAXT) {
-      qt[threadIdx.x] = threadIdx.x < nq ? a.qtok[g * MAXT + threadIdx.x] : 0;
-      kt[threadIdx.x] = threadIdx.x < nk ? a.ktok[g * MAXT + threadIdx.x] : 0;
-    }
-    __syncthreads();
-    load_tile(Ks, a.k, kt, nk, a.C, col0);
-    load_tile(Vs, a.v, kt, nk, a.C, col0);
-    __syncthreads();
-    normalize_tile(Ks, nk, HD, HEADS, nullptr);
-    __syncthreads();
-    const int hcol = hl * HD;
-    for (int i = lane + 32 * sub; i < nq; i += 32 * NSUB) {
-      int64_t row = qt[i];
-      const float* qp = a.q + row * a.C + col0 + hcol;
-      float qv[HD];
-      float s = 0.f;
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float* r) {
 #pragma unroll
-      for (int d = 0; d < HD; ++d) { qv[d] = qp[d]; s += qv[d] * qv[d]; }
-      float inv = inv_tau / fmaxf(sqrtf(s), 1e-12f);
+  for (int d = 0; d < HD; d += 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p + d));
+    r[d] = t.x; r[d + 1] = t.y; r[d + 2] = t.z; r[d + 3] = t.w;
+  }
+}
+template <int HD>
+__device__ __forceinline__ void store_row(float* p, const float* r) {
 #pragma unroll
-      for (int d = 0; d < HD; ++d) qv[d] *= inv;       // q_hat / tau
-      float m = -INFINITY, l = 0.f;
-      float acc[HD];
+  for (int d = 0; d < HD; d += 4) *reinterpret_cast<float4*>(p + d) = make_float4(r[d], r[d + 1], r[d + 2], r[d + 3]);
+}
+template <int HD>
+__device__ __forceinline__ float dot(const float* a, const float* b) {
+  float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-      for (int j = 0; j < nk; ++j) {
-        const float* kp = Ks + j * TWP + hcol;
-        float sc = 0.f;
+  for (int d = 0; d < HD; ++d) s = fmaf(a[d], b[d], s);
+  return s;
+}
+// x / max(|x|, 1e-12)  (F.normalize); returns 1 / max(|x|, eps)
+template <int HD>
+__device__ __forceinline__ float normalize(float* x) {
+  float inv = 1.f / fmaxf(sqrtf(dot<HD>(x, x)), 1e-12f);
 #pragma unroll
-        for (int d = 0; d < HD; ++d) sc = fmaf(qv[d], kp[d], sc);
-        if (sc > m) {
-          float r = __expf(m - sc);
-          l *= r;
+  for (int d = 0; d < HD; ++d) x[d] *= inv;
+  return inv;
+}
+
+// One item against a stationary side given by an accessor.  ST::row(j, h, out) yields the j-th stationary row's
+// head slice; for MODE 0/1 that is (k_hat via .a, v via .b); for MODE 2 it is (q_hat via .a, dO via .b).
+template <int HD, int MODE, class ST>
+__device__ __forceinline__ void run_item(const AttnArgs& a, const ST& st, int n_other, int64_t row, int h, float inv_tau,
+                                         float& dtau_acc) {
+  const int64_t off = row * a.C + h * HD;
+  if (MODE == 0) {
+    float qh[HD];
+    load_row<HD>(a.q + off, qh);
+    float s = inv_tau / fmaxf(sqrtf(dot<HD>(qh, qh)), 1e-12f);
 #pragma unroll
-          for (int d = 0; d < HD; ++d) acc[d] *= r;
-          m = sc;
-        }
-        float p = __expf(sc - m);
-        l += p;
-        const float* vp = Vs + j * TWP + hcol;
+    for (int d = 0; d < HD; ++d) qh[d] *= s;  // q_hat / tau
+    float m = -INFINITY, l = 0.f, acc[HD];
 #pragma unroll
-        for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, vp[d], acc[d]);
+    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+    for (int j = 0; j < n_other; ++j) {
+      float kh[HD], vv[HD];
+      st.a(j, h, kh);
+      st.b(j, h, vv);
+      float sc = dot<HD>(qh, kh);
+      if (sc > m) {
+        float r = __expf(m - sc);
+        l *= r;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] *= r;
+        m = sc;
       }
-      float il = 1.f / l;
-      float* op = a.o + row * a.C + col0 + hcol;
+      float p = __expf(sc - m);
+      l += p;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) op[d] = acc[d] * il;
-      if (a.lse) a.lse[row * a.H + (col0 / HD) + hl] = m + __logf(l);
+      for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, vv[d], acc[d]);
     }
+    float il = 1.f / l;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] *= il;
+    store_row<HD>(a.o + off, acc);
+    if (a.lse) a.lse[row * a.H + h] = m + __logf(l);
+  } else if (MODE == 1) {
+    float qh[HD], dov[HD], dqh[HD], ov[HD];
+    load_row<HD>(a.q + off, qh);
+    float inv = normalize<HD>(qh);
+    load_row<HD>(a.dout + off, dov);
+    load_row<HD>(a.o + off, ov);
+    float Di = dot<HD>(dov, ov), Li = a.lse[row * a.H + h];
+    a.dsum[row * a.H + h] = Di;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) dqh[d] = 0.f;
+    for (int j = 0; j < n_other; ++j) {
+      float kh[HD], vv[HD];
+      st.a(j, h, kh);
+      st.b(j, h, vv);
+      float sc = dot<HD>(qh, kh) * inv_tau;
+      float p = __expf(sc - Li);
+      float ds = p * (dot<HD>(dov, vv) - Di);
+      dtau_acc -= ds * sc;  // d(c/tau)/dtau = -(c/tau)/tau ; the trailing 1/tau is applied once at the end
+      float dsl = ds * inv_tau;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) dqh[d] = fmaf(dsl, kh[d], dqh[d]);
+    }
+    float dt = dot<HD>(dqh, qh);  // through q_hat = q / max(|q|, eps)
+#pragma unroll
+    for (int d = 0; d < HD; ++d) dqh[d] = (dqh[d] - qh[d] * dt) * inv;
+    store_row<HD>(a.dq + off, dqh);
+  } else {
+    float kh[HD], vv[HD], dkh[HD], dvv[HD];
+    load_row<HD>(a.k + off, kh);
+    float inv = normalize<HD>(kh);
+    load_row<HD>(a.v + off, vv);
+#pragma unroll
+    for (int d = 0; d < HD; ++d) { dkh[d] = 0.f; dvv[d] = 0.f; }
+    for (int i = 0; i < n_other; ++i) {
+      float qh[HD], dov[HD];
+      st.a(i, h, qh);
+      st.b(i, h, dov);
+      float sc = dot<HD>(qh, kh) * inv_tau;
+      float p = __expf(sc - st.lse(i, h));
+      float dsl = p * (dot<HD>(dov, vv) - st.dsum(i, h)) * inv_tau;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) { dkh[d] = fmaf(dsl, qh[d], dkh[d]); dvv[d] = fmaf(p, dov[d], dvv[d]); }
+    }
+    float dt = dot<HD>(dkh, kh);
+#pragma unroll
+    for (int d = 0; d < HD; ++d) dkh[d] = (dkh[d] - kh[d] * dt) * inv;
+    store_row<HD>(a.dk + off, dkh);
+    store_row<HD>(a.dv + off, dvv);
   }
 }
 
-// backward: smem holds Q_hat, K_hat, V, dO tiles (4 x 64 x 129 floats) + per-row stats
+// ------------------------------------------------------------------ small windows: warp per window, L1-resident rows
+template <int HD, int MODE>
+struct GlobalSide {
+  const AttnArgs& g;
+  const int* tok;  // stationary token list of this window
+  __device__ __forceinline__ void a(int j, int h, float* out) const {
+    const float* src = (MODE == 2 ? g.q : g.k) + (int64_t)tok[j] * g.C + h * HD;
+    load_row<HD>(src, out);
+    normalize<HD>(out);
+  }
+  __device__ __forceinline__ void b(int j, int h, float* out) const {
+    load_row<HD>((MODE == 2 ? g.dout : g.v) + (int64_t)tok[j] * g.C + h * HD, out);
+  }
+  __device__ __forceinline__ float lse(int i, int h) const { return g.lse[(int64_t)tok[i] * g.H + h]; }
+  __device__ __forceinline__ float dsum(int i, int h) const { return g.dsum[(int64_t)tok[i] * g.H + h]; }
+};
+
+template <int HD, int MODE>
+__global__ void __launch_bounds__(ATT_THREADS) attn_small_kernel(AttnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int n_small = min(*a.small_end, *a.n_win);
+  const float tau_raw = *a.tau;
+  const float inv_tau = 1.f / fmaxf(tau_raw, a.tau_min);
+  float dtau_acc = 0.f;
+  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_small; g += warps) {
+    const int nq = a.qcnt[g], nk = a.kcnt[g];
+    const int* rows_tok = (MODE == 2 ? a.ktok : a.qtok) + g * MAXT;
+    const int n_rows = MODE == 2 ? nk : nq, n_other = MODE == 2 ? nq : nk;
+    GlobalSide<HD, MODE> st{a, (MODE == 2 ? a.qtok : a.ktok) + g * MAXT};
+    for (int it = lane; it < n_rows * a.H; it += 32) {
+      int r = it / a.H, h = it - r * a.H;
+      run_item<HD, MODE>(a, st, n_other, rows_tok[r], h, inv_tau, dtau_acc);
+    }
+  }
+  if (MODE == 1) {
+    dtau_acc = warp_sum(dtau_acc);
+    if (lane == 0 && a.dtau && tau_raw > a.tau_min && dtau_acc != 0.f) atomicAdd(a.dtau, dtau_acc * inv_tau);
+  }
+}
+
+// ------------------------------------------------------------------ large windows: CTA per (window, 128-channel group)
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(AttnArgs a) {
-  extern __shared__ float sm[];
-  float* Qs = sm;
-  float* Ks = Qs + MAXT * TWP;
-  float* Vs = Ks + MAXT * TWP;
-  float* Ds = Vs + MAXT * TWP;          // dO
-  float* qinv = Ds + MAXT * TWP;        // [64][8] 1/|q|
-  float* kinv = qinv + MAXT * 8;        // [64][8]
-  float* lse_s = kinv + MAXT * 8;       // [64][8]
-  float* dsum = lse_s + MAXT * 8;       // [64][8]  D_i = dO_i . O_i
-  __shared__ int qt[MAXT], kt[MAXT];
-  constexpr int HEADS = TW / HD;
-  constexpr int NSUB = 8 / HEADS;
+struct SmemSide {
+  static constexpr int HEADS = TW / HD;
+  static constexpr int HS = HD + 4;            // padded head stride: conflict-free LDS.128 across heads
+  static constexpr int RS = HEADS * HS;        // row stride
+  const float* A; const float* B; const float* L; const float* D;
+  int h0;  // first absolute head of this 128-channel group
+  __device__ __forceinline__ void a(int j, int h, float* out) const {
+    h -= h0;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) {
+      float4 t = *reinterpret_cast<const float4*>(A + j * RS + h * HS + d);
+      out[d] = t.x; out[d + 1] = t.y; out[d + 2] = t.z; out[d + 3] = t.w;
+    }
+  }
+  __device__ __forceinline__ void b(int j, int h, float* out) const {
+    h -= h0;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) {
+      float4 t = *reinterpret_cast<const float4*>(B + j * RS + h * HS + d);
+      out[d] = t.x; out[d + 1] = t.y; out[d + 2] = t.z; out[d + 3] = t.w;
+    }
+  }
+  __device__ __forceinline__ float lse(int i, int h) const { return L[i * HEADS + h - h0]; }
+  __device__ __forceinline__ float dsum(int i, int h) const { return D[i * HEADS + h - h0]; }
+};
+
+template <int HD, int MODE>
+__global__ void __launch_bounds__(ATT_THREADS) attn_large_kernel(AttnArgs a) {
+  using S = SmemSide<HD>;
+  extern __shared__ __align__(16) float sm[];
+  float* As = sm;                       // [64][RS]  k_hat (MODE 0/1) or q_hat (MODE 2)
+  float* Bs = sm + MAXT * S::RS;        // [64][RS]  v or dO
+  float* Ls = Bs + MAXT * S::RS;        // [64][HEADS] lse   (MODE 2)
+  float* Ds = Ls + MAXT * S::HEADS;     // [64][HEADS] D     (MODE 2)
+  __shared__ int stat_tok[MAXT], row_tok[MAXT];
   const int groups = a.C / TW;
-  const int n_items = *a.n_win * groups;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hl = warp / NSUB, sub = warp % NSUB;
+  const int first = min(*a.small_end, *a.n_win);
+  const int n_items = (*a.n_win - first) * groups;
   const float tau_raw = *a.tau;
   const float inv_tau = 1.f / fmaxf(tau_raw, a.tau_min);
   float dtau_acc = 0.f;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    int g = item / groups, col0 = (item - g * groups) * TW;
-    int nq = a.qcnt[g], nk = a.kcnt[g];
+    const int g = first + item / groups, grp = item % groups, col0 = grp * TW;
+    const int nq = a.qcnt[g], nk = a.kcnt[g];
+    const int n_rows = MODE == 2 ? nk : nq, n_other = MODE == 2 ? nq : nk;
     __syncthreads();
     if (threadIdx.x < MAXT) {
-      qt[threadIdx.x] = threadIdx.x < nq ? a.qtok[g * MAXT + threadIdx.x] : 0;
-      kt[threadIdx.x] = threadIdx.x < nk ? a.ktok[g * MAXT + threadIdx.x] : 0;
+      int t = threadIdx.x;
+      stat_tok[t] = t < n_other ? ((MODE == 2 ? a.qtok : a.ktok)[g * MAXT + t]) : 0;
+      row_tok[t] = t < n_rows ? ((MODE == 2 ? a.ktok : a.qtok)[g * MAXT + t]) : 0;
     }
     __syncthreads();
-    load_tile(Qs, a.q, qt, nq, a.C, col0);
-    load_tile(Ds, a.dout, qt, nq, a.C, col0);
-    load_tile(Ks, a.k, kt, nk, a.C, col0);
-    load_tile(Vs, a.v, kt, nk, a.C, col0);
+    const float* srcA = MODE == 2 ? a.q : a.k;
+    const float* srcB = MODE == 2 ? a.dout : a.v;
+    for (int e = threadIdx.x; e < n_other * (TW / 4); e += ATT_THREADS) {  // coalesced 512-byte row segments
+      int j = e / (TW / 4), c4 = (e - j * (TW / 4)) * 4;
+      int h = c4 / HD, d = c4 - h * HD;
+      const int64_t src = (int64_t)stat_tok[j] * a.C + col0 + c4;
+      *reinterpret_cast<float4*>(As + j * S::RS + h * S::HS + d) = __ldg(reinterpret_cast<const float4*>(srcA + src));
+      *reinterpret_cast<float4*>(Bs + j * S::RS + h * S::HS + d) = __ldg(reinterpret_cast<const float4*>(srcB + src));
+    }
     __syncthreads();
-    // D_i and lse per (query, head): O is read from global
-    for (int e = threadIdx.x; e < nq * HEADS; e += ATT_THREADS) {
-      int i = e / HEADS, h = e - i * HEADS;
-      const float* op = a.o + (int64_t)qt[i] * a.C + col0 + h * HD;
-      const float* dp = Ds + i * TWP + h * HD;
+    for (int e = threadIdx.x; e < n_other * S::HEADS; e += ATT_THREADS) {  // F.normalize per (row, head)
+      int j = e / S::HEADS, h = e - j * S::HEADS;
+      float* p = As + j * S::RS + h * S::HS;
       float s = 0.f;
-      for (int d = 0; d < HD; ++d) s += op[d] * dp[d];
-      dsum[i * 8 + h] = s;
-      lse_s[i * 8 + h] = a.lse[(int64_t)qt[i] * a.H + (col0 / HD) + h];
+      for (int d = 0; d < HD; ++d) s = fmaf(p[d], p[d], s);
+      float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);
+      for (int d = 0; d < HD; ++d) p[d] *= inv;
+      if (MODE == 2) {
+        const int64_t r = (int64_t)stat_tok[j] * a.H + grp * S::HEADS + h;
+        Ls[e] = a.lse[r];
+        Ds[e] = a.dsum[r];
+      }
     }
-    normalize_tile(Qs, nq, HD, HEADS, qinv);
-    normalize_tile(Ks, nk, HD, HEADS, kinv);
     __syncthreads();
-    const int hcol = hl * HD;
-    // ---- phase A: lane = query  -> dQ
-    for (int i = lane + 32 * sub; i < nq; i += 32 * NSUB) {
-      float qv[HD], dov[HD], dqh[HD];
-#pragma unroll
-      for (int d = 0; d < HD; ++d) { qv[d] = Qs[i * TWP + hcol + d]; dov[d] = Ds[i * TWP + hcol + d]; dqh[d] = 0.f; }
-      float Di = dsum[i * 8 + hl], Li = lse_s[i * 8 + hl];
-      for (int j = 0; j < nk; ++j) {
-        const float* kp = Ks + j * TWP + hcol;
-        const float* vp = Vs + j * TWP + hcol;
-        float sc = 0.f, dp = 0.f;
-#pragma unroll
-        for (int d = 0; d < HD; ++d) { sc = fmaf(qv[d], kp[d], sc); dp = fmaf(dov[d], vp[d], dp); }
-        sc *= inv_tau;
-        float p = __expf(sc - Li);
-        float ds = p * (dp - Di);
-        dtau_acc -= ds * sc;               // d/dtau of (c / tau) = -(c / tau) / tau ; the 1/tau is applied at the end
-        float dsl = ds * inv_tau;
-#pragma unroll
-        for (int d = 0; d < HD; ++d) dqh[d] = fmaf(dsl, kp[d], dqh[d]);
-      }
-      // through q_hat = q / max(|q|, eps)
-      float dot = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) dot = fmaf(dqh[d], qv[d], dot);
-      float inv = qinv[i * 8 + hl];
-      float* out = a.dq + (int64_t)qt[i] * a.C + col0 + hcol;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) out[d] = (dqh[d] - qv[d] * dot) * inv;
-    }
-    // ---- phase B: lane = key -> dK, dV
-    for (int j = lane + 32 * sub; j < nk; j += 32 * NSUB) {
-      float kv[HD], vv[HD], dkh[HD], dvv[HD];
-#pragma unroll
-      for (int d = 0; d < HD; ++d) { kv[d] = Ks[j * TWP + hcol + d]; vv[d] = Vs[j * TWP + hcol + d]; dkh[d] = 0.f; dvv[d] = 0.f; }
-      for (int i = 0; i < nq; ++i) {
-        const float* qp = Qs + i * TWP + hcol;
-        const float* dop = Ds + i * TWP + hcol;
-        float sc = 0.f, dp = 0.f;
-#pragma unroll
-        for (int d = 0; d < HD; ++d) { sc = fmaf(qp[d], kv[d], sc); dp = fmaf(dop[d], vv[d], dp); }
-        float p = __expf(sc * inv_tau - lse_s[i * 8 + hl]);
-        float dsl = p * (dp - dsum[i * 8 + hl]) * inv_tau;
-#pragma unroll
-        for (int d = 0; d < HD; ++d) { dkh[d] = fmaf(dsl, qp[d], dkh[d]); dvv[d] = fmaf(p, dop[d], dvv[d]); }
-      }
-      float dot = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) dot = fmaf(dkh[d], kv[d], dot);
-      float inv = kinv[j * 8 + hl];
-      float* dko = a.dk + (int64_t)kt[j] * a.C + col0 + hcol;
-      float* dvo = a.dv + (int64_t)kt[j] * a.C + col0 + hcol;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) { dko[d] = (dkh[d] - kv[d] * dot) * inv; dvo[d] = dvv[d]; }
+    S st{As, Bs, Ls, Ds, grp * S::HEADS};
+    for (int it = threadIdx.x; it < n_rows * S::HEADS; it += ATT_THREADS) {
+      int r = it / S::HEADS, h = it - r * S::HEADS;
+      run_item<HD, MODE>(a, st, n_other, row_tok[r], grp * S::HEADS + h, inv_tau, dtau_acc);
     }
   }
-  // tau gradient (clamp passes gradient only where tau > tau_min)
-  dtau_acc = warp_sum(dtau_acc);
-  if (lane == 0 && a.dtau && tau_raw > a.tau_min && dtau_acc != 0.f) atomicAdd(a.dtau, dtau_acc * inv_tau);
+  if (MODE == 1) {
+    dtau_acc = warp_sum(dtau_acc);
+    if ((threadIdx.x & 31) == 0 && a.dtau && tau_raw > a.tau_min && dtau_acc != 0.f) atomicAdd(a.dtau, dtau_acc * inv_tau);
+  }
+}
+
+template <int HD, int MODE>
+static int launch_pass(const AttnArgs& a, int64_t max_windows, cudaStream_t s) {
+  using S = SmemSide<HD>;
+  // small windows: 8 warps per CTA, one window per warp per iteration
+  int64_t warps = max_windows < (int64_t)kNumSMs * 32 ? max_windows : (int64_t)kNumSMs * 32;
+  attn_small_kernel<HD, MODE><<<cdiv(warps * 32, ATT_THREADS), ATT_THREADS, 0, s>>>(a);
+  size_t smem = (size_t)(2 * MAXT * S::RS + 2 * MAXT * S::HEADS) * sizeof(float);
+  auto kern = attn_large_kernel<HD, MODE>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TMAE_ERR_CUDA;
+  int64_t items = max_windows * (a.C / TW);
+  int grid = (int)(items < 2 * kNumSMs ? items : 2 * kNumSMs);
+  kern<<<grid, ATT_THREADS, smem, s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
 }
 
 static int check(const AttnArgs& a, int hd) {
@@ -246,56 +318,38 @@ using namespace tmae;
 
 extern "C" {
 
-/* o[qrow] = softmax(q_hat k_hat^T / max(tau, tau_min)) v per window and head; lse (rows, H) is saved for backward (nullable).
- * Rows of `o` that belong to no window are left untouched (the caller zero-fills for the cross form). */
 int tmae_window_attention_fwd(const float* q, const float* k, const float* v, float* o, float* lse, const int32_t* qtok,
                               const int32_t* qcnt, const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win,
-                              int64_t max_windows, const float* tau, float tau_min, int32_t channels, int32_t heads, void* stream) {
+                              const int32_t* small_end, int64_t max_windows, const float* tau, float tau_min, int32_t channels,
+                              int32_t heads, void* stream) {
   AttnArgs a{};
   a.q = q; a.k = k; a.v = v; a.o = o; a.lse = lse; a.qtok = qtok; a.qcnt = qcnt; a.ktok = ktok; a.kcnt = kcnt; a.n_win = n_win;
-  a.tau = tau; a.tau_min = tau_min; a.C = channels; a.H = heads;
+  a.small_end = small_end; a.tau = tau; a.tau_min = tau_min; a.C = channels; a.H = heads;
   int hd = channels / heads;
   TMAE_CHECK_ARG(check(a, hd) == 0, "channels must be a multiple of 128 and head_dim 16 or 32");
+  TMAE_CHECK_ARG(small_end != nullptr && n_win != nullptr, "n_win / small_end must be device pointers");
   if (max_windows <= 0) return 0;
-  size_t smem = (size_t)2 * MAXT * TWP * sizeof(float);
-  int64_t items = max_windows * (channels / TW);
-  int grid = (int)(items < 4 * kNumSMs ? items : 4 * kNumSMs);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (hd == 16) {
-    TMAE_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_fwd_kernel<16><<<grid, ATT_THREADS, smem, s>>>(a);
-  } else {
-    TMAE_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_fwd_kernel<32><<<grid, ATT_THREADS, smem, s>>>(a);
-  }
-  TMAE_CHECK_LAUNCH();
+  int r = hd == 16 ? launch_pass<16, 0>(a, max_windows, (cudaStream_t)stream) : launch_pass<32, 0>(a, max_windows, (cudaStream_t)stream);
+  if (r) { set_error("tmae_window_attention_fwd: launch failed"); return r; }
   return 0;
 }
 
-/* dq/dk/dv rows that belong to no window are left untouched (caller zero-fills); dtau (1 float) is accumulated. */
 int tmae_window_attention_bwd(const float* dout, const float* q, const float* k, const float* v, const float* o, const float* lse,
-                              float* dq, float* dk, float* dv, float* dtau, const int32_t* qtok, const int32_t* qcnt,
-                              const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win, int64_t max_windows, const float* tau,
-                              float tau_min, int32_t channels, int32_t heads, void* stream) {
+                              float* dsum, float* dq, float* dk, float* dv, float* dtau, const int32_t* qtok, const int32_t* qcnt,
+                              const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win, const int32_t* small_end,
+                              int64_t max_windows, const float* tau, float tau_min, int32_t channels, int32_t heads, void* stream) {
   AttnArgs a{};
-  a.q = q; a.k = k; a.v = v; a.o = (float*)o; a.lse = (float*)lse; a.qtok = qtok; a.qcnt = qcnt; a.ktok = ktok; a.kcnt = kcnt;
-  a.n_win = n_win; a.tau = tau; a.tau_min = tau_min; a.C = channels; a.H = heads;
+  a.q = q; a.k = k; a.v = v; a.o = (float*)o; a.lse = (float*)lse; a.dsum = dsum; a.qtok = qtok; a.qcnt = qcnt; a.ktok = ktok;
+  a.kcnt = kcnt; a.n_win = n_win; a.small_end = small_end; a.tau = tau; a.tau_min = tau_min; a.C = channels; a.H = heads;
   a.dout = dout; a.dq = dq; a.dk = dk; a.dv = dv; a.dtau = dtau;
   int hd = channels / heads;
   TMAE_CHECK_ARG(check(a, hd) == 0, "channels must be a multiple of 128 and head_dim 16 or 32");
+  TMAE_CHECK_ARG(small_end != nullptr && n_win != nullptr && dsum != nullptr, "n_win / small_end / dsum must be device pointers");
   if (max_windows <= 0) return 0;
-  size_t smem = (size_t)(4 * MAXT * TWP + 4 * MAXT * 8) * sizeof(float);
-  int64_t items = max_windows * (channels / TW);
-  int grid = (int)(items < 2 * kNumSMs ? items : 2 * kNumSMs);
   cudaStream_t s = (cudaStream_t)stream;
-  if (hd == 16) {
-    TMAE_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_kernel<16><<<grid, ATT_THREADS, smem, s>>>(a);
-  } else {
-    TMAE_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_kernel<32><<<grid, ATT_THREADS, smem, s>>>(a);
-  }
-  TMAE_CHECK_LAUNCH();
+  int r = hd == 16 ? launch_pass<16, 1>(a, max_windows, s) : launch_pass<32, 1>(a, max_windows, s);
+  if (!r) r = hd == 16 ? launch_pass<16, 2>(a, max_windows, s) : launch_pass<32, 2>(a, max_windows, s);
+  if (r) { set_error("tmae_window_attention_bwd: launch failed"); return r; }
   return 0;
 }
 

@@ -25,7 +25,7 @@ namespace tmae {
 constexpr int TBM = 128;     // UMMA M
 constexpr int TBK = 64;      // k-block per stage
 constexpr int TC_THREADS = 256;
-constexpr int TSTAGES = 3;
+constexpr int TSTAGES = 2;   // two smem stages + one register-resident k-block in flight
 
 enum TcMode { TC_NT = 0, TC_NN = 1, TC_TN = 2 };
 
@@ -119,71 +119,108 @@ __device__ __forceinline__ uint4 pack8(const float4& a, const float4& b) {
   return r;
 }
 
-// Stage a (ROWS x 64) tile whose reduction index is contiguous in HBM (K-major): element (r, k) = src[row(r) * ld + k0 + k].
-// Thread mapping: 8 consecutive lanes take 8 consecutive rows of one 16-byte chunk (conflict-free 128 B stores,
-// 128 contiguous bytes per row per warp load).
+// 32-byte (8 x fp32) global load: one full sector per lane (LDG.E.256 on sm_100)
+__device__ __forceinline__ void ldg8(const float* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ uint4 pack8v(const float* v) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 r;
+  r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
+  r.z = *reinterpret_cast<uint32_t*>(&p2); r.w = *reinterpret_cast<uint32_t*>(&p3);
+  return r;
+}
+
+// A (ROWS x 64) operand tile is moved in two steps so that the global loads of k-block kb+1 are in flight while
+// k-block kb is being consumed: load_* fills a register fragment (one 32-byte sector per lane per chunk),
+// store_* converts to bf16 and writes the canonical no-swizzle UMMA layout.
+//
+// K-major (reduction index contiguous in HBM): element (r, k) = src[row(r) * ld + k0 + k].  8 consecutive lanes take
+// 8 consecutive rows of one 16-byte chunk (conflict-free 128 B shared stores); a warp instruction reads 128
+// contiguous bytes of each of 8 rows.
+template <int ROWS>
+struct FragK { float v[ROWS / 32][8]; };
+
 template <int ROWS, bool GATHER>
-__device__ __forceinline__ void stage_kmajor(uint8_t* dst, const float* __restrict__ src, int64_t ld, int64_t row0, int64_t row_end,
-                                             int64_t k0, int64_t k_end, const int* __restrict__ tab, int taps, int cin) {
+__device__ __forceinline__ void load_kmajor(FragK<ROWS>& f, const float* __restrict__ src, int64_t ld, int64_t row0, int64_t row_end,
+                                            int64_t k0, int64_t k_end, const int* __restrict__ tab, int taps, int cin) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r8 = lane & 7, kcl = lane >> 3;
-  constexpr int COMBOS = (ROWS / 8) * 2;  // (row group, k half)
 #pragma unroll
-  for (int c = warp; c < COMBOS; c += TC_THREADS / 32) {
+  for (int i = 0; i < ROWS / 32; ++i) {
+    int c = warp + i * (TC_THREADS / 32);
     int rg = c >> 1, kc = (c & 1) * 4 + kcl;
     int64_t row = row0 + rg * 8 + r8, k = k0 + kc * 8;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    const float* p = nullptr;
     if (row < row_end && k < k_end) {
-      const float* p;
-      bool ok = true;
       if (GATHER) {
         int tap = (int)(k / cin);
         int srow = tab[row * taps + tap];
-        ok = srow >= 0;
-        p = src + (int64_t)srow * ld + (k - (int64_t)tap * cin);
+        if (srow >= 0) p = src + (int64_t)srow * ld + (k - (int64_t)tap * cin);
       } else {
         p = src + row * ld + k;
       }
-      if (ok) {
-        a = __ldg(reinterpret_cast<const float4*>(p));
-        b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-      }
     }
-    *reinterpret_cast<uint4*>(dst + ((kc * (ROWS / 8) + rg) * 128 + r8 * 16)) = pack8(a, b);
+    if (p) ldg8(p, f.v[i]);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f.v[i][j] = 0.f;
+    }
+  }
+}
+template <int ROWS>
+__device__ __forceinline__ void store_kmajor(uint8_t* dst, const FragK<ROWS>& f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r8 = lane & 7, kcl = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < ROWS / 32; ++i) {
+    int c = warp + i * (TC_THREADS / 32);
+    int rg = c >> 1, kc = (c & 1) * 4 + kcl;
+    *reinterpret_cast<uint4*>(dst + ((kc * (ROWS / 8) + rg) * 128 + r8 * 16)) = pack8v(f.v[i]);
   }
 }
 
-// Stage a (64 x COLS) tile whose output index is contiguous in HBM (MN-major): element (k, c) = src[row(k) * ld + c0 + c].
-// 8 consecutive lanes take the 8 k-rows of one core matrix (128 B contiguous store); a warp covers 4 adjacent
-// column groups = 128 contiguous bytes of each of 8 source rows.
+// MN-major (output index contiguous in HBM): element (k, c) = src[row(k) * ld + c0 + c].  8 consecutive lanes take the
+// 8 k-rows of one core matrix; a warp covers 4 adjacent column groups = 128 contiguous bytes of each of 8 source rows.
 template <int COLS, bool GATHER>
-__device__ __forceinline__ void stage_mnmajor(uint8_t* dst, const float* __restrict__ src, int64_t ld, int64_t k0, int64_t k_end,
-                                              int64_t c0, int64_t c_end, const int* __restrict__ tab, int taps, int cin) {
+__device__ __forceinline__ void load_mnmajor(FragK<COLS>& f, const float* __restrict__ src, int64_t ld, int64_t k0, int64_t k_end,
+                                             int64_t c0, int64_t c_end, const int* __restrict__ tab, int taps, int cin) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k8 = lane & 7, cgl = lane >> 3;
-  constexpr int COMBOS = 8 * (COLS / 32);  // (k group, 4-column-group block)
 #pragma unroll
-  for (int c = warp; c < COMBOS; c += TC_THREADS / 32) {
+  for (int i = 0; i < COLS / 32; ++i) {
+    int c = warp + i * (TC_THREADS / 32);
     int kg = c / (COLS / 32), cg = (c % (COLS / 32)) * 4 + cgl;
     int64_t k = k0 + kg * 8 + k8, col = c0 + cg * 8;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    const float* p = nullptr;
     if (k < k_end && col < c_end) {
-      const float* p;
-      bool ok = true;
       if (GATHER) {
         int tap = (int)(col / cin);
         int srow = tab[k * taps + tap];
-        ok = srow >= 0;
-        p = src + (int64_t)srow * ld + (col - (int64_t)tap * cin);
+        if (srow >= 0) p = src + (int64_t)srow * ld + (col - (int64_t)tap * cin);
       } else {
         p = src + k * ld + col;
       }
-      if (ok) {
-        a = __ldg(reinterpret_cast<const float4*>(p));
-        b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-      }
     }
-    *reinterpret_cast<uint4*>(dst + ((kg * (COLS / 8) + cg) * 128 + k8 * 16)) = pack8(a, b);
+    if (p) ldg8(p, f.v[i]);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f.v[i][j] = 0.f;
+    }
+  }
+}
+template <int COLS>
+__device__ __forceinline__ void store_mnmajor(uint8_t* dst, const FragK<COLS>& f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k8 = lane & 7, cgl = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < COLS / 32; ++i) {
+    int c = warp + i * (TC_THREADS / 32);
+    int kg = c / (COLS / 32), cg = (c % (COLS / 32)) * 4 + cgl;
+    *reinterpret_cast<uint4*>(dst + ((kg * (COLS / 8) + cg) * 128 + k8 * 16)) = pack8v(f.v[i]);
   }
 }
 
@@ -207,6 +244,17 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs g) {
   const int64_t kend = kbeg + g.k_chunk < g.K ? kbeg + g.k_chunk : g.K;
   const int nkb = (int)((kend - kbeg + TBK - 1) / TBK);
 
+  FragK<TBM> fa;
+  FragK<BN> fb;
+  auto prefetch = [&](int kb) {
+    const int64_t k0 = kbeg + (int64_t)kb * TBK;
+    if (MODE == TC_TN) load_mnmajor<TBM, false>(fa, g.A, g.lda, k0, kend, m0, g.M, nullptr, 0, 1);
+    else load_kmajor<TBM, GATHER && MODE == TC_NT>(fa, g.A, g.lda, m0, g.M, k0, kend, g.tab, g.taps, g.cin);
+    if (MODE == TC_NT) load_kmajor<BN, false>(fb, g.B, g.ldb, n0, g.N, k0, kend, nullptr, 0, 1);
+    else load_mnmajor<BN, GATHER && MODE == TC_TN>(fb, g.B, g.ldb, k0, kend, n0, g.N, g.tab, g.taps, g.cin);
+  };
+  if (nkb > 0) prefetch(0);  // in flight during barrier init / TMEM allocation
+
   if (threadIdx.x == 0) {
     for (int s = 0; s < TSTAGES; ++s) mbar_init(&bar_free[s], 1);
     mbar_init(&bar_done, 1);
@@ -223,13 +271,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs g) {
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb % TSTAGES, use = kb / TSTAGES;
     if (use > 0) mbar_wait(&bar_free[s], (use - 1) & 1);  // MMAs that read this stage have retired
-    const int64_t k0 = kbeg + (int64_t)kb * TBK;
     uint8_t* a = sA + s * A_BYTES;
     uint8_t* b = sB + s * B_BYTES;
-    if (MODE == TC_TN) stage_mnmajor<TBM, false>(a, g.A, g.lda, k0, kend, m0, g.M, nullptr, 0, 1);
-    else stage_kmajor<TBM, GATHER && MODE == TC_NT>(a, g.A, g.lda, m0, g.M, k0, kend, g.tab, g.taps, g.cin);
-    if (MODE == TC_NT) stage_kmajor<BN, false>(b, g.B, g.ldb, n0, g.N, k0, kend, nullptr, 0, 1);
-    else stage_mnmajor<BN, GATHER && MODE == TC_TN>(b, g.B, g.ldb, k0, kend, n0, g.N, g.tab, g.taps, g.cin);
+    if (MODE == TC_TN) store_mnmajor<TBM>(a, fa); else store_kmajor<TBM>(a, fa);
+    if (MODE == TC_NT) store_kmajor<BN>(b, fb); else store_mnmajor<BN>(b, fb);
+    if (kb + 1 < nkb) prefetch(kb + 1);  // overlaps the barrier, the MMA issue and the MMAs themselves
     fence_proxy_async();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -248,8 +294,12 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs g) {
   if (nkb > 0) mbar_wait(&bar_done, 0);
   tc_fence_after();
 
-  // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., column half w/4
-  const int64_t row = m0 + (warp & 3) * 32 + lane;
+  // ---- epilogue.  Warp w owns TMEM lanes 32*(w%4).. and the 32-column chunks ch = w/4, w/4+2, ...  Each chunk goes
+  // TMEM -> registers (lane = row) -> padded shared tile -> registers (lane = column), so that every global access
+  // of the epilogue (C, residual, pre-activation) is a 128-byte row segment.  All MMAs have retired: operand
+  // shared memory is reused for the transposition tiles.
+  float* tile = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+  const int64_t rbase = m0 + (warp & 3) * 32;
   constexpr int CHUNKS = BN / 32;
   for (int ch = (warp >> 2); ch < CHUNKS; ch += 2) {
     uint32_t r[32];
@@ -259,22 +309,28 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(TcArgs g) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) r[j] = 0u;
     }
-    if (row >= g.M) continue;
-    const int64_t cbase = n0 + ch * 32;
-    float* crow = g.C + row * g.ldc;
+    __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      int64_t col = cbase + j;
-      if (col >= g.N) break;
-      float v = __uint_as_float(r[j]);
-      if (g.atomic) { atomicAdd(crow + col, v); continue; }
-      if (g.bias) v += g.bias[col];
-      if (g.preact) g.preact[row * g.ldc + col] = v;
-      if (g.act == TMAE_ACT_GELU) v = gelu_erf_tc(v);
-      else if (g.act == TMAE_ACT_RELU) v = fmaxf(v, 0.f);
-      if (g.residual) v += g.residual[row * g.ldc + col];
-      if (g.accumulate) v += crow[col];
-      crow[col] = v;
+    for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]);
+    __syncwarp();
+    const int64_t col = n0 + ch * 32 + lane;
+    if (col < g.N) {
+      const float bias = g.bias ? g.bias[col] : 0.f;
+#pragma unroll 4
+      for (int rr = 0; rr < 32; ++rr) {
+        const int64_t row = rbase + rr;
+        if (row >= g.M) break;
+        float v = tile[rr * 33 + lane];
+        const int64_t o = row * g.ldc + col;
+        if (g.atomic) { atomicAdd(g.C + o, v); continue; }
+        v += bias;
+        if (g.preact) g.preact[o] = v;
+        if (g.act == TMAE_ACT_GELU) v = gelu_erf_tc(v);
+        else if (g.act == TMAE_ACT_RELU) v = fmaxf(v, 0.f);
+        if (g.residual) v += g.residual[o];
+        if (g.accumulate) v += g.C[o];
+        g.C[o] = v;
+      }
     }
   }
   tc_fence_before();
@@ -306,7 +362,7 @@ static int tc_dispatch(TcArgs& g, int splits, cudaStream_t s) {
 }
 
 // ---- entry points used by gemm.cu's ABI functions when precision == TMAE_PREC_BF16
-bool tc_linear_fwd_ok(int64_t m, int64_t n, int64_t k) { return k % TBK == 0 && k >= TBK; }
+bool tc_linear_fwd_ok(int64_t m, int64_t n, int64_t k) { return k % 8 == 0; }  // k tails are zero-filled per 16-byte chunk
 int tc_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact, int64_t m,
                   int64_t n, int64_t k, int act, cudaStream_t s) {
   TcArgs g{};
@@ -315,7 +371,7 @@ int tc_linear_fwd(const float* x, const float* w, const float* bias, const float
   return tc_dispatch<TC_NT, false>(g, 1, s);
 }
 
-bool tc_linear_bwd_data_ok(int64_t m, int64_t n, int64_t k) { return n % TBK == 0 && n >= TBK && k % 8 == 0; }
+bool tc_linear_bwd_data_ok(int64_t m, int64_t n, int64_t k) { return n % 8 == 0 && k % 8 == 0; }
 int tc_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int accumulate, cudaStream_t s) {
   TcArgs g{};
   g.A = dy; g.B = w; g.C = dx; g.M = m; g.N = k; g.K = n; g.lda = n; g.ldb = k; g.ldc = k; g.accumulate = accumulate;
@@ -338,7 +394,7 @@ int tc_linear_bwd_weight(const float* dy, const float* x, float* dw, int64_t m, 
   return tc_dispatch<TC_TN, false>(g, tn_splits((int64_t)cdiv(n, TBM) * cdiv(k, bn), m), s);
 }
 
-bool tc_sparse_conv_ok(int cin, int cout) { return cin % TBK == 0 && cout % 8 == 0; }
+bool tc_sparse_conv_ok(int cin, int cout) { return cin % 8 == 0 && cout % 8 == 0; }
 int tc_sparse_conv_fwd(const float* x, const int* table, const float* w, float* y, int64_t rows_out, int taps, int cin, int cout,
                        int accumulate, cudaStream_t s) {
   TcArgs g{};

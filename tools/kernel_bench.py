@@ -1,0 +1,85 @@
+"""Micro-benchmarks of single library kernels at the bench's shapes (CUDA-event timing, L2 flushed between
+iterations).  Used to pick the ncu target and to compare kernel variants:  python tools/kernel_bench.py [gemm|attn|all]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import tmae_b200  # noqa: E402,F401
+from tmae_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+FLUSH = None
+
+
+def timeit(fn, iters=10, flush=True):
+    global FLUSH
+    if FLUSH is None:
+        FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            FLUSH.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gemm(prec):
+    ops.set_precision(prec)
+    print(f"--- linear ({prec}) : m n k | fwd us TFLOP/s GB/s | bwd_data us | bwd_weight us")
+    for m, n, k in [(56000, 128, 128), (56000, 256, 128), (56000, 128, 256), (50000, 256, 256), (50000, 512, 256), (50000, 256, 512),
+                    (14000, 128, 128), (240000, 128, 64)]:
+        x, w, b = torch.randn(m, k, device=DEV), torch.randn(n, k, device=DEV), torch.randn(n, device=DEV)
+        dy = torch.randn(m, n, device=DEV)
+        dw, db = torch.empty_like(w), torch.empty_like(b)
+        t = timeit(lambda: ops.linear_fwd(x, w, b))
+        t2 = timeit(lambda: ops.linear_bwd_data(dy, w))
+        t3 = timeit(lambda: ops.linear_bwd_weight(dy, x, dw, db))
+        fl, by = 2 * m * n * k, 4 * (m * k + m * n + n * k)
+        print(f"{m:7d} {n:4d} {k:4d} | {t * 1e3:8.1f} {fl / t / 1e9:7.1f} {by / t / 1e6:7.0f} | {t2 * 1e3:8.1f} {fl / t2 / 1e9:7.1f} | {t3 * 1e3:8.1f} {fl / t3 / 1e9:7.1f}")
+
+
+def attn():
+    import numpy as np
+    print("--- window attention : M C | fwd us | bwd us")
+    for M, C, g, B in [(56000, 128, 468, 4), (50000, 256, 234, 4), (28000, 256, 117, 4)]:
+        rng = np.random.default_rng(0)
+        # clustered occupancy like a lidar BEV: sample cells with a radial density
+        cells = np.unique(np.clip((rng.normal(0, g / 5, (M * 3, 2)) + g / 2).astype(np.int64), 0, g - 1) @ np.array([g, 1]))
+        per = min(M // B, cells.shape[0])
+        cells = np.sort(rng.choice(cells, per, replace=False))
+        c = np.concatenate([np.stack([np.full(per, b), cells // g, cells % g], 1) for b in range(B)])
+        coords = torch.tensor(c, dtype=torch.int32, device=DEV)
+        P = ops.window_partition(coords, B, g, g, [(16, 0, 16), (32, 16, 32), (64, 32, 100000)])
+        m = coords.shape[0]
+        q, k, v = (torch.randn(m, C, device=DEV) for _ in range(3))
+        tau = torch.ones(1, device=DEV)
+        H = 8
+        o, lse = ops.window_attention_fwd(q, k, v, P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), min(P.wcap, m), tau, 0.01, H, False)
+        do = torch.randn_like(o)
+        dtau = torch.zeros(1, device=DEV)
+        t = timeit(lambda: ops.window_attention_fwd(q, k, v, P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), min(P.wcap, m), tau, 0.01, H, False))
+        t2 = timeit(lambda: ops.window_attention_bwd(do, q, k, v, o, lse, P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), min(P.wcap, m),
+                                                     tau, 0.01, H, dtau, False))
+        nw = int(P.n_win[0])
+        lb = P.level_base[0].tolist()
+        print(f"{m:7d} {C:4d} windows {nw} levels {lb} | {t * 1e3:8.1f} ({4 * 4 * m * C / t / 1e6:.0f} GB/s) | {t2 * 1e3:8.1f}")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("gemm", "all"):
+        gemm("bf16")
+    if what in ("gemm32",):
+        gemm("fp32")
+    if what in ("attn", "all"):
+        attn()
