@@ -211,6 +211,33 @@ TMAE_API int tmae_chamfer_bwd(const float* grad_loss, const float* pred, const f
                      const int32_t* pt_order, const int64_t* voxel_coords, const float* range_lo, const float* voxel,
                      const void* state, float* dpred, void* stream);
 
+/* ---- A7/A8 whole encoder layer ---------------------------------------------------------------------
+ * One call = one EncoderLayer.forward of pcdet/models/model_utils/sst_basic_block.py:58-84 (x_kv == NULL: windowed
+ * self-attention) or wca_block.py:70-103 (x_kv = previous-frame rows: temporal window cross-attention):
+ *   q = (x + pos) Wq, k = (x_kv + pos_kv) Wk, v = x_kv Wv -> cosine attention per window -> out_proj
+ *   x1 = LN1(x + attn [rows with rowmask == 0 skip the attention term]) ; y = LN2(x1 + W2 gelu(W1 x1)).
+ * `saved` (tmae_encoder_layer_saved_bytes) receives the intermediates backward needs; backward writes the input
+ * gradient(s) and the 13 parameter gradients through a second tmae_layer_params whose pointers are gradient buffers. */
+typedef struct tmae_layer_params {
+  const float *in_w, *in_b, *out_w, *out_b, *tau, *ln1_g, *ln1_b, *w1, *b1, *w2, *b2, *ln2_g, *ln2_b;
+} tmae_layer_params;
+typedef struct tmae_layer_tables {
+  const uint8_t* posidx_q;  /* (m_q)  row of the position table per query row  */
+  const uint8_t* posidx_kv; /* (m_kv) cross only */
+  const int32_t *qtok, *qcnt, *ktok, *kcnt, *n_win, *small_end; /* from tmae_window_partition (one shift) */
+  const uint8_t* rowmask;   /* (m_q) cross only: 1 = row belongs to a paired window */
+  int64_t max_windows;
+} tmae_layer_tables;
+TMAE_API size_t tmae_encoder_layer_saved_bytes(int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t cross);
+TMAE_API size_t tmae_encoder_layer_scratch_bytes(int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t cross);
+TMAE_API int tmae_encoder_layer_fwd(const float* x, const float* x_kv, const tmae_layer_params* P, const tmae_layer_tables* T, const float* pos_lut,
+                           float tau_min, float eps, int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t precision,
+                           float* y, void* saved, size_t saved_size, void* stream);
+TMAE_API int tmae_encoder_layer_bwd(const float* dy, const float* x, const float* x_kv, const tmae_layer_params* P, const tmae_layer_tables* T,
+                           float tau_min, int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t precision,
+                           const void* saved, size_t saved_size, float* dx, float* dx_kv, const tmae_layer_params* G, void* scratch,
+                           size_t scratch_size, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

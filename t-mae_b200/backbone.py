@@ -67,132 +67,28 @@ class _AttnHolder(nn.Module):
         setattr(self, name, CosineMHAParams(C, H, tau_min))
 
 
-def _ffn_fwd(x_in, a, rowmask, p, eps):
-    """LN1(x_in + a) -> Linear/GELU/Linear -> LN2 ; returns output and what backward needs."""
-    g1, b1, W1, bb1, W2, bb2, g2, b2 = p
-    x1, m1, r1 = ops.add_layernorm_fwd(x_in, a, rowmask, g1, b1, eps)
-    h, hpre = ops.linear_fwd(x1, W1, bb1, act=ops.ACT_GELU, want_preact=True)
-    f = ops.linear_fwd(h, W2, bb2)
-    x2, m2, r2 = ops.add_layernorm_fwd(x1, f, None, g2, b2, eps)
-    return x2, (x1, m1, r1, h, hpre, f, m2, r2)
-
-
-def _ffn_bwd(dx2, x_in, a, rowmask, p, saved):
-    """-> (d x_in, d a, grads of the 8 FFN/LN parameters)."""
-    g1, b1, W1, bb1, W2, bb2, g2, b2 = p
-    x1, m1, r1, h, hpre, f, m2, r2 = saved
-    dg2, db2 = torch.empty_like(g2), torch.empty_like(b2)
-    dv2, _ = ops.add_layernorm_bwd(dx2, x1, f, None, g2, m2, r2, dg2, db2)
-    dW2, dbb2 = torch.empty_like(W2), torch.empty_like(bb2)
-    ops.linear_bwd_weight(dv2, h, dW2, dbb2)
-    dh = ops.linear_bwd_data(dv2, W2)
-    dhpre = ops.gelu_bwd(dh, hpre)
-    dW1, dbb1 = torch.empty_like(W1), torch.empty_like(bb1)
-    ops.linear_bwd_weight(dhpre, x1, dW1, dbb1)
-    ops.linear_bwd_data(dhpre, W1, dx=dv2, accumulate=True)  # dv2 now holds d x1
-    dg1, db1 = torch.empty_like(g1), torch.empty_like(b1)
-    dv1, da = ops.add_layernorm_bwd(dv2, x_in, a, rowmask, g1, m1, r1, dg1, db1, want_dres=rowmask is not None)
-    if da is None:
-        da = dv1
-    return dv1, da, (dg1, db1, dW1, dbb1, dW2, dbb2, dg2, db2)
-
-
-class _SelfLayerFn(torch.autograd.Function):
-    """One SST encoder layer (sst_basic_block.py:58-84 with WindowAttention :22-54) on flat voxel rows."""
+class _LayerFn(torch.autograd.Function):
+    """One encoder layer = one library call each way (tmae_encoder_layer_fwd / _bwd): the SST self-attention layer
+    (sst_basic_block.py:58-84) when x_kv is None, the WCA cross-attention layer (wca_block.py:70-103) otherwise."""
 
     @staticmethod
-    def forward(ctx, x, Win, bin_, Wo, bo, tau, g1, b1, W1, bb1, W2, bb2, g2, b2, part, shift, lut, heads, tau_min, eps):
+    def forward(ctx, x, x_kv, part, shift, lut, heads, tau_min, eps, *params):
         x = x.contiguous()
-        M, C = x.shape
-        tok, cnt, nwin = part.tok_a[shift], part.cnt_a[shift], part.n_win[shift:shift + 1]
-        maxw = min(part.wcap, M)
-        xp = ops.add_pos(x, part.posidx_a[shift], lut)
-        q = ops.linear_fwd(xp, Win, bin_, w_offset_rows=0, n=C)
-        k = ops.linear_fwd(xp, Win, bin_, w_offset_rows=C, n=C)
-        v = ops.linear_fwd(x, Win, bin_, w_offset_rows=2 * C, n=C)
-        o, lse = ops.window_attention_fwd(q, k, v, tok, cnt, tok, cnt, nwin, ops.small_end(part, shift), maxw, tau, tau_min, heads, zero_out=False)
-        a = ops.linear_fwd(o, Wo, bo)
-        ffn_p = (g1, b1, W1, bb1, W2, bb2, g2, b2)
-        x2, saved = _ffn_fwd(x, a, None, ffn_p, eps)
-        ctx.save_for_backward(x, xp, q, k, v, o, lse, a, Win, Wo, tau, *ffn_p, *saved)
-        ctx.misc = (part, shift, heads, tau_min, maxw)
-        return x2
+        if x_kv is not None:
+            x_kv = x_kv.contiguous()
+        T = ops.layer_tables(part, shift, x_kv is not None, x.shape[0], x_kv.shape[0] if x_kv is not None else 0)
+        y, saved = ops.encoder_layer_fwd(x, x_kv, params, T, lut, tau_min, eps, heads)
+        ctx.save_for_backward(x, x_kv, saved, *params)
+        ctx.misc = (T, part, heads, tau_min)  # part keeps the device tables alive
+        return y
 
     @staticmethod
-    def backward(ctx, dx2):
-        t = ctx.saved_tensors
-        x, xp, q, k, v, o, lse, a, Win, Wo, tau = t[:11]
-        ffn_p, saved = t[11:19], t[19:]
-        part, shift, heads, tau_min, maxw = ctx.misc
-        C = x.shape[1]
-        tok, cnt, nwin = part.tok_a[shift], part.cnt_a[shift], part.n_win[shift:shift + 1]
-        dx, da, ffn_g = _ffn_bwd(dx2.contiguous(), x, a, None, ffn_p, saved)
-        dWo, dbo = torch.empty_like(Wo), torch.empty(C, dtype=torch.float32, device=x.device)
-        ops.linear_bwd_weight(da, o, dWo, dbo)
-        do = ops.linear_bwd_data(da, Wo)
-        dtau = torch.zeros_like(tau)
-        dq, dk, dv = ops.window_attention_bwd(do, q, k, v, o, lse, tok, cnt, tok, cnt, nwin, ops.small_end(part, shift), maxw, tau, tau_min, heads,
-                                              dtau, zero=False)
-        dWin, dbin = torch.empty_like(Win), torch.empty(3 * C, dtype=torch.float32, device=x.device)
-        ops.linear_bwd_weight(dq, xp, dWin, dbin, w_offset_rows=0)
-        ops.linear_bwd_weight(dk, xp, dWin, dbin, w_offset_rows=C)
-        ops.linear_bwd_weight(dv, x, dWin, dbin, w_offset_rows=2 * C)
-        ops.linear_bwd_data(dq, Win, dx=dx, accumulate=True, w_offset_rows=0)
-        ops.linear_bwd_data(dk, Win, dx=dx, accumulate=True, w_offset_rows=C)
-        ops.linear_bwd_data(dv, Win, dx=dx, accumulate=True, w_offset_rows=2 * C)
-        return (dx, dWin, dbin, dWo, dbo, dtau, *ffn_g, None, None, None, None, None, None)
-
-
-class _CrossLayerFn(torch.autograd.Function):
-    """One WCA encoder layer (wca_block.py:70-103 with WindowCrossAttention :26-67): queries from the current
-    frame, keys/values from the previous frame, attention only inside windows occupied in both frames; rows
-    outside those windows skip the attention term but still take LN/FFN/LN."""
-
-    @staticmethod
-    def forward(ctx, x, xprev, Win, bin_, Wo, bo, tau, g1, b1, W1, bb1, W2, bb2, g2, b2, tp, shift, lut, heads, tau_min, eps):
-        x, xprev = x.contiguous(), xprev.contiguous()
-        M, C = x.shape
-        maxw = min(tp.wcap, M, xprev.shape[0])
-        nwin = tp.n_win[shift:shift + 1]
-        xq = ops.add_pos(x, tp.posidx_a[shift], lut)
-        xk = ops.add_pos(xprev, tp.posidx_b[shift], lut)
-        q = ops.linear_fwd(xq, Win, bin_, w_offset_rows=0, n=C)
-        k = ops.linear_fwd(xk, Win, bin_, w_offset_rows=C, n=C)
-        v = ops.linear_fwd(xprev, Win, bin_, w_offset_rows=2 * C, n=C)
-        o, lse = ops.window_attention_fwd(q, k, v, tp.tok_a[shift], tp.cnt_a[shift], tp.tok_b[shift], tp.cnt_b[shift], nwin,
-                                          ops.small_end(tp, shift), maxw, tau, tau_min, heads, zero_out=True)
-        a = ops.linear_fwd(o, Wo, bo)
-        ffn_p = (g1, b1, W1, bb1, W2, bb2, g2, b2)
-        x2, saved = _ffn_fwd(x, a, tp.keep_a[shift], ffn_p, eps)
-        ctx.save_for_backward(x, xprev, xq, xk, q, k, v, o, lse, a, Win, Wo, tau, *ffn_p, *saved)
-        ctx.misc = (tp, shift, heads, tau_min, maxw)
-        return x2
-
-    @staticmethod
-    def backward(ctx, dx2):
-        t = ctx.saved_tensors
-        x, xprev, xq, xk, q, k, v, o, lse, a, Win, Wo, tau = t[:13]
-        ffn_p, saved = t[13:21], t[21:]
-        tp, shift, heads, tau_min, maxw = ctx.misc
-        C = x.shape[1]
-        nwin = tp.n_win[shift:shift + 1]
-        dx, da, ffn_g = _ffn_bwd(dx2.contiguous(), x, a, tp.keep_a[shift], ffn_p, saved)
-        dWo, dbo = torch.empty_like(Wo), torch.empty(C, dtype=torch.float32, device=x.device)
-        ops.linear_bwd_weight(da, o, dWo, dbo)
-        do = ops.linear_bwd_data(da, Wo)
-        dtau = torch.zeros_like(tau)
-        dq, dk, dv = ops.window_attention_bwd(do, q, k, v, o, lse, tp.tok_a[shift], tp.cnt_a[shift], tp.tok_b[shift], tp.cnt_b[shift],
-                                              nwin, ops.small_end(tp, shift), maxw, tau, tau_min, heads, dtau, zero=True)
-        dWin, dbin = torch.empty_like(Win), torch.empty(3 * C, dtype=torch.float32, device=x.device)
-        ops.linear_bwd_weight(dq, xq, dWin, dbin, w_offset_rows=0)
-        ops.linear_bwd_weight(dk, xk, dWin, dbin, w_offset_rows=C)
-        ops.linear_bwd_weight(dv, xprev, dWin, dbin, w_offset_rows=2 * C)
-        ops.linear_bwd_data(dq, Win, dx=dx, accumulate=True, w_offset_rows=0)
-        dprev = None
-        if ctx.needs_input_grad[1]:
-            dprev = ops.linear_bwd_data(dk, Win, w_offset_rows=C)
-            ops.linear_bwd_data(dv, Win, dx=dprev, accumulate=True, w_offset_rows=2 * C)
-        return (dx, dprev, dWin, dbin, dWo, dbo, dtau, *ffn_g, None, None, None, None, None, None)
+    def backward(ctx, dy):
+        x, x_kv, saved, *params = ctx.saved_tensors
+        T, _, heads, tau_min = ctx.misc
+        dx, dkv, grads = ops.encoder_layer_bwd(dy.contiguous(), x, x_kv, params, T, tau_min, heads, saved,
+                                               x_kv is not None and ctx.needs_input_grad[1])
+        return (dx, dkv, None, None, None, None, None, None, *grads)
 
 
 class EncoderLayer(nn.Module):
@@ -214,10 +110,10 @@ class EncoderLayer(nn.Module):
                 self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias, self.norm2.weight, self.norm2.bias)
 
     def forward_self(self, x, part, shift, lut):
-        return _SelfLayerFn.apply(x, *self._params(), part, shift, lut, self.nhead, self.tau_min, self.norm1.eps)
+        return _LayerFn.apply(x, None, part, shift, lut, self.nhead, self.tau_min, self.norm1.eps, *self._params())
 
     def forward_cross(self, x, xprev, tp, shift, lut):
-        return _CrossLayerFn.apply(x, xprev, *self._params(), tp, shift, lut, self.nhead, self.tau_min, self.norm1.eps)
+        return _LayerFn.apply(x, xprev, tp, shift, lut, self.nhead, self.tau_min, self.norm1.eps, *self._params())
 
 
 class ShiftBlock(nn.Module):

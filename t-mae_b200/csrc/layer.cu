@@ -1,0 +1,172 @@
+// One encoder layer per ABI call: the host-side orchestration of an SST self-attention layer
+// (pcdet/models/model_utils/sst_basic_block.py:58-84) or a WCA cross-attention layer (wca_block.py:70-103),
+// forward and backward.  The reference runs ~25 small kernels per level per layer from Python; here one call
+// enqueues the whole layer's kernel sequence on the stream, with every intermediate carved out of one caller-owned
+// buffer that is handed back for the backward pass.
+#include "common.cuh"
+
+using namespace tmae;
+
+namespace {
+
+struct Carve {
+  float* p;
+  size_t used = 0, cap;
+  Carve(void* base, size_t bytes) : p((float*)base), cap(bytes / sizeof(float)) {}
+  float* take(int64_t n) {
+    size_t a = (size_t)align_up(n, 64);
+    float* r = p + used;
+    used += a;
+    return used <= cap ? r : nullptr;
+  }
+};
+inline size_t carve_sz(int64_t n) { return (size_t)align_up(n, 64) * sizeof(float); }
+
+struct Saved {  // forward intermediates kept for backward
+  float *xq, *xk, *q, *k, *v, *o, *lse, *a, *x1, *m1, *r1, *h, *hpre, *f, *m2, *r2;
+};
+
+bool carve_saved(Saved& s, void* buf, size_t bytes, int64_t mq, int64_t mkv, int c, int ff, int heads, bool cross) {
+  Carve cv(buf, bytes);
+  s.xq = cv.take(mq * c);
+  s.xk = cross ? cv.take(mkv * c) : s.xq;
+  s.q = cv.take(mq * c);
+  s.k = cv.take(mkv * c);
+  s.v = cv.take(mkv * c);
+  s.o = cv.take(mq * c);
+  s.lse = cv.take(mq * heads);
+  s.a = cv.take(mq * c);
+  s.x1 = cv.take(mq * c);
+  s.m1 = cv.take(mq);
+  s.r1 = cv.take(mq);
+  s.h = cv.take(mq * ff);
+  s.hpre = cv.take(mq * ff);
+  s.f = cv.take(mq * c);
+  s.m2 = cv.take(mq);
+  s.r2 = cv.take(mq);
+  return s.r2 != nullptr && cv.used <= cv.cap;
+}
+
+size_t saved_bytes(int64_t mq, int64_t mkv, int c, int ff, int heads, bool cross) {
+  size_t b = 0;
+  b += carve_sz(mq * c) * 6;                       // xq, q, o, a, x1, f
+  b += carve_sz(mkv * c) * (cross ? 3 : 2);        // (xk), k, v
+  b += carve_sz(mq * heads) + carve_sz(mq) * 4;    // lse, m1, r1, m2, r2
+  b += carve_sz(mq * ff) * 2;                      // h, hpre
+  return b + 256;
+}
+
+size_t scratch_bytes(int64_t mq, int64_t mkv, int c, int ff, int heads) {
+  // dx1, da, do, dq (mq*c each) ; dk, dv (mkv*c) ; dh (mq*ff) ; dsum (mq*heads)
+  return carve_sz(mq * c) * 4 + carve_sz(mkv * c) * 2 + carve_sz(mq * ff) + carve_sz(mq * heads) + 256;
+}
+
+#define TRY(call)              \
+  do {                         \
+    int rc__ = (call);         \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+size_t tmae_encoder_layer_saved_bytes(int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t cross) {
+  return saved_bytes(m_q, cross ? m_kv : m_q, c, ff, heads, cross != 0);
+}
+size_t tmae_encoder_layer_scratch_bytes(int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t cross) {
+  return scratch_bytes(m_q, cross ? m_kv : m_q, c, ff, heads);
+}
+
+int tmae_encoder_layer_fwd(const float* x, const float* x_kv, const tmae_layer_params* P, const tmae_layer_tables* T, const float* pos_lut,
+                           float tau_min, float eps, int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t precision,
+                           float* y, void* saved, size_t saved_size, void* stream) {
+  const bool cross = x_kv != nullptr;
+  if (!cross) { m_kv = m_q; x_kv = x; }
+  TMAE_CHECK_ARG(saved_size >= saved_bytes(m_q, m_kv, c, ff, heads, cross), "saved buffer too small");
+  if (m_q <= 0) return 0;
+  Saved s;
+  TMAE_CHECK_ARG(carve_saved(s, saved, saved_size, m_q, m_kv, c, ff, heads, cross), "saved buffer carve failed");
+  // q = k = x + pos ; v = x   (sst_basic_block.py:44 ; wca_block.py:52-56: q from current, k/v from previous)
+  TRY(tmae_add_pos(x, T->posidx_q, pos_lut, s.xq, m_q, c, stream));
+  if (cross) TRY(tmae_add_pos(x_kv, T->posidx_kv, pos_lut, s.xk, m_kv, c, stream));
+  const int64_t cc = (int64_t)c * c;
+  TRY(tmae_linear_fwd(s.xq, P->in_w, P->in_b, nullptr, s.q, nullptr, m_q, c, c, TMAE_ACT_NONE, precision, stream));
+  TRY(tmae_linear_fwd(s.xk, P->in_w + cc, P->in_b + c, nullptr, s.k, nullptr, m_kv, c, c, TMAE_ACT_NONE, precision, stream));
+  TRY(tmae_linear_fwd(x_kv, P->in_w + 2 * cc, P->in_b + 2 * c, nullptr, s.v, nullptr, m_kv, c, c, TMAE_ACT_NONE, precision, stream));
+  if (cross) TMAE_CUDA(cudaMemsetAsync(s.o, 0, (size_t)m_q * c * sizeof(float), (cudaStream_t)stream));  // rows outside paired windows
+  TRY(tmae_window_attention_fwd(s.q, s.k, s.v, s.o, s.lse, T->qtok, T->qcnt, T->ktok, T->kcnt, T->n_win, T->small_end, T->max_windows, P->tau,
+                                tau_min, c, heads, stream));
+  TRY(tmae_linear_fwd(s.o, P->out_w, P->out_b, nullptr, s.a, nullptr, m_q, c, c, TMAE_ACT_NONE, precision, stream));
+  TRY(tmae_add_layernorm_fwd(x, s.a, T->rowmask, P->ln1_g, P->ln1_b, s.x1, s.m1, s.r1, m_q, c, eps, stream));
+  TRY(tmae_linear_fwd(s.x1, P->w1, P->b1, nullptr, s.h, s.hpre, m_q, ff, c, TMAE_ACT_GELU, precision, stream));
+  TRY(tmae_linear_fwd(s.h, P->w2, P->b2, nullptr, s.f, nullptr, m_q, c, ff, TMAE_ACT_NONE, precision, stream));
+  TRY(tmae_add_layernorm_fwd(s.x1, s.f, nullptr, P->ln2_g, P->ln2_b, y, s.m2, s.r2, m_q, c, eps, stream));
+  return 0;
+}
+
+int tmae_encoder_layer_bwd(const float* dy, const float* x, const float* x_kv, const tmae_layer_params* P, const tmae_layer_tables* T,
+                           float tau_min, int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t precision,
+                           const void* saved, size_t saved_size, float* dx, float* dx_kv, const tmae_layer_params* G, void* scratch,
+                           size_t scratch_size, void* stream) {
+  const bool cross = x_kv != nullptr;
+  if (!cross) { m_kv = m_q; x_kv = x; }
+  if (m_q <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  Saved s;
+  TMAE_CHECK_ARG(carve_saved(s, (void*)saved, saved_size, m_q, m_kv, c, ff, heads, cross), "saved buffer carve failed");
+  TMAE_CHECK_ARG(scratch_size >= scratch_bytes(m_q, m_kv, c, ff, heads), "scratch too small");
+  Carve cv(scratch, scratch_size);
+  float* dx1 = cv.take(m_q * c);
+  float* da = cv.take(m_q * c);
+  float* dob = cv.take(m_q * c);
+  float* dq = cv.take(m_q * c);
+  float* dk = cv.take(m_kv * c);
+  float* dv = cv.take(m_kv * c);
+  float* dh = cv.take(m_q * ff);
+  float* dsum = cv.take(m_q * heads);
+  TMAE_CHECK_ARG(dsum != nullptr, "scratch carve failed");
+  const int64_t cc = (int64_t)c * c;
+  // G holds the gradient buffers with the same field meaning as P (const-cast: the struct type is shared)
+  float* g_in_w = (float*)G->in_w; float* g_in_b = (float*)G->in_b; float* g_out_w = (float*)G->out_w; float* g_out_b = (float*)G->out_b;
+  float* g_tau = (float*)G->tau; float* g_ln1_g = (float*)G->ln1_g; float* g_ln1_b = (float*)G->ln1_b; float* g_w1 = (float*)G->w1;
+  float* g_b1 = (float*)G->b1; float* g_w2 = (float*)G->w2; float* g_b2 = (float*)G->b2; float* g_ln2_g = (float*)G->ln2_g;
+  float* g_ln2_b = (float*)G->ln2_b;
+
+  // LN2 -> FFN -> LN1
+  TRY(tmae_add_layernorm_bwd(dy, s.x1, s.f, nullptr, P->ln2_g, s.m2, s.r2, dx1, nullptr, g_ln2_g, g_ln2_b, m_q, c, stream));
+  TRY(tmae_linear_bwd_weight(dx1, s.h, g_w2, g_b2, m_q, c, ff, precision, stream));
+  TRY(tmae_linear_bwd_data(dx1, P->w2, dh, m_q, c, ff, 0, precision, stream));
+  TRY(tmae_gelu_bwd(dh, s.hpre, dh, m_q * (int64_t)ff, stream));
+  TRY(tmae_linear_bwd_weight(dh, s.x1, g_w1, g_b1, m_q, ff, c, precision, stream));
+  TRY(tmae_linear_bwd_data(dh, P->w1, dx1, m_q, ff, c, 1, precision, stream));  // dx1 = grad wrt x1 (both branches)
+  TRY(tmae_add_layernorm_bwd(dx1, x, s.a, T->rowmask, P->ln1_g, s.m1, s.r1, dx, T->rowmask ? da : nullptr, g_ln1_g, g_ln1_b, m_q, c, stream));
+  const float* dap = T->rowmask ? da : dx;  // grad wrt the attention branch (masked rows contribute nothing)
+  // out projection
+  TRY(tmae_linear_bwd_weight(dap, s.o, g_out_w, g_out_b, m_q, c, c, precision, stream));
+  TRY(tmae_linear_bwd_data(dap, P->out_w, dob, m_q, c, c, 0, precision, stream));
+  // attention core
+  TMAE_CUDA(cudaMemsetAsync(g_tau, 0, sizeof(float), st));
+  if (cross) {
+    TMAE_CUDA(cudaMemsetAsync(dq, 0, (size_t)m_q * c * sizeof(float), st));
+    TMAE_CUDA(cudaMemsetAsync(dk, 0, (size_t)m_kv * c * sizeof(float), st));
+    TMAE_CUDA(cudaMemsetAsync(dv, 0, (size_t)m_kv * c * sizeof(float), st));
+  }
+  TRY(tmae_window_attention_bwd(dob, s.q, s.k, s.v, s.o, s.lse, dsum, dq, dk, dv, g_tau, T->qtok, T->qcnt, T->ktok, T->kcnt, T->n_win,
+                                T->small_end, T->max_windows, P->tau, tau_min, c, heads, stream));
+  // in projection
+  TRY(tmae_linear_bwd_weight(dq, s.xq, g_in_w, g_in_b, m_q, c, c, precision, stream));
+  TRY(tmae_linear_bwd_weight(dk, s.xk, g_in_w + cc, g_in_b + c, m_kv, c, c, precision, stream));
+  TRY(tmae_linear_bwd_weight(dv, x_kv, g_in_w + 2 * cc, g_in_b + 2 * c, m_kv, c, c, precision, stream));
+  TRY(tmae_linear_bwd_data(dq, P->in_w, dx, m_q, c, c, 1, precision, stream));
+  if (!cross) {
+    TRY(tmae_linear_bwd_data(dk, P->in_w + cc, dx, m_kv, c, c, 1, precision, stream));
+    TRY(tmae_linear_bwd_data(dv, P->in_w + 2 * cc, dx, m_kv, c, c, 1, precision, stream));
+  } else if (dx_kv) {
+    TRY(tmae_linear_bwd_data(dk, P->in_w + cc, dx_kv, m_kv, c, c, 0, precision, stream));
+    TRY(tmae_linear_bwd_data(dv, P->in_w + 2 * cc, dx_kv, m_kv, c, c, 1, precision, stream));
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -432,3 +432,81 @@ def chamfer_bwd(grad_loss, pred, gt, w, state, gtctx=None):
         ctx = (_p(pk, F32), pk.shape[1], _p(off, I32), _p(order, I32), _p(vc, I64), _f3(rng), _f3(vs))
     _call("chamfer_bwd", _p(grad_loss, F32), _p(pred, F32), _p(gt), _p(w, F32), m, p1, p2, *ctx, _p(state), _p(dpred), _stream())
     return dpred
+
+
+# ------------------------------------------------------------------------------------ whole encoder layer
+class LayerParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("in_w", "in_b", "out_w", "out_b", "tau", "ln1_g", "ln1_b", "w1", "b1", "w2", "b2",
+                                               "ln2_g", "ln2_b")]
+
+
+class LayerTables(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("posidx_q", "posidx_kv", "qtok", "qcnt", "ktok", "kcnt", "n_win", "small_end",
+                                               "rowmask")] + [("max_windows", ctypes.c_int64)]
+
+
+def layer_tables(part, shift, cross, m_q, m_kv):
+    """tmae_layer_tables for one shift of a partition (self: frame a on both sides; cross: a = current, b = previous)."""
+    T = LayerTables()
+    T.posidx_q = _p(part.posidx_a[shift])
+    T.qtok, T.qcnt = _p(part.tok_a[shift]), _p(part.cnt_a[shift])
+    if cross:
+        T.posidx_kv = _p(part.posidx_b[shift])
+        T.ktok, T.kcnt = _p(part.tok_b[shift]), _p(part.cnt_b[shift])
+        T.rowmask = _p(part.keep_a[shift])
+        T.max_windows = min(part.wcap, m_q, m_kv)
+    else:
+        T.posidx_kv = None
+        T.ktok, T.kcnt = T.qtok, T.qcnt
+        T.rowmask = None
+        T.max_windows = min(part.wcap, m_q)
+    T.n_win = _p(part.n_win[shift:shift + 1])
+    T.small_end = _p(small_end(part, shift))
+    return T
+
+
+def _layer_params(tensors):
+    P = LayerParams()
+    for (name, _), t in zip(LayerParams._fields_, tensors):
+        setattr(P, name, _p(t, F32))
+    return P
+
+
+def encoder_layer_fwd(x, x_kv, params, T, lut, tau_min, eps, heads):
+    """params: the 13 tensors in tmae_layer_params order.  -> (y, saved buffer)."""
+    L = lib()
+    m_q, c = x.shape
+    m_kv = x_kv.shape[0] if x_kv is not None else m_q
+    ff = params[7].shape[0]
+    cross = int(x_kv is not None)
+    nb = L.encoder_layer_saved_bytes(m_q, m_kv, c, ff, heads, cross)
+    saved = _ws(nb, x.device)
+    y = torch.empty_like(x)
+    P = _layer_params(params)
+    _call("encoder_layer_fwd", _p(x, F32), _p(x_kv), ctypes.byref(P), ctypes.byref(T), _p(lut, F32), float(tau_min), float(eps), m_q, m_kv,
+          c, ff, heads, _state["precision"], _p(y), _p(saved), nb, _stream())
+    return y, saved
+
+
+def encoder_layer_bwd(dy, x, x_kv, params, T, tau_min, heads, saved, want_dkv):
+    """-> (dx, dx_kv or None, [13 parameter gradients])."""
+    L = lib()
+    m_q, c = x.shape
+    m_kv = x_kv.shape[0] if x_kv is not None else m_q
+    ff = params[7].shape[0]
+    cross = int(x_kv is not None)
+    sizes = [t.numel() for t in params]
+    offs = [0]
+    for n in sizes:
+        offs.append(offs[-1] + (n + 63) // 64 * 64)
+    gbuf = torch.empty(offs[-1], dtype=F32, device=x.device)
+    grads = [gbuf[o:o + n].view(t.shape) for o, n, t in zip(offs, sizes, params)]
+    G = _layer_params(grads)
+    P = _layer_params(params)
+    nb = L.encoder_layer_scratch_bytes(m_q, m_kv, c, ff, heads, cross)
+    scratch = _ws(nb, x.device)
+    dx = torch.empty_like(x)
+    dkv = torch.empty_like(x_kv) if (cross and want_dkv) else None
+    _call("encoder_layer_bwd", _p(dy, F32), _p(x, F32), _p(x_kv), ctypes.byref(P), ctypes.byref(T), float(tau_min), m_q, m_kv, c, ff, heads,
+          _state["precision"], _p(saved), saved.numel(), _p(dx), _p(dkv), ctypes.byref(G), _p(scratch), nb, _stream())
+    return dx, dkv, grads
