@@ -186,15 +186,18 @@ TMAE_API int tmae_scatter_rows(const float* rows, const int32_t* sel, int64_t m,
  * tmae_window_partition (self: q and k tables are the same; cross: q = current frame, k = previous frame).
  * max_windows bounds the grid; the live count is read from n_win on the device.  small_end (device i32) = number of
  * leading windows that hold <= 16 tokens on both sides (= level_base[first level with max_tokens > 16]; windows are
- * level-sorted): those run one warp per window, the rest one CTA per window.  Backward: dsum (q rows, heads) scratch. */
+ * level-sorted): those run one warp per window, the rest one CTA per window with shared memory sized for 32 tokens
+ * (windows [small_end, mid_end), mid_end = level_base[first level with max_tokens > 32]) or 64.  Backward: dsum (q rows,
+ * heads) scratch. */
 TMAE_API int tmae_window_attention_fwd(const float* q, const float* k, const float* v, float* o, float* lse, const int32_t* qtok,
                               const int32_t* qcnt, const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win,
-                              const int32_t* small_end, int64_t max_windows, const float* tau, float tau_min, int32_t channels,
-                              int32_t heads, void* stream);
+                              const int32_t* small_end, const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min,
+                              int32_t channels, int32_t heads, void* stream);
 TMAE_API int tmae_window_attention_bwd(const float* dout, const float* q, const float* k, const float* v, const float* o, const float* lse,
                               float* dsum, float* dq, float* dk, float* dv, float* dtau, const int32_t* qtok, const int32_t* qcnt,
                               const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win, const int32_t* small_end,
-                              int64_t max_windows, const float* tau, float tau_min, int32_t channels, int32_t heads, void* stream);
+                              const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min, int32_t channels,
+                              int32_t heads, void* stream);
 
 /* ---- A10-A11 reconstruction target + Chamfer loss ------------------------------------------------
  * Replaces sst_ops_cuda.group_inner_inds_wrapper (pcdet/ops/sst_ops/src/sst_ops_api.cpp:8, sst_ops_gpu.cu:22-39),
@@ -224,7 +227,7 @@ typedef struct tmae_layer_params {
 typedef struct tmae_layer_tables {
   const uint8_t* posidx_q;  /* (m_q)  row of the position table per query row  */
   const uint8_t* posidx_kv; /* (m_kv) cross only */
-  const int32_t *qtok, *qcnt, *ktok, *kcnt, *n_win, *small_end; /* from tmae_window_partition (one shift) */
+  const int32_t *qtok, *qcnt, *ktok, *kcnt, *n_win, *small_end, *mid_end; /* from tmae_window_partition (one shift) */
   const uint8_t* rowmask;   /* (m_q) cross only: 1 = row belongs to a paired window */
   int64_t max_windows;
 } tmae_layer_tables;

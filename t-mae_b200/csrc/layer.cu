@@ -95,8 +95,8 @@ int tmae_encoder_layer_fwd(const float* x, const float* x_kv, const tmae_layer_p
   TRY(tmae_linear_fwd(s.xk, P->in_w + cc, P->in_b + c, nullptr, s.k, nullptr, m_kv, c, c, TMAE_ACT_NONE, precision, stream));
   TRY(tmae_linear_fwd(x_kv, P->in_w + 2 * cc, P->in_b + 2 * c, nullptr, s.v, nullptr, m_kv, c, c, TMAE_ACT_NONE, precision, stream));
   if (cross) TMAE_CUDA(cudaMemsetAsync(s.o, 0, (size_t)m_q * c * sizeof(float), (cudaStream_t)stream));  // rows outside paired windows
-  TRY(tmae_window_attention_fwd(s.q, s.k, s.v, s.o, s.lse, T->qtok, T->qcnt, T->ktok, T->kcnt, T->n_win, T->small_end, T->max_windows, P->tau,
-                                tau_min, c, heads, stream));
+  TRY(tmae_window_attention_fwd(s.q, s.k, s.v, s.o, s.lse, T->qtok, T->qcnt, T->ktok, T->kcnt, T->n_win, T->small_end, T->mid_end, T->max_windows,
+                                P->tau, tau_min, c, heads, stream));
   TRY(tmae_linear_fwd(s.o, P->out_w, P->out_b, nullptr, s.a, nullptr, m_q, c, c, TMAE_ACT_NONE, precision, stream));
   TRY(tmae_add_layernorm_fwd(x, s.a, T->rowmask, P->ln1_g, P->ln1_b, s.x1, s.m1, s.r1, m_q, c, eps, stream));
   TRY(tmae_linear_fwd(s.x1, P->w1, P->b1, nullptr, s.h, s.hpre, m_q, ff, c, TMAE_ACT_GELU, precision, stream));
@@ -153,7 +153,7 @@ int tmae_encoder_layer_bwd(const float* dy, const float* x, const float* x_kv, c
     TMAE_CUDA(cudaMemsetAsync(dv, 0, (size_t)m_kv * c * sizeof(float), st));
   }
   TRY(tmae_window_attention_bwd(dob, s.q, s.k, s.v, s.o, s.lse, dsum, dq, dk, dv, g_tau, T->qtok, T->qcnt, T->ktok, T->kcnt, T->n_win,
-                                T->small_end, T->max_windows, P->tau, tau_min, c, heads, stream));
+                                T->small_end, T->mid_end, T->max_windows, P->tau, tau_min, c, heads, stream));
   // in projection
   TRY(tmae_linear_bwd_weight(dq, s.xq, g_in_w, g_in_b, m_q, c, c, precision, stream));
   TRY(tmae_linear_bwd_weight(dk, s.xk, g_in_w + cc, g_in_b + c, m_kv, c, c, precision, stream));

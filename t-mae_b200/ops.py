@@ -370,27 +370,31 @@ def gather_nhwc(dense, indices):
 
 
 # ------------------------------------------------------------------------------------ attention
-def small_end(part, shift):
-    """Device pointer holder: number of leading (level-sorted) windows whose level holds <= 16 tokens."""
-    l = next((i for i, t in enumerate(part.tokens) if t > 16), part.n_levels)
+def small_end(part, shift, cap=16):
+    """Device pointer holder: number of leading (level-sorted) windows whose level holds <= cap tokens."""
+    l = next((i for i, t in enumerate(part.tokens) if t > cap), part.n_levels)
     return part.level_base[shift, l:l + 1]
 
 
-def window_attention_fwd(q, k, v, qtok, qcnt, ktok, kcnt, n_win, small, max_windows, tau, tau_min, heads, zero_out):
+def mid_end(part, shift):
+    return small_end(part, shift, 32)
+
+
+def window_attention_fwd(q, k, v, qtok, qcnt, ktok, kcnt, n_win, small, mid, max_windows, tau, tau_min, heads, zero_out):
     mq, c = q.shape
     o = torch.zeros_like(q) if zero_out else torch.empty_like(q)
     lse = torch.empty(max(1, mq), heads, dtype=F32, device=q.device)
     _call("window_attention_fwd", _p(q, F32), _p(k, F32), _p(v, F32), _p(o), _p(lse), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win),
-          _p(small), max_windows, _p(tau, F32), float(tau_min), c, heads, _stream(), nbytes=4 * (q.numel() * 2 + k.numel() * 2))
+          _p(small), _p(mid), max_windows, _p(tau, F32), float(tau_min), c, heads, _stream(), nbytes=4 * (q.numel() * 2 + k.numel() * 2))
     return o, lse
 
 
-def window_attention_bwd(dout, q, k, v, o, lse, qtok, qcnt, ktok, kcnt, n_win, small, max_windows, tau, tau_min, heads, dtau, zero):
+def window_attention_bwd(dout, q, k, v, o, lse, qtok, qcnt, ktok, kcnt, n_win, small, mid, max_windows, tau, tau_min, heads, dtau, zero):
     alloc = torch.zeros_like if zero else torch.empty_like
     dq, dk, dv = alloc(q), alloc(k), alloc(v)
     dsum = torch.empty_like(lse)
     _call("window_attention_bwd", _p(dout, F32), _p(q, F32), _p(k, F32), _p(v, F32), _p(o, F32), _p(lse, F32), _p(dsum), _p(dq), _p(dk),
-          _p(dv), _p(dtau, F32), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win), _p(small), max_windows, _p(tau, F32), float(tau_min), q.shape[1],
+          _p(dv), _p(dtau, F32), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win), _p(small), _p(mid), max_windows, _p(tau, F32), float(tau_min), q.shape[1],
           heads, _stream(), nbytes=4 * (q.numel() * 4 + k.numel() * 4))
     return dq, dk, dv
 
@@ -441,7 +445,7 @@ class LayerParams(ctypes.Structure):
 
 
 class LayerTables(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in ("posidx_q", "posidx_kv", "qtok", "qcnt", "ktok", "kcnt", "n_win", "small_end",
+    _fields_ = [(n, ctypes.c_void_p) for n in ("posidx_q", "posidx_kv", "qtok", "qcnt", "ktok", "kcnt", "n_win", "small_end", "mid_end",
                                                "rowmask")] + [("max_windows", ctypes.c_int64)]
 
 
@@ -462,6 +466,7 @@ def layer_tables(part, shift, cross, m_q, m_kv):
         T.max_windows = min(part.wcap, m_q)
     T.n_win = _p(part.n_win[shift:shift + 1])
     T.small_end = _p(small_end(part, shift))
+    T.mid_end = _p(mid_end(part, shift))
     return T
 
 

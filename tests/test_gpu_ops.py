@@ -382,7 +382,7 @@ def test_window_attention_core(C, cross):
     nw = int(P.n_win[shift])
     qt, qc = P.tok_a[shift], P.cnt_a[shift]
     kt, kc = (P.tok_b[shift], P.cnt_b[shift]) if cross else (qt, qc)
-    o, lse = ops.window_attention_fwd(q.to(DEV), k.to(DEV), v.to(DEV), qt, qc, kt, kc, P.n_win[shift:shift + 1], ops.small_end(P, shift),
+    o, lse = ops.window_attention_fwd(q.to(DEV), k.to(DEV), v.to(DEV), qt, qc, kt, kc, P.n_win[shift:shift + 1], ops.small_end(P, shift), ops.mid_end(P, shift),
                                       min(P.wcap, ma), tau.to(DEV), 0.01, H, zero_out=cross)
     # oracle: identity projections so that the core is isolated
     mha = restated.CosineMHA(C, H).double()
@@ -401,7 +401,7 @@ def test_window_attention_core(C, cross):
     ref.backward(do.double()[ka])
     dtau = torch.zeros(1, 1, 1, device=DEV)
     dq, dk, dv = ops.window_attention_bwd(do.to(DEV), q.to(DEV), k.to(DEV), v.to(DEV), o, lse, qt, qc, kt, kc, P.n_win[shift:shift + 1],
-                                          ops.small_end(P, shift), min(P.wcap, ma), tau.to(DEV), 0.01, H, dtau, zero=cross)
+                                          ops.small_end(P, shift), ops.mid_end(P, shift), min(P.wcap, ma), tau.to(DEV), 0.01, H, dtau, zero=cross)
     assert_close(dq, qd.grad, 1e-4, 1e-5, "dq"), assert_close(dk, kd.grad, 1e-4, 1e-5, "dk"), assert_close(dv, vd.grad, 1e-4, 1e-5, "dv")
     assert_close(dtau, mha.tau.grad, 1e-4, 1e-4, "dtau")
 

@@ -64,11 +64,11 @@ def attn():
         q, k, v = (torch.randn(m, C, device=DEV) for _ in range(3))
         tau = torch.ones(1, device=DEV)
         H = 8
-        o, lse = ops.window_attention_fwd(q, k, v, P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), min(P.wcap, m), tau, 0.01, H, False)
+        o, lse = ops.window_attention_fwd(q, k, v, P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), ops.mid_end(P, 0), min(P.wcap, m), tau, 0.01, H, False)
         do = torch.randn_like(o)
         dtau = torch.zeros(1, device=DEV)
-        t = timeit(lambda: ops.window_attention_fwd(q, k, v, P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), min(P.wcap, m), tau, 0.01, H, False))
-        t2 = timeit(lambda: ops.window_attention_bwd(do, q, k, v, o, lse, P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), min(P.wcap, m),
+        t = timeit(lambda: ops.window_attention_fwd(q, k, v, P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), ops.mid_end(P, 0), min(P.wcap, m), tau, 0.01, H, False))
+        t2 = timeit(lambda: ops.window_attention_bwd(do, q, k, v, o, lse, P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), ops.mid_end(P, 0), min(P.wcap, m),
                                                      tau, 0.01, H, dtau, False))
         nw = int(P.n_win[0])
         lb = P.level_base[0].tolist()
