@@ -55,6 +55,11 @@ extern "C" {
 TMAE_API const char* tmae_last_error_string(void);
 TMAE_API int tmae_version(void);
 TMAE_API int tmae_device_check(void); /* 0 iff the current device is sm_100 */
+/* Per-kernel timing with CUDA events on the launching stream (used by bench.py for the roofline object): begin, run some
+ * steps, end -> text table "name calls total_ms algorithmic_flops algorithmic_bytes" per kernel family. */
+TMAE_API int64_t tmae_launch_count(void); /* instrumented kernel launches so far (lower bound of all launches) */
+TMAE_API void tmae_profile_begin(void);
+TMAE_API int64_t tmae_profile_end(char* buf, int64_t cap);
 TMAE_API int64_t tmae_scan_scratch_elems(int64_t n);
 TMAE_API int tmae_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* total, int32_t* scratch, void* stream);
 

@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 
 namespace tmae {
@@ -13,6 +17,27 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---------------------------------------------------------------- per-kernel profiler (CUDA events)
+struct ProfRec { const char* name; double flops, bytes; cudaEvent_t e0, e1; };
+static bool g_prof = false;
+double g_prof_rows_hint[2] = {0, 0};
+long long g_launch_groups = 0;
+static std::vector<ProfRec> g_recs;
+bool prof_enabled() { return g_prof; }
+void prof_push(const char* name, double flops, double bytes, cudaStream_t s, bool begin) {
+  if (begin) {
+    ProfRec r{name, flops, bytes, nullptr, nullptr};
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, s);
+    g_recs.push_back(r);
+  } else {
+    // scopes do not nest with the same name: the matching record is the most recent one with this name
+    for (size_t i = g_recs.size(); i-- > 0;)
+      if (g_recs[i].name == name) { cudaEventRecord(g_recs[i].e1, s); break; }
+  }
 }
 
 // ---------------------------------------------------------------- exclusive scan (int32)
@@ -134,6 +159,46 @@ int tmae_device_check(void) {
     return TMAE_ERR_UNSUPPORTED;
   }
   return 0;
+}
+
+int64_t tmae_launch_count(void) { return tmae::g_launch_groups; }
+
+void tmae_profile_begin(void) {
+  cudaDeviceSynchronize();
+  for (auto& r : tmae::g_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  tmae::g_recs.clear();
+  tmae::g_prof = true;
+}
+
+/* Writes one line per kernel family: "name calls total_ms flops bytes\n"; returns the length needed. */
+int64_t tmae_profile_end(char* buf, int64_t cap) {
+  cudaDeviceSynchronize();
+  tmae::g_prof = false;
+  struct Agg { double ms = 0, flops = 0, bytes = 0; long calls = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : tmae::g_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      Agg& a = agg[r.name];
+      a.ms += ms; a.flops += r.flops; a.bytes += r.bytes; a.calls += 1;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  tmae::g_recs.clear();
+  cudaGetLastError();
+  std::string out;
+  char line[256];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "%s %ld %.6f %.6e %.6e\n", kv.first.c_str(), kv.second.calls, kv.second.ms, kv.second.flops, kv.second.bytes);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    size_t n = out.size() < (size_t)cap - 1 ? out.size() : (size_t)cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)out.size() + 1;
 }
 
 int64_t tmae_scan_scratch_elems(int64_t n) { return tmae::scan_scratch_elems(n); }

@@ -348,6 +348,11 @@ static int launch_large(const AttnArgs& a, const int* begin, const int* end, int
 
 template <int HD, int MODE>
 static int launch_pass(const AttnArgs& a, int64_t max_windows, cudaStream_t s) {
+  static const char* names[3] = {"attn_fwd", "attn_bwd_dq", "attn_bwd_dkv"};
+  // algorithmic traffic: fwd reads q,k,v writes o ; dq pass reads q,k,v,o,dO writes dq ; dkv pass reads q,k,v,dO writes dk,dv
+  const double rq = g_prof_rows_hint[0] * a.C * 4.0, rk = g_prof_rows_hint[1] * a.C * 4.0;
+  const double bytes = MODE == 0 ? 2 * rq + 2 * rk : (MODE == 1 ? 4 * rq + 2 * rk : 2 * rq + 4 * rk);
+  ProfScope prof(names[MODE], 0, bytes, s);
   // small windows: 8 warps per CTA, one window per warp per iteration
   int64_t warps = max_windows < (int64_t)kNumSMs * 48 ? max_windows : (int64_t)kNumSMs * 48;
   attn_small_kernel<HD, MODE><<<cdiv(warps * 32, ATT_THREADS), ATT_THREADS, 0, s>>>(a);

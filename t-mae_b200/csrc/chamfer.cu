@@ -212,6 +212,7 @@ int tmae_chamfer_fwd(const float* pred, const float* gt, const float* w, int64_t
   ChamferArgs a{};
   a.pred = pred; a.gt = gt; a.w = w; a.m = n_voxels; a.P1 = p1; a.P2 = p2; a.acc = (double*)state; a.loss = loss;
   GtArgs g = make_gt(points_kept, point_stride, voxel_offset, pt_order, voxel_coords, range_lo, voxel, p2);
+  ProfScope prof("chamfer_fwd", (double)n_voxels * p1 * p2 * 8, (double)n_voxels * (p1 * 12.0 + 4.0 + 24.0 * 5), s);
   TMAE_CUDA(cudaMemsetAsync(state, 0, 3 * sizeof(double), s));
   if (n_voxels > 0) chamfer_kernel<false><<<cdiv(n_voxels * 32, 256), 256, 0, s>>>(a, g);
   chamfer_finalize_kernel<<<1, 1, 0, s>>>(a.acc, p1, p2, loss);
@@ -228,6 +229,7 @@ int tmae_chamfer_bwd(const float* grad_loss, const float* pred, const float* gt,
   ChamferArgs a{};
   a.pred = pred; a.gt = gt; a.w = w; a.m = n_voxels; a.P1 = p1; a.P2 = p2; a.acc = (double*)state; a.gout = grad_loss; a.dpred = dpred;
   GtArgs g = make_gt(points_kept, point_stride, voxel_offset, pt_order, voxel_coords, range_lo, voxel, p2);
+  ProfScope prof("chamfer_bwd", (double)n_voxels * p1 * p2 * 8, (double)n_voxels * (p1 * 24.0 + 4.0 + 24.0 * 5), (cudaStream_t)stream);
   chamfer_kernel<true><<<cdiv(n_voxels * 32, 256), 256, 0, (cudaStream_t)stream>>>(a, g);
   TMAE_CHECK_LAUNCH();
   return 0;

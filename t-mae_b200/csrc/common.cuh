@@ -73,4 +73,19 @@ __device__ __forceinline__ float warp_max(float v) {
 
 constexpr int kNumSMs = 148;  // B200
 
+// Optional per-kernel timing with CUDA events on the launching stream (tmae_profile_begin / _end); off by default
+// and free when off.  flops / bytes are the ALGORITHMIC work of the launch.
+bool prof_enabled();
+extern long long g_launch_groups;  // kernel-family launches made by this process (always counted)
+extern double g_prof_rows_hint[2];  // (q rows, kv rows) of the next attention call, set by the layer entry points
+void prof_push(const char* name, double flops, double bytes, cudaStream_t s, bool begin);
+struct ProfScope {
+  const char* name; double flops, bytes; cudaStream_t s; bool on;
+  ProfScope(const char* n, double f, double b, cudaStream_t st) : name(n), flops(f), bytes(b), s(st), on(prof_enabled()) {
+    ++g_launch_groups;
+    if (on) prof_push(name, flops, bytes, s, true);
+  }
+  ~ProfScope() { if (on) prof_push(name, flops, bytes, s, false); }
+};
+
 }  // namespace tmae

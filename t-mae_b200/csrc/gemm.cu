@@ -169,6 +169,7 @@ static int launch(GemmArgs& g, int splits, cudaStream_t s) {
   if (z < 1) z = 1;
   g.atomic = z > 1;
   dim3 grid((unsigned)cdiv(g.N, BN), (unsigned)cdiv(g.M, BM), (unsigned)z);
+  ProfScope prof("gemm_fp32_simt", 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + (double)g.M * g.N), s);
   gemm_kernel<AM, BMD><<<grid, GT, 0, s>>>(g);
   return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
 }
@@ -293,6 +294,7 @@ int tmae_linear_bwd_weight(const float* dy, const float* x, float* dw, float* db
     if (m > 0) {
       int rpb = 512;
       dim3 grid((unsigned)cdiv(n, 32), (unsigned)cdiv(m, rpb));
+      ProfScope prof("colsum", 0, 4.0 * m * n, s);
       colsum_kernel<<<grid, 256, 0, s>>>(dy, m, (int)n, nullptr, dbias, rpb);
       TMAE_CHECK_LAUNCH();
     }
@@ -314,6 +316,7 @@ int tmae_colsum(const float* x, float* out, int64_t rows, int32_t cols, void* st
 
 int tmae_gelu_bwd(const float* dy, const float* preact, float* dx, int64_t n, void* stream) {
   if (n <= 0) return 0;
+  ProfScope prof("gelu_bwd", 0, 12.0 * n, (cudaStream_t)stream);
   gelu_bwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, preact, dx, n);
   TMAE_CHECK_LAUNCH();
   return 0;

@@ -348,8 +348,18 @@ static int tc_launch(TcArgs& g, int splits, cudaStream_t s) {
   g.atomic = z > 1 || g.atomic;
   size_t smem = (size_t)TSTAGES * (TBM * TBK * 2 + BN * TBK * 2);
   auto kern = tc_gemm_kernel<MODE, BN, GATHER>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TMAE_ERR_CUDA;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TMAE_ERR_CUDA;
+    attr_set = true;
+  }
   dim3 grid((unsigned)cdiv(g.N, BN), (unsigned)cdiv(g.M, TBM), (unsigned)z);
+  static const char* names[3][2] = {{"tc_gemm_nt", "tc_gemm_nt_gather"}, {"tc_gemm_nn", "tc_gemm_nn"}, {"tc_gemm_tn", "tc_gemm_tn_gather"}};
+  // algorithmic traffic: every operand element once (gathered rows count once, not once per tap), C once (twice if read-modify-write)
+  double a_el = GATHER && MODE == TC_NT ? (double)g.M * g.cin : (double)g.M * g.K;
+  double b_el = GATHER && MODE == TC_TN ? (double)g.K * g.cin : (double)g.N * g.K;
+  double c_el = (double)g.M * g.N * (1.0 + (g.accumulate || g.residual ? 1.0 : 0.0) + (g.preact ? 1.0 : 0.0));
+  ProfScope prof(names[MODE][GATHER ? 1 : 0], 2.0 * g.M * g.N * g.K, 4.0 * (a_el + b_el + c_el), s);
   kern<<<grid, TC_THREADS, smem, s>>>(g);
   return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
 }

@@ -239,6 +239,7 @@ int tmae_window_partition(const int32_t* coords_a, int64_t m_a, const int32_t* c
   int* total = ws.take<int>(8);
   TMAE_CHECK_ARG(total != nullptr, "workspace carve failed");
 
+  ProfScope prof("window_partition", 0, (double)(m_a + m_b) * (12.0 + 2 * 9.0 + (ref_bwi_a ? 48.0 : 0.0)) + 2.0 * G.wcap * 8, s);
   TMAE_CUDA(cudaMemsetAsync(mask_a, 0, 2ll * G.wcap * 8, s));
   if (temporal) TMAE_CUDA(cudaMemsetAsync(mask_b, 0, 2ll * G.wcap * 8, s));
   TMAE_CUDA(cudaMemsetAsync(flags, 0, nflag * 4, s));

@@ -255,6 +255,7 @@ int tmae_add_pos(const float* x, const uint8_t* posidx, const float* lut, float*
   TMAE_CHECK_ARG(c % 4 == 0, "channels must be a multiple of 4");
   if (rows <= 0) return 0;
   int c4 = c / 4;
+  ProfScope prof("add_pos", 0, 8.0 * rows * c, (cudaStream_t)stream);
   add_pos_kernel<<<cdiv(rows * c4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, posidx, (const float4*)lut, (float4*)y, rows, c4);
   TMAE_CHECK_LAUNCH();
   return 0;
@@ -265,6 +266,7 @@ int tmae_add_layernorm_fwd(const float* x, const float* res, const uint8_t* rowm
   if (rows <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   int grid = cdiv(rows * 32, 256);
+  ProfScope prof("add_layernorm_fwd", 0, 4.0 * rows * c * (res ? 3 : 2), s);
   switch (c) {
     case 64: add_ln_fwd_kernel<2><<<grid, 256, 0, s>>>(x, res, rowmask, gamma, beta, y, mean, rstd, rows, eps); break;
     case 128: add_ln_fwd_kernel<4><<<grid, 256, 0, s>>>(x, res, rowmask, gamma, beta, y, mean, rstd, rows, eps); break;
@@ -286,6 +288,7 @@ int tmae_add_layernorm_bwd(const float* dy, const float* x, const float* res, co
   int rpw = 16;
   int64_t warps = (rows + rpw - 1) / rpw;
   int grid = cdiv(warps * 32, 256);
+  ProfScope prof("add_layernorm_bwd", 0, 4.0 * rows * c * (res ? 4 : 3) + (dres ? 4.0 * rows * c : 0), s);
   switch (c) {
     case 64: add_ln_bwd_kernel<2><<<grid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows, rpw); break;
     case 128: add_ln_bwd_kernel<4><<<grid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows, rpw); break;
@@ -311,6 +314,7 @@ int tmae_bn_train_fwd(const float* x, const float* gamma, const float* beta, flo
   TMAE_CUDA(cudaMemsetAsync(sum, 0, 2 * c * sizeof(double), s));
   int rpb = 256;
   dim3 grid((unsigned)cdiv(c, 128), (unsigned)cdiv(rows, rpb));
+  ProfScope prof("bn_train_fwd", 0, 12.0 * rows * c, s);
   bn_stats_kernel<<<grid, 128, 0, s>>>(x, rows, c, sum, sumsq, rpb);
   bn_finalize_kernel<<<cdiv(c, 128), 128, 0, s>>>(sum, sumsq, rows, c, eps, momentum, save_mean, save_rstd, running_mean, running_var);
   bn_apply_kernel<<<cdiv(rows * c, 256), 256, 0, s>>>(x, save_mean, save_rstd, gamma, beta, y, rows * c, c, relu);
@@ -338,6 +342,7 @@ int tmae_bn_bwd(const float* dy, const float* x, const float* y, const float* me
   TMAE_CUDA(cudaMemsetAsync(a, 0, 2 * c * sizeof(double), s));
   int rpb = 256;
   dim3 grid((unsigned)cdiv(c, 128), (unsigned)cdiv(rows, rpb));
+  ProfScope prof("bn_bwd", 0, 28.0 * rows * c, s);
   bn_bwd_reduce_kernel<<<grid, 128, 0, s>>>(dy, x, y, mean, rstd, rows, c, relu, a, b, rpb);
   bn_bwd_apply_kernel<<<cdiv(rows * c, 256), 256, 0, s>>>(dy, x, y, mean, rstd, gamma, a, b, dx, dgamma, dbeta, rows, c, relu, training);
   TMAE_CHECK_LAUNCH();

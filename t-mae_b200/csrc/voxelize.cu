@@ -189,6 +189,8 @@ int tmae_voxelize(const float* points, int64_t n_points, int32_t point_stride, c
   int* totals = ws.take<int>(8);
   TMAE_CHECK_ARG(totals != nullptr, "workspace carve failed");
 
+  // algorithmic traffic: read n*stride*4 ; write kept points, coords (32 B), inverse (8 B) per point + 48 B per voxel
+  ProfScope prof("voxelize", 0, (double)n_points * (point_stride * 8.0 + 40.0), s);
   TMAE_CUDA(cudaMemsetAsync(occ, 0, cells * sizeof(int), s));
   TMAE_CUDA(cudaMemsetAsync(voxel_npts, 0, mcap * sizeof(int), s));
   TMAE_CUDA(cudaMemsetAsync(cursor, 0, (mcap + 1) * sizeof(int), s));

@@ -26,8 +26,9 @@ def precision():
 
 
 def launch_count():
-    """ABI calls made so far (each enqueues >= 1 kernel of this library)."""
-    return _state["launches"]
+    """Kernel launches of this library so far, counted inside the library at its instrumented launch sites (a lower
+    bound: memsets and a few small kernels are not counted)."""
+    return int(lib().launch_count())
 
 
 def _p(t, dtype=None):
@@ -87,6 +88,20 @@ def profile_end():
         r["calls"] += 1
         r["flops"] += fl
         r["bytes"] += nb
+    return out
+
+
+def lib_profile(fn):
+    """Runs fn() under the library's per-kernel CUDA-event profiler and returns the aggregated table."""
+    L = lib()
+    L.profile_begin()
+    fn()
+    buf = ctypes.create_string_buffer(1 << 16)
+    L.profile_end(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, calls, ms, fl, by = line.split()
+        out[name] = {"calls": int(calls), "ms": float(ms), "flops": float(fl), "bytes": float(by)}
     return out
 
 
