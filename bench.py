@@ -88,11 +88,22 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def shard_seeds(w, n_batches, rank):
+    """Scan-pair sharding: rank r owns scan indices (seeds) [r*n_batches*B, (r+1)*n_batches*B) -- disjoint across ranks."""
+    B = w["batch"]
+    return [[1000 + (rank * n_batches + i) * B + j for j in range(B)] for i in range(n_batches)]
+
+
+def aggregate_value(batch, steps, world, total_ms):
+    """Whole-job scan pairs per second: all ranks' units over the slowest rank's time."""
+    return batch * steps * world / (total_ms / 1e3)
+
+
 def make_batches(w, n_batches, rank):
     from tmae_b200 import synth
     out = []
-    for i in range(n_batches):
-        pts, ptsp = synth.batch(1000 + (rank * n_batches + i) * w["batch"], w["batch"], w["n_points"])
+    for seeds in shard_seeds(w, n_batches, rank):
+        pts, ptsp = synth.batch(seeds[0], w["batch"], w["n_points"])
         out.append((torch.from_numpy(pts).pin_memory(), torch.from_numpy(ptsp).pin_memory()))
     return out
 
@@ -196,8 +207,8 @@ def run_ours(args):
         return float(t)
 
     total, e_total = maxr(total), maxr(e_total)
-    units = w["batch"] * args.steps * world
-    value, e_value = units / (total / 1e3), units / (e_total / 1e3)
+    value = aggregate_value(w["batch"], args.steps, world, total)
+    e_value = aggregate_value(w["batch"], args.steps, world, e_total)
 
     roof, prof_table = None, None
     if rank == 0:

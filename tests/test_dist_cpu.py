@@ -1,0 +1,38 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic of bench.py: scan pairs are sharded by rank with no
+overlap, the step time is the MAX over ranks, and the reported value is the whole-job aggregate."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import bench
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    assert bench.dist_env() == (rank, world, rank)
+    seeds = bench.shard_seeds(bench.WORKLOADS["pretrain"], n_batches=3, rank=rank)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, seeds)
+    flat = [s for r in gathered for b in r for s in b]
+    assert len(flat) == len(set(flat)) == world * 3 * 4, "every rank must get disjoint scan pairs"
+    t = torch.tensor([10.0 + 5 * rank], dtype=torch.float64)  # rank 1 is slower
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    value = bench.aggregate_value(batch=4, steps=10, world=world, total_ms=float(t))
+    out[rank] = (float(t), value)
+    dist.destroy_process_group()
+
+
+def test_sharding_and_max_over_ranks():
+    world = 2
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_worker, args=(world, 29541, out), nprocs=world, join=True)
+        assert out[0] == out[1]
+        t, value = out[0]
+        assert t == 15.0 and abs(value - 4 * 10 * 2 / 0.015) < 1e-6
