@@ -117,7 +117,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=dev)
+        import datetime
+        torch.distributed.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     w = WORKLOADS[args.workload]
     shape = synth.ONCE
     grid = synth.grid_size(shape).tolist()
@@ -153,15 +154,20 @@ def run_ours(args):
     resident = [(a.to(dev), b.to(dev)) for a, b in host]
     h2d = sum(t.numel() * 4 for t in host[0])
 
-    def step(pts, ptsp):
+    def step(pts, ptsp, module=None):
+        m = net if module is None else module
         if w["train"]:
-            loss = net(pts, ptsp)
+            loss = m(pts, ptsp)
             loss.backward()
             opt.step()
             opt.zero_grad(set_to_none=True)
             return loss
         with torch.no_grad():
-            return net(pts, ptsp)
+            return m(pts, ptsp)
+
+    def step_local(pts, ptsp):
+        """Same step on the un-wrapped module: no collective, so rank 0 may run it alone (profiling pass)."""
+        return step(pts, ptsp, model)
 
     def barrier():
         if world > 1:
@@ -212,7 +218,7 @@ def run_ours(args):
 
     roof, prof_table = None, None
     if rank == 0:
-        roof, prof_table = roofline(ops, step, resident, args)
+        roof, prof_table = roofline(ops, step_local, resident, args)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(w, args)
