@@ -238,7 +238,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "kernel_time_table": prof_table,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -332,16 +332,28 @@ def run_reference(args):
     dt = time.perf_counter() - t
     v = round(args.steps / dt, 4)
     sample = f"each step = ONE scan pair (batch 1) of the workload, fp32 torch CPU ops, {cores} threads; sparse convs dense-emulated"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "encoder scans/sec (scan pairs through vfe -> backbone_3d -> loss)", "value": v, "unit": "scans/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "sample": sample},
         "cpu_baseline": {"value": v, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+_OUT = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything libraries print (e.g. NCCL's version banner) was
+    redirected to stderr in main()."""
+    print(json.dumps(obj), file=_OUT or sys.stdout, flush=True)
 
 
 def main():
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
