@@ -42,7 +42,8 @@ extern "C" {
 
 /* GEMM arithmetic selector for the ops that take `precision`. */
 #define TMAE_PREC_FP32 0 /* fp32 FFMA, parity mode (rtol 1e-5 vs the fp32 oracle) */
-#define TMAE_PREC_BF16 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM */
+#define TMAE_PREC_BF16 1 /* tensor-core mode: tcgen05 with fp32 accumulate in TMEM; dense GEMMs read their fp32 operands through
+                            TMA as TF32, the gathered (sparse-conv) GEMMs convert to bf16 while staging */
 
 #define TMAE_ACT_NONE 0
 #define TMAE_ACT_GELU 1 /* exact erf GELU (torch default, sst_basic_block.py:121-122) */
@@ -127,6 +128,8 @@ TMAE_API int tmae_window_partition(const int32_t* coords_a, int64_t m_a, const i
  * Replace torch.nn.functional.linear at cosine_msa.py:57-62,431, sst_basic_block.py:81, wca_block.py:99,
  * network_utils.py:30, SiamWCA_MAE.py:117-119 and their autograd backward.  w is (n, k) row-major
  * (torch Linear layout).  y = act(x w^T + bias) + residual ; preact (nullable) receives x w^T + bias. */
+/* options: "tma" (default 1) -- 0 routes the dense tensor-core GEMMs to the thread-staged bf16 kernel */
+TMAE_API int tmae_set_option(const char* name, int32_t value);
 TMAE_API int tmae_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact,
                     int64_t m, int64_t n, int64_t k, int32_t act, int32_t precision, void* stream);
 TMAE_API int tmae_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int32_t accumulate,

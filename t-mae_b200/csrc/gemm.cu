@@ -8,6 +8,8 @@
 // 4x4 register micro-tiles, operands staged k-major in shared memory); the operand accessors are
 // template modes so forward (NT), backward-data (NN), backward-weight (TN, split over the long
 // reduction with fp32 atomics) and the neighbour-table gathers share the inner loop.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace tmae {
@@ -217,7 +219,15 @@ __global__ void transpose_taps_kernel(const float* __restrict__ w, float* __rest
   wt[((int64_t)c * taps + tt) * cout + o] = w[i];
 }
 
-// tensor-core path (gemm_tc.cu)
+// TMA-fed tf32 tensor-core path (gemm_tma.cu)
+bool tma_linear_fwd_ok(const float* x, const float* w, const float* y, const float* residual, int64_t m, int64_t n, int64_t k);
+int tma_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* preact, int64_t m, int64_t n, int64_t k, int act,
+                   cudaStream_t s);
+bool tma_linear_bwd_data_ok(const float* dy, const float* w, const float* dx, int64_t m, int64_t n, int64_t k);
+int tma_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int accumulate, cudaStream_t s);
+bool tma_linear_bwd_weight_ok(const float* dy, const float* x, const float* dw, int64_t m, int64_t n, int64_t k);
+int tma_linear_bwd_weight(const float* dy, const float* x, float* dw, int64_t m, int64_t n, int64_t k, cudaStream_t s);
+// thread-staged bf16 tensor-core path (gemm_tc.cu)
 bool tc_linear_fwd_ok(int64_t m, int64_t n, int64_t k);
 int tc_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact, int64_t m,
                   int64_t n, int64_t k, int act, cudaStream_t s);
@@ -235,13 +245,25 @@ int tc_sparse_conv_bwd_weight(const float* dy, const float* x, const int* table,
 
 using namespace tmae;
 
+static bool g_use_tma = true;  // tmae_set_option("tma", 0) keeps every tensor-core GEMM on the thread-staged bf16 kernel
+
 #define TMAE_CHECK_PREC(p) TMAE_CHECK_ARG((p) == TMAE_PREC_FP32 || (p) == TMAE_PREC_BF16, "precision must be TMAE_PREC_FP32 or TMAE_PREC_BF16")
 
 extern "C" {
 
+int tmae_set_option(const char* name, int32_t value) {
+  if (name && !strcmp(name, "tma")) { g_use_tma = value != 0; return 0; }
+  set_error("tmae_set_option: unknown option");
+  return TMAE_ERR_INVALID_ARG;
+}
+
 int tmae_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact,
                     int64_t m, int64_t n, int64_t k, int32_t act, int32_t precision, void* stream) {
   TMAE_CHECK_PREC(precision);
+  if (precision == TMAE_PREC_BF16 && g_use_tma && tma_linear_fwd_ok(x, w, y, residual, m, n, k)) {
+    if (tma_linear_fwd(x, w, bias, y, preact, m, n, k, act, (cudaStream_t)stream)) { set_error("tmae_linear_fwd: TMA launch failed"); return TMAE_ERR_CUDA; }
+    return 0;
+  }
   if (precision == TMAE_PREC_BF16 && tc_linear_fwd_ok(m, n, k)) {
     if (tc_linear_fwd(x, w, bias, residual, y, preact, m, n, k, act, (cudaStream_t)stream)) { set_error("tmae_linear_fwd: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
     return 0;
@@ -256,6 +278,10 @@ int tmae_linear_fwd(const float* x, const float* w, const float* bias, const flo
 int tmae_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int32_t accumulate,
                          int32_t precision, void* stream) {
   TMAE_CHECK_PREC(precision);
+  if (precision == TMAE_PREC_BF16 && g_use_tma && tma_linear_bwd_data_ok(dy, w, dx, m, n, k)) {
+    if (tma_linear_bwd_data(dy, w, dx, m, n, k, accumulate, (cudaStream_t)stream)) { set_error("tmae_linear_bwd_data: TMA launch failed"); return TMAE_ERR_CUDA; }
+    return 0;
+  }
   if (precision == TMAE_PREC_BF16 && tc_linear_bwd_data_ok(m, n, k)) {
     if (tc_linear_bwd_data(dy, w, dx, m, n, k, accumulate, (cudaStream_t)stream)) { set_error("tmae_linear_bwd_data: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
     return 0;
@@ -281,7 +307,9 @@ int tmae_linear_bwd_weight(const float* dy, const float* x, float* dw, float* db
   cudaStream_t s = (cudaStream_t)stream;
   // dw[n,k] = sum_m dy[m,n] * x[m,k]   (overwrites dw; reduction over m split across CTAs)
   TMAE_CUDA(cudaMemsetAsync(dw, 0, (size_t)n * k * sizeof(float), s));
-  if (precision == TMAE_PREC_BF16 && tc_linear_bwd_weight_ok(m, n, k)) {
+  if (precision == TMAE_PREC_BF16 && g_use_tma && m > 0 && tma_linear_bwd_weight_ok(dy, x, dw, m, n, k)) {
+    if (tma_linear_bwd_weight(dy, x, dw, m, n, k, s)) { set_error("tmae_linear_bwd_weight: TMA launch failed"); return TMAE_ERR_CUDA; }
+  } else if (precision == TMAE_PREC_BF16 && tc_linear_bwd_weight_ok(m, n, k)) {
     if (tc_linear_bwd_weight(dy, x, dw, m, n, k, s)) { set_error("tmae_linear_bwd_weight: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
   } else {
     GemmArgs g{};

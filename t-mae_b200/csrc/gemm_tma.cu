@@ -1,0 +1,333 @@
+// TMA-fed tcgen05 GEMM for the dense (non-gathered) contractions of the path: operands stay fp32 in HBM and are
+// consumed as TF32 (kind::tf32, fp32 accumulate in TMEM), so no thread ever touches an operand byte:
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B boxes) -> STAGES-deep shared ring, mbarrier tx
+//   warp 1      MMA issuer     tcgen05.mma.kind::tf32, M=128, N=BN, K=8 per instruction; tcgen05.commit frees stages
+//   warps 2..5  epilogue       tcgen05.ld (lane = row) -> bias / GELU / pre-activation copy -> swizzled shared tile
+//                              -> TMA store (or TMA reduce-add for C += and for the split reduction of dW)
+// Modes: NT  C[m,n] = sum_k A[m,k] W[n,k]   (A, B K-major)            linear forward
+//        NN  C[m,n] = sum_k A[m,k] B[k,n]   (A K-major, B MN-major)   linear backward-data
+//        TN  C[m,n] = sum_k A[k,m] B[k,n]   (A, B MN-major)           linear backward-weight, split over k
+// The gathered sparse-conv forms and shapes TMA cannot express (row pitch not a multiple of 16 bytes) stay on
+// gemm_tc.cu.  Every mbarrier wait is bounded and traps instead of hanging.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace tmae {
+
+constexpr int UM = 128;        // UMMA M
+constexpr int KB = 32;         // fp32 elements per k-block = one 128-byte swizzle span
+constexpr int TMA_THREADS = 192;
+
+enum TmaMode { T_NT = 0, T_NN = 1, T_TN = 2 };
+
+struct TmaArgs {
+  int64_t M, N, K;
+  const float* bias;
+  int act, reduce_add, has_preact;
+  int64_t k_chunk;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* b, uint32_t n) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(s_u32(b)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(s_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(s_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1, bool reduce_add) {
+  if (reduce_add)
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(s_u32(src)), "r"(c0), "r"(c1) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(s_u32(src)), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// SWIZZLE_128B UMMA shared-memory descriptor: start >> 4, LBO >> 4 (bit 16), SBO >> 4 (bit 32), version 1 (bit 46),
+// layout type 2 = SWIZZLE_128B (bits 61..63)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32 instruction descriptor: D fp32 (1 << 4), A/B tf32 (2 << 7, 2 << 10), majors, N >> 3, M >> 4
+__device__ __forceinline__ uint32_t idesc_tf32(int a_mn, int b_mn, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(UM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void commit_to(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ld_tmem32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float gelu_erf_t(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+// One stage of the ring: A then B.
+//   K-major operand (rows x 32 fp32): ONE box {32, rows}; 8-row groups 1024 B apart (SBO), k-step = +32 B.
+//   MN-major operand (32 k-rows x cols): cols/32 boxes {32, 32} of 4096 B each (LBO between boxes), k-groups of 8
+//   rows 1024 B apart (SBO), k-step = +1024 B.
+template <int MODE, int BN, int STAGES>
+__global__ void __launch_bounds__(TMA_THREADS) tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                               const __grid_constant__ CUtensorMap map_b,
+                                                               const __grid_constant__ CUtensorMap map_c,
+                                                               const __grid_constant__ CUtensorMap map_p, TmaArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int A_BYTES = UM * KB * 4, B_BYTES = BN * KB * 4, STAGE = A_BYTES + B_BYTES;
+  constexpr int EPI_BYTES = 32 * 32 * 4;  // one 32x32 fp32 tile per epilogue warp and buffer
+  uint8_t* epi = smem + STAGES * STAGE;   // [4 warps][2 outputs][2 buffers][4096]
+  __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * UM, n0 = blockIdx.x * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * g.k_chunk;
+  const int64_t kend = kbeg + g.k_chunk < g.K ? kbeg + g.k_chunk : g.K;
+  const int nkb = (int)((kend - kbeg + KB - 1) / KB);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { bar_init(&bar_full[s], 1); bar_init(&bar_empty[s], 1); }
+    bar_init(&bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(BN < 32 ? 32 : BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, use = kb / STAGES;
+        if (use > 0) bar_wait(&bar_empty[s], (use - 1) & 1);
+        uint8_t* a = smem + s * STAGE;
+        uint8_t* b = a + A_BYTES;
+        const int k0 = (int)(kbeg + (int64_t)kb * KB);
+        bar_expect_tx(&bar_full[s], STAGE);
+        if (MODE == T_TN) {
+#pragma unroll
+          for (int j = 0; j < UM / 32; ++j) tma_load_2d(a + j * 4096, &map_a, m0 + j * 32, k0, &bar_full[s]);
+        } else {
+          tma_load_2d(a, &map_a, k0, m0, &bar_full[s]);
+        }
+        if (MODE == T_NT) {
+          tma_load_2d(b, &map_b, k0, n0, &bar_full[s]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(b + j * 4096, &map_b, n0 + j * 32, k0, &bar_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(MODE == T_TN, MODE != T_NT, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, use = kb / STAGES;
+        bar_wait(&bar_full[s], use & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = s_u32(smem + s * STAGE), b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < KB / 8; ++kk) {
+          uint64_t da = MODE == T_TN ? desc_sw128(a_addr + kk * 1024, 4096, 1024) : desc_sw128(a_addr + kk * 32, 16, 1024);
+          uint64_t db = MODE == T_NT ? desc_sw128(b_addr + kk * 32, 16, 1024) : desc_sw128(b_addr + kk * 1024, 4096, 1024);
+          umma_tf32(tmem_d, da, db, idesc, (kb | kk) ? 1u : 0u);
+        }
+        commit_to(&bar_empty[s]);
+        if (kb == nkb - 1) commit_to(&bar_acc);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps: TMEM lane quarter q = warp % 4
+    const int q = warp & 3;
+    const int row0 = m0 + q * 32;
+    if (nkb > 0) bar_wait(&bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint8_t* my = epi + (warp - 2) * (4 * EPI_BYTES);
+    constexpr int CHUNKS = BN / 32;
+    for (int ch = 0; ch < CHUNKS; ++ch) {
+      const int col0 = n0 + ch * 32;
+      if (col0 >= g.N) break;
+      uint32_t r[32];
+      if (nkb > 0) ld_tmem32(tmem_d + ((uint32_t)(q * 32) << 16) + ch * 32, r);
+      else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      uint8_t* tile_c = my + (ch & 1) * EPI_BYTES;
+      uint8_t* tile_p = my + (2 + (ch & 1)) * EPI_BYTES;
+      if (ch >= 2) {  // the store that read this buffer two chunks ago must have finished reading it
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]);
+        if (g.bias && col0 + j < g.N) x += __ldg(g.bias + col0 + j);
+        v[j] = x;
+      }
+      // swizzled (128B) tile: 16-byte chunk c of row `lane` lives at chunk position c ^ (lane & 7)
+      if (g.has_preact) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(tile_p + lane * 128 + ((c ^ (lane & 7)) * 16)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      }
+      if (g.act == TMAE_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_t(v[j]);
+      } else if (g.act == TMAE_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(tile_c + lane * 128 + ((c ^ (lane & 7)) * 16)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0 && row0 < g.M) {
+        tma_store_2d(&map_c, tile_c, col0, row0, g.reduce_add != 0);
+        if (g.has_preact) tma_store_2d(&map_p, tile_p, col0, row0, false);
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN < 32 ? 32 : BN) : "memory");
+}
+
+// ------------------------------------------------------------------ host side
+static bool make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner,
+                     uint32_t box_outer, bool tf32) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = cuTensorMapEncodeTiled(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims,
+                                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+template <int MODE, int BN>
+static int tma_launch(const float* A, const float* B, float* C, float* preact, int64_t lda, int64_t ldb, int64_t ldc, TmaArgs g, int splits,
+                      cudaStream_t s) {
+  constexpr int STAGES = BN == 256 ? 3 : 4;
+  if (g.M <= 0 || g.N <= 0) return 0;
+  if (splits < 1) splits = 1;
+  g.k_chunk = align_up((g.K + splits - 1) / splits, KB);
+  int z = (int)((g.K + g.k_chunk - 1) / g.k_chunk);
+  if (z < 1) z = 1;
+  if (z > 1) g.reduce_add = 1;
+  CUtensorMap ma, mb, mc, mp;
+  bool ok = true;
+  // A: NT/NN K-major (rows = M, inner = K)  box {32, 128} ; TN MN-major (rows = K, inner = M) box {32, 32}
+  ok &= MODE == T_TN ? make_map(&ma, A, g.M, g.K, lda, 32, 32, true) : make_map(&ma, A, g.K, g.M, lda, KB, UM, true);
+  // B: NT K-major (rows = N, inner = K) box {32, BN} ; NN/TN MN-major (rows = K, inner = N) box {32, 32}
+  ok &= MODE == T_NT ? make_map(&mb, B, g.K, g.N, ldb, KB, BN, true) : make_map(&mb, B, g.N, g.K, ldb, 32, 32, true);
+  ok &= make_map(&mc, C, g.N, g.M, ldc, 32, 32, false);
+  ok &= make_map(&mp, preact ? preact : C, g.N, g.M, ldc, 32, 32, false);
+  if (!ok) return TMAE_ERR_CUDA;
+  g.has_preact = preact != nullptr;
+  size_t smem = (size_t)STAGES * (UM * KB * 4 + BN * KB * 4) + 4 * 4 * 4096 + 1024;
+  auto kern = tma_gemm_kernel<MODE, BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TMAE_ERR_CUDA;
+    attr_set = true;
+  }
+  static const char* names[3] = {"tma_gemm_nt", "tma_gemm_nn", "tma_gemm_tn"};
+  double c_el = (double)g.M * g.N * (1.0 + (g.reduce_add && z == 1 ? 1.0 : 0.0) + (preact ? 1.0 : 0.0));
+  ProfScope prof(names[MODE], 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + c_el), s);
+  dim3 grid((unsigned)cdiv(g.N, BN), (unsigned)cdiv(g.M, UM), (unsigned)z);
+  kern<<<grid, TMA_THREADS, smem, s>>>(ma, mb, mc, mp, g);
+  return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
+}
+
+template <int MODE>
+static int tma_dispatch(const float* A, const float* B, float* C, float* preact, int64_t lda, int64_t ldb, int64_t ldc, const TmaArgs& g,
+                        int splits, cudaStream_t s) {
+  if (g.N > 128) return tma_launch<MODE, 256>(A, B, C, preact, lda, ldb, ldc, g, splits, s);
+  if (g.N > 64) return tma_launch<MODE, 128>(A, B, C, preact, lda, ldb, ldc, g, splits, s);
+  return tma_launch<MODE, 64>(A, B, C, preact, lda, ldb, ldc, g, splits, s);
+}
+
+// ---- entry points (gemm.cu dispatches here for TMAE_PREC_BF16 when the shapes allow TMA)
+bool tma_linear_fwd_ok(const float* x, const float* w, const float* y, const float* residual, int64_t m, int64_t n, int64_t k) {
+  return residual == nullptr && k % 4 == 0 && n % 4 == 0 && aligned16(x) && aligned16(w) && aligned16(y);
+}
+int tma_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* preact, int64_t m, int64_t n, int64_t k, int act,
+                   cudaStream_t s) {
+  TmaArgs g{};
+  g.M = m; g.N = n; g.K = k; g.bias = bias; g.act = act;
+  return tma_dispatch<T_NT>(x, w, y, preact, k, k, n, g, 1, s);
+}
+bool tma_linear_bwd_data_ok(const float* dy, const float* w, const float* dx, int64_t m, int64_t n, int64_t k) {
+  return n % 4 == 0 && k % 4 == 0 && aligned16(dy) && aligned16(w) && aligned16(dx);
+}
+int tma_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int accumulate, cudaStream_t s) {
+  TmaArgs g{};
+  g.M = m; g.N = k; g.K = n; g.reduce_add = accumulate;
+  return tma_dispatch<T_NN>(dy, w, dx, nullptr, n, k, k, g, 1, s);
+}
+bool tma_linear_bwd_weight_ok(const float* dy, const float* x, const float* dw, int64_t m, int64_t n, int64_t k) {
+  return n % 4 == 0 && k % 4 == 0 && aligned16(dy) && aligned16(x) && aligned16(dw);
+}
+// dw must be zero-filled by the caller (split reduction adds into it)
+int tma_linear_bwd_weight(const float* dy, const float* x, float* dw, int64_t m, int64_t n, int64_t k, cudaStream_t s) {
+  TmaArgs g{};
+  g.M = n; g.N = k; g.K = m; g.reduce_add = 1;
+  int bn = k > 128 ? 256 : (k > 64 ? 128 : 64);
+  int64_t tiles = (int64_t)cdiv(n, UM) * cdiv(k, bn);
+  int64_t want = (kNumSMs + tiles - 1) / tiles, maxs = (m + 8 * KB - 1) / (8 * KB);
+  if (want > maxs) want = maxs;
+  return tma_dispatch<T_TN>(dy, x, dw, nullptr, n, k, k, g, (int)(want < 1 ? 1 : want), s);
+}
+
+}  // namespace tmae

@@ -25,6 +25,11 @@ def precision():
     return _state["precision"]
 
 
+def set_option(name, value):
+    """Library options: "tma" (1 = dense tensor-core GEMMs through the TMA-fed TF32 kernel, 0 = thread-staged bf16)."""
+    lib().set_option(name.encode(), int(value))
+
+
 def launch_count():
     """Kernel launches of this library so far, counted inside the library at its instrumented launch sites (a lower
     bound: memsets and a few small kernels are not counted)."""

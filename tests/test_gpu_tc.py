@@ -16,22 +16,41 @@ if torch.cuda.is_available():
     from tmae_b200 import ops
 
 DEV = "cuda"
+TOL = 1e-4
 
 
 def bf(t):
     return t.to(torch.bfloat16).double()
 
 
-@pytest.fixture(autouse=True)
-def _bf16_mode():
+def tf32(t):
+    """fp32 -> TF32 (10 explicit mantissa bits), round to nearest; what the TMA-fed kind::tf32 GEMMs consume."""
+    i = t.float().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32).double()
+
+
+@pytest.fixture(autouse=True, params=["tma_tf32", "staged_bf16"])
+def _tc_mode(request):
     ops.set_precision("bf16")
-    yield
+    ops.set_option("tma", request.param == "tma_tf32")
+    global bf
+    saved = bf
+    if request.param == "tma_tf32":
+        bf = tf32  # dense GEMMs read TF32 operands in this mode (gathered ones still bf16: see test_tc_sparse_conv)
+    yield request.param
+    bf = saved
+    ops.set_option("tma", 1)
     ops.set_precision("fp32")
 
 
 @pytest.mark.parametrize("m,n,k", [(128, 64, 64), (1, 128, 64), (1000, 128, 128), (333, 256, 128), (2049, 256, 512), (4100, 512, 256),
                                    (65, 48, 128), (5000, 128, 256)])
-def test_tc_linear_fwd_bwd(m, n, k):
+def test_tc_linear_fwd_bwd(m, n, k, _tc_mode):
+    # bf16 staging: exact products of rounded operands, only summation order differs -> 1e-4.  TF32 through TMA: the
+    # rounding (nearest vs truncation of the 13 dropped bits) is done by the copy engine / tensor core, so allow one
+    # TF32 ulp (2^-11 relative per operand) on top: 1e-3.
+    global TOL
+    TOL = 1e-3 if _tc_mode == "tma_tf32" else 1e-4
     g = torch.Generator().manual_seed(m + n + k)
     x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k ** .5, torch.randn(n, generator=g)
     r = torch.randn(m, n, generator=g)
@@ -39,16 +58,16 @@ def test_tc_linear_fwd_bwd(m, n, k):
     for act, f in ((ops.ACT_NONE, lambda t: t), (ops.ACT_GELU, torch.nn.functional.gelu)):
         y, pre = ops.linear_fwd(xd, wd, bd, residual=rd, act=act, want_preact=True)
         lin = bf(x) @ bf(w).T + b.double()
-        assert_close(pre, lin, 1e-4, 1e-4, f"tc linear preact m={m}")
-        assert_close(y, f(lin) + r.double(), 1e-4, 1e-4, f"tc linear act={act}")
+        assert_close(pre, lin, TOL, TOL, f"tc linear preact m={m}")
+        assert_close(y, f(lin) + r.double(), TOL, TOL, f"tc linear act={act}")
     dy = torch.randn(m, n, generator=g)
     dx = ops.linear_bwd_data(dy.to(DEV), wd)
-    assert_close(dx, bf(dy) @ bf(w), 1e-4, 1e-4, "tc dx")
+    assert_close(dx, bf(dy) @ bf(w), TOL, TOL, "tc dx")
     dx2 = ops.linear_bwd_data(dy.to(DEV), wd, dx=dx.clone(), accumulate=True)
-    assert_close(dx2, 2 * (bf(dy) @ bf(w)), 1e-4, 2e-4, "tc dx accumulate")
+    assert_close(dx2, 2 * (bf(dy) @ bf(w)), TOL, 2 * TOL, "tc dx accumulate")
     dw, db = torch.empty_like(wd), torch.empty_like(bd)
     ops.linear_bwd_weight(dy.to(DEV), xd, dw, db)
-    assert_close(dw, bf(dy).T @ bf(x), 1e-4, 1e-4 * max(1, m) ** .5, "tc dw")
+    assert_close(dw, bf(dy).T @ bf(x), TOL, TOL * max(1, m) ** .5, "tc dw")
     assert_close(db, dy.double().sum(0), 1e-5, 1e-4 * max(1, m) ** .5, "db")
 
 
@@ -59,7 +78,7 @@ def test_tc_weight_slices():
     x, w, b = torch.randn(m, C, generator=g), torch.randn(3 * C, C, generator=g) / C ** .5, torch.randn(3 * C, generator=g)
     for i in range(3):
         y = ops.linear_fwd(x.to(DEV), w.to(DEV), b.to(DEV), w_offset_rows=i * C, n=C)
-        assert_close(y, bf(x) @ bf(w[i * C:(i + 1) * C]).T + b[i * C:(i + 1) * C].double(), 1e-4, 1e-4, f"slice {i}")
+        assert_close(y, bf(x) @ bf(w[i * C:(i + 1) * C]).T + b[i * C:(i + 1) * C].double(), 1e-3, 1e-3, f"slice {i}")
 
 
 def _coords(seed, m, B, g):
@@ -70,6 +89,7 @@ def _coords(seed, m, B, g):
 
 @pytest.mark.parametrize("seed,m,B,g,cin,cout", [(0, 1500, 2, 96, 128, 128), (1, 700, 2, 47, 128, 256), (2, 3000, 1, 90, 256, 256)])
 def test_tc_sparse_conv(seed, m, B, g, cin, cout):
+    bf = lambda t: t.to(torch.bfloat16).double()  # noqa: E731  the gathered GEMMs always stage bf16
     c = _coords(seed, m, B, g)
     m = c.shape[0]
     gen = torch.Generator().manual_seed(seed)
