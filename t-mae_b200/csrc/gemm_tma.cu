@@ -71,6 +71,12 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major TF32 operands must use the 128-byte swizzle with 32-byte atomicity (layout type 1 = SWIZZLE_128B_BASE32B;
+// CUTLASS: "for mn-major tf32 operands, SW128_32B is the only available smem layout"): atoms of 32 MN x 4 K rows,
+// 32-byte chunks XORed with (row % 4).  TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t desc_sw128_32b(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
 // kind::tf32 instruction descriptor: D fp32 (1 << 4), A/B tf32 (2 << 7, 2 << 10), majors, N >> 3, M >> 4
 __device__ __forceinline__ uint32_t idesc_tf32(int a_mn, int b_mn, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
@@ -172,8 +178,10 @@ __global__ void __launch_bounds__(TMA_THREADS) tma_gemm_kernel(const __grid_cons
         const uint32_t a_addr = s_u32(smem + s * STAGE), b_addr = a_addr + A_BYTES;
 #pragma unroll
         for (int kk = 0; kk < KB / 8; ++kk) {
-          uint64_t da = MODE == T_TN ? desc_sw128(a_addr + kk * 1024, 4096, 1024) : desc_sw128(a_addr + kk * 32, 16, 1024);
-          uint64_t db = MODE == T_NT ? desc_sw128(b_addr + kk * 32, 16, 1024) : desc_sw128(b_addr + kk * 1024, 4096, 1024);
+          // K-major: +32 B per k-step inside the swizzle span; MN-major: boxes of 32 k-rows x 128 B, 4-row K atoms 512 B
+          // apart (SBO), MN atoms 4096 B apart (LBO), +1024 B per k-step of 8 rows
+          uint64_t da = MODE == T_TN ? desc_sw128_32b(a_addr + kk * 1024, 4096, 512) : desc_sw128(a_addr + kk * 32, 16, 1024);
+          uint64_t db = MODE == T_NT ? desc_sw128(b_addr + kk * 32, 16, 1024) : desc_sw128_32b(b_addr + kk * 1024, 4096, 512);
           umma_tf32(tmem_d, da, db, idesc, (kb | kk) ? 1u : 0u);
         }
         commit_to(&bar_empty[s]);
@@ -242,13 +250,14 @@ __global__ void __launch_bounds__(TMA_THREADS) tma_gemm_kernel(const __grid_cons
 
 // ------------------------------------------------------------------ host side
 static bool make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner,
-                     uint32_t box_outer, bool tf32) {
+                     uint32_t box_outer, bool tf32, bool mn_major = false) {
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {pitch_elems * sizeof(float)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = cuTensorMapEncodeTiled(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims,
-                                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -268,9 +277,9 @@ static int tma_launch(const float* A, const float* B, float* C, float* preact, i
   CUtensorMap ma, mb, mc, mp;
   bool ok = true;
   // A: NT/NN K-major (rows = M, inner = K)  box {32, 128} ; TN MN-major (rows = K, inner = M) box {32, 32}
-  ok &= MODE == T_TN ? make_map(&ma, A, g.M, g.K, lda, 32, 32, true) : make_map(&ma, A, g.K, g.M, lda, KB, UM, true);
+  ok &= MODE == T_TN ? make_map(&ma, A, g.M, g.K, lda, 32, 32, true, true) : make_map(&ma, A, g.K, g.M, lda, KB, UM, true);
   // B: NT K-major (rows = N, inner = K) box {32, BN} ; NN/TN MN-major (rows = K, inner = N) box {32, 32}
-  ok &= MODE == T_NT ? make_map(&mb, B, g.K, g.N, ldb, KB, BN, true) : make_map(&mb, B, g.N, g.K, ldb, 32, 32, true);
+  ok &= MODE == T_NT ? make_map(&mb, B, g.K, g.N, ldb, KB, BN, true) : make_map(&mb, B, g.N, g.K, ldb, 32, 32, true, true);
   ok &= make_map(&mc, C, g.N, g.M, ldc, 32, 32, false);
   ok &= make_map(&mp, preact ? preact : C, g.N, g.M, ldc, 32, 32, false);
   if (!ok) return TMAE_ERR_CUDA;

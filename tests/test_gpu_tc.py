@@ -33,12 +33,7 @@ def tf32(t):
 def _tc_mode(request):
     ops.set_precision("bf16")
     ops.set_option("tma", request.param == "tma_tf32")
-    global bf
-    saved = bf
-    if request.param == "tma_tf32":
-        bf = tf32  # dense GEMMs read TF32 operands in this mode (gathered ones still bf16: see test_tc_sparse_conv)
     yield request.param
-    bf = saved
     ops.set_option("tma", 1)
     ops.set_precision("fp32")
 
@@ -49,8 +44,8 @@ def test_tc_linear_fwd_bwd(m, n, k, _tc_mode):
     # bf16 staging: exact products of rounded operands, only summation order differs -> 1e-4.  TF32 through TMA: the
     # rounding (nearest vs truncation of the 13 dropped bits) is done by the copy engine / tensor core, so allow one
     # TF32 ulp (2^-11 relative per operand) on top: 1e-3.
-    global TOL
     TOL = 1e-3 if _tc_mode == "tma_tf32" else 1e-4
+    bf = tf32 if _tc_mode == "tma_tf32" else globals()["bf"]
     g = torch.Generator().manual_seed(m + n + k)
     x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k ** .5, torch.randn(n, generator=g)
     r = torch.randn(m, n, generator=g)
@@ -71,8 +66,9 @@ def test_tc_linear_fwd_bwd(m, n, k, _tc_mode):
     assert_close(db, dy.double().sum(0), 1e-5, 1e-4 * max(1, m) ** .5, "db")
 
 
-def test_tc_weight_slices():
+def test_tc_weight_slices(_tc_mode):
     """packed in_proj: q/k/v slices addressed by row offset, as the encoder layers do."""
+    bf = tf32 if _tc_mode == "tma_tf32" else globals()["bf"]
     g = torch.Generator().manual_seed(0)
     C, m = 128, 900
     x, w, b = torch.randn(m, C, generator=g), torch.randn(3 * C, C, generator=g) / C ** .5, torch.randn(3 * C, generator=g)
