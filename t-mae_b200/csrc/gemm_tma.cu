@@ -61,9 +61,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   else
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(s_u32(src)), "r"(c0), "r"(c1) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// at most one bulk group (= the previous chunk's stores) may still be reading shared memory
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // SWIZZLE_128B UMMA shared-memory descriptor: start >> 4, LBO >> 4 (bit 16), SBO >> 4 (bit 32), version 1 (bit 46),
@@ -108,62 +108,82 @@ __device__ __forceinline__ void ld_tmem32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ float gelu_erf_t(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
+__device__ __forceinline__ void bar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory");
+}
+
+// PERSISTENT kernel: one CTA per SM walks the tile list (n fastest, so CTAs running together share A through L2); the
+// smem ring runs across tile boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the loads
+// and MMAs of tile i+1 overlap the epilogue (TMEM -> registers -> swizzled smem -> TMA store) of tile i.
 // One stage of the ring: A then B.
 //   K-major operand (rows x 32 fp32): ONE box {32, rows}; 8-row groups 1024 B apart (SBO), k-step = +32 B.
-//   MN-major operand (32 k-rows x cols): cols/32 boxes {32, 32} of 4096 B each (LBO between boxes), k-groups of 8
-//   rows 1024 B apart (SBO), k-step = +1024 B.
+//   MN-major operand (32 k-rows x cols): cols/32 boxes {32, 32} of 4096 B each (LBO between boxes), 4-row K atoms 512 B
+//   apart (SBO), k-step (8 rows) = +1024 B.
 template <int MODE, int BN, int STAGES>
-__global__ void __launch_bounds__(TMA_THREADS) tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                               const __grid_constant__ CUtensorMap map_b,
-                                                               const __grid_constant__ CUtensorMap map_c,
-                                                               const __grid_constant__ CUtensorMap map_p, TmaArgs g) {
+__global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                  const __grid_constant__ CUtensorMap map_b,
+                                                                  const __grid_constant__ CUtensorMap map_c,
+                                                                  const __grid_constant__ CUtensorMap map_p, TmaArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int A_BYTES = UM * KB * 4, B_BYTES = BN * KB * 4, STAGE = A_BYTES + B_BYTES;
   constexpr int EPI_BYTES = 32 * 32 * 4;  // one 32x32 fp32 tile per epilogue warp and buffer
   uint8_t* epi = smem + STAGES * STAGE;   // [4 warps][2 outputs][2 buffers][4096]
-  __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc;
+  __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * UM, n0 = blockIdx.x * BN;
-  const int64_t kbeg = (int64_t)blockIdx.z * g.k_chunk;
-  const int64_t kend = kbeg + g.k_chunk < g.K ? kbeg + g.k_chunk : g.K;
-  const int nkb = (int)((kend - kbeg + KB - 1) / KB);
+  const int m_tiles = (int)((g.M + UM - 1) / UM), n_tiles = (int)((g.N + BN - 1) / BN);
+  const int z_tiles = (int)((g.K + g.k_chunk - 1) / g.k_chunk);
+  const int total = m_tiles * n_tiles * z_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { bar_init(&bar_full[s], 1); bar_init(&bar_empty[s], 1); }
-    bar_init(&bar_acc, 1);
+    for (int b = 0; b < 2; ++b) { bar_init(&bar_acc_full[b], 1); bar_init(&bar_acc_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(BN < 32 ? 32 : BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = tmem_slot;
+  const uint32_t tmem_base = tmem_slot;
+
+  auto decode = [&](int t, int& m0, int& n0, int64_t& kbeg, int& nkb) {
+    int nt = t % n_tiles, rest = t / n_tiles;
+    int mt = rest % m_tiles, z = rest / m_tiles;
+    m0 = mt * UM; n0 = nt * BN;
+    kbeg = (int64_t)z * g.k_chunk;
+    int64_t kend = kbeg + g.k_chunk < g.K ? kbeg + g.k_chunk : g.K;
+    nkb = (int)((kend - kbeg + KB - 1) / KB);
+  };
 
   if (warp == 0) {
     // ---------------- TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, use = kb / STAGES;
-        if (use > 0) bar_wait(&bar_empty[s], (use - 1) & 1);
-        uint8_t* a = smem + s * STAGE;
-        uint8_t* b = a + A_BYTES;
-        const int k0 = (int)(kbeg + (int64_t)kb * KB);
-        bar_expect_tx(&bar_full[s], STAGE);
-        if (MODE == T_TN) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int m0, n0, nkb; int64_t kbeg;
+        decode(t, m0, n0, kbeg, nkb);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES, use = it / STAGES;
+          if (use > 0) bar_wait(&bar_empty[s], (use - 1) & 1);
+          uint8_t* a = smem + s * STAGE;
+          uint8_t* b = a + A_BYTES;
+          const int k0 = (int)(kbeg + (int64_t)kb * KB);
+          bar_expect_tx(&bar_full[s], STAGE);
+          if (MODE == T_TN) {
 #pragma unroll
-          for (int j = 0; j < UM / 32; ++j) tma_load_2d(a + j * 4096, &map_a, m0 + j * 32, k0, &bar_full[s]);
-        } else {
-          tma_load_2d(a, &map_a, k0, m0, &bar_full[s]);
-        }
-        if (MODE == T_NT) {
-          tma_load_2d(b, &map_b, k0, n0, &bar_full[s]);
-        } else {
+            for (int j = 0; j < UM / 32; ++j) tma_load_2d(a + j * 4096, &map_a, m0 + j * 32, k0, &bar_full[s]);
+          } else {
+            tma_load_2d(a, &map_a, k0, m0, &bar_full[s]);
+          }
+          if (MODE == T_NT) {
+            tma_load_2d(b, &map_b, k0, n0, &bar_full[s]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_2d(b + j * 4096, &map_b, n0 + j * 32, k0, &bar_full[s]);
+            for (int j = 0; j < BN / 32; ++j) tma_load_2d(b + j * 4096, &map_b, n0 + j * 32, k0, &bar_full[s]);
+          }
         }
       }
     }
@@ -171,81 +191,99 @@ __global__ void __launch_bounds__(TMA_THREADS) tma_gemm_kernel(const __grid_cons
     // ---------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(MODE == T_TN, MODE != T_NT, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, use = kb / STAGES;
-        bar_wait(&bar_full[s], use & 1);
+      int it = 0, i = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+        int m0, n0, nkb; int64_t kbeg;
+        decode(t, m0, n0, kbeg, nkb);
+        const int buf = i & 1, round = i >> 1;
+        if (round > 0) bar_wait(&bar_acc_empty[buf], (round - 1) & 1);  // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = s_u32(smem + s * STAGE), b_addr = a_addr + A_BYTES;
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES, use = it / STAGES;
+          bar_wait(&bar_full[s], use & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = s_u32(smem + s * STAGE), b_addr = a_addr + A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < KB / 8; ++kk) {
-          // K-major: +32 B per k-step inside the swizzle span; MN-major: boxes of 32 k-rows x 128 B, 4-row K atoms 512 B
-          // apart (SBO), MN atoms 4096 B apart (LBO), +1024 B per k-step of 8 rows
-          uint64_t da = MODE == T_TN ? desc_sw128_32b(a_addr + kk * 1024, 4096, 512) : desc_sw128(a_addr + kk * 32, 16, 1024);
-          uint64_t db = MODE == T_NT ? desc_sw128(b_addr + kk * 32, 16, 1024) : desc_sw128_32b(b_addr + kk * 1024, 4096, 512);
-          umma_tf32(tmem_d, da, db, idesc, (kb | kk) ? 1u : 0u);
+          for (int kk = 0; kk < KB / 8; ++kk) {
+            uint64_t da = MODE == T_TN ? desc_sw128_32b(a_addr + kk * 1024, 4096, 512) : desc_sw128(a_addr + kk * 32, 16, 1024);
+            uint64_t db = MODE == T_NT ? desc_sw128(b_addr + kk * 32, 16, 1024) : desc_sw128_32b(b_addr + kk * 1024, 4096, 512);
+            umma_tf32(tmem_d, da, db, idesc, (kb | kk) ? 1u : 0u);
+          }
+          commit_to(&bar_empty[s]);
         }
-        commit_to(&bar_empty[s]);
-        if (kb == nkb - 1) commit_to(&bar_acc);
+        commit_to(&bar_acc_full[buf]);
       }
     }
   } else {
     // ---------------- epilogue warps: TMEM lane quarter q = warp % 4
     const int q = warp & 3;
-    const int row0 = m0 + q * 32;
-    if (nkb > 0) bar_wait(&bar_acc, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint8_t* my = epi + (warp - 2) * (4 * EPI_BYTES);
     constexpr int CHUNKS = BN / 32;
-    for (int ch = 0; ch < CHUNKS; ++ch) {
-      const int col0 = n0 + ch * 32;
-      if (col0 >= g.N) break;
-      uint32_t r[32];
-      if (nkb > 0) ld_tmem32(tmem_d + ((uint32_t)(q * 32) << 16) + ch * 32, r);
-      else {
+    int i = 0, cnt = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+      int m0, n0, nkb; int64_t kbeg;
+      decode(t, m0, n0, kbeg, nkb);
+      const int buf = i & 1, round = i >> 1;
+      const int row0 = m0 + q * 32;
+      bar_wait(&bar_acc_full[buf], round & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + buf * BN;
+      for (int ch = 0; ch < CHUNKS; ++ch, ++cnt) {
+        const int col0 = n0 + ch * 32;
+        uint32_t r[32];
+        ld_tmem32(tmem_d + ((uint32_t)(q * 32) << 16) + ch * 32, r);
+        if (ch == CHUNKS - 1) {  // this warp has read everything it needs from the accumulator
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) bar_arrive(&bar_acc_empty[buf]);
+        }
+        if (col0 >= g.N) continue;
+        uint8_t* tile_c = my + (cnt & 1) * EPI_BYTES;
+        uint8_t* tile_p = my + (2 + (cnt & 1)) * EPI_BYTES;
+        if (cnt >= 2) {  // the store that read this buffer two chunks ago must have finished reading it
+          if (lane == 0) tma_store_wait_read1();
+          __syncwarp();
+        }
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-      uint8_t* tile_c = my + (ch & 1) * EPI_BYTES;
-      uint8_t* tile_p = my + (2 + (ch & 1)) * EPI_BYTES;
-      if (ch >= 2) {  // the store that read this buffer two chunks ago must have finished reading it
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
-      }
-      float v[32];
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          if (g.bias && col0 + j < g.N) x += __ldg(g.bias + col0 + j);
+          v[j] = x;
+        }
+        // swizzled (128B) tile: 16-byte chunk c of row `lane` lives at chunk position c ^ (lane & 7)
+        if (g.has_preact) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]);
-        if (g.bias && col0 + j < g.N) x += __ldg(g.bias + col0 + j);
-        v[j] = x;
-      }
-      // swizzled (128B) tile: 16-byte chunk c of row `lane` lives at chunk position c ^ (lane & 7)
-      if (g.has_preact) {
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(tile_p + lane * 128 + ((c ^ (lane & 7)) * 16)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+        if (g.act == TMAE_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_t(v[j]);
+        } else if (g.act == TMAE_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<float4*>(tile_p + lane * 128 + ((c ^ (lane & 7)) * 16)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-      }
-      if (g.act == TMAE_ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_t(v[j]);
-      } else if (g.act == TMAE_ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<float4*>(tile_c + lane * 128 + ((c ^ (lane & 7)) * 16)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0 && row0 < g.M) {
-        tma_store_2d(&map_c, tile_c, col0, row0, g.reduce_add != 0);
-        if (g.has_preact) tma_store_2d(&map_p, tile_p, col0, row0, false);
+          *reinterpret_cast<float4*>(tile_c + lane * 128 + ((c ^ (lane & 7)) * 16)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (row0 < g.M) {
+            tma_store_2d(&map_c, tile_c, col0, row0, g.reduce_add != 0);
+            if (g.has_preact) tma_store_2d(&map_p, tile_p, col0, row0, false);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // one group per chunk, even when nothing was stored
+        }
       }
     }
     if (lane == 0) tma_store_wait_all();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN < 32 ? 32 : BN) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
 }
 
 // ------------------------------------------------------------------ host side
@@ -267,7 +305,7 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 template <int MODE, int BN>
 static int tma_launch(const float* A, const float* B, float* C, float* preact, int64_t lda, int64_t ldb, int64_t ldc, TmaArgs g, int splits,
                       cudaStream_t s) {
-  constexpr int STAGES = BN == 256 ? 3 : 4;
+  constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
   if (g.M <= 0 || g.N <= 0) return 0;
   if (splits < 1) splits = 1;
   g.k_chunk = align_up((g.K + splits - 1) / splits, KB);
@@ -294,7 +332,8 @@ static int tma_launch(const float* A, const float* B, float* C, float* preact, i
   static const char* names[3] = {"tma_gemm_nt", "tma_gemm_nn", "tma_gemm_tn"};
   double c_el = (double)g.M * g.N * (1.0 + (g.reduce_add && z == 1 ? 1.0 : 0.0) + (preact ? 1.0 : 0.0));
   ProfScope prof(names[MODE], 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + c_el), s);
-  dim3 grid((unsigned)cdiv(g.N, BN), (unsigned)cdiv(g.M, UM), (unsigned)z);
+  int64_t tiles = (int64_t)cdiv(g.N, BN) * cdiv(g.M, UM) * z;
+  dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
   kern<<<grid, TMA_THREADS, smem, s>>>(ma, mb, mc, mp, g);
   return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
 }
