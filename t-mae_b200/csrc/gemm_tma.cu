@@ -2,8 +2,8 @@
 // consumed as TF32 (kind::tf32, fp32 accumulate in TMEM), so no thread ever touches an operand byte:
 //   warp 0      TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B boxes) -> STAGES-deep shared ring, mbarrier tx
 //   warp 1      MMA issuer     tcgen05.mma.kind::tf32, M=128, N=BN, K=8 per instruction; tcgen05.commit frees stages
-//   warps 2..5  epilogue       tcgen05.ld (lane = row) -> bias / GELU / pre-activation copy -> swizzled shared tile
-//                              -> TMA store (or TMA reduce-add for C += and for the split reduction of dW)
+//   warps 2..5  epilogue       tcgen05.ld (lane = row) -> bias / GELU / pre-activation copy -> 128-bit stores of the
+//                              lane's 128-byte row segment (vector atomics for C += and the split reduction of dW)
 // Modes: NT  C[m,n] = sum_k A[m,k] W[n,k]   (A, B K-major)            linear forward
 //        NN  C[m,n] = sum_k A[m,k] B[k,n]   (A K-major, B MN-major)   linear backward-data
 //        TN  C[m,n] = sum_k A[k,m] B[k,n]   (A, B MN-major)           linear backward-weight, split over k
@@ -24,6 +24,7 @@ enum TmaMode { T_NT = 0, T_NN = 1, T_TN = 2 };
 struct TmaArgs {
   int64_t M, N, K;
   const float* bias;
+  float* C; float* P; int64_t ldc;   // output, optional pre-activation copy
   int act, reduce_add, has_preact;
   int64_t k_chunk;
 };
@@ -121,13 +122,9 @@ __device__ __forceinline__ void bar_arrive(uint64_t* b) {
 //   apart (SBO), k-step (8 rows) = +1024 B.
 template <int MODE, int BN, int STAGES>
 __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                                  const __grid_constant__ CUtensorMap map_b,
-                                                                  const __grid_constant__ CUtensorMap map_c,
-                                                                  const __grid_constant__ CUtensorMap map_p, TmaArgs g) {
+                                                                  const __grid_constant__ CUtensorMap map_b, TmaArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int A_BYTES = UM * KB * 4, B_BYTES = BN * KB * 4, STAGE = A_BYTES + B_BYTES;
-  constexpr int EPI_BYTES = 32 * 32 * 4;  // one 32x32 fp32 tile per epilogue warp and buffer
-  uint8_t* epi = smem + STAGES * STAGE;   // [4 warps][2 outputs][2 buffers][4096]
   __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -216,21 +213,24 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
       }
     }
   } else {
-    // ---------------- epilogue warps: TMEM lane quarter q = warp % 4
+    // ---------------- epilogue warps: TMEM lane quarter q = warp % 4.  tcgen05.ld gives every lane one output row
+    // (32 consecutive fp32 = one 128-byte line per chunk), which it writes straight to HBM with 128-bit stores: the
+    // L2 merges the 16-byte pieces of a line, and there is no shared-memory staging, proxy fence or bulk-store wait on
+    // the critical path (measured: the TMA-store variant spent ~2 us per 32x32 chunk waiting on them).
     const int q = warp & 3;
-    uint8_t* my = epi + (warp - 2) * (4 * EPI_BYTES);
     constexpr int CHUNKS = BN / 32;
-    int i = 0, cnt = 0;
+    int i = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
       int m0, n0, nkb; int64_t kbeg;
       decode(t, m0, n0, kbeg, nkb);
       const int buf = i & 1, round = i >> 1;
-      const int row0 = m0 + q * 32;
+      const int64_t row = m0 + q * 32 + lane;
       bar_wait(&bar_acc_full[buf], round & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + buf * BN;
-      for (int ch = 0; ch < CHUNKS; ++ch, ++cnt) {
+      for (int ch = 0; ch < CHUNKS; ++ch) {
         const int col0 = n0 + ch * 32;
+        const float bl = (g.bias && col0 + lane < g.N) ? __ldg(g.bias + col0 + lane) : 0.f;  // in flight during the TMEM load
         uint32_t r[32];
         ld_tmem32(tmem_d + ((uint32_t)(q * 32) << 16) + ch * 32, r);
         if (ch == CHUNKS - 1) {  // this warp has read everything it needs from the accumulator
@@ -239,24 +239,16 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
           if (lane == 0) bar_arrive(&bar_acc_empty[buf]);
         }
         if (col0 >= g.N) continue;
-        uint8_t* tile_c = my + (cnt & 1) * EPI_BYTES;
-        uint8_t* tile_p = my + (2 + (cnt & 1)) * EPI_BYTES;
-        if (cnt >= 2) {  // the store that read this buffer two chunks ago must have finished reading it
-          if (lane == 0) tma_store_wait_read1();
-          __syncwarp();
-        }
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          if (g.bias && col0 + j < g.N) x += __ldg(g.bias + col0 + j);
-          v[j] = x;
-        }
-        // swizzled (128B) tile: 16-byte chunk c of row `lane` lives at chunk position c ^ (lane & 7)
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
+        if (row >= g.M) continue;
+        float* crow = g.C + row * g.ldc + col0;
         if (g.has_preact) {
+          float* prow = g.P + row * g.ldc + col0;
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4*>(tile_p + lane * 128 + ((c ^ (lane & 7)) * 16)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            if (col0 + 4 * c < g.N) *reinterpret_cast<float4*>(prow + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
         if (g.act == TMAE_ACT_GELU) {
 #pragma unroll
@@ -265,21 +257,17 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
+        if (g.reduce_add) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<float4*>(tile_c + lane * 128 + ((c ^ (lane & 7)) * 16)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          if (row0 < g.M) {
-            tma_store_2d(&map_c, tile_c, col0, row0, g.reduce_add != 0);
-            if (g.has_preact) tma_store_2d(&map_p, tile_p, col0, row0, false);
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // one group per chunk, even when nothing was stored
+          for (int c = 0; c < 8; ++c)
+            if (col0 + 4 * c < g.N) atomicAdd(reinterpret_cast<float4*>(crow + 4 * c), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (col0 + 4 * c < g.N) *reinterpret_cast<float4*>(crow + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
       }
     }
-    if (lane == 0) tma_store_wait_all();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -305,24 +293,23 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 template <int MODE, int BN>
 static int tma_launch(const float* A, const float* B, float* C, float* preact, int64_t lda, int64_t ldb, int64_t ldc, TmaArgs g, int splits,
                       cudaStream_t s) {
-  constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
+  constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   if (g.M <= 0 || g.N <= 0) return 0;
   if (splits < 1) splits = 1;
   g.k_chunk = align_up((g.K + splits - 1) / splits, KB);
   int z = (int)((g.K + g.k_chunk - 1) / g.k_chunk);
   if (z < 1) z = 1;
   if (z > 1) g.reduce_add = 1;
-  CUtensorMap ma, mb, mc, mp;
+  CUtensorMap ma, mb;
   bool ok = true;
   // A: NT/NN K-major (rows = M, inner = K)  box {32, 128} ; TN MN-major (rows = K, inner = M) box {32, 32}
   ok &= MODE == T_TN ? make_map(&ma, A, g.M, g.K, lda, 32, 32, true, true) : make_map(&ma, A, g.K, g.M, lda, KB, UM, true);
   // B: NT K-major (rows = N, inner = K) box {32, BN} ; NN/TN MN-major (rows = K, inner = N) box {32, 32}
   ok &= MODE == T_NT ? make_map(&mb, B, g.K, g.N, ldb, KB, BN, true) : make_map(&mb, B, g.N, g.K, ldb, 32, 32, true, true);
-  ok &= make_map(&mc, C, g.N, g.M, ldc, 32, 32, false);
-  ok &= make_map(&mp, preact ? preact : C, g.N, g.M, ldc, 32, 32, false);
   if (!ok) return TMAE_ERR_CUDA;
   g.has_preact = preact != nullptr;
-  size_t smem = (size_t)STAGES * (UM * KB * 4 + BN * KB * 4) + 4 * 4 * 4096 + 1024;
+  g.C = C; g.P = preact; g.ldc = ldc;
+  size_t smem = (size_t)STAGES * (UM * KB * 4 + BN * KB * 4) + 1024;
   auto kern = tma_gemm_kernel<MODE, BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -334,7 +321,7 @@ static int tma_launch(const float* A, const float* B, float* C, float* preact, i
   ProfScope prof(names[MODE], 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + c_el), s);
   int64_t tiles = (int64_t)cdiv(g.N, BN) * cdiv(g.M, UM) * z;
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
-  kern<<<grid, TMA_THREADS, smem, s>>>(ma, mb, mc, mp, g);
+  kern<<<grid, TMA_THREADS, smem, s>>>(ma, mb, g);
   return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
 }
 
