@@ -134,6 +134,8 @@ TMAE_API int tmae_linear_fwd(const float* x, const float* w, const float* bias, 
                     int64_t m, int64_t n, int64_t k, int32_t act, int32_t precision, void* stream);
 TMAE_API int tmae_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int32_t accumulate,
                          int32_t precision, void* stream);
+TMAE_API int tmae_linear_bwd_data_gelu(const float* dy, const float* w, const float* preact, float* dx, int64_t m, int64_t n, int64_t k,
+                              int32_t precision, void* stream); /* dx = (dy w) * gelu'(preact) */
 TMAE_API int tmae_linear_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int64_t m, int64_t n, int64_t k,
                            int32_t precision, void* stream);
 TMAE_API int tmae_colsum(const float* x, float* out, int64_t rows, int32_t cols, void* stream);
@@ -185,6 +187,10 @@ TMAE_API int tmae_segment_max_bwd(const float* dout, const int32_t* argmax, int6
 TMAE_API int tmae_densify_nhwc(const float* rows, const int32_t* indices, int64_t m, int32_t c, int32_t batch, int32_t y, int32_t x,
                       float* dense, int32_t zero_fill, void* stream);
 TMAE_API int tmae_gather_nhwc(const float* dense, const int32_t* indices, int64_t m, int32_t c, int32_t y, int32_t x, float* rows, void* stream);
+/* same with a bf16 dense map (the cuDNN decoder runs bf16 channels-last in throughput mode) */
+TMAE_API int tmae_densify_nhwc_bf16(const float* rows, const int32_t* indices, int64_t m, int32_t c, int32_t batch, int32_t y, int32_t x,
+                           void* dense, int32_t zero_fill, void* stream);
+TMAE_API int tmae_gather_nhwc_bf16(const void* dense, const int32_t* indices, int64_t m, int32_t c, int32_t y, int32_t x, float* rows, void* stream);
 TMAE_API int tmae_gather_rows(const float* src, const int32_t* sel, int64_t m, int32_t c, float* out, void* stream);
 TMAE_API int tmae_scatter_rows(const float* rows, const int32_t* sel, int64_t m, int32_t c, float* dst, void* stream);
 

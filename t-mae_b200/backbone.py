@@ -241,11 +241,13 @@ class SiamWCA(nn.Module):
 
     def _dense(self, sps):
         de, out = getattr(self, self._deblocks_name), getattr(self, self._conv_out_name)
-        maps = [sps[src].dense() for src in self.model_cfg["FEATURES_SOURCE"]]
         if self.decoder_autocast is not None:
+            # throughput mode: the BEV maps are written directly in bf16 channels-last, the cuDNN decoder runs under
+            # autocast and `spatial_features` stays bf16 (the reference's AMP run returns fp16 here)
+            maps = [sps[src].dense(self.decoder_autocast) for src in self.model_cfg["FEATURES_SOURCE"]]
             with torch.autocast("cuda", dtype=self.decoder_autocast):
-                y = out(torch.cat([de[i](m) for i, m in enumerate(maps)], 1))
-            return y.float()
+                return out(torch.cat([de[i](m) for i, m in enumerate(maps)], 1))
+        maps = [sps[src].dense() for src in self.model_cfg["FEATURES_SOURCE"]]
         return out(torch.cat([de[i](m) for i, m in enumerate(maps)], 1))
 
     def _strides(self, sps):

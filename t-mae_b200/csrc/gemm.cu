@@ -224,7 +224,8 @@ bool tma_linear_fwd_ok(const float* x, const float* w, const float* y, const flo
 int tma_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* preact, int64_t m, int64_t n, int64_t k, int act,
                    cudaStream_t s);
 bool tma_linear_bwd_data_ok(const float* dy, const float* w, const float* dx, int64_t m, int64_t n, int64_t k);
-int tma_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int accumulate, cudaStream_t s);
+int tma_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int accumulate, const float* gelu_pre,
+                        cudaStream_t s);
 bool tma_linear_bwd_weight_ok(const float* dy, const float* x, const float* dw, int64_t m, int64_t n, int64_t k);
 int tma_linear_bwd_weight(const float* dy, const float* x, float* dw, int64_t m, int64_t n, int64_t k, cudaStream_t s);
 // thread-staged bf16 tensor-core path (gemm_tc.cu)
@@ -279,7 +280,7 @@ int tmae_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, 
                          int32_t precision, void* stream) {
   TMAE_CHECK_PREC(precision);
   if (precision == TMAE_PREC_BF16 && g_use_tma && tma_linear_bwd_data_ok(dy, w, dx, m, n, k)) {
-    if (tma_linear_bwd_data(dy, w, dx, m, n, k, accumulate, (cudaStream_t)stream)) { set_error("tmae_linear_bwd_data: TMA launch failed"); return TMAE_ERR_CUDA; }
+    if (tma_linear_bwd_data(dy, w, dx, m, n, k, accumulate, nullptr, (cudaStream_t)stream)) { set_error("tmae_linear_bwd_data: TMA launch failed"); return TMAE_ERR_CUDA; }
     return 0;
   }
   if (precision == TMAE_PREC_BF16 && tc_linear_bwd_data_ok(m, n, k)) {
@@ -291,6 +292,25 @@ int tmae_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, 
   g.A = dy; g.B = w; g.C = dx; g.M = m; g.N = k; g.K = n; g.lda = n; g.ldb = k; g.ldc = k; g.accumulate = accumulate;
   if (launch<A_KCONTIG, B_NCONTIG>(g, 1, (cudaStream_t)stream)) { set_error("tmae_linear_bwd_data: launch failed"); return TMAE_ERR_CUDA; }
   return 0;
+}
+
+}  // extern "C"
+
+extern "C" int tmae_gelu_bwd(const float* dy, const float* preact, float* dx, int64_t n, void* stream);
+
+extern "C" {
+
+/* dx = (dy w) * gelu'(preact): backward through  h = gelu(preact), f = h w2^T  in one pass (sst_basic_block.py:81) */
+int tmae_linear_bwd_data_gelu(const float* dy, const float* w, const float* preact, float* dx, int64_t m, int64_t n, int64_t k,
+                              int32_t precision, void* stream) {
+  TMAE_CHECK_PREC(precision);
+  if (precision == TMAE_PREC_BF16 && g_use_tma && tma_linear_bwd_data_ok(dy, w, dx, m, n, k) && ((uintptr_t)preact & 15) == 0) {
+    if (tma_linear_bwd_data(dy, w, dx, m, n, k, 0, preact, (cudaStream_t)stream)) { set_error("tmae_linear_bwd_data_gelu: TMA launch failed"); return TMAE_ERR_CUDA; }
+    return 0;
+  }
+  int r = tmae_linear_bwd_data(dy, w, dx, m, n, k, 0, precision, stream);
+  if (r) return r;
+  return tmae_gelu_bwd(dx, preact, dx, m * k, stream);
 }
 
 static int pick_splits(int64_t out_tiles, int64_t k) {

@@ -25,6 +25,7 @@ struct TmaArgs {
   int64_t M, N, K;
   const float* bias;
   float* C; float* P; int64_t ldc;   // output, optional pre-activation copy
+  const float* gelu_pre;             // optional: multiply the result by gelu'(gelu_pre[m,n])  (fused GELU backward)
   int act, reduce_add, has_preact;
   int64_t k_chunk;
 };
@@ -108,6 +109,9 @@ __device__ __forceinline__ void ld_tmem32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ float gelu_erf_t(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_t(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+}
 
 __device__ __forceinline__ void bar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory");
@@ -250,6 +254,15 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
           for (int c = 0; c < 8; ++c)
             if (col0 + 4 * c < g.N) *reinterpret_cast<float4*>(prow + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
+        if (g.gelu_pre) {
+          const float* hrow = g.gelu_pre + row * g.ldc + col0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (col0 + 4 * c >= g.N) break;
+            float4 h = __ldg(reinterpret_cast<const float4*>(hrow + 4 * c));
+            v[4 * c] *= gelu_grad_t(h.x); v[4 * c + 1] *= gelu_grad_t(h.y); v[4 * c + 2] *= gelu_grad_t(h.z); v[4 * c + 3] *= gelu_grad_t(h.w);
+          }
+        }
         if (g.act == TMAE_ACT_GELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf_t(v[j]);
@@ -275,13 +288,30 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------ host side
+// cuTensorMapEncodeTiled is fetched through the runtime (cudaGetDriverEntryPoint) so that the library has no link-time
+// dependency on libcuda.so.1 and still loads on a machine without a driver (build / ABI checks on CPU boxes).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
 static bool make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner,
                      uint32_t box_outer, bool tf32, bool mn_major = false) {
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {pitch_elems * sizeof(float)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = cuTensorMapEncodeTiled(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims,
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  CUresult r = enc(m, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims,
                                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                       mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -346,9 +376,10 @@ int tma_linear_fwd(const float* x, const float* w, const float* bias, float* y, 
 bool tma_linear_bwd_data_ok(const float* dy, const float* w, const float* dx, int64_t m, int64_t n, int64_t k) {
   return n % 4 == 0 && k % 4 == 0 && aligned16(dy) && aligned16(w) && aligned16(dx);
 }
-int tma_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int accumulate, cudaStream_t s) {
+int tma_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int accumulate, const float* gelu_pre,
+                        cudaStream_t s) {
   TmaArgs g{};
-  g.M = m; g.N = k; g.K = n; g.reduce_add = accumulate;
+  g.M = m; g.N = k; g.K = n; g.reduce_add = accumulate; g.gelu_pre = gelu_pre;
   return tma_dispatch<T_NN>(dy, w, dx, nullptr, n, k, k, g, 1, s);
 }
 bool tma_linear_bwd_weight_ok(const float* dy, const float* x, const float* dw, int64_t m, int64_t n, int64_t k) {

@@ -137,8 +137,7 @@ int tmae_encoder_layer_bwd(const float* dy, const float* x, const float* x_kv, c
   // LN2 -> FFN -> LN1
   TRY(tmae_add_layernorm_bwd(dy, s.x1, s.f, nullptr, P->ln2_g, s.m2, s.r2, dx1, nullptr, g_ln2_g, g_ln2_b, m_q, c, stream));
   TRY(tmae_linear_bwd_weight(dx1, s.h, g_w2, g_b2, m_q, c, ff, precision, stream));
-  TRY(tmae_linear_bwd_data(dx1, P->w2, dh, m_q, c, ff, 0, precision, stream));
-  TRY(tmae_gelu_bwd(dh, s.hpre, dh, m_q * (int64_t)ff, stream));
+  TRY(tmae_linear_bwd_data_gelu(dx1, P->w2, s.hpre, dh, m_q, c, ff, precision, stream));
   TRY(tmae_linear_bwd_weight(dh, s.x1, g_w1, g_b1, m_q, ff, c, precision, stream));
   TRY(tmae_linear_bwd_data(dh, P->w1, dx1, m_q, ff, c, 1, precision, stream));  // dx1 = grad wrt x1 (both branches)
   TRY(tmae_add_layernorm_bwd(dx1, x, s.a, T->rowmask, P->ln1_g, s.m1, s.r1, dx, T->rowmask ? da : nullptr, g_ln1_g, g_ln1_b, m_q, c, stream));

@@ -3,6 +3,8 @@
 // All are HBM-bound: one pass over the rows, coalesced along channels, warp per row where a row
 // reduction is needed.  Replaces ATen elementwise/reduction kernels, torch_scatter.scatter_max
 // (temporal_dyn_vfe.py:113) and SparseConvTensor.dense() (SiamWCA_MAE.py:235).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace tmae {
@@ -233,6 +235,30 @@ __global__ void rows_dense_kernel(float4* __restrict__ rows, float4* __restrict_
   else rows[t] = dense[d];
 }
 
+// bf16 dense map variant (the cuDNN decoder runs in bf16 channels-last): rows stay fp32
+__global__ void rows_dense_bf16_kernel(float4* __restrict__ rows, uint2* __restrict__ dense, const int* __restrict__ idx, int64_t m,
+                                       int c4, int Y, int X, int mode) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m * c4) return;
+  int64_t i = t / c4;
+  int c = (int)(t - i * c4);
+  const int* p = idx + i * 3;
+  int64_t d = (((int64_t)p[0] * Y + p[1]) * X + p[2]) * c4 + c;
+  if (mode == 0) {
+    float4 v = rows[t];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    dense[d] = o;
+  } else {
+    uint2 o = dense[d];
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&o.x), b = *reinterpret_cast<__nv_bfloat162*>(&o.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    rows[t] = make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+}
+
 // rows[i,:] (+)= src[sel[i],:]  /  dst[sel[i],:] = rows[i,:]   (row gather / scatter by index list)
 __global__ void rows_index_kernel(float4* __restrict__ a, float4* __restrict__ b, const int* __restrict__ sel, int64_t m, int c4,
                                   int mode) {
@@ -383,6 +409,28 @@ int tmae_gather_nhwc(const float* dense, const int32_t* indices, int64_t m, int3
   TMAE_CHECK_ARG(c % 4 == 0, "channels must be a multiple of 4");
   if (m <= 0) return 0;
   rows_dense_kernel<<<cdiv(m * (c / 4), 256), 256, 0, (cudaStream_t)stream>>>((float4*)rows, (float4*)dense, indices, m, c / 4, y, x, 1);
+  TMAE_CHECK_LAUNCH();
+  return 0;
+}
+
+/* bf16 dense map variants (dense is (B,Y,X,C) bf16) */
+int tmae_densify_nhwc_bf16(const float* rows, const int32_t* indices, int64_t m, int32_t c, int32_t batch, int32_t y, int32_t x,
+                           void* dense, int32_t zero_fill, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  TMAE_CHECK_ARG(c % 4 == 0, "channels must be a multiple of 4");
+  if (zero_fill) TMAE_CUDA(cudaMemsetAsync(dense, 0, (size_t)batch * y * x * c * 2, s));
+  if (m <= 0) return 0;
+  ProfScope prof("densify_bf16", 0, 6.0 * m * c + (zero_fill ? 2.0 * batch * y * x * c : 0), s);
+  rows_dense_bf16_kernel<<<cdiv(m * (c / 4), 256), 256, 0, s>>>((float4*)rows, (uint2*)dense, indices, m, c / 4, y, x, 0);
+  TMAE_CHECK_LAUNCH();
+  return 0;
+}
+
+int tmae_gather_nhwc_bf16(const void* dense, const int32_t* indices, int64_t m, int32_t c, int32_t y, int32_t x, float* rows, void* stream) {
+  TMAE_CHECK_ARG(c % 4 == 0, "channels must be a multiple of 4");
+  if (m <= 0) return 0;
+  ProfScope prof("gather_bf16", 0, 6.0 * m * c, (cudaStream_t)stream);
+  rows_dense_bf16_kernel<<<cdiv(m * (c / 4), 256), 256, 0, (cudaStream_t)stream>>>((float4*)rows, (uint2*)dense, indices, m, c / 4, y, x, 1);
   TMAE_CHECK_LAUNCH();
   return 0;
 }

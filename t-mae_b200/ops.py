@@ -374,18 +374,22 @@ def segment_max_bwd(dout, arg, n_points):
     return dx
 
 
-def densify_nhwc(rows, indices, batch, Y, X):
+def densify_nhwc(rows, indices, batch, Y, X, dtype=F32):
+    """(B,Y,X,C) map of dtype fp32 or bf16 from fp32 rows."""
     m, c = rows.shape
-    dense = torch.empty(batch, Y, X, c, dtype=F32, device=rows.device)
-    _call("densify_nhwc", _p(rows, F32), _p(indices, I32), m, c, batch, Y, X, _p(dense), 1, _stream())
+    dense = torch.empty(batch, Y, X, c, dtype=dtype, device=rows.device)
+    name = "densify_nhwc" if dtype == F32 else "densify_nhwc_bf16"
+    _call(name, _p(rows, F32), _p(indices, I32), m, c, batch, Y, X, _p(dense), 1, _stream())
     return dense
 
 
 def gather_nhwc(dense, indices):
+    """fp32 rows from a (B,Y,X,C) fp32 or bf16 map."""
     _, Y, X, c = dense.shape
     m = indices.shape[0]
     rows = torch.empty(m, c, dtype=F32, device=dense.device)
-    _call("gather_nhwc", _p(dense, F32), _p(indices, I32), m, c, Y, X, _p(rows), _stream())
+    name = "gather_nhwc" if dense.dtype == F32 else "gather_nhwc_bf16"
+    _call(name, _p(dense), _p(indices, I32), m, c, Y, X, _p(rows), _stream())
     return rows
 
 

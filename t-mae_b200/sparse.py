@@ -16,28 +16,28 @@ from .vfe import bn_relu
 
 class _DensifyFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rows, indices, batch, Y, X):
+    def forward(ctx, rows, indices, batch, Y, X, dtype):
         ctx.save_for_backward(indices)
-        return ops.densify_nhwc(rows.contiguous(), indices, batch, Y, X)
+        return ops.densify_nhwc(rows.contiguous(), indices, batch, Y, X, dtype)
 
     @staticmethod
     def backward(ctx, d):
         (indices,) = ctx.saved_tensors
-        return ops.gather_nhwc(d.contiguous(), indices), None, None, None, None
+        return ops.gather_nhwc(d.contiguous(), indices), None, None, None, None, None
 
 
 class _GatherNhwcFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dense, indices):
         ctx.save_for_backward(indices)
-        ctx.shape = dense.shape
+        ctx.shape, ctx.dtype = dense.shape, dense.dtype
         return ops.gather_nhwc(dense, indices)
 
     @staticmethod
     def backward(ctx, drows):
         (indices,) = ctx.saved_tensors
         B, Y, X, _ = ctx.shape
-        return ops.densify_nhwc(drows.contiguous(), indices, B, Y, X), None
+        return ops.densify_nhwc(drows.contiguous(), indices, B, Y, X, ctx.dtype), None
 
 
 def gather_bev(spatial_features, indices):
@@ -56,10 +56,10 @@ class SparseConvTensor:
     def replace_feature(self, f):
         return SparseConvTensor(f, self.indices, self.spatial_shape, self.batch_size)
 
-    def dense(self):
-        """(B, C, Y, X), stored channels-last."""
+    def dense(self, dtype=torch.float32):
+        """(B, C, Y, X), stored channels-last; dtype fp32 or bf16 (features stay fp32)."""
         Y, X = self.spatial_shape
-        return _DensifyFn.apply(self.features, self.indices, self.batch_size, Y, X).permute(0, 3, 1, 2)
+        return _DensifyFn.apply(self.features, self.indices, self.batch_size, Y, X, dtype).permute(0, 3, 1, 2)
 
 
 class _SparseConvFn(torch.autograd.Function):
