@@ -128,7 +128,8 @@ TMAE_API int tmae_window_partition(const int32_t* coords_a, int64_t m_a, const i
  * Replace torch.nn.functional.linear at cosine_msa.py:57-62,431, sst_basic_block.py:81, wca_block.py:99,
  * network_utils.py:30, SiamWCA_MAE.py:117-119 and their autograd backward.  w is (n, k) row-major
  * (torch Linear layout).  y = act(x w^T + bias) + residual ; preact (nullable) receives x w^T + bias. */
-/* options: "tma" (default 1) -- 0 routes the dense tensor-core GEMMs to the thread-staged bf16 kernel */
+/* options: "tma" (default 1) -- 0 routes the dense tensor-core GEMMs to the thread-staged bf16 kernel;
+ * "attn_tc" (default 0; the layer entry points set it from `precision`) -- windows above 16 tokens on mma.sync TF32 */
 TMAE_API int tmae_set_option(const char* name, int32_t value);
 TMAE_API int tmae_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact,
                     int64_t m, int64_t n, int64_t k, int32_t act, int32_t precision, void* stream);

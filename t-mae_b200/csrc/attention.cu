@@ -346,6 +346,27 @@ static int launch_large(const AttnArgs& a, const int* begin, const int* end, int
   return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
 }
 
+// tensor-core path for windows with more than 16 tokens (attention_mma.cu)
+struct AttnMmaArgs {
+  const float* q; const float* k; const float* v; float* o; float* lse;
+  const int* qtok; const int* qcnt; const int* ktok; const int* kcnt;
+  const int* n_win; const int* begin;
+  const float* tau; float tau_min;
+  int C, H;
+  const float* dout; float* dq; float* dk; float* dv; float* dtau;
+};
+int attn_mma_fwd(const AttnMmaArgs& a, int hd, int64_t max_windows, cudaStream_t s);
+int attn_mma_bwd(const AttnMmaArgs& a, int hd, int64_t max_windows, cudaStream_t s);
+bool g_attn_tc = false;  // set by the layer entry points (tensor-core precision mode) or tmae_set_option("attn_tc", 1)
+
+static AttnMmaArgs to_mma(const AttnArgs& a) {
+  AttnMmaArgs m{};
+  m.q = a.q; m.k = a.k; m.v = a.v; m.o = a.o; m.lse = a.lse; m.qtok = a.qtok; m.qcnt = a.qcnt; m.ktok = a.ktok; m.kcnt = a.kcnt;
+  m.n_win = a.n_win; m.begin = a.small_end; m.tau = a.tau; m.tau_min = a.tau_min; m.C = a.C; m.H = a.H;
+  m.dout = a.dout; m.dq = a.dq; m.dk = a.dk; m.dv = a.dv; m.dtau = a.dtau;
+  return m;
+}
+
 template <int HD, int MODE>
 static int launch_pass(const AttnArgs& a, int64_t max_windows, cudaStream_t s) {
   static const char* names[3] = {"attn_fwd", "attn_bwd_dq", "attn_bwd_dkv"};
@@ -356,6 +377,11 @@ static int launch_pass(const AttnArgs& a, int64_t max_windows, cudaStream_t s) {
   // small windows: 8 warps per CTA, one window per warp per iteration
   int64_t warps = max_windows < (int64_t)kNumSMs * 48 ? max_windows : (int64_t)kNumSMs * 48;
   attn_small_kernel<HD, MODE><<<cdiv(warps * 32, ATT_THREADS), ATT_THREADS, 0, s>>>(a);
+  if (g_attn_tc) {  // windows above 16 tokens on mma.sync TF32: forward, and ONE fused backward pass (dQ, dK, dV, dtau)
+    if (MODE == 0) return attn_mma_fwd(to_mma(a), HD, max_windows, s);
+    if (MODE == 1) return attn_mma_bwd(to_mma(a), HD, max_windows, s);
+    return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
+  }
   int r = launch_large<HD, MODE, 32>(a, a.small_end, a.mid_end, max_windows, s);
   if (!r) r = launch_large<HD, MODE, 64>(a, a.mid_end, a.n_win, max_windows, s);
   return r;

@@ -1,0 +1,357 @@
+// Tensor-core attention for the windows with more than 16 tokens (stages 2-3 of a lidar scan are dense: these windows
+// hold most of the query-key pairs).  One 128-thread CTA per (window, head); warp w owns the 16-row strip w of the
+// 64-slot window.  Everything a (window, head) needs -- Q_hat, K_hat, V (and dO) head slices, <= 64 x 32 fp32 each --
+// is gathered once through the partition's token table into shared memory (TF32-rounded, rows padded so that the
+// mma.sync fragment loads are bank-conflict free), and S = Q_hat K_hat^T, P = softmax, O = P V run on
+// mma.sync.m16n8k8 TF32 with fp32 accumulation; the softmax and the C-fragment -> A-fragment re-layout of P stay in
+// registers (quad shuffles).  Backward is ONE pass: each warp first acts on its query strip (S, P, dP = dO V^T,
+// dS -> dQ, dtau) and then on its key strip with the roles transposed (S^T, P^T, dP^T -> dV = P^T dO, dK = dS^T Q_hat),
+// so no cross-warp reduction is needed.  tcgen05 is not used here on purpose: the MMAs are 16x8x8..64x64x32, far below
+// a UMMA tile, and every product feeds a register-resident softmax.
+// Reference: cosine_msa.py:114-176 (the per-window bmm / softmax / bmm) and its autograd backward.
+#include "common.cuh"
+
+namespace tmae {
+
+constexpr int MT = TMAE_WIN_TOKENS;  // 64 slots
+constexpr int MMA_THREADS = 128;
+
+struct AttnMmaArgs {
+  const float* q; const float* k; const float* v; float* o; float* lse;
+  const int* qtok; const int* qcnt; const int* ktok; const int* kcnt;
+  const int* n_win; const int* begin;   // windows [*begin, *n_win)
+  const float* tau; float tau_min;
+  int C, H;
+  const float* dout; float* dq; float* dk; float* dv; float* dtau;
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+// C fragment (rows g / g+8, cols 2t, 2t+1 of an 8-wide tile) -> A fragment (rows g / g+8, cols t, t+4) of the same tile
+__device__ __forceinline__ void c_to_a(const float* c, uint32_t* a, int lane) {
+  const int t = lane & 3;
+  const int src0 = (lane & ~3) | (t >> 1), src1 = src0 + 2;
+  const bool odd = t & 1;
+  float v00 = __shfl_sync(0xffffffffu, c[0], src0), v01 = __shfl_sync(0xffffffffu, c[1], src0);
+  float v10 = __shfl_sync(0xffffffffu, c[2], src0), v11 = __shfl_sync(0xffffffffu, c[3], src0);
+  float w00 = __shfl_sync(0xffffffffu, c[0], src1), w01 = __shfl_sync(0xffffffffu, c[1], src1);
+  float w10 = __shfl_sync(0xffffffffu, c[2], src1), w11 = __shfl_sync(0xffffffffu, c[3], src1);
+  a[0] = to_tf32(odd ? v01 : v00);
+  a[1] = to_tf32(odd ? v11 : v10);
+  a[2] = to_tf32(odd ? w01 : w00);
+  a[3] = to_tf32(odd ? w11 : w10);
+}
+
+// Gather `n` rows (head slice of HD floats) into dst[row][STRIDE] as TF32; optionally L2-normalise each row first and
+// record 1 / max(|row|, eps).  One thread per row.
+template <int HD, int STRIDE>
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, const int* __restrict__ tok, int n, int C, int col0,
+                                           bool normalise, float* inv_out, int tid0, int nthreads) {
+  for (int r = threadIdx.x - tid0; r < MT; r += nthreads) {
+    float x[HD];
+    if (r < n) {
+      const float* p = src + (int64_t)tok[r] * C + col0;
+#pragma unroll
+      for (int d = 0; d < HD; d += 4) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p + d));
+        x[d] = t.x; x[d + 1] = t.y; x[d + 2] = t.z; x[d + 3] = t.w;
+      }
+      if (normalise) {
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) s = fmaf(x[d], x[d], s);
+        float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);
+#pragma unroll
+        for (int d = 0; d < HD; ++d) x[d] *= inv;
+        if (inv_out) inv_out[r] = inv;
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < HD; ++d) x[d] = 0.f;
+      if (normalise && inv_out) inv_out[r] = 0.f;
+    }
+#pragma unroll
+    for (int d = 0; d < HD; d += 4)
+      *reinterpret_cast<uint4*>(dst + r * STRIDE + d) = make_uint4(to_tf32(x[d]), to_tf32(x[d + 1]), to_tf32(x[d + 2]), to_tf32(x[d + 3]));
+  }
+}
+
+// strip (16 rows starting at r0) of  X[rows][HD] (stride XS)  times  Y[cols][HD]^T (stride YS)  -> acc[8 col tiles][4]
+template <int HD, int XS, int YS>
+__device__ __forceinline__ void strip_xyT(const float* X, const float* Y, int r0, int lane, float acc[8][4]) {
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t a[HD / 8][4];
+#pragma unroll
+  for (int ks = 0; ks < HD / 8; ++ks) {
+    a[ks][0] = __float_as_uint(X[(r0 + g) * XS + ks * 8 + t]);
+    a[ks][1] = __float_as_uint(X[(r0 + g + 8) * XS + ks * 8 + t]);
+    a[ks][2] = __float_as_uint(X[(r0 + g) * XS + ks * 8 + t + 4]);
+    a[ks][3] = __float_as_uint(X[(r0 + g + 8) * XS + ks * 8 + t + 4]);
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < HD / 8; ++ks)
+      mma_tf32(acc[nt], a[ks], __float_as_uint(Y[(nt * 8 + g) * YS + ks * 8 + t]), __float_as_uint(Y[(nt * 8 + g) * YS + ks * 8 + t + 4]));
+  }
+}
+// out[HD/8 tiles][4] (16 x HD strip) = P (16 x 64, C-fragment layout per 8-wide tile) times Z[64][HD] (stride ZS)
+template <int HD, int ZS>
+__device__ __forceinline__ void strip_pz(const float p[8][4], const float* Z, int lane, float out[HD / 8][4]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int dt = 0; dt < HD / 8; ++dt) out[dt][0] = out[dt][1] = out[dt][2] = out[dt][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 8; ++kt) {
+    uint32_t a[4];
+    c_to_a(p[kt], a, lane);
+#pragma unroll
+    for (int dt = 0; dt < HD / 8; ++dt)
+      mma_tf32(out[dt], a, __float_as_uint(Z[(kt * 8 + t) * ZS + dt * 8 + g]), __float_as_uint(Z[(kt * 8 + t + 4) * ZS + dt * 8 + g]));
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(MMA_THREADS) attn_mma_fwd_kernel(AttnMmaArgs a) {
+  constexpr int KS = HD + 4, VS = HD + 8;
+  __shared__ __align__(16) float Qs[MT * KS], Ks[MT * KS], Vs[MT * VS];
+  __shared__ int qt[MT], kt[MT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nw = *a.n_win, first = min(*a.begin, nw);
+  const int n_items = (nw - first) * a.H;
+  const float inv_tau = 1.f / fmaxf(*a.tau, a.tau_min);
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int w = first + item / a.H, h = item % a.H, col0 = h * HD;
+    const int nq = min(a.qcnt[w], MT), nk = min(a.kcnt[w], MT);
+    __syncthreads();
+    if (threadIdx.x < MT) {
+      qt[threadIdx.x] = threadIdx.x < nq ? a.qtok[w * MT + threadIdx.x] : 0;
+      kt[threadIdx.x] = threadIdx.x < nk ? a.ktok[w * MT + threadIdx.x] : 0;
+    }
+    __syncthreads();
+    stage_rows<HD, KS>(Qs, a.q, qt, nq, a.C, col0, true, nullptr, 0, MMA_THREADS);
+    stage_rows<HD, KS>(Ks, a.k, kt, nk, a.C, col0, true, nullptr, 0, MMA_THREADS);
+    stage_rows<HD, VS>(Vs, a.v, kt, nk, a.C, col0, false, nullptr, 0, MMA_THREADS);
+    __syncthreads();
+    const int r0 = warp * 16;
+    if (r0 < nq) {
+      float s[8][4];
+      strip_xyT<HD, KS, KS>(Qs, Ks, r0, lane, s);
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int col = nt * 8 + 2 * t + (e & 1);
+          s[nt][e] = col < nk ? s[nt][e] * inv_tau : -INFINITY;
+        }
+        m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+        m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      m0 = quad_max(m0); m1 = quad_max(m1);
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
+        s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
+        l0 += s[nt][0] + s[nt][1];
+        l1 += s[nt][2] + s[nt][3];
+      }
+      l0 = quad_sum(l0); l1 = quad_sum(l1);
+      float o[HD / 8][4];
+      strip_pz<HD, VS>(s, Vs, lane, o);
+      const float i0 = 1.f / l0, i1 = 1.f / l1;
+      const int ra = r0 + g, rb = r0 + g + 8;
+#pragma unroll
+      for (int dt = 0; dt < HD / 8; ++dt) {
+        if (ra < nq) *reinterpret_cast<float2*>(a.o + (int64_t)qt[ra] * a.C + col0 + dt * 8 + 2 * t) = make_float2(o[dt][0] * i0, o[dt][1] * i0);
+        if (rb < nq) *reinterpret_cast<float2*>(a.o + (int64_t)qt[rb] * a.C + col0 + dt * 8 + 2 * t) = make_float2(o[dt][2] * i1, o[dt][3] * i1);
+      }
+      if (a.lse && t == 0) {
+        if (ra < nq) a.lse[(int64_t)qt[ra] * a.H + h] = m0 + __logf(l0);
+        if (rb < nq) a.lse[(int64_t)qt[rb] * a.H + h] = m1 + __logf(l1);
+      }
+    }
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(MMA_THREADS) attn_mma_bwd_kernel(AttnMmaArgs a) {
+  constexpr int KS = HD + 4, VS = HD + 8;
+  __shared__ __align__(16) float Qs[MT * KS], Ks[MT * KS], Vs[MT * VS], Ds[MT * KS];  // Ds = dO
+  __shared__ float qinv[MT], kinv[MT], lse_s[MT], dsum[MT];
+  __shared__ int qt[MT], kt[MT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nw = *a.n_win, first = min(*a.begin, nw);
+  const int n_items = (nw - first) * a.H;
+  const float tau_raw = *a.tau;
+  const float inv_tau = 1.f / fmaxf(tau_raw, a.tau_min);
+  float dtau_acc = 0.f;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int w = first + item / a.H, h = item % a.H, col0 = h * HD;
+    const int nq = min(a.qcnt[w], MT), nk = min(a.kcnt[w], MT);
+    __syncthreads();
+    if (threadIdx.x < MT) {
+      qt[threadIdx.x] = threadIdx.x < nq ? a.qtok[w * MT + threadIdx.x] : 0;
+      kt[threadIdx.x] = threadIdx.x < nk ? a.ktok[w * MT + threadIdx.x] : 0;
+    }
+    __syncthreads();
+    stage_rows<HD, KS>(Qs, a.q, qt, nq, a.C, col0, true, qinv, 0, MMA_THREADS);
+    stage_rows<HD, KS>(Ks, a.k, kt, nk, a.C, col0, true, kinv, 0, MMA_THREADS);
+    stage_rows<HD, VS>(Vs, a.v, kt, nk, a.C, col0, false, nullptr, 0, MMA_THREADS);
+    // dO rows + D = dO . O + lse (one thread per query row; D uses the un-rounded fp32 values)
+    for (int r = threadIdx.x; r < MT; r += MMA_THREADS) {
+      float x[HD];
+      float d = 0.f;
+      if (r < nq) {
+        const float* p = a.dout + (int64_t)qt[r] * a.C + col0;
+        const float* po = a.o + (int64_t)qt[r] * a.C + col0;
+#pragma unroll
+        for (int e = 0; e < HD; e += 4) {
+          float4 u = __ldg(reinterpret_cast<const float4*>(p + e)), v = __ldg(reinterpret_cast<const float4*>(po + e));
+          x[e] = u.x; x[e + 1] = u.y; x[e + 2] = u.z; x[e + 3] = u.w;
+          d += u.x * v.x + u.y * v.y + u.z * v.z + u.w * v.w;
+        }
+        lse_s[r] = a.lse[(int64_t)qt[r] * a.H + h];
+      } else {
+#pragma unroll
+        for (int e = 0; e < HD; ++e) x[e] = 0.f;
+        lse_s[r] = 0.f;
+      }
+      dsum[r] = d;
+#pragma unroll
+      for (int e = 0; e < HD; e += 4)
+        *reinterpret_cast<uint4*>(Ds + r * KS + e) = make_uint4(to_tf32(x[e]), to_tf32(x[e + 1]), to_tf32(x[e + 2]), to_tf32(x[e + 3]));
+    }
+    __syncthreads();
+    const int r0 = warp * 16, ra = r0 + g, rb = r0 + g + 8;
+    // ---------------- query strip: dQ (+ dtau)
+    if (r0 < nq) {
+      float s[8][4], dp[8][4];
+      strip_xyT<HD, KS, KS>(Qs, Ks, r0, lane, s);    // S = Q_hat K_hat^T
+      strip_xyT<HD, KS, VS>(Ds, Vs, r0, lane, dp);   // dP = dO V^T
+      const float La = lse_s[ra], Lb = lse_s[rb], Da = dsum[ra], Db = dsum[rb];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = nt * 8 + 2 * t + (e & 1);
+          const bool up = e < 2;
+          const bool valid = col < nk && (up ? ra : rb) < nq;
+          const float sc = s[nt][e] * inv_tau;
+          const float p = valid ? __expf(sc - (up ? La : Lb)) : 0.f;
+          const float ds = p * (dp[nt][e] - (up ? Da : Db));
+          dtau_acc -= ds * sc;
+          s[nt][e] = ds * inv_tau;  // dS / tau
+        }
+      }
+      float dqh[HD / 8][4];
+      strip_pz<HD, KS>(s, Ks, lane, dqh);  // dQ_hat = dS K_hat / tau
+      // through q_hat = q / max(|q|, eps): dq = (dq_hat - q_hat (q_hat . dq_hat)) / |q|
+      float da = 0.f, db = 0.f;
+#pragma unroll
+      for (int dt = 0; dt < HD / 8; ++dt) {
+        const float* qa = Qs + ra * KS + dt * 8 + 2 * t;
+        const float* qb = Qs + rb * KS + dt * 8 + 2 * t;
+        da += dqh[dt][0] * qa[0] + dqh[dt][1] * qa[1];
+        db += dqh[dt][2] * qb[0] + dqh[dt][3] * qb[1];
+      }
+      da = quad_sum(da); db = quad_sum(db);
+#pragma unroll
+      for (int dt = 0; dt < HD / 8; ++dt) {
+        const float* qa = Qs + ra * KS + dt * 8 + 2 * t;
+        const float* qb = Qs + rb * KS + dt * 8 + 2 * t;
+        if (ra < nq)
+          *reinterpret_cast<float2*>(a.dq + (int64_t)qt[ra] * a.C + col0 + dt * 8 + 2 * t) =
+              make_float2((dqh[dt][0] - qa[0] * da) * qinv[ra], (dqh[dt][1] - qa[1] * da) * qinv[ra]);
+        if (rb < nq)
+          *reinterpret_cast<float2*>(a.dq + (int64_t)qt[rb] * a.C + col0 + dt * 8 + 2 * t) =
+              make_float2((dqh[dt][2] - qb[0] * db) * qinv[rb], (dqh[dt][3] - qb[1] * db) * qinv[rb]);
+      }
+    }
+    // ---------------- key strip (roles transposed): dV, dK
+    if (r0 < nk) {
+      float s[8][4], dp[8][4];
+      strip_xyT<HD, KS, KS>(Ks, Qs, r0, lane, s);    // S^T = K_hat Q_hat^T      (rows = keys, cols = queries)
+      strip_xyT<HD, VS, KS>(Vs, Ds, r0, lane, dp);   // dP^T = V dO^T
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = nt * 8 + 2 * t + (e & 1);   // query index
+          const bool valid = col < nq && (e < 2 ? ra : rb) < nk;
+          const float p = valid ? __expf(s[nt][e] * inv_tau - lse_s[col]) : 0.f;
+          const float ds = p * (dp[nt][e] - dsum[col]);
+          s[nt][e] = p;                // P^T
+          dp[nt][e] = ds * inv_tau;    // dS^T / tau
+        }
+      }
+      float dvv[HD / 8][4], dkh[HD / 8][4];
+      strip_pz<HD, KS>(s, Ds, lane, dvv);    // dV = P^T dO
+      strip_pz<HD, KS>(dp, Qs, lane, dkh);   // dK_hat = dS^T Q_hat / tau
+      float da = 0.f, db = 0.f;
+#pragma unroll
+      for (int dt = 0; dt < HD / 8; ++dt) {
+        const float* ka = Ks + ra * KS + dt * 8 + 2 * t;
+        const float* kb = Ks + rb * KS + dt * 8 + 2 * t;
+        da += dkh[dt][0] * ka[0] + dkh[dt][1] * ka[1];
+        db += dkh[dt][2] * kb[0] + dkh[dt][3] * kb[1];
+      }
+      da = quad_sum(da); db = quad_sum(db);
+#pragma unroll
+      for (int dt = 0; dt < HD / 8; ++dt) {
+        const float* ka = Ks + ra * KS + dt * 8 + 2 * t;
+        const float* kb = Ks + rb * KS + dt * 8 + 2 * t;
+        const int c = col0 + dt * 8 + 2 * t;
+        if (ra < nk) {
+          *reinterpret_cast<float2*>(a.dk + (int64_t)kt[ra] * a.C + c) = make_float2((dkh[dt][0] - ka[0] * da) * kinv[ra], (dkh[dt][1] - ka[1] * da) * kinv[ra]);
+          *reinterpret_cast<float2*>(a.dv + (int64_t)kt[ra] * a.C + c) = make_float2(dvv[dt][0], dvv[dt][1]);
+        }
+        if (rb < nk) {
+          *reinterpret_cast<float2*>(a.dk + (int64_t)kt[rb] * a.C + c) = make_float2((dkh[dt][2] - kb[0] * db) * kinv[rb], (dkh[dt][3] - kb[1] * db) * kinv[rb]);
+          *reinterpret_cast<float2*>(a.dv + (int64_t)kt[rb] * a.C + c) = make_float2(dvv[dt][2], dvv[dt][3]);
+        }
+      }
+    }
+  }
+  dtau_acc = warp_sum(dtau_acc);
+  if (lane == 0 && a.dtau && tau_raw > a.tau_min && dtau_acc != 0.f) atomicAdd(a.dtau, dtau_acc * inv_tau);
+}
+
+int attn_mma_fwd(const AttnMmaArgs& a, int hd, int64_t max_windows, cudaStream_t s) {
+  int64_t items = max_windows * a.H;
+  int grid = (int)(items < (int64_t)8 * kNumSMs ? items : (int64_t)8 * kNumSMs);
+  ProfScope prof("attn_mma_fwd", 0, 0, s);
+  if (hd == 16) attn_mma_fwd_kernel<16><<<grid, MMA_THREADS, 0, s>>>(a);
+  else attn_mma_fwd_kernel<32><<<grid, MMA_THREADS, 0, s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
+}
+int attn_mma_bwd(const AttnMmaArgs& a, int hd, int64_t max_windows, cudaStream_t s) {
+  int64_t items = max_windows * a.H;
+  int grid = (int)(items < (int64_t)4 * kNumSMs ? items : (int64_t)4 * kNumSMs);
+  ProfScope prof("attn_mma_bwd", 0, 0, s);
+  if (hd == 16) attn_mma_bwd_kernel<16><<<grid, MMA_THREADS, 0, s>>>(a);
+  else attn_mma_bwd_kernel<32><<<grid, MMA_THREADS, 0, s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
+}
+
+}  // namespace tmae

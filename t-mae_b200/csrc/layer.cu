@@ -7,6 +7,8 @@
 
 using namespace tmae;
 
+namespace tmae { extern bool g_attn_tc; }
+
 namespace {
 
 struct Carve {
@@ -96,6 +98,7 @@ int tmae_encoder_layer_fwd(const float* x, const float* x_kv, const tmae_layer_p
   TRY(tmae_linear_fwd(x_kv, P->in_w + 2 * cc, P->in_b + 2 * c, nullptr, s.v, nullptr, m_kv, c, c, TMAE_ACT_NONE, precision, stream));
   if (cross) TMAE_CUDA(cudaMemsetAsync(s.o, 0, (size_t)m_q * c * sizeof(float), (cudaStream_t)stream));  // rows outside paired windows
   g_prof_rows_hint[0] = (double)m_q; g_prof_rows_hint[1] = (double)m_kv;
+  g_attn_tc = precision == TMAE_PREC_BF16;
   TRY(tmae_window_attention_fwd(s.q, s.k, s.v, s.o, s.lse, T->qtok, T->qcnt, T->ktok, T->kcnt, T->n_win, T->small_end, T->mid_end, T->max_windows,
                                 P->tau, tau_min, c, heads, stream));
   TRY(tmae_linear_fwd(s.o, P->out_w, P->out_b, nullptr, s.a, nullptr, m_q, c, c, TMAE_ACT_NONE, precision, stream));
@@ -153,6 +156,7 @@ int tmae_encoder_layer_bwd(const float* dy, const float* x, const float* x_kv, c
     TMAE_CUDA(cudaMemsetAsync(dv, 0, (size_t)m_kv * c * sizeof(float), st));
   }
   g_prof_rows_hint[0] = (double)m_q; g_prof_rows_hint[1] = (double)m_kv;
+  g_attn_tc = precision == TMAE_PREC_BF16;
   TRY(tmae_window_attention_bwd(dob, s.q, s.k, s.v, s.o, s.lse, dsum, dq, dk, dv, g_tau, T->qtok, T->qcnt, T->ktok, T->kcnt, T->n_win,
                                 T->small_end, T->mid_end, T->max_windows, P->tau, tau_min, c, heads, stream));
   // in projection
