@@ -246,7 +246,7 @@ int tc_sparse_conv_bwd_weight(const float* dy, const float* x, const int* table,
 
 using namespace tmae;
 
-extern bool g_attn_tc;          // attention.cu
+namespace tmae { extern bool g_attn_tc; }  // attention.cu
 static bool g_use_tma = true;  // tmae_set_option("tma", 0) keeps every tensor-core GEMM on the thread-staged bf16 kernel
 
 #define TMAE_CHECK_PREC(p) TMAE_CHECK_ARG((p) == TMAE_PREC_FP32 || (p) == TMAE_PREC_BF16, "precision must be TMAE_PREC_FP32 or TMAE_PREC_BF16")
