@@ -228,7 +228,7 @@ def run_ours(args):
             "metric": "encoder scans/sec (scan pairs through vfe -> backbone_3d -> loss)", "value": round(value, 3), "unit": "scans/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total / args.steps, 3),
             "p50_ms_per_scan": round(float(np.median(per)) / w["batch"], 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32/bf16 tensor-core operands, f32 accumulate+storage", "data": "synthetic",
             "config": {"workload": w["name"], "precision": f"encoder kernels {args.precision}; cuDNN decoder {args.decoder}",
                        "parallelism": f"dp{world} (scan-pair sharding" + (", DDP NCCL gradient all-reduce)" if w["train"] else ", no collective)"),
                        "l2": f"inputs cycle over {args.batches} distinct batches; per-step activation working set >> 126 MB L2"},
@@ -360,7 +360,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pretrain", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
+                    help="bf16 = tensor-core mode (TF32 tcgen05 dense GEMMs + TF32 mma attention, bf16 sparse-conv GEMMs, fp32 accumulate and storage); fp32 = FFMA parity mode")
     ap.add_argument("--decoder", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

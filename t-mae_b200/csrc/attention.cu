@@ -16,9 +16,7 @@
 // their partial dot products with one shuffle.  The other side of the window is the "stationary"
 // side every item loops over.
 //   * small windows (the partition sorts windows by level, so windows [0, small_end) hold <= 16
-//     tokens -- 87 % of the windows of a lidar scan): one WARP per window, lanes = items, the
-//     stationary rows are read through L1 (every row is re-read by all items of the warp).  No
-//     shared memory, no block barriers, full occupancy.
+//     tokens -- 87 % of the windows of a lidar scan): register-resident warp kernels, see below.
 //   * larger windows: one 128-thread CTA per (window, 128-channel group); the stationary rows are
 //     gathered once into shared memory (slices padded to 20 floats so the 8 slices read by a quarter
 //     warp hit distinct banks with 128-bit loads), normalised there, threads = items.  Shared memory
@@ -174,51 +172,254 @@ __device__ __forceinline__ void run_item(const AttnArgs& a, const ST& st, int n_
   }
 }
 
-// ------------------------------------------------------------------ small windows: warp per window, L1-resident rows
-template <int SPLIT, int MODE>
-struct GlobalSide {
-  const AttnArgs& g;
-  const int* tok;  // stationary token list of this window
-  __device__ __forceinline__ void a(int j, int col, float* out, unsigned mask) const {
-    load_row((MODE == 2 ? g.q : g.k) + (int64_t)tok[j] * g.C + col, out);
-    normalize<SPLIT>(out, mask);
-  }
-  __device__ __forceinline__ void b(int j, int col, float* out) const {
-    load_row((MODE == 2 ? g.dout : g.v) + (int64_t)tok[j] * g.C + col, out);
-  }
-  __device__ __forceinline__ float lse(int i, int h) const { return g.lse[(int64_t)tok[i] * g.H + h]; }
-  __device__ __forceinline__ float dsum(int i, int h) const { return g.dsum[(int64_t)tok[i] * g.H + h]; }
-};
+// ------------------------------------------------------------------ small windows (<= 16 tokens per side): register-resident
+// One WARP per (window, 128-channel group).  A lane owns 4 consecutive channels of every row, so a row is one coalesced
+// 512-byte access and a head of HD channels spans HL = HD/4 adjacent lanes (per-head sums = HL-lane butterfly).  The
+// stationary side (K_hat, V) is loaded ONCE into registers -- all row loads of the window are issued before the first
+// use -- and the moving side streams through with one row of prefetch; every row of q/k/v/o/dO is read from memory
+// exactly once (twice in the backward when the window has more than 8 keys) and every output row is written once.
+constexpr int SW_T = 16;  // tokens per side handled here
+constexpr int SW_THREADS = 128;
 
-template <int HD, int MODE>
-__global__ void __launch_bounds__(ATT_THREADS) attn_small_kernel(AttnArgs a) {
-  constexpr int SPLIT = HD / HT;
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  const int n_small = min(*a.small_end, *a.n_win);
-  const float tau_raw = *a.tau;
-  const float inv_tau = 1.f / fmaxf(tau_raw, a.tau_min);
-  const int slices = a.C / HT;  // items per row
-  float dtau_acc = 0.f;
-  for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_small; g += warps) {
-    const int nq = a.qcnt[g], nk = a.kcnt[g];
-    const int* rows_tok = (MODE == 2 ? a.ktok : a.qtok) + g * MAXT;
-    const int n_rows = MODE == 2 ? nk : nq, n_other = MODE == 2 ? nq : nk;
-    GlobalSide<SPLIT, MODE> st{a, (MODE == 2 ? a.qtok : a.ktok) + g * MAXT};
-    const int n_items = n_rows * slices;
-    for (int base = 0; base < n_items; base += 32) {
-      const int it = base + lane;
-      const unsigned mask = __ballot_sync(0xffffffffu, it < n_items);
-      if (it < n_items) {
-        int r = it / slices, sl = it - r * slices;
-        run_item<SPLIT, MODE>(a, st, n_other, rows_tok[r], sl * HT, sl / SPLIT, inv_tau, dtau_acc, mask);
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ void axpy4(float4& y, float s, const float4& x) {
+  y.x = fmaf(s, x.x, y.x); y.y = fmaf(s, x.y, y.y); y.z = fmaf(s, x.z, y.z); y.w = fmaf(s, x.w, y.w);
+}
+__device__ __forceinline__ void scale4(float4& y, float s) { y.x *= s; y.y *= s; y.z *= s; y.w *= s; }
+template <int HL>
+__device__ __forceinline__ float head_sum(float v) {
+#pragma unroll
+  for (int o = 1; o < HL; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// predicated 128-bit read-only load (zero when the predicate is off): keeps the per-key loops branch-free
+__device__ __forceinline__ float4 ldg4_if(const float* p, bool on) {
+  float4 r;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+      "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+      : "l"(p), "r"((int)on));
+  return r;
+}
+// 1 / max(sqrt(ss), 1e-12)  (F.normalize) on the MUFU path
+__device__ __forceinline__ float inv_norm(float ss) { return rsqrtf(fmaxf(ss, 1e-24f)); }
+
+// The moving side (q rows; q, dO, o rows and lse in the backward) is staged with cp.async into LANE-PRIVATE shared
+// memory (every lane reads back only the 16 bytes it copied, so no barrier is needed): all of a window's rows are in
+// flight at once, and the second key chunk of the backward re-reads them from shared memory, not from L2.
+// The per-window work is instantiated for padded key counts NK in {4, 8, 16} (the count is warp-uniform) so that
+// every inner loop is branch-free with NK (x ROWS) independent dependency chains; padded keys are zero rows whose
+// probability is forced to zero.
+template <int HL, int NK, int ROWS>
+__device__ __forceinline__ void small_fwd_window(const AttnArgs& a, const float4 (*qs)[32], int nq, int nk, int tokv, int col, int lane,
+                                                 float scale) {
+  constexpr float LN2 = 0.6931471805599453f;
+  float4 kr[NK], vr[NK];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) {
+    const int t = __shfl_sync(0xffffffffu, tokv, j);
+    const int64_t off = (int64_t)t * a.C + col;
+    kr[j] = ldg4_if(a.k + off, j < nk);
+    vr[j] = ldg4_if(a.v + off, j < nk);
+  }
+#pragma unroll
+  for (int j = 0; j < NK; ++j) scale4(kr[j], inv_norm(head_sum<HL>(dot4(kr[j], kr[j]))));
+  cp_async_wait_all();
+  for (int i = 0; i < nq; i += ROWS) {
+    float4 q[ROWS], acc[ROWS];
+    float sc[ROWS][NK], m[ROWS], l[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      q[r] = qs[(i + r) & (SW_T - 1)][lane];
+      scale4(q[r], scale * inv_norm(head_sum<HL>(dot4(q[r], q[r]))));
+      m[r] = -INFINITY;
+    }
+#pragma unroll
+    for (int j = 0; j < NK; ++j)
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const float s = head_sum<HL>(dot4(q[r], kr[j]));
+        sc[r][j] = j < nk ? s : -INFINITY;
+        m[r] = fmaxf(m[r], sc[r][j]);
+      }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) { l[r] = 0.f; acc[r] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+    for (int j = 0; j < NK; ++j)
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const float p = fast_exp2(sc[r][j] - m[r]);
+        l[r] += p;
+        axpy4(acc[r], p, vr[j]);
+      }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      if (i + r < nq) {
+        const int row = __shfl_sync(0xffffffffu, tokv, SW_T + ((i + r) & (SW_T - 1)));
+        scale4(acc[r], __fdividef(1.f, l[r]));
+        *reinterpret_cast<float4*>(a.o + (int64_t)row * a.C + col) = acc[r];
+        if (a.lse && (lane & (HL - 1)) == 0) a.lse[(int64_t)row * a.H + (col / (HL * 4))] = (m[r] + __log2f(l[r])) * LN2;
       }
     }
   }
-  if (MODE == 1) {
-    dtau_acc = warp_sum(dtau_acc);
-    if (lane == 0 && a.dtau && tau_raw > a.tau_min && dtau_acc != 0.f) atomicAdd(a.dtau, dtau_acc * inv_tau);
+}
+
+template <int HD>
+__global__ void __launch_bounds__(SW_THREADS, 3) attn_small_fwd_kernel(AttnArgs a) {
+  constexpr int HL = HD / 4;
+  __shared__ float4 q_s[SW_THREADS / 32][SW_T][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int n_small = min(*a.small_end, *a.n_win);
+  const int groups = a.C >> 7;
+  const int n_items = n_small * groups;
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float scale = LOG2E / fmaxf(*a.tau, a.tau_min);  // scores are kept in the log2 domain
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += warps) {
+    const int w = item / groups, col = (item - w * groups) * 128 + lane * 4;
+    const int nq = min(a.qcnt[w], SW_T), nk = min(a.kcnt[w], SW_T);
+    const int tokv = lane < SW_T ? a.ktok[w * MAXT + lane] : a.qtok[w * MAXT + lane - SW_T];
+#pragma unroll
+    for (int i = 0; i < SW_T; ++i) {
+      const int t = __shfl_sync(0xffffffffu, tokv, SW_T + i);
+      if (i < nq) cp_async16(&q_s[wib][i][lane], a.q + (int64_t)t * a.C + col);
+    }
+    if (nk <= 4) small_fwd_window<HL, 4, 2>(a, q_s[wib], nq, nk, tokv, col, lane, scale);
+    else if (nk <= 8) small_fwd_window<HL, 8, 2>(a, q_s[wib], nq, nk, tokv, col, lane, scale);
+    else small_fwd_window<HL, 16, 1>(a, q_s[wib], nq, nk, tokv, col, lane, scale);
   }
+}
+
+// Fused backward: dQ, dK, dV and dtau in one pass.  Keys are processed in register chunks of up to 8 (K_hat, V and the
+// dK_hat, dV accumulators = 128 registers); windows with 9..16 keys run the query loop twice and add the second
+// chunk's dQ contribution to the row written by the first (the normalisation Jacobian is linear in dQ_hat).
+constexpr int SW_KC = 8;
+struct SmallBwdSmem {
+  float4 q[SW_T][32], g[SW_T][32], o[SW_T][32];
+  float lse[SW_T][32];
+};
+template <int HL, int NC>
+__device__ __forceinline__ void small_bwd_chunk(const AttnArgs& a, const SmallBwdSmem& S, int nq, int kc, int nc, int tokv, int col, int lane,
+                                                float inv_tau, float& dtau_acc, bool first) {
+  const bool lead = (lane & (HL - 1)) == 0;
+  float4 kr[NC], vr[NC], dk[NC], dv[NC];
+  float kinv[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    const int t = __shfl_sync(0xffffffffu, tokv, (kc + j) & (SW_T - 1));
+    const int64_t off = (int64_t)t * a.C + col;
+    kr[j] = ldg4_if(a.k + off, j < nc);
+    vr[j] = ldg4_if(a.v + off, j < nc);
+    dk[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    kinv[j] = inv_norm(head_sum<HL>(dot4(kr[j], kr[j])));
+    scale4(kr[j], kinv[j]);
+  }
+  if (first) cp_async_wait_all();
+  for (int i = 0; i < nq; ++i) {
+    float4 qh = S.q[i][lane];
+    const float4 g = S.g[i][lane], o = S.o[i][lane];
+    const float L = S.lse[i][lane];
+    const float qinv = inv_norm(head_sum<HL>(dot4(qh, qh)));
+    scale4(qh, qinv);
+    const float D = head_sum<HL>(dot4(g, o));
+    float4 dqh = make_float4(0.f, 0.f, 0.f, 0.f);
+    float s[NC], dp[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      s[j] = head_sum<HL>(dot4(qh, kr[j])) * inv_tau;
+      dp[j] = head_sum<HL>(dot4(g, vr[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const float p = j < nc ? __expf(s[j] - L) : 0.f;
+      const float ds = p * (dp[j] - D);
+      if (lead) dtau_acc = fmaf(-ds, s[j], dtau_acc);
+      const float dsl = ds * inv_tau;
+      axpy4(dqh, dsl, kr[j]);
+      axpy4(dk[j], dsl, qh);
+      axpy4(dv[j], p, g);
+    }
+    const float dt = head_sum<HL>(dot4(dqh, qh));
+    float4 dq = make_float4((dqh.x - qh.x * dt) * qinv, (dqh.y - qh.y * dt) * qinv, (dqh.z - qh.z * dt) * qinv, (dqh.w - qh.w * dt) * qinv);
+    const int row = __shfl_sync(0xffffffffu, tokv, SW_T + i);
+    float4* dst = reinterpret_cast<float4*>(a.dq + (int64_t)row * a.C + col);
+    if (!first) { const float4 prev = *dst; dq.x += prev.x; dq.y += prev.y; dq.z += prev.z; dq.w += prev.w; }
+    *dst = dq;
+  }
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    const int t = __shfl_sync(0xffffffffu, tokv, (kc + j) & (SW_T - 1));
+    const float dt = head_sum<HL>(dot4(dk[j], kr[j]));
+    if (j < nc) {
+      const float4 r = make_float4((dk[j].x - kr[j].x * dt) * kinv[j], (dk[j].y - kr[j].y * dt) * kinv[j],
+                                   (dk[j].z - kr[j].z * dt) * kinv[j], (dk[j].w - kr[j].w * dt) * kinv[j]);
+      *reinterpret_cast<float4*>(a.dk + (int64_t)t * a.C + col) = r;
+      *reinterpret_cast<float4*>(a.dv + (int64_t)t * a.C + col) = dv[j];
+    }
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(SW_THREADS, 2) attn_small_bwd_kernel(AttnArgs a) {
+  constexpr int HL = HD / 4;
+  extern __shared__ __align__(16) unsigned char sw_raw[];
+  SmallBwdSmem& S = reinterpret_cast<SmallBwdSmem*>(sw_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int n_small = min(*a.small_end, *a.n_win);
+  const int groups = a.C >> 7;
+  const int n_items = n_small * groups;
+  const float tau_raw = *a.tau;
+  const float inv_tau = 1.f / fmaxf(tau_raw, a.tau_min);
+  float dtau_acc = 0.f;
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += warps) {
+    const int w = item / groups, col = (item - w * groups) * 128 + lane * 4;
+    const int head = col / HD;
+    const int nq = min(a.qcnt[w], SW_T), nk = min(a.kcnt[w], SW_T);
+    const int tokv = lane < SW_T ? a.ktok[w * MAXT + lane] : a.qtok[w * MAXT + lane - SW_T];
+#pragma unroll
+    for (int i = 0; i < SW_T; ++i) {
+      const int t = __shfl_sync(0xffffffffu, tokv, SW_T + i);
+      if (i < nq) {
+        const int64_t off = (int64_t)t * a.C + col;
+        cp_async16(&S.q[i][lane], a.q + off);
+        cp_async16(&S.g[i][lane], a.dout + off);
+        cp_async16(&S.o[i][lane], a.o + off);
+        cp_async4(&S.lse[i][lane], a.lse + (int64_t)t * a.H + head);
+      }
+    }
+    for (int kc = 0; kc < nk; kc += SW_KC) {
+      const int nc = min(SW_KC, nk - kc);
+      if (nc <= 4) small_bwd_chunk<HL, 4>(a, S, nq, kc, nc, tokv, col, lane, inv_tau, dtau_acc, kc == 0);
+      else small_bwd_chunk<HL, 8>(a, S, nq, kc, nc, tokv, col, lane, inv_tau, dtau_acc, kc == 0);
+    }
+    if (nk == 0) cp_async_wait_all();  // nothing consumed the staged rows of this window
+  }
+  dtau_acc = warp_sum(dtau_acc);
+  if (lane == 0 && a.dtau && tau_raw > a.tau_min && dtau_acc != 0.f) atomicAdd(a.dtau, dtau_acc * inv_tau);
 }
 
 // ------------------------------------------------------------------ larger windows: CTA per (window, 128-channel group)
@@ -367,23 +568,56 @@ static AttnMmaArgs to_mma(const AttnArgs& a) {
   return m;
 }
 
-template <int HD, int MODE>
-static int launch_pass(const AttnArgs& a, int64_t max_windows, cudaStream_t s) {
-  static const char* names[3] = {"attn_fwd", "attn_bwd_dq", "attn_bwd_dkv"};
-  // algorithmic traffic: fwd reads q,k,v writes o ; dq pass reads q,k,v,o,dO writes dq ; dkv pass reads q,k,v,dO writes dk,dv
+static void attn_bytes(const AttnArgs& a, double& fwd, double& bwd) {
+  // algorithmic traffic: fwd reads q,k,v writes o ; bwd reads q,k,v,o,dO writes dq,dk,dv
   const double rq = g_prof_rows_hint[0] * a.C * 4.0, rk = g_prof_rows_hint[1] * a.C * 4.0;
-  const double bytes = MODE == 0 ? 2 * rq + 2 * rk : (MODE == 1 ? 4 * rq + 2 * rk : 2 * rq + 4 * rk);
-  ProfScope prof(names[MODE], 0, bytes, s);
-  // small windows: 8 warps per CTA, one window per warp per iteration
-  int64_t warps = max_windows < (int64_t)kNumSMs * 48 ? max_windows : (int64_t)kNumSMs * 48;
-  attn_small_kernel<HD, MODE><<<cdiv(warps * 32, ATT_THREADS), ATT_THREADS, 0, s>>>(a);
-  if (g_attn_tc) {  // windows above 16 tokens on mma.sync TF32: forward, and ONE fused backward pass (dQ, dK, dV, dtau)
-    if (MODE == 0) return attn_mma_fwd(to_mma(a), HD, max_windows, s);
-    if (MODE == 1) return attn_mma_bwd(to_mma(a), HD, max_windows, s);
-    return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
+  fwd = 2 * rq + 2 * rk;
+  bwd = 4 * rq + 4 * rk;
+}
+
+// Forward: small windows on the register-resident warp kernel; larger ones on mma.sync TF32 (tensor-core mode) or the
+// fp32 shared-memory kernels (parity mode).  The profiler attributes the whole call's algorithmic bytes to the small
+// kernel's scope when it is the only one (share of rows unknown on the host), so the scopes are kept separate and
+// the mma scopes carry no byte count.
+template <int HD>
+static int launch_fwd(const AttnArgs& a, int64_t max_windows, cudaStream_t s) {
+  double fb, bb;
+  attn_bytes(a, fb, bb);
+  {
+    ProfScope prof("attn_small_fwd", 0, fb, s);
+    int64_t items = max_windows * (a.C / 128);
+    int64_t warps = items < (int64_t)kNumSMs * 32 ? items : (int64_t)kNumSMs * 32;
+    attn_small_fwd_kernel<HD><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, 0, s>>>(a);
   }
-  int r = launch_large<HD, MODE, 32>(a, a.small_end, a.mid_end, max_windows, s);
-  if (!r) r = launch_large<HD, MODE, 64>(a, a.mid_end, a.n_win, max_windows, s);
+  if (g_attn_tc) return attn_mma_fwd(to_mma(a), HD, max_windows, s);
+  ProfScope prof("attn_large_fwd", 0, 0, s);
+  int r = launch_large<HD, 0, 32>(a, a.small_end, a.mid_end, max_windows, s);
+  if (!r) r = launch_large<HD, 0, 64>(a, a.mid_end, a.n_win, max_windows, s);
+  return r;
+}
+
+template <int HD>
+static int launch_bwd(const AttnArgs& a, int64_t max_windows, cudaStream_t s) {
+  double fb, bb;
+  attn_bytes(a, fb, bb);
+  {
+    ProfScope prof("attn_small_bwd", 0, bb, s);
+    int64_t items = max_windows * (a.C / 128);
+    int64_t warps = items < (int64_t)kNumSMs * 24 ? items : (int64_t)kNumSMs * 24;
+    constexpr int smem = (int)sizeof(SmallBwdSmem) * (SW_THREADS / 32);
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(attn_small_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TMAE_ERR_CUDA;
+      attr_set = true;
+    }
+    attn_small_bwd_kernel<HD><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, smem, s>>>(a);
+  }
+  if (g_attn_tc) return attn_mma_bwd(to_mma(a), HD, max_windows, s);  // ONE fused pass (dQ, dK, dV, dtau)
+  ProfScope prof("attn_large_bwd", 0, 0, s);
+  int r = launch_large<HD, 1, 32>(a, a.small_end, a.mid_end, max_windows, s);
+  if (!r) r = launch_large<HD, 1, 64>(a, a.mid_end, a.n_win, max_windows, s);
+  if (!r) r = launch_large<HD, 2, 32>(a, a.small_end, a.mid_end, max_windows, s);
+  if (!r) r = launch_large<HD, 2, 64>(a, a.mid_end, a.n_win, max_windows, s);
   return r;
 }
 
@@ -409,7 +643,7 @@ int tmae_window_attention_fwd(const float* q, const float* k, const float* v, fl
   TMAE_CHECK_ARG(check(a, hd) == 0, "channels must be a multiple of 128 and head_dim 16 or 32");
   TMAE_CHECK_ARG(small_end && mid_end && n_win, "n_win / small_end / mid_end must be device pointers");
   if (max_windows <= 0) return 0;
-  int r = hd == 16 ? launch_pass<16, 0>(a, max_windows, (cudaStream_t)stream) : launch_pass<32, 0>(a, max_windows, (cudaStream_t)stream);
+  int r = hd == 16 ? launch_fwd<16>(a, max_windows, (cudaStream_t)stream) : launch_fwd<32>(a, max_windows, (cudaStream_t)stream);
   if (r) { set_error("tmae_window_attention_fwd: launch failed"); return r; }
   return 0;
 }
@@ -428,8 +662,7 @@ int tmae_window_attention_bwd(const float* dout, const float* q, const float* k,
   TMAE_CHECK_ARG(small_end && mid_end && n_win && dsum, "n_win / small_end / mid_end / dsum must be device pointers");
   if (max_windows <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  int r = hd == 16 ? launch_pass<16, 1>(a, max_windows, s) : launch_pass<32, 1>(a, max_windows, s);
-  if (!r) r = hd == 16 ? launch_pass<16, 2>(a, max_windows, s) : launch_pass<32, 2>(a, max_windows, s);
+  int r = hd == 16 ? launch_bwd<16>(a, max_windows, s) : launch_bwd<32>(a, max_windows, s);
   if (r) { set_error("tmae_window_attention_bwd: launch failed"); return r; }
   return 0;
 }

@@ -33,25 +33,45 @@ def timeit(fn, iters=10, flush=True):
     return ts[len(ts) // 2]
 
 
+def timeit_queue(fns, reps=3):
+    """GPU-only time per call: the GPU is parked on a spin kernel while the host enqueues every call, so host launch
+    overhead is not in the interval; `fns` should cycle over distinct buffers whose total size exceeds L2."""
+    for f in fns:
+        f()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        torch.cuda._sleep(40_000_000)  # ~20 ms
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for f in fns:
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / len(fns))
+    return best
+
+
 def gemm(prec):
     ops.set_precision(prec)
-    print(f"--- linear ({prec}) : m n k | fwd us TFLOP/s GB/s | bwd_data us | bwd_weight us")
-    for m, n, k in [(56000, 128, 128), (56000, 256, 128), (56000, 128, 256), (50000, 256, 256), (50000, 512, 256), (50000, 256, 512),
-                    (14000, 128, 128), (240000, 128, 64)]:
-        x, w, b = torch.randn(m, k, device=DEV), torch.randn(n, k, device=DEV), torch.randn(n, device=DEV)
-        dy = torch.randn(m, n, device=DEV)
+    print(f"--- linear ({prec}) : m n k | fwd us TFLOP/s GB/s | bwd_data us GB/s | bwd_weight us GB/s")
+    for m, n, k in [(56000, 128, 128), (56000, 384, 128), (56000, 256, 128), (56000, 128, 256), (50000, 256, 256), (50000, 768, 256), (50000, 512, 256),
+                    (50000, 256, 512), (14000, 128, 128), (14000, 256, 256), (240000, 128, 64)]:
+        w, b = torch.randn(n, k, device=DEV), torch.randn(n, device=DEV)
+        sets = [(torch.randn(m, k, device=DEV), torch.randn(m, n, device=DEV)) for _ in range(4)]
         dw, db = torch.empty_like(w), torch.empty_like(b)
-        t = timeit(lambda: ops.linear_fwd(x, w, b))
-        t2 = timeit(lambda: ops.linear_bwd_data(dy, w))
-        t3 = timeit(lambda: ops.linear_bwd_weight(dy, x, dw, db))
+        t = timeit_queue([lambda s=s: ops.linear_fwd(s[0], w, b) for s in sets] * 2)
+        t2 = timeit_queue([lambda s=s: ops.linear_bwd_data(s[1], w) for s in sets] * 2)
+        t3 = timeit_queue([lambda s=s: ops.linear_bwd_weight(s[1], s[0], dw, db) for s in sets] * 2)
         fl, by = 2 * m * n * k, 4 * (m * k + m * n + n * k)
-        print(f"{m:7d} {n:4d} {k:4d} | {t * 1e3:8.1f} {fl / t / 1e9:7.1f} {by / t / 1e6:7.0f} | {t2 * 1e3:8.1f} {fl / t2 / 1e9:7.1f} | {t3 * 1e3:8.1f} {fl / t3 / 1e9:7.1f}")
+        print(f"{m:7d} {n:4d} {k:4d} | {t * 1e3:8.1f} {fl / t / 1e9:7.1f} {by / t / 1e6:7.0f} | {t2 * 1e3:8.1f} {by / t2 / 1e6:7.0f} | {t3 * 1e3:8.1f} {by / t3 / 1e6:7.0f}")
 
 
-def attn():
+def attn(tc=1):
     import numpy as np
-    print("--- window attention : M C | fwd us | bwd us")
-    for M, C, g, B in [(56000, 128, 468, 4), (50000, 256, 234, 4), (28000, 256, 117, 4)]:
+    ops.set_option("attn_tc", tc)
+    print(f"--- window attention (attn_tc={tc}) : M C | fwd us (GB/s of 4*M*C*4) | bwd us (GB/s of 8*M*C*4)")
+    for M, C, g, B in [(56000, 128, 468, 4), (14000, 128, 468, 4), (50000, 256, 234, 4), (28000, 256, 117, 4)]:
         rng = np.random.default_rng(0)
         # clustered occupancy like a lidar BEV: sample cells with a radial density
         cells = np.unique(np.clip((rng.normal(0, g / 5, (M * 3, 2)) + g / 2).astype(np.int64), 0, g - 1) @ np.array([g, 1]))
@@ -61,18 +81,26 @@ def attn():
         coords = torch.tensor(c, dtype=torch.int32, device=DEV)
         P = ops.window_partition(coords, B, g, g, [(16, 0, 16), (32, 16, 32), (64, 32, 100000)])
         m = coords.shape[0]
-        q, k, v = (torch.randn(m, C, device=DEV) for _ in range(3))
         tau = torch.ones(1, device=DEV)
         H = 8
-        o, lse = ops.window_attention_fwd(q, k, v, P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), ops.mid_end(P, 0), min(P.wcap, m), tau, 0.01, H, False)
-        do = torch.randn_like(o)
+        args = (P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), ops.mid_end(P, 0), min(P.wcap, m), tau, 0.01, H)
+        sets = []
+        for _ in range(4):
+            q, k, v = (torch.randn(m, C, device=DEV) for _ in range(3))
+            o, lse = ops.window_attention_fwd(q, k, v, *args, False)
+            sets.append((q, k, v, o, lse, torch.randn_like(o)))
         dtau = torch.zeros(1, device=DEV)
-        t = timeit(lambda: ops.window_attention_fwd(q, k, v, P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), ops.mid_end(P, 0), min(P.wcap, m), tau, 0.01, H, False))
-        t2 = timeit(lambda: ops.window_attention_bwd(do, q, k, v, o, lse, P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), ops.mid_end(P, 0), min(P.wcap, m),
-                                                     tau, 0.01, H, dtau, False))
+        t = timeit_queue([lambda s=s: ops.window_attention_fwd(s[0], s[1], s[2], *args, False) for s in sets] * 2)
+        t2 = timeit_queue([lambda s=s: ops.window_attention_bwd(s[5], s[0], s[1], s[2], s[3], s[4], *args, dtau, False) for s in sets] * 2)
         nw = int(P.n_win[0])
         lb = P.level_base[0].tolist()
-        print(f"{m:7d} {C:4d} windows {nw} levels {lb} | {t * 1e3:8.1f} ({4 * 4 * m * C / t / 1e6:.0f} GB/s) | {t2 * 1e3:8.1f}")
+        cnt = P.cnt_a[0][:nw].long()
+        pairs = int((cnt * cnt).sum())
+        print(f"{m:7d} {C:4d} windows {nw} levels {lb} pairs {pairs} | {t * 1e3:8.1f} ({4 * 4 * m * C / t / 1e6:.0f} GB/s) | {t2 * 1e3:8.1f} ({8 * 4 * m * C / t2 / 1e6:.0f} GB/s)")
+        tab = ops.lib_profile(lambda: [ops.window_attention_fwd(s[0], s[1], s[2], *args, False) for s in sets] +
+                              [ops.window_attention_bwd(s[5], s[0], s[1], s[2], s[3], s[4], *args, dtau, False) for s in sets])
+        print("     " + "  ".join(f"{k} {v['ms'] / v['calls'] * 1e3:.1f}us" for k, v in tab.items()))
+    ops.set_option("attn_tc", 0)
 
 
 if __name__ == "__main__":
