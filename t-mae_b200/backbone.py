@@ -12,6 +12,8 @@ What differs is how it runs.  All coordinate-only work is done once per forward 
 autograd node that launches the library kernels in sequence.  The dense decoder (ConvTranspose2d /
 Conv2d + BatchNorm2d, SiamWCA_MAE.py:79-115) stays on cuDNN in channels-last layout.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -151,14 +153,15 @@ class SSTBlockV1(_EncBlockBase):
             [ShiftBlock(C, enc["NHEAD"], enc["DIM_FEEDFORWARD"], enc["LAYER_CFG"], False) for _ in range(enc["NUM_BLOCKS"])])
         self.conv_out = ConvBNReLU(C, C)
 
-    def forward(self, feats, stage):
+    def forward(self, feats, stage, bounds=None, order=None):
+        """`bounds` / `order`: row segments (frames of the Siamese-batched set) whose BatchNorm statistics stay separate."""
         if self.conv_down is not None:
-            feats = self.conv_down(feats, stage.down, stage.down_t, False, stage.m)
+            feats = self.conv_down(feats, stage.down, stage.down_t, False, stage.m, bounds, order)
         x = feats
         for blk in self.encoder_blocks:
             for s, layer in enumerate(blk.encoder_list):
                 x = layer.forward_self(x, stage.part, s, self.pos_lut)
-        return self.conv_out(feats + x, stage.subm, stage.subm, True, stage.m)
+        return self.conv_out(feats + x, stage.subm, stage.subm, True, stage.m, bounds, order)
 
 
 class WCABlock(_EncBlockBase):
@@ -218,6 +221,7 @@ class SiamWCA(nn.Module):
         setattr(self, self._conv_out_name, out)
         self.decoder_autocast = None  # e.g. torch.bfloat16 for the cuDNN decoder in throughput runs
         self.debug_refs = False       # emit reference-format partition tables and check the status word
+        self.siamese_batched = os.environ.get("TMAE_SIAMESE", "1") != "0"  # both frames through the shared SST blocks as one row set
         self.last_plan = None
 
     # ---- pieces -------------------------------------------------------------------------------
@@ -232,6 +236,19 @@ class SiamWCA(nn.Module):
             x = blk(x, st)
             hidden.append(x)
         return hidden
+
+    def _encode_siamese(self, feats, feats_prev, fp_all, fp_cur):
+        """Both frames through the shared-weight SST blocks as ONE row set [current rows ; previous rows] (samples
+        B..2B-1 are the previous frame): every per-row op and every window (windows never span samples) is exactly
+        what two separate passes compute; BatchNorm statistics stay per frame, visited previous-first like the
+        reference (SiamWCA_MAE.py:265-284 / SiamWCA.py:630-640).  Halves the launches of the encoder."""
+        hid, hid_prev = [], []
+        x = torch.cat([feats, feats_prev], 0)
+        for blk, st, st_cur in zip(self.sst_blocks, fp_all.stages, fp_cur.stages):
+            x = blk(x, st, (0, st_cur.m, st.m), (1, 0))
+            hid.append(x[:st_cur.m])
+            hid_prev.append(x[st_cur.m:])
+        return hid, hid_prev
 
     def _cross(self, hid, hid_prev, fp, tparts):
         return [blk(hid[i], hid_prev[i], fp.stages[i], tparts[i]) for i, blk in enumerate(self.wca_blocks)]
@@ -265,11 +282,20 @@ class SiamWCA(nn.Module):
 
     def _run(self, bd, feats, coords, feats_prev, coords_prev):
         B = int(bd["batch_size"])
-        plans, tparts = build_plans([self._indices(coords), self._indices(coords_prev)], B, self.sparse_shape, self.block_cfgs,
-                                    temporal_pair=(0, 1), want_ref=self.debug_refs, check=self.debug_refs)
-        self.last_plan = (plans, tparts)
-        hid_prev = self._encode(feats_prev, plans[1])
-        hid = self._encode(feats, plans[0])
+        idx_c, idx_p = self._indices(coords), self._indices(coords_prev)
+        if self.siamese_batched:
+            idx_all = torch.cat([idx_c, idx_p + torch.tensor([B, 0, 0], dtype=idx_p.dtype, device=idx_p.device)], 0)
+            plans, tparts = build_plans([idx_c, idx_p, idx_all], B, self.sparse_shape, self.block_cfgs, temporal_pair=(0, 1),
+                                        want_ref=self.debug_refs, check=self.debug_refs, batches=[B, B, 2 * B],
+                                        need=[("subm", "part") if self.debug_refs else ("subm",), ("part",) if self.debug_refs else (), ("subm", "part")])
+            self.last_plan = (plans, tparts)
+            hid, hid_prev = self._encode_siamese(feats, feats_prev, plans[2], plans[0])
+        else:
+            plans, tparts = build_plans([idx_c, idx_p], B, self.sparse_shape, self.block_cfgs,
+                                        temporal_pair=(0, 1), want_ref=self.debug_refs, check=self.debug_refs)
+            self.last_plan = (plans, tparts)
+            hid_prev = self._encode(feats_prev, plans[1])
+            hid = self._encode(feats, plans[0])
         hid = self._cross(hid, hid_prev, plans[0], tparts)
         sps = {f"x_conv{i + 1}": self._sp(h, plans[0].stages[i], B) for i, h in enumerate(hid)}
         strides = self._strides(sps)

@@ -221,7 +221,11 @@ __device__ __forceinline__ float4 ldg4_if(const float* p, bool on) {
   return r;
 }
 // 1 / max(sqrt(ss), 1e-12)  (F.normalize) on the MUFU path
-__device__ __forceinline__ float inv_norm(float ss) { return rsqrtf(fmaxf(ss, 1e-24f)); }
+// EXACT = fp32 parity mode (IEEE sqrt / divide / expf, the reference's own op sequence); otherwise the MUFU path
+template <bool EXACT>
+__device__ __forceinline__ float inv_norm(float ss) {
+  return EXACT ? 1.f / fmaxf(sqrtf(ss), 1e-12f) : rsqrtf(fmaxf(ss, 1e-24f));
+}
 
 // The moving side (q rows; q, dO, o rows and lse in the backward) is staged with cp.async into LANE-PRIVATE shared
 // memory (every lane reads back only the 16 bytes it copied, so no barrier is needed): all of a window's rows are in
@@ -229,7 +233,7 @@ __device__ __forceinline__ float inv_norm(float ss) { return rsqrtf(fmaxf(ss, 1e
 // The per-window work is instantiated for padded key counts NK in {4, 8, 16} (the count is warp-uniform) so that
 // every inner loop is branch-free with NK (x ROWS) independent dependency chains; padded keys are zero rows whose
 // probability is forced to zero.
-template <int HL, int NK, int ROWS>
+template <int HL, int NK, int ROWS, bool EXACT>
 __device__ __forceinline__ void small_fwd_window(const AttnArgs& a, const float4 (*qs)[32], int nq, int nk, int tokv, int col, int lane,
                                                  float scale) {
   constexpr float LN2 = 0.6931471805599453f;
@@ -242,7 +246,7 @@ __device__ __forceinline__ void small_fwd_window(const AttnArgs& a, const float4
     vr[j] = ldg4_if(a.v + off, j < nk);
   }
 #pragma unroll
-  for (int j = 0; j < NK; ++j) scale4(kr[j], inv_norm(head_sum<HL>(dot4(kr[j], kr[j]))));
+  for (int j = 0; j < NK; ++j) scale4(kr[j], inv_norm<EXACT>(head_sum<HL>(dot4(kr[j], kr[j]))));
   cp_async_wait_all();
   for (int i = 0; i < nq; i += ROWS) {
     float4 q[ROWS], acc[ROWS];
@@ -250,7 +254,7 @@ __device__ __forceinline__ void small_fwd_window(const AttnArgs& a, const float4
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       q[r] = qs[(i + r) & (SW_T - 1)][lane];
-      scale4(q[r], scale * inv_norm(head_sum<HL>(dot4(q[r], q[r]))));
+      scale4(q[r], scale * inv_norm<EXACT>(head_sum<HL>(dot4(q[r], q[r]))));
       m[r] = -INFINITY;
     }
 #pragma unroll
@@ -267,7 +271,7 @@ __device__ __forceinline__ void small_fwd_window(const AttnArgs& a, const float4
     for (int j = 0; j < NK; ++j)
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) {
-        const float p = fast_exp2(sc[r][j] - m[r]);
+        const float p = EXACT ? exp2f(sc[r][j] - m[r]) : fast_exp2(sc[r][j] - m[r]);
         l[r] += p;
         axpy4(acc[r], p, vr[j]);
       }
@@ -275,15 +279,15 @@ __device__ __forceinline__ void small_fwd_window(const AttnArgs& a, const float4
     for (int r = 0; r < ROWS; ++r) {
       if (i + r < nq) {
         const int row = __shfl_sync(0xffffffffu, tokv, SW_T + ((i + r) & (SW_T - 1)));
-        scale4(acc[r], __fdividef(1.f, l[r]));
+        scale4(acc[r], EXACT ? 1.f / l[r] : __fdividef(1.f, l[r]));
         *reinterpret_cast<float4*>(a.o + (int64_t)row * a.C + col) = acc[r];
-        if (a.lse && (lane & (HL - 1)) == 0) a.lse[(int64_t)row * a.H + (col / (HL * 4))] = (m[r] + __log2f(l[r])) * LN2;
+        if (a.lse && (lane & (HL - 1)) == 0) a.lse[(int64_t)row * a.H + (col / (HL * 4))] = (m[r] + (EXACT ? log2f(l[r]) : __log2f(l[r]))) * LN2;
       }
     }
   }
 }
 
-template <int HD>
+template <int HD, bool EXACT>
 __global__ void __launch_bounds__(SW_THREADS, 3) attn_small_fwd_kernel(AttnArgs a) {
   constexpr int HL = HD / 4;
   __shared__ float4 q_s[SW_THREADS / 32][SW_T][32];
@@ -303,9 +307,9 @@ __global__ void __launch_bounds__(SW_THREADS, 3) attn_small_fwd_kernel(AttnArgs 
       const int t = __shfl_sync(0xffffffffu, tokv, SW_T + i);
       if (i < nq) cp_async16(&q_s[wib][i][lane], a.q + (int64_t)t * a.C + col);
     }
-    if (nk <= 4) small_fwd_window<HL, 4, 2>(a, q_s[wib], nq, nk, tokv, col, lane, scale);
-    else if (nk <= 8) small_fwd_window<HL, 8, 2>(a, q_s[wib], nq, nk, tokv, col, lane, scale);
-    else small_fwd_window<HL, 16, 1>(a, q_s[wib], nq, nk, tokv, col, lane, scale);
+    if (nk <= 4) small_fwd_window<HL, 4, 2, EXACT>(a, q_s[wib], nq, nk, tokv, col, lane, scale);
+    else if (nk <= 8) small_fwd_window<HL, 8, 2, EXACT>(a, q_s[wib], nq, nk, tokv, col, lane, scale);
+    else small_fwd_window<HL, 16, 1, EXACT>(a, q_s[wib], nq, nk, tokv, col, lane, scale);
   }
 }
 
@@ -317,7 +321,7 @@ struct SmallBwdSmem {
   float4 q[SW_T][32], g[SW_T][32], o[SW_T][32];
   float lse[SW_T][32];
 };
-template <int HL, int NC>
+template <int HL, int NC, bool EXACT>
 __device__ __forceinline__ void small_bwd_chunk(const AttnArgs& a, const SmallBwdSmem& S, int nq, int kc, int nc, int tokv, int col, int lane,
                                                 float inv_tau, float& dtau_acc, bool first) {
   const bool lead = (lane & (HL - 1)) == 0;
@@ -334,7 +338,7 @@ __device__ __forceinline__ void small_bwd_chunk(const AttnArgs& a, const SmallBw
   }
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
-    kinv[j] = inv_norm(head_sum<HL>(dot4(kr[j], kr[j])));
+    kinv[j] = inv_norm<EXACT>(head_sum<HL>(dot4(kr[j], kr[j])));
     scale4(kr[j], kinv[j]);
   }
   if (first) cp_async_wait_all();
@@ -342,7 +346,7 @@ __device__ __forceinline__ void small_bwd_chunk(const AttnArgs& a, const SmallBw
     float4 qh = S.q[i][lane];
     const float4 g = S.g[i][lane], o = S.o[i][lane];
     const float L = S.lse[i][lane];
-    const float qinv = inv_norm(head_sum<HL>(dot4(qh, qh)));
+    const float qinv = inv_norm<EXACT>(head_sum<HL>(dot4(qh, qh)));
     scale4(qh, qinv);
     const float D = head_sum<HL>(dot4(g, o));
     float4 dqh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -354,7 +358,7 @@ __device__ __forceinline__ void small_bwd_chunk(const AttnArgs& a, const SmallBw
     }
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
-      const float p = j < nc ? __expf(s[j] - L) : 0.f;
+      const float p = j < nc ? (EXACT ? expf(s[j] - L) : __expf(s[j] - L)) : 0.f;
       const float ds = p * (dp[j] - D);
       if (lead) dtau_acc = fmaf(-ds, s[j], dtau_acc);
       const float dsl = ds * inv_tau;
@@ -382,7 +386,7 @@ __device__ __forceinline__ void small_bwd_chunk(const AttnArgs& a, const SmallBw
   }
 }
 
-template <int HD>
+template <int HD, bool EXACT>
 __global__ void __launch_bounds__(SW_THREADS, 2) attn_small_bwd_kernel(AttnArgs a) {
   constexpr int HL = HD / 4;
   extern __shared__ __align__(16) unsigned char sw_raw[];
@@ -413,8 +417,8 @@ __global__ void __launch_bounds__(SW_THREADS, 2) attn_small_bwd_kernel(AttnArgs 
     }
     for (int kc = 0; kc < nk; kc += SW_KC) {
       const int nc = min(SW_KC, nk - kc);
-      if (nc <= 4) small_bwd_chunk<HL, 4>(a, S, nq, kc, nc, tokv, col, lane, inv_tau, dtau_acc, kc == 0);
-      else small_bwd_chunk<HL, 8>(a, S, nq, kc, nc, tokv, col, lane, inv_tau, dtau_acc, kc == 0);
+      if (nc <= 4) small_bwd_chunk<HL, 4, EXACT>(a, S, nq, kc, nc, tokv, col, lane, inv_tau, dtau_acc, kc == 0);
+      else small_bwd_chunk<HL, 8, EXACT>(a, S, nq, kc, nc, tokv, col, lane, inv_tau, dtau_acc, kc == 0);
     }
     if (nk == 0) cp_async_wait_all();  // nothing consumed the staged rows of this window
   }
@@ -587,7 +591,8 @@ static int launch_fwd(const AttnArgs& a, int64_t max_windows, cudaStream_t s) {
     ProfScope prof("attn_small_fwd", 0, fb, s);
     int64_t items = max_windows * (a.C / 128);
     int64_t warps = items < (int64_t)kNumSMs * 32 ? items : (int64_t)kNumSMs * 32;
-    attn_small_fwd_kernel<HD><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, 0, s>>>(a);
+    if (g_attn_tc) attn_small_fwd_kernel<HD, false><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, 0, s>>>(a);
+    else attn_small_fwd_kernel<HD, true><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, 0, s>>>(a);
   }
   if (g_attn_tc) return attn_mma_fwd(to_mma(a), HD, max_windows, s);
   ProfScope prof("attn_large_fwd", 0, 0, s);
@@ -607,10 +612,13 @@ static int launch_bwd(const AttnArgs& a, int64_t max_windows, cudaStream_t s) {
     constexpr int smem = (int)sizeof(SmallBwdSmem) * (SW_THREADS / 32);
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
-      if (cudaFuncSetAttribute(attn_small_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return TMAE_ERR_CUDA;
+      if (cudaFuncSetAttribute(attn_small_bwd_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+          cudaFuncSetAttribute(attn_small_bwd_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return TMAE_ERR_CUDA;
       attr_set = true;
     }
-    attn_small_bwd_kernel<HD><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, smem, s>>>(a);
+    if (g_attn_tc) attn_small_bwd_kernel<HD, false><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, smem, s>>>(a);
+    else attn_small_bwd_kernel<HD, true><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, smem, s>>>(a);
   }
   if (g_attn_tc) return attn_mma_bwd(to_mma(a), HD, max_windows, s);  // ONE fused pass (dQ, dK, dV, dtau)
   ProfScope prof("attn_large_bwd", 0, 0, s);

@@ -326,10 +326,10 @@ def add_layernorm_bwd(dy, x, res, rowmask, gamma, mean, rstd, dgamma, dbeta, wan
     return dv, dres
 
 
-def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, relu):
+def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, relu, out=None):
     L = lib()
     rows, c = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if out is None else out
     mean = torch.empty(c, dtype=F32, device=x.device)
     rstd = torch.empty(c, dtype=F32, device=x.device)
     wsb = L.bn_workspace_bytes(c)
@@ -339,17 +339,17 @@ def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, relu)
     return y, mean, rstd
 
 
-def bn_apply(x, mean, rstd, gamma, beta, relu):
-    y = torch.empty_like(x)
+def bn_apply(x, mean, rstd, gamma, beta, relu, out=None):
+    y = torch.empty_like(x) if out is None else out
     _call("bn_apply", _p(x, F32), _p(mean, F32), _p(rstd, F32), _p(gamma, F32), _p(beta, F32), _p(y), x.shape[0], x.shape[1], int(relu),
           _stream())
     return y
 
 
-def bn_bwd(dy, x, y, mean, rstd, gamma, relu, training):
+def bn_bwd(dy, x, y, mean, rstd, gamma, relu, training, out=None):
     L = lib()
     rows, c = x.shape
-    dx = torch.empty_like(x)
+    dx = torch.empty_like(x) if out is None else out
     dgamma = torch.empty(c, dtype=F32, device=x.device)
     dbeta = torch.empty(c, dtype=F32, device=x.device)
     wsb = L.bn_workspace_bytes(c)

@@ -35,13 +35,17 @@ def check_status(part, what):
         raise RuntimeError(f"window partition ({what}): " + "; ".join(msgs))
 
 
-def build_plans(indices_list, batch, sparse_shape, block_cfgs, temporal_pair=None, want_ref=False, check=False):
+def build_plans(indices_list, batch, sparse_shape, block_cfgs, temporal_pair=None, want_ref=False, check=False, batches=None, need=None):
     """indices_list: per frame (M,3) i32 stage-1 sites.  temporal_pair = (i_cur, i_prev) adds the temporal
-    partitions.  Returns (frame plans, temporal partitions per stage or None)."""
+    partitions.  `batches[i]` overrides the sample count of frame set i (the Siamese-batched set holds 2B samples);
+    `need[i]` is a subset of {"subm", "part"} (default both).  Returns (frame plans, temporal partitions per stage
+    or None)."""
     Y, X = int(sparse_shape[0]), int(sparse_shape[1])
     n_stage = len(block_cfgs)
+    batches = [batch] * len(indices_list) if batches is None else batches
+    need = [("subm", "part")] * len(indices_list) if need is None else need
     plans, pending = [], []
-    for idx in indices_list:
+    for idx, batch_i in zip(indices_list, batches):
         fp = FramePlan()
         st = Stage()
         st.indices, st.m, st.Y, st.X, st.down, st.down_t = idx, idx.shape[0], Y, X, None, None
@@ -50,7 +54,7 @@ def build_plans(indices_list, batch, sparse_shape, block_cfgs, temporal_pair=Non
         for s in range(1, n_stage):
             assert block_cfgs[s]["ENCODER"]["STRIDE"] == 2
             prev = fp.stages[-1]
-            idx_out, n_out, table, table_t, (y, x) = ops.strided_table(prev.indices, batch, prev.Y, prev.X, rows_dev)
+            idx_out, n_out, table, table_t, (y, x) = ops.strided_table(prev.indices, batch_i, prev.Y, prev.X, rows_dev)
             st = Stage()
             st.indices, st.m, st.Y, st.X, st.down, st.down_t = idx_out, None, y, x, table, table_t
             fp.stages.append(st)
@@ -68,12 +72,14 @@ def build_plans(indices_list, batch, sparse_shape, block_cfgs, temporal_pair=Non
                 st.down = st.down[:st.m]
                 if s + 1 < n_stage:
                     fp.stages[s + 1].down_t = fp.stages[s + 1].down_t[:st.m]
-    for fp in plans:
+    for fp, batch_i, nd in zip(plans, batches, need):
         for s, st in enumerate(fp.stages):
-            st.subm = ops.subm_table(st.indices, batch, st.Y, st.X)
-            st.part = ops.window_partition(st.indices, batch, st.X, st.Y, _levels(block_cfgs[s]["PREPROCESS"]), want_ref=want_ref)
-            if check:
-                check_status(st.part, f"stage {s}")
+            st.subm = ops.subm_table(st.indices, batch_i, st.Y, st.X) if "subm" in nd else None
+            st.part = None
+            if "part" in nd:
+                st.part = ops.window_partition(st.indices, batch_i, st.X, st.Y, _levels(block_cfgs[s]["PREPROCESS"]), want_ref=want_ref)
+                if check:
+                    check_status(st.part, f"stage {s}")
     tparts = None
     if temporal_pair is not None:
         a, b = plans[temporal_pair[0]], plans[temporal_pair[1]]

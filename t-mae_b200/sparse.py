@@ -97,6 +97,6 @@ class ConvBNReLU(nn.Module):
         self.add_module("1", nn.BatchNorm1d(cout, eps=1e-3, momentum=0.01))
         self.add_module("2", nn.ReLU())
 
-    def forward(self, feats, table, table_t, flip, rows_out):
+    def forward(self, feats, table, table_t, flip, rows_out, bounds=None, order=None):
         y = _SparseConvFn.apply(feats.contiguous(), self._modules["0"].weight, table, table_t, flip, rows_out)
-        return bn_relu(y, self._modules["1"], relu=True)
+        return bn_relu(y, self._modules["1"], relu=True, bounds=bounds, order=order)

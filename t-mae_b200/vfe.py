@@ -53,12 +53,61 @@ class _BnReluFn(torch.autograd.Function):
         return dx, dg, db, None, None, None, None, None, None
 
 
-def bn_relu(x, bn, relu=True):
-    """Applies an nn.BatchNorm1d's parameters/buffers with the library kernels (train or eval)."""
+class _BnReluSegFn(torch.autograd.Function):
+    """The same BatchNorm1d + ReLU applied to several row segments of one tensor, each with its OWN batch
+    statistics -- what the reference computes when it calls the module once per frame (current and previous frame
+    share the Siamese encoder weights, SiamWCA_MAE.py:265-284); `order` is the reference's call order, which fixes
+    the running-statistics update sequence."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, training, relu, bounds, order):
+        y = torch.empty_like(x)
+        stats = [None] * (len(bounds) - 1)
+        for i in order:
+            a, b = bounds[i], bounds[i + 1]
+            if b <= a:
+                continue
+            if training:
+                _, mean, rstd = ops.bn_train_fwd(x[a:b], gamma, beta, running_mean, running_var, momentum, eps, relu, out=y[a:b])
+            else:
+                mean, rstd = running_mean, torch.rsqrt(running_var + eps)
+                ops.bn_apply(x[a:b], mean, rstd, gamma, beta, relu, out=y[a:b])
+            stats[i] = (mean, rstd)
+        ctx.save_for_backward(x, y, gamma, *[t for s in stats if s is not None for t in s])
+        ctx.misc = (relu, training, bounds, [s is not None for s in stats])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, *flat = ctx.saved_tensors
+        relu, training, bounds, present = ctx.misc
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dg = db = None
+        k = 0
+        for i, has in enumerate(present):
+            if not has:
+                continue
+            mean, rstd = flat[2 * k], flat[2 * k + 1]
+            k += 1
+            a, b = bounds[i], bounds[i + 1]
+            _, g, bb = ops.bn_bwd(dy[a:b], x[a:b], y[a:b], mean, rstd, gamma, relu, training, out=dx[a:b])
+            dg, db = (g, bb) if dg is None else (dg + g, db + bb)
+        return dx, dg, db, None, None, None, None, None, None, None, None
+
+
+def bn_relu(x, bn, relu=True, bounds=None, order=None):
+    """Applies an nn.BatchNorm1d's parameters/buffers with the library kernels (train or eval).  `bounds` = row
+    boundaries [0, m0, m0+m1, ...] of segments normalised independently, visited in `order`."""
     training = bn.training or bn.running_mean is None
+    n_seg = 1 if bounds is None else sum(1 for i in range(len(bounds) - 1) if bounds[i + 1] > bounds[i])
     if training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
-    return _BnReluFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, training, relu)
+        bn.num_batches_tracked += n_seg
+    if bounds is None:
+        return _BnReluFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, training, relu)
+    order = list(range(len(bounds) - 1)) if order is None else order
+    return _BnReluSegFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, training, relu,
+                              tuple(int(b) for b in bounds), tuple(order))
 
 
 class _SegMaxFn(torch.autograd.Function):

@@ -1,9 +1,11 @@
 """GPU parity tests of the drop-in modules (vfe -> backbone_3d.forward -> get_loss) against the tier-2 oracle
 and the committed golden tensors made from the reference's own modules (tests/golden/make_golden.py)."""
+import os
+
 import pytest
 import torch
 
-from common import assert_close, assert_equal_int, golden_inputs, load_golden, run_tier2
+from common import GOLDEN, assert_close, assert_equal_int, golden_inputs, load_golden, run_tier2
 from oracle import cases
 
 pytestmark = pytest.mark.gpu
@@ -127,20 +129,55 @@ def test_pretrain_loss_and_gradients(both):
     assert abs(loss.item() - g["loss"]) <= 1e-4 * abs(g["loss"])
     loss.backward()
     oloss.backward()
-    worst = []
+    g64 = torch.load(os.path.join(GOLDEN, "small_pretrain_grad64.pt"), weights_only=False)
+    assert abs(loss.item() - g64["loss"]) <= 1e-6 * abs(g64["loss"])
+    worst, worst32 = [], []
     for m, om, pre in ((vfe, ovfe, "vfe."), (bb, obb, "backbone_3d.")):
         op = dict(om.named_parameters())
         for k, p in m.named_parameters():
             assert p.grad is not None, k
+            scale, sample = g64["grads"][pre + k]
+            worst.append(((p.grad.flatten()[::g64["stride"]].cpu().double() - sample.double()).abs().max().item() / (scale + 1e-12), pre + k))
             ref = op[k].grad
-            scale = ref.abs().max().item() + 1e-12
-            err = (p.grad.cpu() - ref).abs().max().item() / scale
-            worst.append((err, pre + k))
+            worst32.append(((p.grad.cpu() - ref).abs().max().item() / (ref.abs().max().item() + 1e-12), pre + k))
             ga = p.grad.double().abs().sum().item()
             assert abs(ga - g["grad_abs_sum"][k]) <= 5e-3 * g["grad_abs_sum"][k] + 1e-7, k
-    worst.sort(reverse=True)
-    # gradients: relative to each tensor's largest entry (fp32 atomics / split reductions over ~10^3..10^4 rows)
+    worst.sort(reverse=True), worst32.sort(reverse=True)
+    # Gradient parity is pinned to the oracle evaluated in FLOAT64 (tests/golden/make_grad64.py): on this case the
+    # fp32 oracle itself sits up to 6e-3 of a tensor's scale (median 2e-4) away from exact arithmetic -- 18 encoder
+    # layers + 13 BatchNorms amplify rounding -- so fp32-vs-fp32 agreement below that only measures how similar the
+    # op ORDER is.  Against float64: every tensor within 2e-3 of its scale, the median tensor within 1e-4.
     assert worst[0][0] < 2e-3, worst[:5]
+    assert worst[len(worst) // 2][0] < 1e-4, worst[len(worst) // 2]
+    # and against the fp32 oracle: within the oracle's own distance from float64 (x3)
+    assert worst32[0][0] < 2e-2, worst32[:5]
+
+
+def test_siamese_batched_equals_separate():
+    """Both frames through the shared SST blocks as one row set (default) vs. one pass per frame like the reference:
+    same features, loss, gradients and BatchNorm running statistics."""
+    pts, ptsp = cases.small_points(77, 900, 2)
+    outs = []
+    for batched in (True, False):
+        vfe, bb = tmae_b200.build_model("pretrain", S["grid"], S["voxel"], S["range"])
+        cases.fill_params(vfe), cases.fill_params(bb)
+        vfe.to(DEV), bb.to(DEV)
+        bb.siamese_batched = batched
+        bd = vfe(dict(points=torch.from_numpy(pts).to(DEV), points_prev=torch.from_numpy(ptsp).to(DEV), batch_size=2))
+        bd["voxel_mae_mask_in"] = cases.fixed_mask(bd["voxel_coords"].cpu(), 2, 0.75, 5).to(DEV)
+        bd = bb(bd)
+        loss, _ = bb.get_loss()
+        loss.backward()
+        outs.append((bd["spatial_features"].detach(), loss.detach(), {k: p.grad for k, p in bb.named_parameters()},
+                     {k: v for k, v in bb.state_dict().items() if "running" in k or "num_batches" in k}))
+    (sf_a, l_a, g_a, st_a), (sf_b, l_b, g_b, st_b) = outs
+    assert_close(sf_a, sf_b, 1e-5, 1e-5, "spatial_features")
+    assert abs(l_a.item() - l_b.item()) <= 1e-5 * abs(l_b.item())
+    for k in g_b:
+        scale = g_b[k].abs().max().item() + 1e-12
+        assert (g_a[k] - g_b[k]).abs().max().item() / scale < 1e-3, k
+    for k in st_b:
+        assert_close(st_a[k].float(), st_b[k].float(), 1e-5, 1e-6, k)
 
 
 def test_eval_mode_forward():

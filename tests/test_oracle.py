@@ -189,3 +189,24 @@ def test_partition_invariants(seed, m):
             win = t[dl][0] // T
             assert win.unique().numel() == int(win.max()) + 1
             assert (t[dl][0] % T < T).all() and t[dl][0].unique().numel() == t[dl][0].numel()
+
+
+def test_fp32_oracle_distance_from_float64_gradients():
+    """Documents the noise floor of gradient parity: the fp32 tier-2 oracle against the same oracle in float64
+    (tests/golden/small_pretrain_grad64.pt).  The worst tensor is a few 1e-3 of its scale away, the median ~2e-4 --
+    the GPU tests therefore pin gradients to the float64 fixture, not to the fp32 run."""
+    g = load_golden("pretrain")
+    pts, ptsp = golden_inputs(g)
+    vfe, bb, av, bd = run_tier2("pretrain", pts, ptsp, g["meta"]["batch"], g["meta"]["mask_seed"])
+    loss, _ = bb.get_loss()
+    loss.backward()
+    g64 = torch.load(os.path.join(GOLDEN, "small_pretrain_grad64.pt"), weights_only=False)
+    assert abs(loss.item() - g64["loss"]) <= 1e-6 * abs(g64["loss"])
+    dev = []
+    for pre, m in (("vfe.", vfe), ("backbone_3d.", bb)):
+        for k, p in m.named_parameters():
+            scale, sample = g64["grads"][pre + k]
+            dev.append((p.grad.flatten()[::g64["stride"]].double() - sample.double()).abs().max().item() / (scale + 1e-12))
+    dev.sort()
+    assert dev[-1] < 2e-2 and dev[len(dev) // 2] < 1e-3
+    assert dev[-1] > 1e-4, "the fp32 oracle is closer to float64 than documented: tighten the GPU gradient tolerances"
