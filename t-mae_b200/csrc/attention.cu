@@ -555,7 +555,7 @@ static int launch_large(const AttnArgs& a, const int* begin, const int* end, int
 struct AttnMmaArgs {
   const float* q; const float* k; const float* v; float* o; float* lse;
   const int* qtok; const int* qcnt; const int* ktok; const int* kcnt;
-  const int* n_win; const int* begin;
+  const int* n_win; const int* begin; const int* mid; const int* end;
   const float* tau; float tau_min;
   int C, H;
   const float* dout; float* dq; float* dk; float* dv; float* dtau;
@@ -567,7 +567,7 @@ bool g_attn_tc = false;  // set by the layer entry points (tensor-core precision
 static AttnMmaArgs to_mma(const AttnArgs& a) {
   AttnMmaArgs m{};
   m.q = a.q; m.k = a.k; m.v = a.v; m.o = a.o; m.lse = a.lse; m.qtok = a.qtok; m.qcnt = a.qcnt; m.ktok = a.ktok; m.kcnt = a.kcnt;
-  m.n_win = a.n_win; m.begin = a.small_end; m.tau = a.tau; m.tau_min = a.tau_min; m.C = a.C; m.H = a.H;
+  m.n_win = a.n_win; m.begin = a.small_end; m.mid = a.mid_end; m.end = a.n_win; m.tau = a.tau; m.tau_min = a.tau_min; m.C = a.C; m.H = a.H;
   m.dout = a.dout; m.dq = a.dq; m.dk = a.dk; m.dv = a.dv; m.dtau = a.dtau;
   return m;
 }

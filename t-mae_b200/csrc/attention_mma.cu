@@ -1,7 +1,9 @@
 // Tensor-core attention for the windows with more than 16 tokens (stages 2-3 of a lidar scan are dense: these windows
-// hold most of the query-key pairs).  One 128-thread CTA per (window, head); warp w owns the 16-row strip w of the
-// 64-slot window.  Everything a (window, head) needs -- Q_hat, K_hat, V (and dO) head slices, <= 64 x 32 fp32 each --
-// is gathered once through the partition's token table into shared memory (TF32-rounded, rows padded so that the
+// hold most of the query-key pairs).  One CTA per (window, head); warp w owns the 16-row strip w of the window: 2-warp
+// CTAs for windows of <= 32 tokens, 4-warp CTAs for <= 64 (the partition sorts windows by level), and column tiles
+// beyond the window's token count are skipped.  Everything a (window, head) needs -- Q_hat, K_hat, V (and dO) head
+// slices, <= 64 x 32 fp32 each -- is gathered once through the partition's token table into shared memory by ALL
+// threads with every load in flight before the first use (TF32-rounded, rows padded so that the
 // mma.sync fragment loads are bank-conflict free), and S = Q_hat K_hat^T, P = softmax, O = P V run on
 // mma.sync.m16n8k8 TF32 with fp32 accumulation; the softmax and the C-fragment -> A-fragment re-layout of P stay in
 // registers (quad shuffles).  Backward is ONE pass: each warp first acts on its query strip (S, P, dP = dO V^T,
@@ -14,12 +16,11 @@
 namespace tmae {
 
 constexpr int MT = TMAE_WIN_TOKENS;  // 64 slots
-constexpr int MMA_THREADS = 128;
 
 struct AttnMmaArgs {
   const float* q; const float* k; const float* v; float* o; float* lse;
   const int* qtok; const int* qcnt; const int* ktok; const int* kcnt;
-  const int* n_win; const int* begin;   // windows [*begin, *n_win)
+  const int* n_win; const int* begin; const int* mid; const int* end;   // windows [*begin, *mid) <= 32 tokens, [*mid, *n_win) <= 64
   const float* tau; float tau_min;
   int C, H;
   const float* dout; float* dq; float* dk; float* dv; float* dtau;
@@ -60,43 +61,51 @@ __device__ __forceinline__ void c_to_a(const float* c, uint32_t* a, int lane) {
   a[3] = to_tf32(odd ? w11 : w10);
 }
 
-// Gather `n` rows (head slice of HD floats) into dst[row][STRIDE] as TF32; optionally L2-normalise each row first and
-// record 1 / max(|row|, eps).  One thread per row.
-template <int HD, int STRIDE>
-__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, const int* __restrict__ tok, int n, int C, int col0,
-                                           bool normalise, float* inv_out, int tid0, int nthreads) {
-  for (int r = threadIdx.x - tid0; r < MT; r += nthreads) {
-    float x[HD];
-    if (r < n) {
-      const float* p = src + (int64_t)tok[r] * C + col0;
+// ---- staging: ALL threads of the CTA, LPR = HD/4 adjacent lanes per row (one 16-byte piece each, so a row's head
+// slice is one coalesced 64/128-byte segment), every load of every operand issued before the first use.
+template <int HD, int TCAP, int THREADS>
+struct Stage {
+  static constexpr int LPR = HD / 4, RPP = THREADS / LPR, PASSES = TCAP / RPP;
+  float4 x[PASSES];
+  // tok: global token list of the window (n valid entries)
+  __device__ __forceinline__ void load(const float* __restrict__ src, const int* __restrict__ tok, int n, int C, int col0) {
+    const int sub = threadIdx.x % LPR, r0 = threadIdx.x / LPR;
 #pragma unroll
-      for (int d = 0; d < HD; d += 4) {
-        float4 t = __ldg(reinterpret_cast<const float4*>(p + d));
-        x[d] = t.x; x[d + 1] = t.y; x[d + 2] = t.z; x[d + 3] = t.w;
-      }
-      if (normalise) {
-        float s = 0.f;
-#pragma unroll
-        for (int d = 0; d < HD; ++d) s = fmaf(x[d], x[d], s);
-        float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);
-#pragma unroll
-        for (int d = 0; d < HD; ++d) x[d] *= inv;
-        if (inv_out) inv_out[r] = inv;
-      }
-    } else {
-#pragma unroll
-      for (int d = 0; d < HD; ++d) x[d] = 0.f;
-      if (normalise && inv_out) inv_out[r] = 0.f;
+    for (int p = 0; p < PASSES; ++p) {
+      const int r = p * RPP + r0;
+      x[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < n) x[p] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)__ldg(tok + r) * C + col0 + sub * 4));
     }
-#pragma unroll
-    for (int d = 0; d < HD; d += 4)
-      *reinterpret_cast<uint4*>(dst + r * STRIDE + d) = make_uint4(to_tf32(x[d]), to_tf32(x[d + 1]), to_tf32(x[d + 2]), to_tf32(x[d + 3]));
   }
-}
+  // per-row reduction over the LPR lanes that hold the row
+  __device__ __forceinline__ static float row_sum(float v) {
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  // optional L2 normalisation (records 1 / max(|row|, eps)), TF32 rounding, store to dst[row][STRIDE]
+  template <int STRIDE>
+  __device__ __forceinline__ void store(float* dst, bool normalise, float* inv_out) {
+    const int sub = threadIdx.x % LPR, r0 = threadIdx.x / LPR;
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+      const int r = p * RPP + r0;
+      float4 v = x[p];
+      if (normalise) {
+        const float ss = row_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+        const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+        if (inv_out && sub == 0) inv_out[r] = ss > 0.f ? inv : 0.f;
+      }
+      *reinterpret_cast<uint4*>(dst + r * STRIDE + sub * 4) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    }
+  }
+};
 
-// strip (16 rows starting at r0) of  X[rows][HD] (stride XS)  times  Y[cols][HD]^T (stride YS)  -> acc[8 col tiles][4]
-template <int HD, int XS, int YS>
-__device__ __forceinline__ void strip_xyT(const float* X, const float* Y, int r0, int lane, float acc[8][4]) {
+// strip (16 rows starting at r0) of  X[rows][HD] (stride XS)  times  Y[cols][HD]^T (stride YS)  -> acc[NT col tiles][4];
+// only the first `tiles` column tiles are computed (the rest of the window side is empty)
+template <int HD, int XS, int YS, int NT>
+__device__ __forceinline__ void strip_xyT(const float* X, const float* Y, int r0, int lane, int tiles, float acc[NT][4]) {
   const int g = lane >> 2, t = lane & 3;
   uint32_t a[HD / 8][4];
 #pragma unroll
@@ -107,58 +116,64 @@ __device__ __forceinline__ void strip_xyT(const float* X, const float* Y, int r0
     a[ks][3] = __float_as_uint(X[(r0 + g + 8) * XS + ks * 8 + t + 4]);
   }
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
+  for (int nt = 0; nt < NT; ++nt) {
     acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    if (nt < tiles) {
 #pragma unroll
-    for (int ks = 0; ks < HD / 8; ++ks)
-      mma_tf32(acc[nt], a[ks], __float_as_uint(Y[(nt * 8 + g) * YS + ks * 8 + t]), __float_as_uint(Y[(nt * 8 + g) * YS + ks * 8 + t + 4]));
+      for (int ks = 0; ks < HD / 8; ++ks)
+        mma_tf32(acc[nt], a[ks], __float_as_uint(Y[(nt * 8 + g) * YS + ks * 8 + t]), __float_as_uint(Y[(nt * 8 + g) * YS + ks * 8 + t + 4]));
+    }
   }
 }
-// out[HD/8 tiles][4] (16 x HD strip) = P (16 x 64, C-fragment layout per 8-wide tile) times Z[64][HD] (stride ZS)
-template <int HD, int ZS>
-__device__ __forceinline__ void strip_pz(const float p[8][4], const float* Z, int lane, float out[HD / 8][4]) {
+// out[HD/8 tiles][4] (16 x HD strip) = P (16 x 8*NT, C-fragment layout per 8-wide tile) times Z[8*NT][HD] (stride ZS)
+template <int HD, int ZS, int NT>
+__device__ __forceinline__ void strip_pz(const float p[NT][4], const float* Z, int lane, int tiles, float out[HD / 8][4]) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int dt = 0; dt < HD / 8; ++dt) out[dt][0] = out[dt][1] = out[dt][2] = out[dt][3] = 0.f;
 #pragma unroll
-  for (int kt = 0; kt < 8; ++kt) {
-    uint32_t a[4];
-    c_to_a(p[kt], a, lane);
+  for (int kt = 0; kt < NT; ++kt) {
+    if (kt < tiles) {
+      uint32_t a[4];
+      c_to_a(p[kt], a, lane);
 #pragma unroll
-    for (int dt = 0; dt < HD / 8; ++dt)
-      mma_tf32(out[dt], a, __float_as_uint(Z[(kt * 8 + t) * ZS + dt * 8 + g]), __float_as_uint(Z[(kt * 8 + t + 4) * ZS + dt * 8 + g]));
+      for (int dt = 0; dt < HD / 8; ++dt)
+        mma_tf32(out[dt], a, __float_as_uint(Z[(kt * 8 + t) * ZS + dt * 8 + g]), __float_as_uint(Z[(kt * 8 + t + 4) * ZS + dt * 8 + g]));
+    }
   }
 }
 
-template <int HD>
-__global__ void __launch_bounds__(MMA_THREADS) attn_mma_fwd_kernel(AttnMmaArgs a) {
-  constexpr int KS = HD + 4, VS = HD + 8;
-  __shared__ __align__(16) float Qs[MT * KS], Ks[MT * KS], Vs[MT * VS];
-  __shared__ int qt[MT], kt[MT];
+// windows [*a.begin, *a.end) of the level-sorted list hold at most TCAP tokens per side; CTA = TCAP/16 warps
+template <int HD, int TCAP>
+__global__ void __launch_bounds__(TCAP * 2) attn_mma_fwd_kernel(AttnMmaArgs a) {
+  constexpr int KS = HD + 4, VS = HD + 8, NT = TCAP / 8, THREADS = TCAP * 2;
+  __shared__ __align__(16) float Qs[TCAP * KS], Ks[TCAP * KS], Vs[TCAP * VS];
+  __shared__ int qt[TCAP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int nw = *a.n_win, first = min(*a.begin, nw);
-  const int n_items = (nw - first) * a.H;
+  const int nw = *a.n_win, first = min(*a.begin, nw), last = min(*a.end, nw);
+  const int n_items = (last - first) * a.H;
   const float inv_tau = 1.f / fmaxf(*a.tau, a.tau_min);
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int w = first + item / a.H, h = item % a.H, col0 = h * HD;
-    const int nq = min(a.qcnt[w], MT), nk = min(a.kcnt[w], MT);
-    __syncthreads();
-    if (threadIdx.x < MT) {
-      qt[threadIdx.x] = threadIdx.x < nq ? a.qtok[w * MT + threadIdx.x] : 0;
-      kt[threadIdx.x] = threadIdx.x < nk ? a.ktok[w * MT + threadIdx.x] : 0;
-    }
-    __syncthreads();
-    stage_rows<HD, KS>(Qs, a.q, qt, nq, a.C, col0, true, nullptr, 0, MMA_THREADS);
-    stage_rows<HD, KS>(Ks, a.k, kt, nk, a.C, col0, true, nullptr, 0, MMA_THREADS);
-    stage_rows<HD, VS>(Vs, a.v, kt, nk, a.C, col0, false, nullptr, 0, MMA_THREADS);
+    const int nq = min(a.qcnt[w], TCAP), nk = min(a.kcnt[w], TCAP);
+    Stage<HD, TCAP, THREADS> sq, sk, sv;
+    sq.load(a.q, a.qtok + w * MT, nq, a.C, col0);
+    sk.load(a.k, a.ktok + w * MT, nk, a.C, col0);
+    sv.load(a.v, a.ktok + w * MT, nk, a.C, col0);
+    __syncthreads();  // the previous item's readers are done with shared memory
+    if (threadIdx.x < TCAP) qt[threadIdx.x] = threadIdx.x < nq ? a.qtok[w * MT + threadIdx.x] : 0;
+    sq.template store<KS>(Qs, true, nullptr);
+    sk.template store<KS>(Ks, true, nullptr);
+    sv.template store<VS>(Vs, false, nullptr);
     __syncthreads();
     const int r0 = warp * 16;
+    const int ktiles = (nk + 7) >> 3;
     if (r0 < nq) {
-      float s[8][4];
-      strip_xyT<HD, KS, KS>(Qs, Ks, r0, lane, s);
+      float s[NT][4];
+      strip_xyT<HD, KS, KS, NT>(Qs, Ks, r0, lane, ktiles, s);
       float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           int col = nt * 8 + 2 * t + (e & 1);
@@ -170,7 +185,7 @@ __global__ void __launch_bounds__(MMA_THREADS) attn_mma_fwd_kernel(AttnMmaArgs a
       m0 = quad_max(m0); m1 = quad_max(m1);
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < NT; ++nt) {
         s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
         s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
         l0 += s[nt][0] + s[nt][1];
@@ -178,7 +193,7 @@ __global__ void __launch_bounds__(MMA_THREADS) attn_mma_fwd_kernel(AttnMmaArgs a
       }
       l0 = quad_sum(l0); l1 = quad_sum(l1);
       float o[HD / 8][4];
-      strip_pz<HD, VS>(s, Vs, lane, o);
+      strip_pz<HD, VS, NT>(s, Vs, lane, ktiles, o);
       const float i0 = 1.f / l0, i1 = 1.f / l1;
       const int ra = r0 + g, rb = r0 + g + 8;
 #pragma unroll
@@ -194,64 +209,58 @@ __global__ void __launch_bounds__(MMA_THREADS) attn_mma_fwd_kernel(AttnMmaArgs a
   }
 }
 
-template <int HD>
-__global__ void __launch_bounds__(MMA_THREADS) attn_mma_bwd_kernel(AttnMmaArgs a) {
-  constexpr int KS = HD + 4, VS = HD + 8;
-  __shared__ __align__(16) float Qs[MT * KS], Ks[MT * KS], Vs[MT * VS], Ds[MT * KS];  // Ds = dO
-  __shared__ float qinv[MT], kinv[MT], lse_s[MT], dsum[MT];
-  __shared__ int qt[MT], kt[MT];
+template <int HD, int TCAP>
+__global__ void __launch_bounds__(TCAP * 2) attn_mma_bwd_kernel(AttnMmaArgs a) {
+  constexpr int KS = HD + 4, VS = HD + 8, NT = TCAP / 8, THREADS = TCAP * 2;
+  __shared__ __align__(16) float Qs[TCAP * KS], Ks[TCAP * KS], Vs[TCAP * VS], Ds[TCAP * KS];  // Ds = dO
+  __shared__ float qinv[TCAP], kinv[TCAP], lse_s[TCAP], dsum[TCAP];
+  __shared__ int qt[TCAP], kt[TCAP];
+  using St = Stage<HD, TCAP, THREADS>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int nw = *a.n_win, first = min(*a.begin, nw);
-  const int n_items = (nw - first) * a.H;
+  const int nw = *a.n_win, first = min(*a.begin, nw), last = min(*a.end, nw);
+  const int n_items = (last - first) * a.H;
   const float tau_raw = *a.tau;
   const float inv_tau = 1.f / fmaxf(tau_raw, a.tau_min);
   float dtau_acc = 0.f;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int w = first + item / a.H, h = item % a.H, col0 = h * HD;
-    const int nq = min(a.qcnt[w], MT), nk = min(a.kcnt[w], MT);
-    __syncthreads();
-    if (threadIdx.x < MT) {
-      qt[threadIdx.x] = threadIdx.x < nq ? a.qtok[w * MT + threadIdx.x] : 0;
-      kt[threadIdx.x] = threadIdx.x < nk ? a.ktok[w * MT + threadIdx.x] : 0;
+    const int nq = min(a.qcnt[w], TCAP), nk = min(a.kcnt[w], TCAP);
+    St sq, sk, sv, sg, so;
+    sq.load(a.q, a.qtok + w * MT, nq, a.C, col0);
+    sk.load(a.k, a.ktok + w * MT, nk, a.C, col0);
+    sv.load(a.v, a.ktok + w * MT, nk, a.C, col0);
+    sg.load(a.dout, a.qtok + w * MT, nq, a.C, col0);
+    so.load(a.o, a.qtok + w * MT, nq, a.C, col0);
+    __syncthreads();  // the previous item's readers are done with shared memory
+    if (threadIdx.x < TCAP) {
+      const int r = threadIdx.x;
+      qt[r] = r < nq ? a.qtok[w * MT + r] : 0;
+      kt[r] = r < nk ? a.ktok[w * MT + r] : 0;
+      lse_s[r] = r < nq ? a.lse[(int64_t)qt[r] * a.H + h] : 0.f;
     }
-    __syncthreads();
-    stage_rows<HD, KS>(Qs, a.q, qt, nq, a.C, col0, true, qinv, 0, MMA_THREADS);
-    stage_rows<HD, KS>(Ks, a.k, kt, nk, a.C, col0, true, kinv, 0, MMA_THREADS);
-    stage_rows<HD, VS>(Vs, a.v, kt, nk, a.C, col0, false, nullptr, 0, MMA_THREADS);
-    // dO rows + D = dO . O + lse (one thread per query row; D uses the un-rounded fp32 values)
-    for (int r = threadIdx.x; r < MT; r += MMA_THREADS) {
-      float x[HD];
-      float d = 0.f;
-      if (r < nq) {
-        const float* p = a.dout + (int64_t)qt[r] * a.C + col0;
-        const float* po = a.o + (int64_t)qt[r] * a.C + col0;
+    sq.template store<KS>(Qs, true, qinv);
+    sk.template store<KS>(Ks, true, kinv);
+    sv.template store<VS>(Vs, false, nullptr);
+    {  // D = dO . O per query row, on the un-rounded fp32 values
+      const int sub = threadIdx.x % St::LPR, rr = threadIdx.x / St::LPR;
 #pragma unroll
-        for (int e = 0; e < HD; e += 4) {
-          float4 u = __ldg(reinterpret_cast<const float4*>(p + e)), v = __ldg(reinterpret_cast<const float4*>(po + e));
-          x[e] = u.x; x[e + 1] = u.y; x[e + 2] = u.z; x[e + 3] = u.w;
-          d += u.x * v.x + u.y * v.y + u.z * v.z + u.w * v.w;
-        }
-        lse_s[r] = a.lse[(int64_t)qt[r] * a.H + h];
-      } else {
-#pragma unroll
-        for (int e = 0; e < HD; ++e) x[e] = 0.f;
-        lse_s[r] = 0.f;
+      for (int p = 0; p < St::PASSES; ++p) {
+        const float d = St::row_sum(sg.x[p].x * so.x[p].x + sg.x[p].y * so.x[p].y + sg.x[p].z * so.x[p].z + sg.x[p].w * so.x[p].w);
+        if (sub == 0) dsum[p * St::RPP + rr] = d;
       }
-      dsum[r] = d;
-#pragma unroll
-      for (int e = 0; e < HD; e += 4)
-        *reinterpret_cast<uint4*>(Ds + r * KS + e) = make_uint4(to_tf32(x[e]), to_tf32(x[e + 1]), to_tf32(x[e + 2]), to_tf32(x[e + 3]));
     }
+    sg.template store<KS>(Ds, false, nullptr);
     __syncthreads();
     const int r0 = warp * 16, ra = r0 + g, rb = r0 + g + 8;
+    const int qtiles = (nq + 7) >> 3, ktiles = (nk + 7) >> 3;
     // ---------------- query strip: dQ (+ dtau)
     if (r0 < nq) {
-      float s[8][4], dp[8][4];
-      strip_xyT<HD, KS, KS>(Qs, Ks, r0, lane, s);    // S = Q_hat K_hat^T
-      strip_xyT<HD, KS, VS>(Ds, Vs, r0, lane, dp);   // dP = dO V^T
+      float s[NT][4], dp[NT][4];
+      strip_xyT<HD, KS, KS, NT>(Qs, Ks, r0, lane, ktiles, s);    // S = Q_hat K_hat^T
+      strip_xyT<HD, KS, VS, NT>(Ds, Vs, r0, lane, ktiles, dp);   // dP = dO V^T
       const float La = lse_s[ra], Lb = lse_s[rb], Da = dsum[ra], Db = dsum[rb];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int col = nt * 8 + 2 * t + (e & 1);
@@ -265,7 +274,7 @@ __global__ void __launch_bounds__(MMA_THREADS) attn_mma_bwd_kernel(AttnMmaArgs a
         }
       }
       float dqh[HD / 8][4];
-      strip_pz<HD, KS>(s, Ks, lane, dqh);  // dQ_hat = dS K_hat / tau
+      strip_pz<HD, KS, NT>(s, Ks, lane, ktiles, dqh);  // dQ_hat = dS K_hat / tau
       // through q_hat = q / max(|q|, eps): dq = (dq_hat - q_hat (q_hat . dq_hat)) / |q|
       float da = 0.f, db = 0.f;
 #pragma unroll
@@ -290,11 +299,11 @@ __global__ void __launch_bounds__(MMA_THREADS) attn_mma_bwd_kernel(AttnMmaArgs a
     }
     // ---------------- key strip (roles transposed): dV, dK
     if (r0 < nk) {
-      float s[8][4], dp[8][4];
-      strip_xyT<HD, KS, KS>(Ks, Qs, r0, lane, s);    // S^T = K_hat Q_hat^T      (rows = keys, cols = queries)
-      strip_xyT<HD, VS, KS>(Vs, Ds, r0, lane, dp);   // dP^T = V dO^T
+      float s[NT][4], dp[NT][4];
+      strip_xyT<HD, KS, KS, NT>(Ks, Qs, r0, lane, qtiles, s);    // S^T = K_hat Q_hat^T      (rows = keys, cols = queries)
+      strip_xyT<HD, VS, KS, NT>(Vs, Ds, r0, lane, qtiles, dp);   // dP^T = V dO^T
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int col = nt * 8 + 2 * t + (e & 1);   // query index
@@ -306,8 +315,8 @@ __global__ void __launch_bounds__(MMA_THREADS) attn_mma_bwd_kernel(AttnMmaArgs a
         }
       }
       float dvv[HD / 8][4], dkh[HD / 8][4];
-      strip_pz<HD, KS>(s, Ds, lane, dvv);    // dV = P^T dO
-      strip_pz<HD, KS>(dp, Qs, lane, dkh);   // dK_hat = dS^T Q_hat / tau
+      strip_pz<HD, KS, NT>(s, Ds, lane, qtiles, dvv);    // dV = P^T dO
+      strip_pz<HD, KS, NT>(dp, Qs, lane, qtiles, dkh);   // dK_hat = dS^T Q_hat / tau
       float da = 0.f, db = 0.f;
 #pragma unroll
       for (int dt = 0; dt < HD / 8; ++dt) {
@@ -337,21 +346,27 @@ __global__ void __launch_bounds__(MMA_THREADS) attn_mma_bwd_kernel(AttnMmaArgs a
   if (lane == 0 && a.dtau && tau_raw > a.tau_min && dtau_acc != 0.f) atomicAdd(a.dtau, dtau_acc * inv_tau);
 }
 
-int attn_mma_fwd(const AttnMmaArgs& a, int hd, int64_t max_windows, cudaStream_t s) {
+template <int HD, int TCAP>
+static void launch_mma(bool bwd, const AttnMmaArgs& a, int64_t max_windows, cudaStream_t s) {
   int64_t items = max_windows * a.H;
-  int grid = (int)(items < (int64_t)8 * kNumSMs ? items : (int64_t)8 * kNumSMs);
-  ProfScope prof("attn_mma_fwd", 0, 0, s);
-  if (hd == 16) attn_mma_fwd_kernel<16><<<grid, MMA_THREADS, 0, s>>>(a);
-  else attn_mma_fwd_kernel<32><<<grid, MMA_THREADS, 0, s>>>(a);
+  const int per_sm = bwd ? (TCAP == 32 ? 10 : 4) : (TCAP == 32 ? 14 : 7);
+  int grid = (int)(items < (int64_t)per_sm * kNumSMs ? items : (int64_t)per_sm * kNumSMs);
+  if (bwd) attn_mma_bwd_kernel<HD, TCAP><<<grid, TCAP * 2, 0, s>>>(a);
+  else attn_mma_fwd_kernel<HD, TCAP><<<grid, TCAP * 2, 0, s>>>(a);
+}
+
+static int attn_mma_run(bool bwd, AttnMmaArgs a, int hd, int64_t max_windows, cudaStream_t s) {
+  ProfScope prof(bwd ? "attn_mma_bwd" : "attn_mma_fwd", 0, 0, s);
+  // windows [small_end, mid_end): <= 32 tokens per side, 2-warp CTAs ; [mid_end, n_win): <= 64 tokens, 4-warp CTAs
+  AttnMmaArgs mid = a, big = a;
+  mid.end = a.mid;
+  big.begin = a.mid; big.end = a.n_win;
+  if (hd == 16) { launch_mma<16, 32>(bwd, mid, max_windows, s); launch_mma<16, 64>(bwd, big, max_windows, s); }
+  else { launch_mma<32, 32>(bwd, mid, max_windows, s); launch_mma<32, 64>(bwd, big, max_windows, s); }
   return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
 }
-int attn_mma_bwd(const AttnMmaArgs& a, int hd, int64_t max_windows, cudaStream_t s) {
-  int64_t items = max_windows * a.H;
-  int grid = (int)(items < (int64_t)4 * kNumSMs ? items : (int64_t)4 * kNumSMs);
-  ProfScope prof("attn_mma_bwd", 0, 0, s);
-  if (hd == 16) attn_mma_bwd_kernel<16><<<grid, MMA_THREADS, 0, s>>>(a);
-  else attn_mma_bwd_kernel<32><<<grid, MMA_THREADS, 0, s>>>(a);
-  return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
-}
+
+int attn_mma_fwd(const AttnMmaArgs& a, int hd, int64_t max_windows, cudaStream_t s) { return attn_mma_run(false, a, hd, max_windows, s); }
+int attn_mma_bwd(const AttnMmaArgs& a, int hd, int64_t max_windows, cudaStream_t s) { return attn_mma_run(true, a, hd, max_windows, s); }
 
 }  // namespace tmae
