@@ -131,6 +131,10 @@ TMAE_API int tmae_window_partition(const int32_t* coords_a, int64_t m_a, const i
 /* options: "tma" (default 1) -- 0 routes the dense tensor-core GEMMs to the thread-staged bf16 kernel;
  * "attn_tc" (default 0; the layer entry points set it from `precision`) -- windows above 16 tokens on mma.sync TF32 */
 TMAE_API int tmae_set_option(const char* name, int32_t value);
+/* Diagnostics: when device_u64 is non-null, CTA 0 of every following TMA GEMM launch writes a timeline of its TMA
+ * producer, MMA issuer and epilogue (four equal slices of `capacity` 64-bit words: event << 56 | index << 40 | SM clock).
+ * Pass NULL to switch it off.  Not part of the data path (no reference counterpart). */
+TMAE_API int tmae_debug_set_trace(void* device_u64, int64_t capacity);
 TMAE_API int tmae_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact,
                     int64_t m, int64_t n, int64_t k, int32_t act, int32_t precision, void* stream);
 TMAE_API int tmae_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int32_t accumulate,
@@ -175,9 +179,20 @@ TMAE_API int tmae_bn_train_fwd(const float* x, const float* gamma, const float* 
                       void* workspace, size_t workspace_bytes, void* stream);
 TMAE_API int tmae_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y, int64_t rows,
                   int32_t c, int32_t relu, void* stream);
-TMAE_API int tmae_bn_bwd(const float* dy, const float* x, const float* y, const float* mean, const float* rstd, const float* gamma, float* dx,
-                float* dgamma, float* dbeta, int64_t rows, int32_t c, int32_t relu, int32_t training, void* workspace,
+/* y may be NULL: the ReLU mask is recomputed from x with the forward's own expression (beta is needed for that) */
+TMAE_API int tmae_bn_bwd(const float* dy, const float* x, const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                float* dx, float* dgamma, float* dbeta, int64_t rows, int32_t c, int32_t relu, int32_t training, void* workspace,
                 size_t workspace_bytes, void* stream);
+/* BatchNorm2d (+ReLU) of the dense decoder (SiamWCA_MAE.py:79-115, nn.BatchNorm2d eps 1e-3 momentum 0.01) on a
+ * channels-last bf16 map viewed as (B*Y*X, C) rows with explicit row pitches (elements): the output may be a column
+ * slice of the concatenated (rows, 384) decoder buffer, which replaces torch.cat (SiamWCA_MAE.py:246-249).
+ * Statistics and arithmetic in fp32 / double; training = 0 applies the given mean / rstd. */
+TMAE_API int tmae_bn_bf16_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     float momentum, float eps, void* y, int64_t ldy, float* mean, float* rstd, int64_t rows, int32_t c, int32_t relu,
+                     int32_t training, void* workspace, size_t workspace_bytes, void* stream);
+TMAE_API int tmae_bn_bf16_bwd(const void* dy, int64_t ldd, const void* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
+                     const float* beta, void* dx, int64_t ldo, float* dgamma, float* dbeta, int64_t rows, int32_t c, int32_t relu,
+                     int32_t training, void* workspace, size_t workspace_bytes, void* stream);
 /* per-voxel max over its points: torch_scatter.scatter_max (temporal_dyn_vfe.py:113) through the CSR */
 TMAE_API int tmae_segment_max_fwd(const float* x, const int32_t* voxel_offset, const int32_t* pt_order, int64_t n_voxels, int32_t c, float* out,
                          int32_t* argmax, void* stream);

@@ -182,6 +182,62 @@ class WCABlock(_EncBlockBase):
         return self.conv_out(feats + x, stage.subm, stage.subm, True, stage.m)
 
 
+class _Bn2dReluCatFn(torch.autograd.Function):
+    """BatchNorm2d + ReLU of several channels-last bf16 maps, each with its own parameters and batch statistics,
+    written side by side into ONE (B, Y, X, sum C) buffer: the reference's `torch.cat([deblock_i(x_i)], dim=1)`
+    (SiamWCA_MAE.py:246-249) without BatchNorm / ReLU / cat passes of their own.  Inputs are the raw
+    ConvTranspose2d / Conv2d outputs (cuDNN).  args = n maps followed by (weight, bias) of every BatchNorm."""
+
+    @staticmethod
+    def forward(ctx, training, bns, n, *args):
+        xs = args[:n]
+        B, _, Y, X = xs[0].shape
+        rows = B * Y * X
+        cs = [x.shape[1] for x in xs]
+        xr = [x.permute(0, 2, 3, 1).contiguous().view(rows, c) for x, c in zip(xs, cs)]  # free for channels-last maps
+        out = torch.empty(rows, sum(cs), dtype=torch.bfloat16, device=xs[0].device)
+        saved, off = [], 0
+        for x, c, bn in zip(xr, cs, bns):
+            if training:
+                mean, rstd = ops.bn_bf16_fwd(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, True, True,
+                                             out[:, off:off + c])
+            else:
+                mean, rstd = bn.running_mean, torch.rsqrt(bn.running_var + bn.eps)
+                ops.bn_bf16_fwd(x, bn.weight, bn.bias, None, None, 0.0, bn.eps, True, False, out[:, off:off + c], mean, rstd)
+            saved += [x, mean, rstd, bn.weight, bn.bias]
+            off += c
+        ctx.save_for_backward(*saved)
+        ctx.misc = (training, cs, (B, Y, X))
+        return out.view(B, Y, X, sum(cs)).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, d):
+        training, cs, (B, Y, X) = ctx.misc
+        rows = B * Y * X
+        dr = d.permute(0, 2, 3, 1).contiguous().view(rows, sum(cs))
+        if dr.dtype != torch.bfloat16:
+            dr = dr.bfloat16()
+        grads_x, grads_p, off = [], [], 0
+        sv = ctx.saved_tensors
+        for i, c in enumerate(cs):
+            x, mean, rstd, gamma, beta = sv[5 * i:5 * i + 5]
+            dx, dg, db = ops.bn_bf16_bwd(dr[:, off:off + c], x, mean, rstd, gamma, beta, True, training)
+            grads_x.append(dx.view(B, Y, X, c).permute(0, 3, 1, 2))
+            grads_p += [dg, db]
+            off += c
+        return (None, None, None, *grads_x, *grads_p)
+
+
+def _bn2d_relu_cat(bns, xs):
+    """Applies the nn.BatchNorm2d modules `bns` (+ReLU) to the bf16 maps `xs` and concatenates along channels."""
+    training = bns[0].training
+    if training:
+        for bn in bns:
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+    return _Bn2dReluCatFn.apply(training, bns, len(xs), *xs, *[p for bn in bns for p in (bn.weight, bn.bias)])
+
+
 def _deblocks(cfg):
     blocks, cin = nn.ModuleList(), 0
     for src in cfg["FEATURES_SOURCE"]:
@@ -220,6 +276,7 @@ class SiamWCA(nn.Module):
         setattr(self, self._deblocks_name, de)
         setattr(self, self._conv_out_name, out)
         self.decoder_autocast = None  # e.g. torch.bfloat16 for the cuDNN decoder in throughput runs
+        self.fused_decoder_bn = os.environ.get("TMAE_FUSED_DECODER_BN", "1") != "0"
         self.debug_refs = False       # emit reference-format partition tables and check the status word
         self.siamese_batched = os.environ.get("TMAE_SIAMESE", "1") != "0"  # both frames through the shared SST blocks as one row set
         self.last_plan = None
@@ -262,6 +319,14 @@ class SiamWCA(nn.Module):
             # throughput mode: the BEV maps are written directly in bf16 channels-last, the cuDNN decoder runs under
             # autocast and `spatial_features` stays bf16 (the reference's AMP run returns fp16 here)
             maps = [sps[src].dense(self.decoder_autocast) for src in self.model_cfg["FEATURES_SOURCE"]]
+            if self.decoder_autocast == torch.bfloat16 and self.fused_decoder_bn:
+                # convolutions on cuDNN; BatchNorm2d + ReLU (+ the channel concat) on the library's bf16 row kernels
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    ups = [de[i][0](m) for i, m in enumerate(maps)]
+                cat = _bn2d_relu_cat([de[i][1] for i in range(len(ups))], ups)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    v = out[0](cat)
+                return _bn2d_relu_cat([out[1]], [v])
             with torch.autocast("cuda", dtype=self.decoder_autocast):
                 return out(torch.cat([de[i](m) for i, m in enumerate(maps)], 1))
         maps = [sps[src].dense() for src in self.model_cfg["FEATURES_SOURCE"]]

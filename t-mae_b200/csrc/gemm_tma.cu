@@ -21,6 +21,13 @@ constexpr int TMA_THREADS = 192;
 
 enum TmaMode { T_NT = 0, T_NN = 1, T_TN = 2 };
 
+// Optional timeline of CTA 0 (diagnostics, tmae_debug_set_trace): records (event id << 56 | index << 40 | clock) words.
+unsigned long long* g_trace_buf = nullptr;
+long long g_trace_cap = 0;
+__device__ __forceinline__ void trace_ev(unsigned long long* buf, int& n, int cap, int ev, int idx) {
+  if (buf && n < cap) buf[n++] = ((unsigned long long)ev << 56) | ((unsigned long long)(idx & 0xffff) << 40) | (clock64() & 0xffffffffffull);
+}
+
 struct TmaArgs {
   int64_t M, N, K;
   const float* bias;
@@ -28,6 +35,7 @@ struct TmaArgs {
   const float* gelu_pre;             // optional: multiply the result by gelu'(gelu_pre[m,n])  (fused GELU backward)
   int act, reduce_add, has_preact;
   int64_t k_chunk;
+  unsigned long long* trace; int trace_cap;
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -163,12 +171,15 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
     // ---------------- TMA producer
     if (lane == 0) {
       int it = 0;
+      unsigned long long* tb = blockIdx.x == 0 ? g.trace : nullptr;
+      int tn = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         int m0, n0, nkb; int64_t kbeg;
         decode(t, m0, n0, kbeg, nkb);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES, use = it / STAGES;
           if (use > 0) bar_wait(&bar_empty[s], (use - 1) & 1);
+          trace_ev(tb, tn, g.trace_cap / 4, 1, it);
           uint8_t* a = smem + s * STAGE;
           uint8_t* b = a + A_BYTES;
           const int k0 = (int)(kbeg + (int64_t)kb * KB);
@@ -193,16 +204,20 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(MODE == T_TN, MODE != T_NT, BN);
       int it = 0, i = 0;
+      unsigned long long* tb = blockIdx.x == 0 && g.trace ? g.trace + g.trace_cap / 4 : nullptr;
+      int tn = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
         int m0, n0, nkb; int64_t kbeg;
         decode(t, m0, n0, kbeg, nkb);
         const int buf = i & 1, round = i >> 1;
         if (round > 0) bar_wait(&bar_acc_empty[buf], (round - 1) & 1);  // epilogue drained this accumulator
+        trace_ev(tb, tn, g.trace_cap / 4, 2, i);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + buf * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES, use = it / STAGES;
           bar_wait(&bar_full[s], use & 1);
+          trace_ev(tb, tn, g.trace_cap / 4, 3, it);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_addr = s_u32(smem + s * STAGE), b_addr = a_addr + A_BYTES;
 #pragma unroll
@@ -224,12 +239,16 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
     const int q = warp & 3;
     constexpr int CHUNKS = BN / 32;
     int i = 0;
+    unsigned long long* tb = blockIdx.x == 0 && g.trace && warp == 2 && lane == 0 ? g.trace + 2 * (g.trace_cap / 4) : nullptr;
+    int tn = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
       int m0, n0, nkb; int64_t kbeg;
       decode(t, m0, n0, kbeg, nkb);
       const int buf = i & 1, round = i >> 1;
       const int64_t row = m0 + q * 32 + lane;
+      trace_ev(tb, tn, g.trace_cap / 4, 4, i);
       bar_wait(&bar_acc_full[buf], round & 1);
+      trace_ev(tb, tn, g.trace_cap / 4, 5, i);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + buf * BN;
       for (int ch = 0; ch < CHUNKS; ++ch) {
@@ -280,6 +299,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
             if (col0 + 4 * c < g.N) *reinterpret_cast<float4*>(crow + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
       }
+      trace_ev(tb, tn, g.trace_cap / 4, 6, i);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -338,6 +358,7 @@ static int tma_launch(const float* A, const float* B, float* C, float* preact, i
   ok &= MODE == T_NT ? make_map(&mb, B, g.K, g.N, ldb, KB, BN, true) : make_map(&mb, B, g.N, g.K, ldb, 32, 32, true, true);
   if (!ok) return TMAE_ERR_CUDA;
   g.has_preact = preact != nullptr;
+  g.trace = g_trace_buf; g.trace_cap = (int)g_trace_cap;
   g.C = C; g.P = preact; g.ldc = ldc;
   size_t smem = (size_t)STAGES * (UM * KB * 4 + BN * KB * 4) + 1024;
   auto kern = tma_gemm_kernel<MODE, BN, STAGES>;
@@ -397,3 +418,9 @@ int tma_linear_bwd_weight(const float* dy, const float* x, float* dw, int64_t m,
 }
 
 }  // namespace tmae
+
+extern "C" int tmae_debug_set_trace(void* device_u64, int64_t capacity) {
+  tmae::g_trace_buf = (unsigned long long*)device_u64;
+  tmae::g_trace_cap = device_u64 ? capacity : 0;
+  return 0;
+}

@@ -104,94 +104,6 @@ __global__ void add_ln_bwd_kernel(const float* __restrict__ dy, const float* __r
   }
 }
 
-// ------------------------------------------------------------------ BatchNorm1d over rows
-// column sums of x and x^2 (double accumulators in global memory)
-__global__ void bn_stats_kernel(const float* __restrict__ x, int64_t rows, int C, double* __restrict__ sum, double* __restrict__ sumsq,
-                                int rows_per_block) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
-  int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  float s = 0.f, q = 0.f;
-  for (int64_t r = r0; r < r1; ++r) {
-    float v = x[r * C + c];
-    s += v;
-    q += v * v;
-  }
-  atomicAdd(sum + c, (double)s);
-  atomicAdd(sumsq + c, (double)q);
-}
-
-__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, int64_t rows, int C, float eps,
-                                   float momentum, float* __restrict__ mean, float* __restrict__ rstd,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double m = sum[c] / (double)rows;
-  double var = sumsq[c] / (double)rows - m * m;
-  if (var < 0) var = 0;
-  mean[c] = (float)m;
-  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) {
-    double unb = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
-    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
-    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unb);
-  }
-}
-
-__global__ void bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
-                                int64_t n, int C, int relu) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int c = (int)(i % C);
-  float v = (x[i] - mean[c]) * rstd[c] * gamma[c] + beta[c];
-  y[i] = relu ? fmaxf(v, 0.f) : v;
-}
-
-// pass 1 of backward: sum(dy'), sum(dy' * xhat) with dy' = dy * (y > 0)
-__global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
-                                     const float* __restrict__ mean, const float* __restrict__ rstd, int64_t rows, int C, int relu,
-                                     double* __restrict__ s_dy, double* __restrict__ s_dyx, int rows_per_block) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
-  int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  float m = mean[c], rs = rstd[c];
-  float a = 0.f, b = 0.f;
-  for (int64_t r = r0; r < r1; ++r) {
-    float d = dy[r * C + c];
-    if (relu && !(y[r * C + c] > 0.f)) d = 0.f;
-    a += d;
-    b += d * (x[r * C + c] - m) * rs;
-  }
-  atomicAdd(s_dy + c, (double)a);
-  atomicAdd(s_dyx + c, (double)b);
-}
-
-// pass 2: dx ; train: gamma*rstd*(dy' - mean(dy') - xhat*mean(dy' xhat)) ; eval: gamma*rstd*dy'
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
-                                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                    const double* __restrict__ s_dy, const double* __restrict__ s_dyx, float* __restrict__ dx,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C, int relu, int training) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < C) {
-    dgamma[i] = (float)s_dyx[i];
-    dbeta[i] = (float)s_dy[i];
-  }
-  if (i >= rows * C) return;
-  int c = (int)(i % C);
-  float d = dy[i];
-  if (relu && !(y[i] > 0.f)) d = 0.f;
-  float rs = rstd[c];
-  if (training) {
-    float xh = (x[i] - mean[c]) * rs;
-    float inv = 1.f / (float)rows;
-    d = d - (float)s_dy[c] * inv - xh * (float)s_dyx[c] * inv;
-  }
-  dx[i] = gamma[c] * rs * d;
-}
-
 // ------------------------------------------------------------------ per-voxel max over its points (CSR)
 // warp per voxel; lanes stride channels; first maximum in ascending point order wins the argmax.
 __global__ void segmax_fwd_kernel(const float* __restrict__ x, const int* __restrict__ offset, const int* __restrict__ order,
@@ -322,55 +234,6 @@ int tmae_add_layernorm_bwd(const float* dy, const float* x, const float* res, co
     case 512: add_ln_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows, rpw); break;
     default: set_error("tmae_add_layernorm_bwd: channels must be 64/128/256/512"); return TMAE_ERR_UNSUPPORTED;
   }
-  TMAE_CHECK_LAUNCH();
-  return 0;
-}
-
-size_t tmae_bn_workspace_bytes(int32_t c) { return (size_t)2 * c * sizeof(double) + 256; }
-
-/* training-mode BatchNorm1d (+ReLU) over rows: batch statistics, running-stat update, apply */
-int tmae_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
-                      float eps, float* y, float* save_mean, float* save_rstd, int64_t rows, int32_t c, int32_t relu,
-                      void* workspace, size_t workspace_bytes, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  TMAE_CHECK_ARG(workspace_bytes >= tmae_bn_workspace_bytes(c), "workspace too small");
-  TMAE_CHECK_ARG(rows > 0, "BatchNorm needs at least one row");
-  double* sum = (double*)workspace;
-  double* sumsq = sum + c;
-  TMAE_CUDA(cudaMemsetAsync(sum, 0, 2 * c * sizeof(double), s));
-  int rpb = 256;
-  dim3 grid((unsigned)cdiv(c, 128), (unsigned)cdiv(rows, rpb));
-  ProfScope prof("bn_train_fwd", 0, 12.0 * rows * c, s);
-  bn_stats_kernel<<<grid, 128, 0, s>>>(x, rows, c, sum, sumsq, rpb);
-  bn_finalize_kernel<<<cdiv(c, 128), 128, 0, s>>>(sum, sumsq, rows, c, eps, momentum, save_mean, save_rstd, running_mean, running_var);
-  bn_apply_kernel<<<cdiv(rows * c, 256), 256, 0, s>>>(x, save_mean, save_rstd, gamma, beta, y, rows * c, c, relu);
-  TMAE_CHECK_LAUNCH();
-  return 0;
-}
-
-/* apply with given mean / rstd (eval mode: running statistics) */
-int tmae_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, float* y, int64_t rows,
-                  int32_t c, int32_t relu, void* stream) {
-  if (rows <= 0) return 0;
-  bn_apply_kernel<<<cdiv(rows * c, 256), 256, 0, (cudaStream_t)stream>>>(x, mean, rstd, gamma, beta, y, rows * c, c, relu);
-  TMAE_CHECK_LAUNCH();
-  return 0;
-}
-
-int tmae_bn_bwd(const float* dy, const float* x, const float* y, const float* mean, const float* rstd, const float* gamma, float* dx,
-                float* dgamma, float* dbeta, int64_t rows, int32_t c, int32_t relu, int32_t training, void* workspace,
-                size_t workspace_bytes, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  TMAE_CHECK_ARG(workspace_bytes >= tmae_bn_workspace_bytes(c), "workspace too small");
-  TMAE_CHECK_ARG(rows > 0, "BatchNorm needs at least one row");
-  double* a = (double*)workspace;
-  double* b = a + c;
-  TMAE_CUDA(cudaMemsetAsync(a, 0, 2 * c * sizeof(double), s));
-  int rpb = 256;
-  dim3 grid((unsigned)cdiv(c, 128), (unsigned)cdiv(rows, rpb));
-  ProfScope prof("bn_bwd", 0, 28.0 * rows * c, s);
-  bn_bwd_reduce_kernel<<<grid, 128, 0, s>>>(dy, x, y, mean, rstd, rows, c, relu, a, b, rpb);
-  bn_bwd_apply_kernel<<<cdiv(rows * c, 256), 256, 0, s>>>(dy, x, y, mean, rstd, gamma, a, b, dx, dgamma, dbeta, rows, c, relu, training);
   TMAE_CHECK_LAUNCH();
   return 0;
 }

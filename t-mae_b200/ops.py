@@ -346,7 +346,7 @@ def bn_apply(x, mean, rstd, gamma, beta, relu, out=None):
     return y
 
 
-def bn_bwd(dy, x, y, mean, rstd, gamma, relu, training, out=None):
+def bn_bwd(dy, x, beta, mean, rstd, gamma, relu, training, out=None):
     L = lib()
     rows, c = x.shape
     dx = torch.empty_like(x) if out is None else out
@@ -354,8 +354,43 @@ def bn_bwd(dy, x, y, mean, rstd, gamma, relu, training, out=None):
     dbeta = torch.empty(c, dtype=F32, device=x.device)
     wsb = L.bn_workspace_bytes(c)
     ws = _ws(wsb, x.device)
-    _call("bn_bwd", _p(dy, F32), _p(x, F32), _p(y, F32), _p(mean), _p(rstd), _p(gamma, F32), _p(dx), _p(dgamma), _p(dbeta), rows, c,
+    _call("bn_bwd", _p(dy, F32), _p(x, F32), None, _p(mean), _p(rstd), _p(gamma, F32), _p(beta, F32), _p(dx), _p(dgamma), _p(dbeta), rows, c,
           int(relu), int(training), _p(ws), wsb, _stream())
+    return dx, dgamma, dbeta
+
+
+BF16 = torch.bfloat16
+
+
+def bn_bf16_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, relu, training, out, mean=None, rstd=None):
+    """x (rows, C) bf16 contiguous; out (rows, C) bf16 view with any row pitch (a column slice of the concat buffer)."""
+    L = lib()
+    rows, c = x.shape
+    if not (x.is_cuda and x.dtype == BF16 and out.dtype == BF16 and x.stride(1) == 1 and out.stride(1) == 1):
+        raise RuntimeError("bn_bf16_fwd needs bf16 CUDA tensors with unit column stride")
+    if training:
+        mean = torch.empty(c, dtype=F32, device=x.device)
+        rstd = torch.empty(c, dtype=F32, device=x.device)
+    wsb = L.bn_workspace_bytes(c)
+    ws = _ws(wsb, x.device)
+    _call("bn_bf16_fwd", x.data_ptr(), x.stride(0), _p(gamma, F32), _p(beta, F32), _p(running_mean), _p(running_var), float(momentum), float(eps),
+          out.data_ptr(), out.stride(0), _p(mean), _p(rstd), rows, c, int(relu), int(training), _p(ws), wsb, _stream())
+    return mean, rstd
+
+
+def bn_bf16_bwd(dy, x, mean, rstd, gamma, beta, relu, training):
+    """dy (rows, C) bf16 view with any row pitch; x (rows, C) bf16 contiguous -> dx bf16 contiguous, dgamma, dbeta."""
+    L = lib()
+    rows, c = x.shape
+    if not (dy.dtype == BF16 and x.dtype == BF16 and dy.stride(1) == 1 and x.stride(1) == 1):
+        raise RuntimeError("bn_bf16_bwd needs bf16 tensors with unit column stride")
+    dx = torch.empty(rows, c, dtype=BF16, device=x.device)
+    dgamma = torch.empty(c, dtype=F32, device=x.device)
+    dbeta = torch.empty(c, dtype=F32, device=x.device)
+    wsb = L.bn_workspace_bytes(c)
+    ws = _ws(wsb, x.device)
+    _call("bn_bf16_bwd", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), _p(mean, F32), _p(rstd, F32), _p(gamma, F32), _p(beta, F32),
+          dx.data_ptr(), dx.stride(0), _p(dgamma), _p(dbeta), rows, c, int(relu), int(training), _p(ws), wsb, _stream())
     return dx, dgamma, dbeta
 
 

@@ -41,15 +41,15 @@ class _BnReluFn(torch.autograd.Function):
         else:
             mean, rstd = running_mean, torch.rsqrt(running_var + eps)
             y = ops.bn_apply(x, mean, rstd, gamma, beta, relu)
-        ctx.save_for_backward(x, y, mean, rstd, gamma)
+        ctx.save_for_backward(x, beta, mean, rstd, gamma)   # the ReLU mask is recomputed from x: y is not kept
         ctx.flags = (relu, training)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, mean, rstd, gamma = ctx.saved_tensors
+        x, beta, mean, rstd, gamma = ctx.saved_tensors
         relu, training = ctx.flags
-        dx, dg, db = ops.bn_bwd(dy.contiguous(), x, y, mean, rstd, gamma, relu, training)
+        dx, dg, db = ops.bn_bwd(dy.contiguous(), x, beta, mean, rstd, gamma, relu, training)
         return dx, dg, db, None, None, None, None, None, None
 
 
@@ -73,13 +73,13 @@ class _BnReluSegFn(torch.autograd.Function):
                 mean, rstd = running_mean, torch.rsqrt(running_var + eps)
                 ops.bn_apply(x[a:b], mean, rstd, gamma, beta, relu, out=y[a:b])
             stats[i] = (mean, rstd)
-        ctx.save_for_backward(x, y, gamma, *[t for s in stats if s is not None for t in s])
+        ctx.save_for_backward(x, beta, gamma, *[t for s in stats if s is not None for t in s])
         ctx.misc = (relu, training, bounds, [s is not None for s in stats])
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, gamma, *flat = ctx.saved_tensors
+        x, beta, gamma, *flat = ctx.saved_tensors
         relu, training, bounds, present = ctx.misc
         dy = dy.contiguous()
         dx = torch.empty_like(x)
@@ -91,7 +91,7 @@ class _BnReluSegFn(torch.autograd.Function):
             mean, rstd = flat[2 * k], flat[2 * k + 1]
             k += 1
             a, b = bounds[i], bounds[i + 1]
-            _, g, bb = ops.bn_bwd(dy[a:b], x[a:b], y[a:b], mean, rstd, gamma, relu, training, out=dx[a:b])
+            _, g, bb = ops.bn_bwd(dy[a:b], x[a:b], beta, mean, rstd, gamma, relu, training, out=dx[a:b])
             dg, db = (g, bb) if dg is None else (dg + g, db + bb)
         return dx, dg, db, None, None, None, None, None, None, None, None
 

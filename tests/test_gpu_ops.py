@@ -282,7 +282,7 @@ def test_batchnorm_rows(rows, C, relu):
     y, mean, rstd = ops.bn_train_fwd(x.to(DEV), ga, be, rm, rv, 0.01, 1e-3, relu)
     assert_close(y, ref.detach(), 1e-5, 1e-5, "BN fwd")
     assert_close(rm, bn.running_mean, 1e-5, 1e-6, "running mean"), assert_close(rv, bn.running_var, 1e-5, 1e-6, "running var")
-    dx, dg, db = ops.bn_bwd(dy.to(DEV), x.to(DEV), y, mean, rstd, ga, relu, True)
+    dx, dg, db = ops.bn_bwd(dy.to(DEV), x.to(DEV), be, mean, rstd, ga, relu, True)
     assert_close(dx, xd.grad, 1e-4, 1e-5, "BN dx")
     assert_close(dg, bn.weight.grad, 1e-4, 1e-4 * rows ** .5, "BN dgamma"), assert_close(db, bn.bias.grad, 1e-4, 1e-4 * rows ** .5, "BN dbeta")
     # eval mode
@@ -293,8 +293,41 @@ def test_batchnorm_rows(rows, C, relu):
     m_e, r_e = bn.running_mean.float().to(DEV), torch.rsqrt(bn.running_var + 1e-3).float().to(DEV)
     ye = ops.bn_apply(x.to(DEV), m_e, r_e, ga, be, relu)
     assert_close(ye, re.detach(), 1e-5, 1e-5, "BN eval fwd")
-    dxe, _, _ = ops.bn_bwd(dy.to(DEV), x.to(DEV), ye, m_e, r_e, ga, relu, False)
+    dxe, _, _ = ops.bn_bwd(dy.to(DEV), x.to(DEV), be, m_e, r_e, ga, relu, False)
     assert_close(dxe, xe.grad, 1e-4, 1e-5, "BN eval dx")
+
+
+@pytest.mark.parametrize("rows,C", [(7, 128), (4099, 128), (2000, 64)])
+def test_batchnorm_bf16_strided(rows, C):
+    """BatchNorm2d + ReLU of the decoder on a channels-last bf16 map: output written into a column slice of a wider
+    buffer (replaces torch.cat), gradient read from a column slice.  Reference: float64 BatchNorm on the same
+    bf16-rounded input; tolerance = bf16 output rounding (rtol 2^-8)."""
+    g = torch.Generator().manual_seed(rows * 3 + C)
+    x = (torch.randn(rows, C, generator=g) * 1.5 + 0.3).bfloat16()
+    bn = torch.nn.BatchNorm1d(C, eps=1e-3, momentum=0.01).double()
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.1 * torch.randn(C, generator=g)), bn.bias.copy_(0.1 * torch.randn(C, generator=g))
+    rm, rv = bn.running_mean.clone().float().to(DEV), bn.running_var.clone().float().to(DEV)
+    ga, be = bn.weight.detach().float().to(DEV), bn.bias.detach().float().to(DEV)
+    xd = x.double().requires_grad_()
+    ref = torch.relu(bn(xd))
+    wide = torch.full((rows, 3 * C), 7.0, dtype=torch.bfloat16, device=DEV)
+    mean, rstd = ops.bn_bf16_fwd(x.to(DEV), ga, be, rm, rv, 0.01, 1e-3, True, True, wide[:, C:2 * C])
+    assert_close(wide[:, C:2 * C].float(), ref.detach(), 2 ** -8, 1e-3, "BN bf16 fwd")
+    assert (wide[:, :C] == 7).all() and (wide[:, 2 * C:] == 7).all(), "neighbouring column slices were touched"
+    assert_close(rm, bn.running_mean, 1e-4, 1e-5, "running mean"), assert_close(rv, bn.running_var, 1e-4, 1e-5, "running var")
+    dwide = torch.randn(rows, 3 * C, generator=g).bfloat16()
+    ref.backward(dwide[:, C:2 * C].double())
+    dx, dg, db = ops.bn_bf16_bwd(dwide.to(DEV)[:, C:2 * C], x.to(DEV), mean, rstd, ga, be, True, True)
+    assert_close(dx.float(), xd.grad, 2 ** -7, 2e-3, "BN bf16 dx")
+    assert_close(dg, bn.weight.grad, 1e-3, 1e-3 * rows ** .5, "BN bf16 dgamma"), assert_close(db, bn.bias.grad, 1e-3, 1e-3 * rows ** .5, "BN bf16 dbeta")
+    # eval mode: given statistics
+    bn.eval()
+    re = torch.relu(bn(x.double()))
+    m_e, r_e = bn.running_mean.float().to(DEV), torch.rsqrt(bn.running_var + 1e-3).float().to(DEV)
+    out = torch.empty(rows, C, dtype=torch.bfloat16, device=DEV)
+    ops.bn_bf16_fwd(x.to(DEV), ga, be, None, None, 0.01, 1e-3, True, False, out, m_e, r_e)
+    assert_close(out.float(), re, 2 ** -8, 1e-3, "BN bf16 eval")
 
 
 def test_segment_max_and_rows():

@@ -17,6 +17,12 @@ if what == "nn":
     dy, w = torch.randn(m, n, device=DEV), torch.randn(n, k, device=DEV)
     for _ in range(4):
         ops.linear_bwd_data(dy, w)
+elif what == "nt128":
+    m, n, k = 56000, 128, 128
+    xs = [torch.randn(m, k, device=DEV) for _ in range(4)]
+    w, b = torch.randn(n, k, device=DEV), torch.randn(n, device=DEV)
+    for i in range(8):
+        ops.linear_fwd(xs[i % 4], w, b)
 elif what == "nt":
     m, n, k = 50000, 256, 256
     x, w, b = torch.randn(m, k, device=DEV), torch.randn(n, k, device=DEV), torch.randn(n, device=DEV)
