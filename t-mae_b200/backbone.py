@@ -284,7 +284,9 @@ class SiamWCA(nn.Module):
     # ---- pieces -------------------------------------------------------------------------------
     @staticmethod
     def _indices(coords):
-        return coords[:, [0, 2, 3]].contiguous().int()  # (bs_idx, y_idx, x_idx), SiamWCA.py:553-557
+        # (bs_idx, y_idx, x_idx), SiamWCA.py:553-557; column views, no index tensor (a Python list index costs a
+        # host-to-device copy and a sync per call)
+        return torch.stack((coords[:, 0], coords[:, 2], coords[:, 3]), 1).int()
 
     def _encode(self, feats, fp):
         hidden = []
@@ -345,20 +347,42 @@ class SiamWCA(nn.Module):
         if int(self.grid_size[2]) != 1:
             raise RuntimeError("the backbone needs a single z slab (pillars)")
 
-    def _run(self, bd, feats, coords, feats_prev, coords_prev):
+    @staticmethod
+    def _prepass(bd, fn):
+        """Runs the coordinate-only part of the forward.  With batch_dict["side_stream"] (opt-in, see ops.side_stream)
+        it runs on that stream -- its host reads of row counts then wait for a handful of tiny kernels, not for the
+        main stream's backlog -- and the main stream is made to wait for it."""
+        side = bd.get("side_stream")
+        if side is None:
+            return fn()
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(side):
+            out = fn()
+        main.wait_stream(side)
+        ops.record_all(out, main)
+        return out
+
+    def _geometry(self, bd, coords, coords_prev):
+        """Every coordinate-only table of the forward (plan.build_plans): no feature or weight is touched."""
         B = int(bd["batch_size"])
         idx_c, idx_p = self._indices(coords), self._indices(coords_prev)
         if self.siamese_batched:
-            idx_all = torch.cat([idx_c, idx_p + torch.tensor([B, 0, 0], dtype=idx_p.dtype, device=idx_p.device)], 0)
-            plans, tparts = build_plans([idx_c, idx_p, idx_all], B, self.sparse_shape, self.block_cfgs, temporal_pair=(0, 1),
-                                        want_ref=self.debug_refs, check=self.debug_refs, batches=[B, B, 2 * B],
-                                        need=[("subm", "part") if self.debug_refs else ("subm",), ("part",) if self.debug_refs else (), ("subm", "part")])
-            self.last_plan = (plans, tparts)
+            idx_p2 = idx_p.clone()
+            idx_p2[:, 0] += B  # samples B..2B-1 of the Siamese-batched set are the previous frame
+            idx_all = torch.cat([idx_c, idx_p2], 0)
+            return build_plans([idx_c, idx_p, idx_all], B, self.sparse_shape, self.block_cfgs, temporal_pair=(0, 1),
+                               want_ref=self.debug_refs, check=self.debug_refs, batches=[B, B, 2 * B],
+                               need=[("subm", "part") if self.debug_refs else ("subm",), ("part",) if self.debug_refs else (), ("subm", "part")])
+        return build_plans([idx_c, idx_p], B, self.sparse_shape, self.block_cfgs, temporal_pair=(0, 1), want_ref=self.debug_refs,
+                           check=self.debug_refs)
+
+    def _run(self, bd, feats, coords, feats_prev, coords_prev, geom=None):
+        B = int(bd["batch_size"])
+        plans, tparts = self._prepass(bd, lambda: self._geometry(bd, coords, coords_prev)) if geom is None else geom
+        self.last_plan = (plans, tparts)
+        if self.siamese_batched:
             hid, hid_prev = self._encode_siamese(feats, feats_prev, plans[2], plans[0])
         else:
-            plans, tparts = build_plans([idx_c, idx_p], B, self.sparse_shape, self.block_cfgs,
-                                        temporal_pair=(0, 1), want_ref=self.debug_refs, check=self.debug_refs)
-            self.last_plan = (plans, tparts)
             hid_prev = self._encode(feats_prev, plans[1])
             hid = self._encode(feats, plans[0])
         hid = self._cross(hid, hid_prev, plans[0], tparts)
@@ -459,20 +483,24 @@ class SiamWCA_MAE(SiamWCA):
         self._check_z(batch_dict)
         bd = batch_dict
         feats, coords = bd["voxel_features"], bd["voxel_coords"]
-        if "voxel_mae_mask_in" in bd:  # caller-supplied mask (tests, reproducible runs)
-            mask = bd["voxel_mae_mask_in"].float()
-            n_vis = int((mask == 0).sum())
-        else:
-            vps = bd.get("voxels_per_sample")
-            if vps is None:
-                vps = torch.bincount(coords[:, 0], minlength=int(bd["batch_size"])).tolist()
-            mask, n_vis = self.mask_voxels(coords, vps)
+
+        def pre():  # coordinate-only: mask, visible set, geometry plans
+            if "voxel_mae_mask_in" in bd:  # caller-supplied mask (tests, reproducible runs)
+                mask = bd["voxel_mae_mask_in"].float()
+                n_vis = int((mask == 0).sum())
+            else:
+                vps = bd.get("voxels_per_sample")
+                if vps is None:
+                    vps = torch.bincount(coords[:, 0], minlength=int(bd["batch_size"])).tolist()
+                mask, n_vis = self.mask_voxels(coords, vps)
+            vis = torch.nonzero_static(mask == 0, size=n_vis).view(-1).int()
+            vis_coords = coords[vis.long()]
+            return mask, vis, vis_coords, self._indices(coords), self._geometry(bd, vis_coords, bd["voxel_coords_prev"])
+
+        mask, vis, vis_coords, all_idx, geom = self._prepass(bd, pre)
         bd["voxel_mae_mask"] = mask
-        vis = torch.nonzero_static(mask == 0, size=n_vis).view(-1).int()
         vis_feats = _GatherRowsFn.apply(feats, vis)
-        vis_coords = coords[vis.long()]
-        sf = self._run(bd, vis_feats, vis_coords, bd["voxel_features_prev"], bd["voxel_coords_prev"])
-        all_idx = self._indices(coords)
+        sf = self._run(bd, vis_feats, vis_coords, bd["voxel_features_prev"], bd["voxel_coords_prev"], geom)
         vf = gather_bev(sf, all_idx)
         bd["voxel_features"], bd["voxel_coords"] = vf, coords
         bd["voxel_shuffle_inds"] = torch.arange(coords.shape[0], device=coords.device)

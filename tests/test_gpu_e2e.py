@@ -184,6 +184,36 @@ def test_siamese_batched_equals_separate():
         assert_close(st_a[k].float(), st_b[k].float(), 1e-5, 1e-6, k)
 
 
+def test_side_stream_prepass_is_equivalent():
+    """batch_dict["side_stream"]: the coordinate-only pre-pass on the library's side stream gives the same integers
+    bit for bit and the same loss / features as the single-stream path, over several steps with the main stream busy."""
+    pts, ptsp = cases.small_points(79, 900, 2)
+    res = []
+    for use_side in (False, True):
+        vfe, bb = tmae_b200.build_model("pretrain", S["grid"], S["voxel"], S["range"])
+        cases.fill_params(vfe), cases.fill_params(bb)
+        vfe.to(DEV), bb.to(DEV)
+        bb.mask_generator = torch.Generator(device=DEV).manual_seed(7)
+        side = ops.side_stream(DEV) if use_side else None
+        outs = []
+        for it in range(3):
+            with torch.cuda.stream(side) if use_side else torch.cuda.stream(torch.cuda.current_stream()):
+                p, pp = torch.from_numpy(pts).to(DEV, non_blocking=True), torch.from_numpy(ptsp).to(DEV, non_blocking=True)
+            bd = dict(points=p, points_prev=pp, batch_size=2)
+            if use_side:
+                bd["side_stream"] = side
+            bd = bb(vfe(bd))
+            loss, _ = bb.get_loss()
+            loss.backward()
+            outs.append((bd["voxel_coords"].clone(), bd["voxel_mae_mask"].clone(), bd["spatial_features"].detach().clone(), loss.detach().clone()))
+        torch.cuda.synchronize()
+        res.append(outs)
+    for (c0, m0, s0, l0), (c1, m1, s1, l1) in zip(*res):
+        assert_equal_int(c0, c1, "voxel_coords"), assert_close(m0, m1, 0, 0, "mask")
+        assert_close(s0, s1, 1e-5, 1e-5, "spatial_features")
+        assert abs(l0.item() - l1.item()) <= 1e-5 * abs(l0.item())
+
+
 def test_fused_decoder_batchnorm_matches_torch():
     """Throughput mode: the decoder's BatchNorm2d + ReLU + concat on the library's bf16 kernels against the same
     decoder with torch's BatchNorm2d / ReLU / cat under autocast (both bf16): features, loss, gradients and
