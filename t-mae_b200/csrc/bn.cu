@@ -125,8 +125,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
   }
 }
 
-// MODE 0: y = [relu]((x - mean) rstd gamma + beta)
-// MODE 1: dx = gamma rstd (dy' - [train] (mean(dy') + xhat mean(dy' xhat)))   (also writes dgamma / dbeta once)
+// MODE 0: y = [relu](x sc + sh)                       with sc = rstd gamma, sh = beta - mean sc
+// MODE 1: dx = sc dy' + x kb + kc                      (also writes dgamma / dbeta once)
+//         = gamma rstd (dy' - [train] (mean(dy') + xhat mean(dy' xhat))),  dy' = dy [x sc + sh > 0]
+// Four per-channel constants per thread keep the register count low enough for 2+ blocks per SM.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(BN_THREADS) bn_rows_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t ldd,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -135,18 +137,21 @@ __global__ void __launch_bounds__(BN_THREADS) bn_rows_kernel(const T* __restrict
                                                               T* __restrict__ out, int64_t ldo, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, int64_t rows, int C) {
   constexpr int V = Vec<T>::N;
+  constexpr int U = MODE == 1 ? 2 : BN_UNROLL;
   const int tpr = C / V, rpb = BN_THREADS / tpr;
   const int ch = (threadIdx.x % tpr) * V, rg = threadIdx.x / tpr;
-  float sc[V], sh[V], k0[V], k1[V], m[V], rs[V], ga[V], be[V];
+  float sc[V], sh[V], kb[V], kc[V];
   const float inv = 1.f / (float)rows;
 #pragma unroll
   for (int j = 0; j < V; ++j) {
-    m[j] = mean[ch + j]; rs[j] = rstd[ch + j]; ga[j] = gamma[ch + j]; be[j] = beta ? beta[ch + j] : 0.f;
-    sc[j] = rs[j] * ga[j];
-    sh[j] = be[j] - m[j] * sc[j];
+    const float m = mean[ch + j], rs = rstd[ch + j];
+    sc[j] = rs * gamma[ch + j];
+    sh[j] = (beta ? beta[ch + j] : 0.f) - m * sc[j];
     if (MODE == 1) {
-      k0[j] = training ? (float)s_dy[ch + j] * inv : 0.f;
-      k1[j] = training ? (float)s_dyx[ch + j] * inv : 0.f;
+      const float k0 = training ? (float)s_dy[ch + j] * inv : 0.f;
+      const float k1 = training ? (float)s_dyx[ch + j] * inv : 0.f;
+      kb[j] = -sc[j] * k1 * rs;
+      kc[j] = -sc[j] * k0 - kb[j] * m;
     }
   }
   if (MODE == 1 && blockIdx.x == 0 && rg == 0) {
@@ -154,10 +159,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_rows_kernel(const T* __restrict
     for (int j = 0; j < V; ++j) { dgamma[ch + j] = (float)s_dyx[ch + j]; dbeta[ch + j] = (float)s_dy[ch + j]; }
   }
   const int64_t stride = (int64_t)gridDim.x * rpb;
-  for (int64_t r = (int64_t)blockIdx.x * rpb + rg; r < rows; r += stride * BN_UNROLL) {
-    float xv[BN_UNROLL][V], dv[BN_UNROLL][V];
+  for (int64_t r = (int64_t)blockIdx.x * rpb + rg; r < rows; r += stride * U) {
+    float xv[U][V], dv[U][V];
 #pragma unroll
-    for (int u = 0; u < BN_UNROLL; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int64_t rr = r + u * stride;
       if (rr < rows) {
         Vec<T>::load(x + rr * ldx + ch, xv[u]);
@@ -165,20 +170,18 @@ __global__ void __launch_bounds__(BN_THREADS) bn_rows_kernel(const T* __restrict
       }
     }
 #pragma unroll
-    for (int u = 0; u < BN_UNROLL; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int64_t rr = r + u * stride;
       if (rr >= rows) continue;
       float o[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) {
+        const float v = fmaf(xv[u][j], sc[j], sh[j]);
         if (MODE == 0) {
-          const float v = fmaf(xv[u][j], sc[j], sh[j]);
           o[j] = relu ? fmaxf(v, 0.f) : v;
         } else {
-          const float xh = (xv[u][j] - m[j]) * rs[j];
-          float d = dv[u][j];
-          if (relu && !(fmaf(xv[u][j], sc[j], sh[j]) > 0.f)) d = 0.f;
-          o[j] = sc[j] * (d - k0[j] - xh * k1[j]);
+          const float d = (relu && !(v > 0.f)) ? 0.f : dv[u][j];
+          o[j] = fmaf(sc[j], d, fmaf(xv[u][j], kb[j], kc[j]));
         }
       }
       Vec<T>::store(out + rr * ldo + ch, o);
@@ -194,7 +197,7 @@ static bool bn_shape_ok(int c) {
 static int bn_grid(int64_t rows, int c, int vec) {
   int rpb = BN_THREADS / (c / vec);
   int64_t blocks = (rows + (int64_t)rpb * BN_UNROLL - 1) / ((int64_t)rpb * BN_UNROLL);
-  int64_t cap = (int64_t)kNumSMs * 8;
+  int64_t cap = (int64_t)kNumSMs * 16;
   return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 

@@ -104,6 +104,158 @@ __global__ void add_ln_bwd_kernel(const float* __restrict__ dy, const float* __r
   }
 }
 
+// ------------------------------------------------------------------ LayerNorm(x + res), vectorised (C = 128 * VPL)
+// One warp per row, a lane owns VPL float4 column chunks (coalesced 512-byte row segments), two rows in flight per warp.
+// The backward keeps its dgamma / dbeta partial sums in registers over a grid-stride walk of the rows, reduces them
+// across the block's warps in shared memory and issues 2C atomics per BLOCK (the scalar version issued them per warp).
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float sum4(const float4& a) { return (a.x + a.y) + (a.z + a.w); }
+
+template <int VPL>
+__global__ void __launch_bounds__(256) add_ln_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                             const uint8_t* __restrict__ rowmask, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* __restrict__ y,
+                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, float eps) {
+  constexpr int C = VPL * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 g[VPL], b[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) { g[k] = ld4(gamma + k * 128 + lane * 4); b[k] = ld4(beta + k * 128 + lane * 4); }
+  for (int64_t r0 = warp * 2; r0 < rows; r0 += nwarps * 2) {
+    float4 v[2][VPL];
+    bool ok[2], use[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t r = r0 + u;
+      ok[u] = r < rows;
+      use[u] = ok[u] && res && (!rowmask || rowmask[r]);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        v[u][k] = ok[u] ? ld4(x + r * C + k * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (use[u]) {
+          const float4 t = ld4(res + r * C + k * 128 + lane * 4);
+          v[u][k].x += t.x; v[u][k].y += t.y; v[u][k].z += t.z; v[u][k].w += t.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;  // warp-uniform
+      const int64_t r = r0 + u;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) s += sum4(v[u][k]);
+      const float mean = warp_sum(s) * (1.f / C);
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const float dx = v[u][k].x - mean, dy = v[u][k].y - mean, dz = v[u][k].z - mean, dw = v[u][k].w - mean;
+        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+      const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        float4 o;
+        o.x = (v[u][k].x - mean) * rstd * g[k].x + b[k].x;
+        o.y = (v[u][k].y - mean) * rstd * g[k].y + b[k].y;
+        o.z = (v[u][k].z - mean) * rstd * g[k].z + b[k].z;
+        o.w = (v[u][k].w - mean) * rstd * g[k].w + b[k].w;
+        *reinterpret_cast<float4*>(y + r * C + k * 128 + lane * 4) = o;
+      }
+      if (lane == 0) {
+        if (mean_out) mean_out[r] = mean;
+        if (rstd_out) rstd_out[r] = rstd;
+      }
+    }
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) add_ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                             const float* __restrict__ res, const uint8_t* __restrict__ rowmask,
+                                                             const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                             const float* __restrict__ rstd_in, float* __restrict__ dv,
+                                                             float* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                             int64_t rows) {
+  constexpr int C = VPL * 128;
+  __shared__ float red[2][8][C];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 g[VPL], dg[VPL], db[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    g[k] = ld4(gamma + k * 128 + lane * 4);
+    dg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t r0 = warp * 2; r0 < rows; r0 += nwarps * 2) {
+    float4 v[2][VPL], d[2][VPL];
+    bool ok[2], use[2];
+    float mean[2], rstd[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t r = r0 + u;
+      ok[u] = r < rows;
+      use[u] = ok[u] && res && (!rowmask || rowmask[r]);
+      mean[u] = ok[u] ? mean_in[r] : 0.f;
+      rstd[u] = ok[u] ? rstd_in[r] : 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int64_t off = r * C + k * 128 + lane * 4;
+        v[u][k] = ok[u] ? ld4(x + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        d[u][k] = ok[u] ? ld4(dy + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (use[u]) {
+          const float4 t = ld4(res + off);
+          v[u][k].x += t.x; v[u][k].y += t.y; v[u][k].z += t.z; v[u][k].w += t.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;  // warp-uniform
+      const int64_t r = r0 + u;
+      float s1 = 0.f, s2 = 0.f;
+      float4 xh[VPL], gg[VPL];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        xh[k].x = (v[u][k].x - mean[u]) * rstd[u]; xh[k].y = (v[u][k].y - mean[u]) * rstd[u];
+        xh[k].z = (v[u][k].z - mean[u]) * rstd[u]; xh[k].w = (v[u][k].w - mean[u]) * rstd[u];
+        gg[k].x = d[u][k].x * g[k].x; gg[k].y = d[u][k].y * g[k].y; gg[k].z = d[u][k].z * g[k].z; gg[k].w = d[u][k].w * g[k].w;
+        dg[k].x = fmaf(d[u][k].x, xh[k].x, dg[k].x); dg[k].y = fmaf(d[u][k].y, xh[k].y, dg[k].y);
+        dg[k].z = fmaf(d[u][k].z, xh[k].z, dg[k].z); dg[k].w = fmaf(d[u][k].w, xh[k].w, dg[k].w);
+        db[k].x += d[u][k].x; db[k].y += d[u][k].y; db[k].z += d[u][k].z; db[k].w += d[u][k].w;
+        s1 += sum4(gg[k]);
+        s2 += (gg[k].x * xh[k].x + gg[k].y * xh[k].y) + (gg[k].z * xh[k].z + gg[k].w * xh[k].w);
+      }
+      s1 = warp_sum(s1) * (1.f / C);
+      s2 = warp_sum(s2) * (1.f / C);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        float4 o;
+        o.x = rstd[u] * (gg[k].x - s1 - xh[k].x * s2); o.y = rstd[u] * (gg[k].y - s1 - xh[k].y * s2);
+        o.z = rstd[u] * (gg[k].z - s1 - xh[k].z * s2); o.w = rstd[u] * (gg[k].w - s1 - xh[k].w * s2);
+        const int64_t off = r * C + k * 128 + lane * 4;
+        *reinterpret_cast<float4*>(dv + off) = o;
+        if (dres) *reinterpret_cast<float4*>(dres + off) = use[u] ? o : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    *reinterpret_cast<float4*>(&red[0][wib][k * 128 + lane * 4]) = dg[k];
+    *reinterpret_cast<float4*>(&red[1][wib][k * 128 + lane * 4]) = db[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += red[0][w][c]; b += red[1][w][c]; }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, b);
+  }
+}
+
 // ------------------------------------------------------------------ per-voxel max over its points (CSR)
 // warp per voxel; lanes stride channels; first maximum in ascending point order wins the argmax.
 __global__ void segmax_fwd_kernel(const float* __restrict__ x, const int* __restrict__ offset, const int* __restrict__ order,
@@ -204,12 +356,14 @@ int tmae_add_layernorm_fwd(const float* x, const float* res, const uint8_t* rowm
   if (rows <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   int grid = cdiv(rows * 32, 256);
+  int64_t vb = (rows + 15) / 16;  // vectorised kernels: 8 warps x 2 rows per block iteration
+  int vgrid = (int)(vb < (int64_t)kNumSMs * 8 ? vb : (int64_t)kNumSMs * 8);
   ProfScope prof("add_layernorm_fwd", 0, 4.0 * rows * c * (res ? 3 : 2), s);
   switch (c) {
     case 64: add_ln_fwd_kernel<2><<<grid, 256, 0, s>>>(x, res, rowmask, gamma, beta, y, mean, rstd, rows, eps); break;
-    case 128: add_ln_fwd_kernel<4><<<grid, 256, 0, s>>>(x, res, rowmask, gamma, beta, y, mean, rstd, rows, eps); break;
-    case 256: add_ln_fwd_kernel<8><<<grid, 256, 0, s>>>(x, res, rowmask, gamma, beta, y, mean, rstd, rows, eps); break;
-    case 512: add_ln_fwd_kernel<16><<<grid, 256, 0, s>>>(x, res, rowmask, gamma, beta, y, mean, rstd, rows, eps); break;
+    case 128: add_ln_fwd_vec_kernel<1><<<vgrid, 256, 0, s>>>(x, res, rowmask, gamma, beta, y, mean, rstd, rows, eps); break;
+    case 256: add_ln_fwd_vec_kernel<2><<<vgrid, 256, 0, s>>>(x, res, rowmask, gamma, beta, y, mean, rstd, rows, eps); break;
+    case 512: add_ln_fwd_vec_kernel<4><<<vgrid, 256, 0, s>>>(x, res, rowmask, gamma, beta, y, mean, rstd, rows, eps); break;
     default: set_error("tmae_add_layernorm_fwd: channels must be 64/128/256/512"); return TMAE_ERR_UNSUPPORTED;
   }
   TMAE_CHECK_LAUNCH();
@@ -227,11 +381,13 @@ int tmae_add_layernorm_bwd(const float* dy, const float* x, const float* res, co
   int64_t warps = (rows + rpw - 1) / rpw;
   int grid = cdiv(warps * 32, 256);
   ProfScope prof("add_layernorm_bwd", 0, 4.0 * rows * c * (res ? 4 : 3) + (dres ? 4.0 * rows * c : 0), s);
+  int64_t vb = (rows + 63) / 64;  // vectorised kernels: every warp walks >= 8 rows so the per-block reduction amortises
+  int vgrid = (int)(vb < (int64_t)kNumSMs * 6 ? vb : (int64_t)kNumSMs * 6);
   switch (c) {
     case 64: add_ln_bwd_kernel<2><<<grid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows, rpw); break;
-    case 128: add_ln_bwd_kernel<4><<<grid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows, rpw); break;
-    case 256: add_ln_bwd_kernel<8><<<grid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows, rpw); break;
-    case 512: add_ln_bwd_kernel<16><<<grid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows, rpw); break;
+    case 128: add_ln_bwd_vec_kernel<1><<<vgrid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows); break;
+    case 256: add_ln_bwd_vec_kernel<2><<<vgrid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows); break;
+    case 512: add_ln_bwd_vec_kernel<4><<<vgrid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows); break;
     default: set_error("tmae_add_layernorm_bwd: channels must be 64/128/256/512"); return TMAE_ERR_UNSUPPORTED;
   }
   TMAE_CHECK_LAUNCH();
