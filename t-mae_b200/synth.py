@@ -10,6 +10,11 @@ ONCE = dict(range=[-74.88, -74.88, -5.0, 74.88, 74.88, 3.0], voxel=[0.32, 0.32, 
             elev=(-25.0, 15.0), feats=4)
 WAYMO = dict(range=[-75.2, -75.2, -2.0, 75.2, 75.2, 4.0], voxel=[0.32, 0.32, 6.0], beams=64,
              elev=(-17.6, 2.4), feats=5)
+# The released ONCE model block needs a BEV grid divisible by 4 (two stride-2 sparse convs, then x1/x2/x4 transposed
+# convs concatenated, SiamWCA_MAE.py:231-253); 75.2 m / 0.32 m = 470 is not, and no Waymo model YAML is released
+# (README.md:21).  "waymo" = the Waymo-shaped scan on the nearest usable grid (472^2, +-75.52 m).
+WAYMO_DATASET_RANGE = list(WAYMO["range"])
+WAYMO = dict(WAYMO, range=[-75.52, -75.52, -2.0, 75.52, 75.52, 4.0])
 SHAPES = {"once": ONCE, "waymo": WAYMO}
 
 
