@@ -36,3 +36,36 @@ def test_sharding_and_max_over_ranks():
         assert out[0] == out[1]
         t, value = out[0]
         assert t == 15.0 and abs(value - 4 * 10 * 2 / 0.015) < 1e-6
+
+
+def _allreduce_worker(rank, world, port, out):
+    import importlib
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tdist = importlib.import_module("tmae_b200.dist")
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 2))]
+    ps[0].grad = torch.full((3, 4), float(rank + 1))
+    ps[1].grad = torch.arange(5.0) * (rank + 1)
+    ps[2].grad = None if rank == 1 else torch.ones(2, 2)  # missing on one rank: counts as zeros
+    tdist.allreduce_gradients(ps)
+    out[rank] = [p.grad.clone() for p in ps]
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_gloo_world2():
+    """The pretraining gradient exchange (one flat all-reduce, mean over ranks) on 2 CPU ranks over gloo."""
+    import torch
+    import torch.multiprocessing as mp
+    import tmae_b200  # noqa: F401  (package alias)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_allreduce_worker, args=(2, 29533, out), nprocs=2, join=True)
+    for r in range(2):
+        g0, g1, g2 = out[r]
+        assert torch.equal(g0, torch.full((3, 4), 1.5))
+        assert torch.equal(g1, torch.arange(5.0) * 1.5)
+        assert torch.equal(g2, torch.full((2, 2), 0.5))
