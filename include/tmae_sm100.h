@@ -137,6 +137,25 @@ TMAE_API int tmae_set_option(const char* name, int32_t value);
 TMAE_API int tmae_debug_set_trace(void* device_u64, int64_t capacity);
 TMAE_API int tmae_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact,
                     int64_t m, int64_t n, int64_t k, int32_t act, int32_t precision, void* stream);
+/* y[m, :] = x[m, :] @ w^T + lut[rowidx[m], :]: the packed q/k/v projection of an encoder layer with the window position
+ * embedding folded in.  q = (x + pos) Wq^T + bq = x Wq^T + (pos_lut Wq^T + bq)[posidx] because the embedding depends only on
+ * the voxel's cell inside its 8x8 window (64 rows, spt_backbone.py:186-231); lut = tmae_pos_table output, (64, n). */
+TMAE_API int tmae_linear_fwd_lut(const float* x, const float* w, const float* lut, const uint8_t* rowidx, float* y, int64_t m, int64_t n,
+                        int64_t k, int32_t precision, void* stream);
+/* table[p, j] = (j < n_pos ? sum_c pos_lut[p, c] * w[j, c] : 0) + bias[j]   for p < 64, j < n   (always fp32) */
+TMAE_API int tmae_pos_table(const float* pos_lut, const float* w, const float* bias, float* table, float* table_t, int32_t n, int32_t n_pos,
+                   int32_t c, void* stream);
+/* The tensor-core form of the same projection: y = x w^T + x2 w2^T in ONE GEMM whose reduction runs over k then k2
+ * (x2 = tmae_onehot64(posidx) (m, 64), w2 = table_t (n, 64) from tmae_pos_table, so x2 w2^T = table[posidx]). */
+TMAE_API int tmae_linear_fwd_dual(const float* x, const float* w, const float* x2, const float* w2, float* y, int64_t m, int64_t n, int64_t k,
+                         int64_t k2, int32_t precision, void* stream);
+TMAE_API int tmae_onehot64(const uint8_t* idx, float* out, int64_t m, void* stream);
+/* backward of the table bias: dtable[p, :] = sum over rows with rowidx == p of dy[row, :]  (64 x n, overwritten);
+ * dbias[j] = sum_p dtable[p, j];  dw[j, :] += sum_p dtable[p, j] * pos_lut[p, :] for j < n_pos (adds to dw).
+ * transposed = 1: dtable is (n, 64) = dy^T onehot, i.e. tmae_linear_bwd_weight(dy, onehot) -- the tensor-core form. */
+TMAE_API int tmae_binned_colsum(const float* dy, const uint8_t* rowidx, float* dtable, int64_t rows, int32_t n, void* stream);
+TMAE_API int tmae_pos_table_bwd(const float* dtable, int32_t transposed, const float* pos_lut, float* dw, float* dbias, int32_t n, int32_t n_pos,
+                       int32_t c, void* stream);
 TMAE_API int tmae_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int32_t accumulate,
                          int32_t precision, void* stream);
 TMAE_API int tmae_linear_bwd_data_gelu(const float* dy, const float* w, const float* preact, float* dx, int64_t m, int64_t n, int64_t k,
@@ -218,16 +237,17 @@ TMAE_API int tmae_scatter_rows(const float* rows, const int32_t* sel, int64_t m,
  * leading windows that hold <= 16 tokens on both sides (= level_base[first level with max_tokens > 16]; windows are
  * level-sorted): those run one warp per window, the rest one CTA per window with shared memory sized for 32 tokens
  * (windows [small_end, mid_end), mid_end = level_base[first level with max_tokens > 32]) or 64.  Backward: dsum (q rows,
- * heads) scratch. */
+ * heads) scratch.  ld_q / ld_k / ld_v: row pitches (elements, >= channels, multiples of 4) of q / k / v and of
+ * dq / dk / dv, so the three may be column blocks of one packed projection output (rows, 3*channels); o, dout: channels. */
 TMAE_API int tmae_window_attention_fwd(const float* q, const float* k, const float* v, float* o, float* lse, const int32_t* qtok,
                               const int32_t* qcnt, const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win,
                               const int32_t* small_end, const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min,
-                              int32_t channels, int32_t heads, void* stream);
+                              int32_t channels, int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, void* stream);
 TMAE_API int tmae_window_attention_bwd(const float* dout, const float* q, const float* k, const float* v, const float* o, const float* lse,
                               float* dsum, float* dq, float* dk, float* dv, float* dtau, const int32_t* qtok, const int32_t* qcnt,
                               const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win, const int32_t* small_end,
                               const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min, int32_t channels,
-                              int32_t heads, void* stream);
+                              int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, void* stream);
 
 /* ---- A10-A11 reconstruction target + Chamfer loss ------------------------------------------------
  * Replaces sst_ops_cuda.group_inner_inds_wrapper (pcdet/ops/sst_ops/src/sst_ops_api.cpp:8, sst_ops_gpu.cu:22-39),
@@ -260,6 +280,8 @@ typedef struct tmae_layer_tables {
   const int32_t *qtok, *qcnt, *ktok, *kcnt, *n_win, *small_end, *mid_end; /* from tmae_window_partition (one shift) */
   const uint8_t* rowmask;   /* (m_q) cross only: 1 = row belongs to a paired window */
   int64_t max_windows;
+  const float* onehot_q;    /* (m_q, 64) tmae_onehot64(posidx_q); NULL = use the table-bias epilogue (fp32 SIMT path) */
+  const float* onehot_kv;   /* (m_kv, 64) cross only */
 } tmae_layer_tables;
 TMAE_API size_t tmae_encoder_layer_saved_bytes(int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t cross);
 TMAE_API size_t tmae_encoder_layer_scratch_bytes(int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t cross);
@@ -267,7 +289,7 @@ TMAE_API int tmae_encoder_layer_fwd(const float* x, const float* x_kv, const tma
                            float tau_min, float eps, int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t precision,
                            float* y, void* saved, size_t saved_size, void* stream);
 TMAE_API int tmae_encoder_layer_bwd(const float* dy, const float* x, const float* x_kv, const tmae_layer_params* P, const tmae_layer_tables* T,
-                           float tau_min, int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t precision,
+                           const float* pos_lut, float tau_min, int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t precision,
                            const void* saved, size_t saved_size, float* dx, float* dx_kv, const tmae_layer_params* G, void* scratch,
                            size_t scratch_size, void* stream);
 

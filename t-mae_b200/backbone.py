@@ -80,15 +80,15 @@ class _LayerFn(torch.autograd.Function):
             x_kv = x_kv.contiguous()
         T = ops.layer_tables(part, shift, x_kv is not None, x.shape[0], x_kv.shape[0] if x_kv is not None else 0)
         y, saved = ops.encoder_layer_fwd(x, x_kv, params, T, lut, tau_min, eps, heads)
-        ctx.save_for_backward(x, x_kv, saved, *params)
+        ctx.save_for_backward(x, x_kv, saved, lut, *params)
         ctx.misc = (T, part, heads, tau_min)  # part keeps the device tables alive
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, x_kv, saved, *params = ctx.saved_tensors
+        x, x_kv, saved, lut, *params = ctx.saved_tensors
         T, _, heads, tau_min = ctx.misc
-        dx, dkv, grads = ops.encoder_layer_bwd(dy.contiguous(), x, x_kv, params, T, tau_min, heads, saved,
+        dx, dkv, grads = ops.encoder_layer_bwd(dy.contiguous(), x, x_kv, params, T, lut, tau_min, heads, saved,
                                                x_kv is not None and ctx.needs_input_grad[1])
         return (dx, dkv, None, None, None, None, None, None, *grads)
 

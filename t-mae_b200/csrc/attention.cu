@@ -45,6 +45,7 @@ struct AttnArgs {
   const int* mid_end;                                // device: windows [*small_end, *mid_end) hold <= 32 tokens
   const float* tau; float tau_min;
   int C, H;
+  int ldq, ldk, ldv;                                 // row pitches (elements) of q / k / v and of dq / dk / dv; o, dO: C
   const float* dout; float* dq; float* dk; float* dv; float* dtau;
 };
 
@@ -83,11 +84,12 @@ __device__ __forceinline__ float normalize(float* x, unsigned mask) {
 template <int SPLIT, int MODE, class ST>
 __device__ __forceinline__ void run_item(const AttnArgs& a, const ST& st, int n_other, int64_t row, int col, int head, float inv_tau,
                                          float& dtau_acc, unsigned mask) {
-  const int64_t off = row * a.C + col;
+  const int64_t off = row * a.C + col;                       // o, dO
+  const int64_t offq = row * a.ldq + col, offk = row * a.ldk + col, offv = row * a.ldv + col;
   const bool lead = SPLIT == 1 || (col % (HT * SPLIT)) == 0;  // one lane of a pair owns the per-head scalars
   if (MODE == 0) {
     float qh[HT];
-    load_row(a.q + off, qh);
+    load_row(a.q + offq, qh);
     float s = inv_tau / fmaxf(sqrtf(dot<SPLIT>(qh, qh, mask)), 1e-12f);
 #pragma unroll
     for (int d = 0; d < HT; ++d) qh[d] *= s;  // q_hat / tau
@@ -118,7 +120,7 @@ __device__ __forceinline__ void run_item(const AttnArgs& a, const ST& st, int n_
     if (a.lse && lead) a.lse[row * a.H + head] = m + __logf(l);
   } else if (MODE == 1) {
     float qh[HT], dov[HT], dqh[HT];
-    load_row(a.q + off, qh);
+    load_row(a.q + offq, qh);
     float inv = normalize<SPLIT>(qh, mask);
     load_row(a.dout + off, dov);
     float Di;
@@ -146,12 +148,12 @@ __device__ __forceinline__ void run_item(const AttnArgs& a, const ST& st, int n_
     float dt = dot<SPLIT>(dqh, qh, mask);  // through q_hat = q / max(|q|, eps)
 #pragma unroll
     for (int d = 0; d < HT; ++d) dqh[d] = (dqh[d] - qh[d] * dt) * inv;
-    store_row(a.dq + off, dqh);
+    store_row(a.dq + offq, dqh);
   } else {
     float kh[HT], vv[HT], dkh[HT], dvv[HT];
-    load_row(a.k + off, kh);
+    load_row(a.k + offk, kh);
     float inv = normalize<SPLIT>(kh, mask);
-    load_row(a.v + off, vv);
+    load_row(a.v + offv, vv);
 #pragma unroll
     for (int d = 0; d < HT; ++d) { dkh[d] = 0.f; dvv[d] = 0.f; }
     for (int i = 0; i < n_other; ++i) {
@@ -167,8 +169,8 @@ __device__ __forceinline__ void run_item(const AttnArgs& a, const ST& st, int n_
     float dt = dot<SPLIT>(dkh, kh, mask);
 #pragma unroll
     for (int d = 0; d < HT; ++d) dkh[d] = (dkh[d] - kh[d] * dt) * inv;
-    store_row(a.dk + off, dkh);
-    store_row(a.dv + off, dvv);
+    store_row(a.dk + offk, dkh);
+    store_row(a.dv + offv, dvv);
   }
 }
 
@@ -241,9 +243,8 @@ __device__ __forceinline__ void small_fwd_window(const AttnArgs& a, const float4
 #pragma unroll
   for (int j = 0; j < NK; ++j) {
     const int t = __shfl_sync(0xffffffffu, tokv, j);
-    const int64_t off = (int64_t)t * a.C + col;
-    kr[j] = ldg4_if(a.k + off, j < nk);
-    vr[j] = ldg4_if(a.v + off, j < nk);
+    kr[j] = ldg4_if(a.k + (int64_t)t * a.ldk + col, j < nk);
+    vr[j] = ldg4_if(a.v + (int64_t)t * a.ldv + col, j < nk);
   }
 #pragma unroll
   for (int j = 0; j < NK; ++j) scale4(kr[j], inv_norm<EXACT>(head_sum<HL>(dot4(kr[j], kr[j]))));
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(SW_THREADS, 3) attn_small_fwd_kernel(AttnArgs 
 #pragma unroll
     for (int i = 0; i < SW_T; ++i) {
       const int t = __shfl_sync(0xffffffffu, tokv, SW_T + i);
-      if (i < nq) cp_async16(&q_s[wib][i][lane], a.q + (int64_t)t * a.C + col);
+      if (i < nq) cp_async16(&q_s[wib][i][lane], a.q + (int64_t)t * a.ldq + col);
     }
     if (nk <= 4) small_fwd_window<HL, 4, 2, EXACT>(a, q_s[wib], nq, nk, tokv, col, lane, scale);
     else if (nk <= 8) small_fwd_window<HL, 8, 2, EXACT>(a, q_s[wib], nq, nk, tokv, col, lane, scale);
@@ -330,9 +331,8 @@ __device__ __forceinline__ void small_bwd_chunk(const AttnArgs& a, const SmallBw
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
     const int t = __shfl_sync(0xffffffffu, tokv, (kc + j) & (SW_T - 1));
-    const int64_t off = (int64_t)t * a.C + col;
-    kr[j] = ldg4_if(a.k + off, j < nc);
-    vr[j] = ldg4_if(a.v + off, j < nc);
+    kr[j] = ldg4_if(a.k + (int64_t)t * a.ldk + col, j < nc);
+    vr[j] = ldg4_if(a.v + (int64_t)t * a.ldv + col, j < nc);
     dk[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     dv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -369,7 +369,7 @@ __device__ __forceinline__ void small_bwd_chunk(const AttnArgs& a, const SmallBw
     const float dt = head_sum<HL>(dot4(dqh, qh));
     float4 dq = make_float4((dqh.x - qh.x * dt) * qinv, (dqh.y - qh.y * dt) * qinv, (dqh.z - qh.z * dt) * qinv, (dqh.w - qh.w * dt) * qinv);
     const int row = __shfl_sync(0xffffffffu, tokv, SW_T + i);
-    float4* dst = reinterpret_cast<float4*>(a.dq + (int64_t)row * a.C + col);
+    float4* dst = reinterpret_cast<float4*>(a.dq + (int64_t)row * a.ldq + col);
     if (!first) { const float4 prev = *dst; dq.x += prev.x; dq.y += prev.y; dq.z += prev.z; dq.w += prev.w; }
     *dst = dq;
   }
@@ -380,8 +380,8 @@ __device__ __forceinline__ void small_bwd_chunk(const AttnArgs& a, const SmallBw
     if (j < nc) {
       const float4 r = make_float4((dk[j].x - kr[j].x * dt) * kinv[j], (dk[j].y - kr[j].y * dt) * kinv[j],
                                    (dk[j].z - kr[j].z * dt) * kinv[j], (dk[j].w - kr[j].w * dt) * kinv[j]);
-      *reinterpret_cast<float4*>(a.dk + (int64_t)t * a.C + col) = r;
-      *reinterpret_cast<float4*>(a.dv + (int64_t)t * a.C + col) = dv[j];
+      *reinterpret_cast<float4*>(a.dk + (int64_t)t * a.ldk + col) = r;
+      *reinterpret_cast<float4*>(a.dv + (int64_t)t * a.ldv + col) = dv[j];
     }
   }
 }
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(SW_THREADS, 2) attn_small_bwd_kernel(AttnArgs 
       const int t = __shfl_sync(0xffffffffu, tokv, SW_T + i);
       if (i < nq) {
         const int64_t off = (int64_t)t * a.C + col;
-        cp_async16(&S.q[i][lane], a.q + off);
+        cp_async16(&S.q[i][lane], a.q + (int64_t)t * a.ldq + col);
         cp_async16(&S.g[i][lane], a.dout + off);
         cp_async16(&S.o[i][lane], a.o + off);
         cp_async4(&S.lse[i][lane], a.lse + (int64_t)t * a.H + head);
@@ -489,9 +489,10 @@ __global__ void __launch_bounds__(LARGE_THREADS) attn_large_kernel(AttnArgs a, c
     for (int e = threadIdx.x; e < n_other * (TW / 4); e += LARGE_THREADS) {  // coalesced 512-byte row segments
       int j = e / (TW / 4), c4 = (e - j * (TW / 4)) * 4;
       int sl = c4 / HT, d = c4 - sl * HT;
-      const int64_t src = (int64_t)stat_tok[j] * a.C + col0 + c4;
-      *reinterpret_cast<float4*>(As + j * RS + sl * SS + d) = __ldg(reinterpret_cast<const float4*>(srcA + src));
-      *reinterpret_cast<float4*>(Bs + j * RS + sl * SS + d) = __ldg(reinterpret_cast<const float4*>(srcB + src));
+      const int64_t srca = (int64_t)stat_tok[j] * (MODE == 2 ? a.ldq : a.ldk) + col0 + c4;
+      const int64_t srcb = (int64_t)stat_tok[j] * (MODE == 2 ? a.C : a.ldv) + col0 + c4;
+      *reinterpret_cast<float4*>(As + j * RS + sl * SS + d) = __ldg(reinterpret_cast<const float4*>(srcA + srca));
+      *reinterpret_cast<float4*>(Bs + j * RS + sl * SS + d) = __ldg(reinterpret_cast<const float4*>(srcB + srcb));
     }
     __syncthreads();
     for (int e = threadIdx.x; e < n_other * HEADS; e += LARGE_THREADS) {  // F.normalize per (row, head)
@@ -558,6 +559,7 @@ struct AttnMmaArgs {
   const int* n_win; const int* begin; const int* mid; const int* end;
   const float* tau; float tau_min;
   int C, H;
+  int ldq, ldk, ldv;
   const float* dout; float* dq; float* dk; float* dv; float* dtau;
 };
 int attn_mma_fwd(const AttnMmaArgs& a, int hd, int64_t max_windows, cudaStream_t s);
@@ -567,7 +569,7 @@ bool g_attn_tc = false;  // set by the layer entry points (tensor-core precision
 static AttnMmaArgs to_mma(const AttnArgs& a) {
   AttnMmaArgs m{};
   m.q = a.q; m.k = a.k; m.v = a.v; m.o = a.o; m.lse = a.lse; m.qtok = a.qtok; m.qcnt = a.qcnt; m.ktok = a.ktok; m.kcnt = a.kcnt;
-  m.n_win = a.n_win; m.begin = a.small_end; m.mid = a.mid_end; m.end = a.n_win; m.tau = a.tau; m.tau_min = a.tau_min; m.C = a.C; m.H = a.H;
+  m.n_win = a.n_win; m.begin = a.small_end; m.mid = a.mid_end; m.end = a.n_win; m.tau = a.tau; m.tau_min = a.tau_min; m.C = a.C; m.H = a.H; m.ldq = a.ldq; m.ldk = a.ldk; m.ldv = a.ldv;
   m.dout = a.dout; m.dq = a.dq; m.dk = a.dk; m.dv = a.dv; m.dtau = a.dtau;
   return m;
 }
@@ -630,6 +632,7 @@ static int launch_bwd(const AttnArgs& a, int64_t max_windows, cudaStream_t s) {
 }
 
 static int check(const AttnArgs& a, int hd) {
+  if (a.ldq < a.C || a.ldk < a.C || a.ldv < a.C || (a.ldq | a.ldk | a.ldv) % 4 != 0) return -1;
   if (a.C % TW != 0 || a.H != a.C / hd || (hd != 16 && hd != 32)) return -1;
   return 0;
 }
@@ -643,8 +646,9 @@ extern "C" {
 int tmae_window_attention_fwd(const float* q, const float* k, const float* v, float* o, float* lse, const int32_t* qtok,
                               const int32_t* qcnt, const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win,
                               const int32_t* small_end, const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min,
-                              int32_t channels, int32_t heads, void* stream) {
+                              int32_t channels, int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, void* stream) {
   AttnArgs a{};
+  a.ldq = ld_q; a.ldk = ld_k; a.ldv = ld_v;
   a.q = q; a.k = k; a.v = v; a.o = o; a.lse = lse; a.qtok = qtok; a.qcnt = qcnt; a.ktok = ktok; a.kcnt = kcnt; a.n_win = n_win;
   a.small_end = small_end; a.mid_end = mid_end; a.tau = tau; a.tau_min = tau_min; a.C = channels; a.H = heads;
   int hd = channels / heads;
@@ -660,8 +664,9 @@ int tmae_window_attention_bwd(const float* dout, const float* q, const float* k,
                               float* dsum, float* dq, float* dk, float* dv, float* dtau, const int32_t* qtok, const int32_t* qcnt,
                               const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win, const int32_t* small_end,
                               const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min, int32_t channels,
-                              int32_t heads, void* stream) {
+                              int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, void* stream) {
   AttnArgs a{};
+  a.ldq = ld_q; a.ldk = ld_k; a.ldv = ld_v;
   a.q = q; a.k = k; a.v = v; a.o = (float*)o; a.lse = (float*)lse; a.dsum = dsum; a.qtok = qtok; a.qcnt = qcnt; a.ktok = ktok;
   a.kcnt = kcnt; a.n_win = n_win; a.small_end = small_end; a.mid_end = mid_end; a.tau = tau; a.tau_min = tau_min; a.C = channels;
   a.H = heads; a.dout = dout; a.dq = dq; a.dk = dk; a.dv = dv; a.dtau = dtau;

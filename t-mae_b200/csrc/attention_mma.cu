@@ -23,6 +23,7 @@ struct AttnMmaArgs {
   const int* n_win; const int* begin; const int* mid; const int* end;   // windows [*begin, *mid) <= 32 tokens, [*mid, *n_win) <= 64
   const float* tau; float tau_min;
   int C, H;
+  int ldq, ldk, ldv;                    // row pitches of q / k / v (and dq / dk / dv); o and dO have pitch C
   const float* dout; float* dq; float* dk; float* dv; float* dtau;
 };
 
@@ -157,9 +158,9 @@ __global__ void __launch_bounds__(TCAP * 2) attn_mma_fwd_kernel(AttnMmaArgs a) {
     const int w = first + item / a.H, h = item % a.H, col0 = h * HD;
     const int nq = min(a.qcnt[w], TCAP), nk = min(a.kcnt[w], TCAP);
     Stage<HD, TCAP, THREADS> sq, sk, sv;
-    sq.load(a.q, a.qtok + w * MT, nq, a.C, col0);
-    sk.load(a.k, a.ktok + w * MT, nk, a.C, col0);
-    sv.load(a.v, a.ktok + w * MT, nk, a.C, col0);
+    sq.load(a.q, a.qtok + w * MT, nq, a.ldq, col0);
+    sk.load(a.k, a.ktok + w * MT, nk, a.ldk, col0);
+    sv.load(a.v, a.ktok + w * MT, nk, a.ldv, col0);
     __syncthreads();  // the previous item's readers are done with shared memory
     if (threadIdx.x < TCAP) qt[threadIdx.x] = threadIdx.x < nq ? a.qtok[w * MT + threadIdx.x] : 0;
     sq.template store<KS>(Qs, true, nullptr);
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(TCAP * 2) attn_mma_fwd_kernel(AttnMmaArgs a) {
 }
 
 template <int HD, int TCAP>
-__global__ void __launch_bounds__(TCAP * 2) attn_mma_bwd_kernel(AttnMmaArgs a) {
+__global__ void __launch_bounds__(TCAP * 2, TCAP == 64 ? 4 : 8) attn_mma_bwd_kernel(AttnMmaArgs a) {
   constexpr int KS = HD + 4, VS = HD + 8, NT = TCAP / 8, THREADS = TCAP * 2;
   __shared__ __align__(16) float Qs[TCAP * KS], Ks[TCAP * KS], Vs[TCAP * VS], Ds[TCAP * KS];  // Ds = dO
   __shared__ float qinv[TCAP], kinv[TCAP], lse_s[TCAP], dsum[TCAP];
@@ -226,9 +227,9 @@ __global__ void __launch_bounds__(TCAP * 2) attn_mma_bwd_kernel(AttnMmaArgs a) {
     const int w = first + item / a.H, h = item % a.H, col0 = h * HD;
     const int nq = min(a.qcnt[w], TCAP), nk = min(a.kcnt[w], TCAP);
     St sq, sk, sv, sg, so;
-    sq.load(a.q, a.qtok + w * MT, nq, a.C, col0);
-    sk.load(a.k, a.ktok + w * MT, nk, a.C, col0);
-    sv.load(a.v, a.ktok + w * MT, nk, a.C, col0);
+    sq.load(a.q, a.qtok + w * MT, nq, a.ldq, col0);
+    sk.load(a.k, a.ktok + w * MT, nk, a.ldk, col0);
+    sv.load(a.v, a.ktok + w * MT, nk, a.ldv, col0);
     sg.load(a.dout, a.qtok + w * MT, nq, a.C, col0);
     so.load(a.o, a.qtok + w * MT, nq, a.C, col0);
     __syncthreads();  // the previous item's readers are done with shared memory
@@ -290,10 +291,10 @@ __global__ void __launch_bounds__(TCAP * 2) attn_mma_bwd_kernel(AttnMmaArgs a) {
         const float* qa = Qs + ra * KS + dt * 8 + 2 * t;
         const float* qb = Qs + rb * KS + dt * 8 + 2 * t;
         if (ra < nq)
-          *reinterpret_cast<float2*>(a.dq + (int64_t)qt[ra] * a.C + col0 + dt * 8 + 2 * t) =
+          *reinterpret_cast<float2*>(a.dq + (int64_t)qt[ra] * a.ldq + col0 + dt * 8 + 2 * t) =
               make_float2((dqh[dt][0] - qa[0] * da) * qinv[ra], (dqh[dt][1] - qa[1] * da) * qinv[ra]);
         if (rb < nq)
-          *reinterpret_cast<float2*>(a.dq + (int64_t)qt[rb] * a.C + col0 + dt * 8 + 2 * t) =
+          *reinterpret_cast<float2*>(a.dq + (int64_t)qt[rb] * a.ldq + col0 + dt * 8 + 2 * t) =
               make_float2((dqh[dt][2] - qb[0] * db) * qinv[rb], (dqh[dt][3] - qb[1] * db) * qinv[rb]);
       }
     }
@@ -332,12 +333,12 @@ __global__ void __launch_bounds__(TCAP * 2) attn_mma_bwd_kernel(AttnMmaArgs a) {
         const float* kb = Ks + rb * KS + dt * 8 + 2 * t;
         const int c = col0 + dt * 8 + 2 * t;
         if (ra < nk) {
-          *reinterpret_cast<float2*>(a.dk + (int64_t)kt[ra] * a.C + c) = make_float2((dkh[dt][0] - ka[0] * da) * kinv[ra], (dkh[dt][1] - ka[1] * da) * kinv[ra]);
-          *reinterpret_cast<float2*>(a.dv + (int64_t)kt[ra] * a.C + c) = make_float2(dvv[dt][0], dvv[dt][1]);
+          *reinterpret_cast<float2*>(a.dk + (int64_t)kt[ra] * a.ldk + c) = make_float2((dkh[dt][0] - ka[0] * da) * kinv[ra], (dkh[dt][1] - ka[1] * da) * kinv[ra]);
+          *reinterpret_cast<float2*>(a.dv + (int64_t)kt[ra] * a.ldv + c) = make_float2(dvv[dt][0], dvv[dt][1]);
         }
         if (rb < nk) {
-          *reinterpret_cast<float2*>(a.dk + (int64_t)kt[rb] * a.C + c) = make_float2((dkh[dt][2] - kb[0] * db) * kinv[rb], (dkh[dt][3] - kb[1] * db) * kinv[rb]);
-          *reinterpret_cast<float2*>(a.dv + (int64_t)kt[rb] * a.C + c) = make_float2(dvv[dt][2], dvv[dt][3]);
+          *reinterpret_cast<float2*>(a.dk + (int64_t)kt[rb] * a.ldk + c) = make_float2((dkh[dt][2] - kb[0] * db) * kinv[rb], (dkh[dt][3] - kb[1] * db) * kinv[rb]);
+          *reinterpret_cast<float2*>(a.dv + (int64_t)kt[rb] * a.ldv + c) = make_float2(dvv[dt][2], dvv[dt][3]);
         }
       }
     }

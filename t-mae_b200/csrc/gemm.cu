@@ -26,6 +26,7 @@ struct GemmArgs {
   int64_t M, N, K;
   int64_t lda, ldb, ldc;
   const float* bias;      // per n
+  const float* lut; const uint8_t* rowidx; int64_t ldlut;  // optional per-row table bias: + lut[rowidx[m]][n]
   const float* residual;  // same layout as C
   float* preact;          // optional copy of the pre-activation (for GELU backward)
   const int* tab;         // neighbour table (rows, taps), -1 = absent
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(GT) gemm_kernel(GemmArgs g) {
         continue;
       }
       if (g.bias) v += g.bias[nn];
+      if (g.lut) v += g.lut[(int64_t)g.rowidx[mm] * g.ldlut + nn];
       if (g.preact) g.preact[o] = v;
       if (g.act == TMAE_ACT_GELU) v = gelu_erf(v);
       else if (g.act == TMAE_ACT_RELU) v = fmaxf(v, 0.f);
@@ -198,6 +200,78 @@ __global__ void colsum_kernel(const float* __restrict__ x, int64_t rows, int col
   }
 }
 
+// table[p][j] = (j < n_pos ? pos_lut[p] . w[j] : 0) + bias[j]: 64 x n dot products of length c (one warp each);
+// table_t (optional) receives the transpose (n, 64), the K-major second weight operand of tmae_linear_fwd_dual
+__global__ void pos_table_kernel(const float* __restrict__ lut, const float* __restrict__ w, const float* __restrict__ bias,
+                                 float* __restrict__ table, float* __restrict__ table_t, int n, int n_pos, int c) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= 64 * n) return;
+  const int p = warp / n, j = warp - p * n;
+  float s = 0.f;
+  if (j < n_pos)
+    for (int k = lane; k < c; k += 32) s = fmaf(lut[p * c + k], w[(int64_t)j * c + k], s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    const float v = s + (bias ? bias[j] : 0.f);
+    if (table) table[(int64_t)p * n + j] = v;
+    if (table_t) table_t[(int64_t)j * 64 + p] = v;
+  }
+}
+
+// dtable[p][:] = sum of dy rows whose rowidx == p.  Block = 256 threads = 8 row lanes x 32 column lanes x float4 (128
+// columns per blockIdx.x), per-block partial bins in shared memory (64 x 128 floats), one atomicAdd per bin entry per block.
+__global__ void __launch_bounds__(256) binned_colsum_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ rowidx,
+                                                            float* __restrict__ dtable, int64_t rows, int n, int rows_per_block) {
+  __shared__ float bins[64][128];
+  for (int i = threadIdx.x; i < 64 * 128; i += 256) (&bins[0][0])[i] = 0.f;
+  __syncthreads();
+  const int c0 = blockIdx.x * 128 + (threadIdx.x & 31) * 4, rl = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  if (c0 < n) {
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(dy + r * n + c0));
+      float* b = &bins[rowidx[r] & 63][(threadIdx.x & 31) * 4];
+      atomicAdd(b, v.x); atomicAdd(b + 1, v.y); atomicAdd(b + 2, v.z); atomicAdd(b + 3, v.w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 128; i += 256) {
+    const int p = i >> 7, c = blockIdx.x * 128 + (i & 127);
+    const float v = bins[p][i & 127];
+    if (c < n && v != 0.f) atomicAdd(dtable + (int64_t)p * n + c, v);
+  }
+}
+
+// dbias[j] = sum_p dtable[p][j] ; dw[j][:] += sum_p dtable[p][j] * lut[p][:] for j < n_pos.  One block per j.
+__global__ void pos_table_bwd_kernel(const float* __restrict__ dtable, const float* __restrict__ lut, float* __restrict__ dw,
+                                     float* __restrict__ dbias, int n, int n_pos, int c, int transposed) {
+  __shared__ float col[64];
+  const int j = blockIdx.x;
+  if (threadIdx.x < 64) col[threadIdx.x] = transposed ? dtable[(int64_t)j * 64 + threadIdx.x] : dtable[(int64_t)threadIdx.x * n + j];
+  __syncthreads();
+  if (threadIdx.x == 0 && dbias) {
+    float s = 0.f;
+    for (int p = 0; p < 64; ++p) s += col[p];
+    dbias[j] = s;
+  }
+  if (j < n_pos)
+    for (int k = threadIdx.x; k < c; k += blockDim.x) {
+      float s = 0.f;
+#pragma unroll 8
+      for (int p = 0; p < 64; ++p) s = fmaf(col[p], lut[p * c + k], s);
+      dw[(int64_t)j * c + k] += s;
+    }
+}
+
+// out[m][p] = (p == idx[m]): the (rows, 64) one-hot form of the window-cell index, the second A operand of the packed projection
+__global__ void onehot64_kernel(const uint8_t* __restrict__ idx, float4* __restrict__ out, int64_t m) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 (4 bins) per thread
+  if (i >= m * 16) return;
+  const int p = idx[i >> 4] & 63, b = (int)(i & 15) * 4;
+  out[i] = make_float4(p == b ? 1.f : 0.f, p == b + 1 ? 1.f : 0.f, p == b + 2 ? 1.f : 0.f, p == b + 3 ? 1.f : 0.f);
+}
+
 __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, float* __restrict__ dx, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -221,6 +295,10 @@ __global__ void transpose_taps_kernel(const float* __restrict__ w, float* __rest
 
 // TMA-fed tf32 tensor-core path (gemm_tma.cu)
 bool tma_linear_fwd_ok(const float* x, const float* w, const float* y, const float* residual, int64_t m, int64_t n, int64_t k);
+bool tma_linear_fwd_dual_ok(const float* x, const float* w, const float* x2, const float* w2, const float* y, int64_t m, int64_t n, int64_t k,
+                            int64_t k2);
+int tma_linear_fwd_dual(const float* x, const float* w, const float* x2, const float* w2, float* y, int64_t m, int64_t n, int64_t k, int64_t k2,
+                        cudaStream_t s);
 int tma_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* preact, int64_t m, int64_t n, int64_t k, int act,
                    cudaStream_t s);
 bool tma_linear_bwd_data_ok(const float* dy, const float* w, const float* dx, int64_t m, int64_t n, int64_t k);
@@ -275,6 +353,34 @@ int tmae_linear_fwd(const float* x, const float* w, const float* bias, const flo
   g.A = x; g.B = w; g.C = y; g.M = m; g.N = n; g.K = k; g.lda = k; g.ldb = k; g.ldc = n;
   g.bias = bias; g.residual = residual; g.preact = preact; g.act = act;
   if (launch<A_KCONTIG, B_KCONTIG>(g, 1, (cudaStream_t)stream)) { set_error("tmae_linear_fwd: launch failed"); return TMAE_ERR_CUDA; }
+  return 0;
+}
+
+int tmae_linear_fwd_lut(const float* x, const float* w, const float* lut, const uint8_t* rowidx, float* y, int64_t m, int64_t n,
+                        int64_t k, int32_t precision, void* stream) {
+  TMAE_CHECK_PREC(precision);
+  TMAE_CHECK_ARG(lut && rowidx, "lut and rowidx are required");
+  GemmArgs g{};  // always the fp32 SIMT kernel: the tensor-core form of the same product is tmae_linear_fwd_dual
+  g.A = x; g.B = w; g.C = y; g.M = m; g.N = n; g.K = k; g.lda = k; g.ldb = k; g.ldc = n;
+  g.lut = lut; g.rowidx = rowidx; g.ldlut = n;
+  if (launch<A_KCONTIG, B_KCONTIG>(g, 1, (cudaStream_t)stream)) { set_error("tmae_linear_fwd_lut: launch failed"); return TMAE_ERR_CUDA; }
+  return 0;
+}
+
+/* y = x w^T + x2 w2^T: the packed projection with the position term as a second (one-hot, table) source pair */
+int tmae_linear_fwd_dual(const float* x, const float* w, const float* x2, const float* w2, float* y, int64_t m, int64_t n, int64_t k, int64_t k2,
+                         int32_t precision, void* stream) {
+  TMAE_CHECK_PREC(precision);
+  if (precision == TMAE_PREC_BF16 && g_use_tma && tma_linear_fwd_dual_ok(x, w, x2, w2, y, m, n, k, k2)) {
+    if (tma_linear_fwd_dual(x, w, x2, w2, y, m, n, k, k2, (cudaStream_t)stream)) { set_error("tmae_linear_fwd_dual: TMA launch failed"); return TMAE_ERR_CUDA; }
+    return 0;
+  }
+  GemmArgs g{};
+  g.A = x; g.B = w; g.C = y; g.M = m; g.N = n; g.K = k; g.lda = k; g.ldb = k; g.ldc = n;
+  if (launch<A_KCONTIG, B_KCONTIG>(g, 1, (cudaStream_t)stream)) { set_error("tmae_linear_fwd_dual: launch failed"); return TMAE_ERR_CUDA; }
+  GemmArgs h{};
+  h.A = x2; h.B = w2; h.C = y; h.M = m; h.N = n; h.K = k2; h.lda = k2; h.ldb = k2; h.ldc = n; h.accumulate = 1;
+  if (launch<A_KCONTIG, B_KCONTIG>(h, 1, (cudaStream_t)stream)) { set_error("tmae_linear_fwd_dual: launch failed"); return TMAE_ERR_CUDA; }
   return 0;
 }
 
@@ -361,6 +467,42 @@ int tmae_colsum(const float* x, float* out, int64_t rows, int32_t cols, void* st
     colsum_kernel<<<grid, 256, 0, s>>>(x, rows, cols, nullptr, out, rpb);
     TMAE_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+int tmae_pos_table(const float* pos_lut, const float* w, const float* bias, float* table, float* table_t, int32_t n, int32_t n_pos, int32_t c,
+                   void* stream) {
+  if (n <= 0) return 0;
+  pos_table_kernel<<<cdiv((int64_t)64 * n * 32, 256), 256, 0, (cudaStream_t)stream>>>(pos_lut, w, bias, table, table_t, n, n_pos, c);
+  TMAE_CHECK_LAUNCH();
+  return 0;
+}
+
+int tmae_binned_colsum(const float* dy, const uint8_t* rowidx, float* dtable, int64_t rows, int32_t n, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  TMAE_CHECK_ARG(n % 4 == 0, "n must be a multiple of 4");
+  TMAE_CUDA(cudaMemsetAsync(dtable, 0, (size_t)64 * n * sizeof(float), s));
+  if (rows <= 0) return 0;
+  int rpb = 1024;
+  dim3 grid((unsigned)cdiv(n, 128), (unsigned)cdiv(rows, rpb));
+  ProfScope prof("binned_colsum", 0, 4.0 * rows * n, s);
+  binned_colsum_kernel<<<grid, 256, 0, s>>>(dy, rowidx, dtable, rows, n, rpb);
+  TMAE_CHECK_LAUNCH();
+  return 0;
+}
+
+int tmae_pos_table_bwd(const float* dtable, int32_t transposed, const float* pos_lut, float* dw, float* dbias, int32_t n, int32_t n_pos, int32_t c,
+                       void* stream) {
+  if (n <= 0) return 0;
+  pos_table_bwd_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(dtable, pos_lut, dw, dbias, n, n_pos, c, transposed);
+  TMAE_CHECK_LAUNCH();
+  return 0;
+}
+
+int tmae_onehot64(const uint8_t* idx, float* out, int64_t m, void* stream) {
+  if (m <= 0) return 0;
+  onehot64_kernel<<<cdiv(m * 16, 256), 256, 0, (cudaStream_t)stream>>>(idx, (float4*)out, m);
+  TMAE_CHECK_LAUNCH();
   return 0;
 }
 

@@ -31,6 +31,7 @@ __device__ __forceinline__ void trace_ev(unsigned long long* buf, int& n, int ca
 struct TmaArgs {
   int64_t M, N, K;
   const float* bias;
+  int64_t k_split;                   // NT dual source: k-blocks at k >= k_split come from the second pair of tensor maps
   float* C; float* P; int64_t ldc;   // output, optional pre-activation copy
   const float* gelu_pre;             // optional: multiply the result by gelu'(gelu_pre[m,n])  (fused GELU backward)
   int act, reduce_add, has_preact;
@@ -134,7 +135,9 @@ __device__ __forceinline__ void bar_arrive(uint64_t* b) {
 //   apart (SBO), k-step (8 rows) = +1024 B.
 template <int MODE, int BN, int STAGES>
 __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                                  const __grid_constant__ CUtensorMap map_b, TmaArgs g) {
+                                                                  const __grid_constant__ CUtensorMap map_b,
+                                                                  const __grid_constant__ CUtensorMap map_a2,
+                                                                  const __grid_constant__ CUtensorMap map_b2, TmaArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int A_BYTES = UM * KB * 4, B_BYTES = BN * KB * 4, STAGE = A_BYTES + B_BYTES;
   __shared__ uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc_full[2], bar_acc_empty[2];
@@ -187,10 +190,14 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
           if (MODE == T_TN) {
 #pragma unroll
             for (int j = 0; j < UM / 32; ++j) tma_load_2d(a + j * 4096, &map_a, m0 + j * 32, k0, &bar_full[s]);
+          } else if (MODE == T_NT && k0 >= g.k_split) {   // second source pair: C = A1 B1^T + A2 B2^T
+            tma_load_2d(a, &map_a2, k0 - (int)g.k_split, m0, &bar_full[s]);
           } else {
             tma_load_2d(a, &map_a, k0, m0, &bar_full[s]);
           }
-          if (MODE == T_NT) {
+          if (MODE == T_NT && k0 >= g.k_split) {
+            tma_load_2d(b, &map_b2, k0 - (int)g.k_split, n0, &bar_full[s]);
+          } else if (MODE == T_NT) {
             tma_load_2d(b, &map_b, k0, n0, &bar_full[s]);
           } else {
 #pragma unroll
@@ -266,6 +273,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
         if (row >= g.M) continue;
+
         float* crow = g.C + row * g.ldc + col0;
         if (g.has_preact) {
           float* prow = g.P + row * g.ldc + col0;
@@ -340,12 +348,16 @@ static bool make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+struct DualSrc { const float* A2; const float* B2; int64_t K2; };  // optional second source pair of an NT GEMM (K-major, pitch K2)
+
 template <int MODE, int BN>
 static int tma_launch(const float* A, const float* B, float* C, float* preact, int64_t lda, int64_t ldb, int64_t ldc, TmaArgs g, int splits,
-                      cudaStream_t s) {
+                      cudaStream_t s, DualSrc d2 = DualSrc{nullptr, nullptr, 0}) {
   constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   if (g.M <= 0 || g.N <= 0) return 0;
   if (splits < 1) splits = 1;
+  const int64_t k_first = g.K;
+  if (MODE == T_NT && d2.A2) g.K += d2.K2;  // the reduction runs over K (first pair) then K2 (second pair)
   g.k_chunk = align_up((g.K + splits - 1) / splits, KB);
   int z = (int)((g.K + g.k_chunk - 1) / g.k_chunk);
   if (z < 1) z = 1;
@@ -353,9 +365,16 @@ static int tma_launch(const float* A, const float* B, float* C, float* preact, i
   CUtensorMap ma, mb;
   bool ok = true;
   // A: NT/NN K-major (rows = M, inner = K)  box {32, 128} ; TN MN-major (rows = K, inner = M) box {32, 32}
-  ok &= MODE == T_TN ? make_map(&ma, A, g.M, g.K, lda, 32, 32, true, true) : make_map(&ma, A, g.K, g.M, lda, KB, UM, true);
+  ok &= MODE == T_TN ? make_map(&ma, A, g.M, g.K, lda, 32, 32, true, true) : make_map(&ma, A, k_first, g.M, lda, KB, UM, true);
   // B: NT K-major (rows = N, inner = K) box {32, BN} ; NN/TN MN-major (rows = K, inner = N) box {32, 32}
-  ok &= MODE == T_NT ? make_map(&mb, B, g.K, g.N, ldb, KB, BN, true) : make_map(&mb, B, g.N, g.K, ldb, 32, 32, true, true);
+  ok &= MODE == T_NT ? make_map(&mb, B, k_first, g.N, ldb, KB, BN, true) : make_map(&mb, B, g.N, g.K, ldb, 32, 32, true, true);
+  CUtensorMap ma2 = ma, mb2 = mb;
+  g.k_split = g.K;
+  if (MODE == T_NT && d2.A2) {  // both reduction lengths are multiples of the 32-wide k-block
+    ok &= make_map(&ma2, d2.A2, d2.K2, g.M, d2.K2, KB, UM, true);
+    ok &= make_map(&mb2, d2.B2, d2.K2, g.N, d2.K2, KB, BN, true);
+    g.k_split = k_first;
+  }
   if (!ok) return TMAE_ERR_CUDA;
   g.has_preact = preact != nullptr;
   g.trace = g_trace_buf; g.trace_cap = (int)g_trace_cap;
@@ -372,16 +391,18 @@ static int tma_launch(const float* A, const float* B, float* C, float* preact, i
   ProfScope prof(names[MODE], 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + c_el), s);
   int64_t tiles = (int64_t)cdiv(g.N, BN) * cdiv(g.M, UM) * z;
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
-  kern<<<grid, TMA_THREADS, smem, s>>>(ma, mb, g);
+  kern<<<grid, TMA_THREADS, smem, s>>>(ma, mb, ma2, mb2, g);
   return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
 }
 
 template <int MODE>
 static int tma_dispatch(const float* A, const float* B, float* C, float* preact, int64_t lda, int64_t ldb, int64_t ldc, const TmaArgs& g,
-                        int splits, cudaStream_t s) {
-  if (g.N > 128) return tma_launch<MODE, 256>(A, B, C, preact, lda, ldb, ldc, g, splits, s);
-  if (g.N > 64) return tma_launch<MODE, 128>(A, B, C, preact, lda, ldb, ldc, g, splits, s);
-  return tma_launch<MODE, 64>(A, B, C, preact, lda, ldb, ldc, g, splits, s);
+                        int splits, cudaStream_t s, DualSrc d2 = DualSrc{nullptr, nullptr, 0}) {
+  // N = 384 (packed q/k/v projection at 128 channels): three full 128-wide tiles instead of a full and a half-empty 256
+  if (g.N > 128 && !(g.N % 256 != 0 && g.N % 128 == 0 && g.N <= 384))
+    return tma_launch<MODE, 256>(A, B, C, preact, lda, ldb, ldc, g, splits, s, d2);
+  if (g.N > 64) return tma_launch<MODE, 128>(A, B, C, preact, lda, ldb, ldc, g, splits, s, d2);
+  return tma_launch<MODE, 64>(A, B, C, preact, lda, ldb, ldc, g, splits, s, d2);
 }
 
 // ---- entry points (gemm.cu dispatches here for TMAE_PREC_BF16 when the shapes allow TMA)
@@ -393,6 +414,17 @@ int tma_linear_fwd(const float* x, const float* w, const float* bias, float* y, 
   TmaArgs g{};
   g.M = m; g.N = n; g.K = k; g.bias = bias; g.act = act;
   return tma_dispatch<T_NT>(x, w, y, preact, k, k, n, g, 1, s);
+}
+// y = x w^T + x2 w2^T in one pass (x2 (m, k2), w2 (n, k2), both K-major; k and k2 multiples of 32)
+bool tma_linear_fwd_dual_ok(const float* x, const float* w, const float* x2, const float* w2, const float* y, int64_t m, int64_t n, int64_t k,
+                            int64_t k2) {
+  return k % KB == 0 && k2 % KB == 0 && n % 4 == 0 && aligned16(x) && aligned16(w) && aligned16(x2) && aligned16(w2) && aligned16(y);
+}
+int tma_linear_fwd_dual(const float* x, const float* w, const float* x2, const float* w2, float* y, int64_t m, int64_t n, int64_t k, int64_t k2,
+                        cudaStream_t s) {
+  TmaArgs g{};
+  g.M = m; g.N = n; g.K = k;
+  return tma_dispatch<T_NT>(x, w, y, nullptr, k, k, n, g, 1, s, DualSrc{x2, w2, k2});
 }
 bool tma_linear_bwd_data_ok(const float* dy, const float* w, const float* dx, int64_t m, int64_t n, int64_t k) {
   return n % 4 == 0 && k % 4 == 0 && aligned16(dy) && aligned16(w) && aligned16(dx);

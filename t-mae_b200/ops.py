@@ -197,7 +197,7 @@ class Partition:
     """Device tables of one window partition (both shifts); see tmae_window_partition."""
     __slots__ = ("m_a", "m_b", "wcap", "n_levels", "tokens", "win_a", "slot_a", "posidx_a", "tok_a", "cnt_a", "win_b", "slot_b",
                  "posidx_b", "tok_b", "cnt_b", "win_level", "n_win", "level_base", "status", "ref_a", "ref_b", "temporal",
-                 "keep_a", "keep_b")
+                 "keep_a", "keep_b", "onehot_a", "onehot_b")
 
 
 def window_partition(coords_a, batch, grid_x, grid_y, levels, coords_b=None, want_ref=False):
@@ -243,7 +243,17 @@ def window_partition(coords_a, batch, grid_x, grid_y, levels, coords_b=None, wan
           _p(P.win_b), _p(P.slot_b), _p(P.posidx_b), _p(P.tok_b), _p(P.cnt_b),
           _p(P.win_level), _p(P.n_win), _p(P.level_base), _p(P.status), *ra, *rb, _p(ws), wsb, _stream())
     P.keep_a = P.keep_b = None
+    # (2, m, 64) one-hot form of posidx: second A operand of the packed q/k/v projection in tensor-core mode
+    P.onehot_a = onehot64(P.posidx_a) if (_state["precision"] == PREC_BF16 and P.m_a > 0) else None
+    P.onehot_b = onehot64(P.posidx_b) if (_state["precision"] == PREC_BF16 and P.temporal and P.m_b > 0) else None
     return P
+
+
+def onehot64(idx):
+    """idx (..., m) u8 -> (..., m, 64) fp32 one-hot."""
+    out = torch.empty(*idx.shape, 64, dtype=F32, device=idx.device)
+    _call("onehot64", _p(idx, U8), _p(out), idx.numel(), _stream())
+    return out
 
 
 # ------------------------------------------------------------------------------------ GEMMs
@@ -258,6 +268,49 @@ def linear_fwd(x, w, bias=None, residual=None, act=ACT_NONE, want_preact=False, 
     _call("linear_fwd", _p(x, F32), wp, bp, _p(residual), _p(y), _p(pre), m, n, k, act, _state["precision"], _stream(),
           flops=2 * m * n * k, nbytes=4 * (m * k + n * k + m * n))
     return (y, pre) if want_preact else y
+
+
+def linear_fwd_lut(x, w, lut, rowidx):
+    """y = x @ w.T + lut[rowidx]  (lut (64, n) from pos_table, rowidx (m,) u8)."""
+    m, k = x.shape
+    n = w.shape[0]
+    y = torch.empty(m, n, dtype=F32, device=x.device)
+    _call("linear_fwd_lut", _p(x, F32), _p(w, F32), _p(lut, F32), _p(rowidx, U8), _p(y), m, n, k, _state["precision"], _stream(),
+          flops=2 * m * n * k, nbytes=4 * (m * k + n * k + m * n))
+    return y
+
+
+def pos_table(pos_lut, w, bias, n_pos):
+    """(64, n) table  pos_lut @ w[:n_pos].T (zero for the other columns) + bias, and its transpose (n, 64)."""
+    n, c = w.shape
+    t = torch.empty(64, n, dtype=F32, device=w.device)
+    tt = torch.empty(n, 64, dtype=F32, device=w.device)
+    _call("pos_table", _p(pos_lut, F32), _p(w, F32), _p(bias, F32), _p(t), _p(tt), n, n_pos, c, _stream())
+    return t, tt
+
+
+def linear_fwd_dual(x, w, x2, w2):
+    """y = x @ w.T + x2 @ w2.T in one GEMM (tensor-core mode) or two accumulating SIMT GEMMs (fp32)."""
+    m, k = x.shape
+    n, k2 = w.shape[0], x2.shape[1]
+    y = torch.empty(m, n, dtype=F32, device=x.device)
+    _call("linear_fwd_dual", _p(x, F32), _p(w, F32), _p(x2, F32), _p(w2, F32), _p(y), m, n, k, k2, _state["precision"], _stream(),
+          flops=2 * m * n * (k + k2), nbytes=4 * (m * (k + k2) + n * (k + k2) + m * n))
+    return y
+
+
+def binned_colsum(dy, rowidx):
+    t = torch.empty(64, dy.shape[1], dtype=F32, device=dy.device)
+    _call("binned_colsum", _p(dy, F32), _p(rowidx, U8), _p(t), dy.shape[0], dy.shape[1], _stream())
+    return t
+
+
+def pos_table_bwd(dtable, pos_lut, dw, n_pos, transposed=False):
+    """dbias = dtable.sum(0); dw[:n_pos] += dtable[:, :n_pos].T @ pos_lut (in place).  transposed: dtable is (n, 64)."""
+    n = dtable.shape[0] if transposed else dtable.shape[1]
+    db = torch.empty(n, dtype=F32, device=dtable.device)
+    _call("pos_table_bwd", _p(dtable, F32), int(transposed), _p(pos_lut, F32), _p(dw, F32), _p(db), n, n_pos, pos_lut.shape[1], _stream())
+    return db
 
 
 def linear_bwd_data(dy, w, dx=None, accumulate=False, w_offset_rows=0):
@@ -477,22 +530,35 @@ def mid_end(part, shift):
     return small_end(part, shift, 32)
 
 
+def _pv(t):
+    """pointer of a (rows, C) fp32 view with unit column stride (a column block of a packed projection is allowed)."""
+    if not (t.is_cuda and t.dtype == F32 and t.stride(1) == 1 and t.stride(0) % 4 == 0):
+        raise RuntimeError("expected an fp32 CUDA matrix with unit column stride and a row pitch that is a multiple of 4")
+    return t.data_ptr()
+
+
 def window_attention_fwd(q, k, v, qtok, qcnt, ktok, kcnt, n_win, small, mid, max_windows, tau, tau_min, heads, zero_out):
     mq, c = q.shape
-    o = torch.zeros_like(q) if zero_out else torch.empty_like(q)
+    o = torch.zeros(mq, c, dtype=F32, device=q.device) if zero_out else torch.empty(mq, c, dtype=F32, device=q.device)
     lse = torch.empty(max(1, mq), heads, dtype=F32, device=q.device)
-    _call("window_attention_fwd", _p(q, F32), _p(k, F32), _p(v, F32), _p(o), _p(lse), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win),
-          _p(small), _p(mid), max_windows, _p(tau, F32), float(tau_min), c, heads, _stream(), nbytes=4 * (q.numel() * 2 + k.numel() * 2))
+    _call("window_attention_fwd", _pv(q), _pv(k), _pv(v), _p(o), _p(lse), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win),
+          _p(small), _p(mid), max_windows, _p(tau, F32), float(tau_min), c, heads, q.stride(0), k.stride(0), v.stride(0), _stream(),
+          nbytes=4 * (q.numel() * 2 + k.numel() * 2))
     return o, lse
 
 
 def window_attention_bwd(dout, q, k, v, o, lse, qtok, qcnt, ktok, kcnt, n_win, small, mid, max_windows, tau, tau_min, heads, dtau, zero):
-    alloc = torch.zeros_like if zero else torch.empty_like
-    dq, dk, dv = alloc(q), alloc(k), alloc(v)
+    alloc = torch.zeros if zero else torch.empty
+    packed = q.stride(0) == 3 * q.shape[1] and k.data_ptr() == q.data_ptr() + 4 * q.shape[1]   # gradients mirror the packed layout
+    if packed:
+        buf = alloc(q.shape[0], 3 * q.shape[1], dtype=F32, device=q.device)
+        dq, dk, dv = buf[:, :q.shape[1]], buf[:, q.shape[1]:2 * q.shape[1]], buf[:, 2 * q.shape[1]:]
+    else:
+        dq, dk, dv = (alloc(t.shape[0], t.shape[1], dtype=F32, device=t.device) for t in (q, k, v))
     dsum = torch.empty_like(lse)
-    _call("window_attention_bwd", _p(dout, F32), _p(q, F32), _p(k, F32), _p(v, F32), _p(o, F32), _p(lse, F32), _p(dsum), _p(dq), _p(dk),
-          _p(dv), _p(dtau, F32), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win), _p(small), _p(mid), max_windows, _p(tau, F32), float(tau_min), q.shape[1],
-          heads, _stream(), nbytes=4 * (q.numel() * 4 + k.numel() * 4))
+    _call("window_attention_bwd", _p(dout, F32), _pv(q), _pv(k), _pv(v), _p(o, F32), _p(lse, F32), _p(dsum), _pv(dq), _pv(dk),
+          _pv(dv), _p(dtau, F32), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win), _p(small), _p(mid), max_windows, _p(tau, F32), float(tau_min), q.shape[1],
+          heads, q.stride(0), k.stride(0), v.stride(0), _stream(), nbytes=4 * (q.numel() * 4 + k.numel() * 4))
     return dq, dk, dv
 
 
@@ -543,7 +609,8 @@ class LayerParams(ctypes.Structure):
 
 class LayerTables(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("posidx_q", "posidx_kv", "qtok", "qcnt", "ktok", "kcnt", "n_win", "small_end", "mid_end",
-                                               "rowmask")] + [("max_windows", ctypes.c_int64)]
+                                               "rowmask")] + [("max_windows", ctypes.c_int64), ("onehot_q", ctypes.c_void_p),
+                                                              ("onehot_kv", ctypes.c_void_p)]
 
 
 def layer_tables(part, shift, cross, m_q, m_kv):
@@ -561,6 +628,9 @@ def layer_tables(part, shift, cross, m_q, m_kv):
         T.ktok, T.kcnt = T.qtok, T.qcnt
         T.rowmask = None
         T.max_windows = min(part.wcap, m_q)
+    oa, ob = getattr(part, "onehot_a", None), getattr(part, "onehot_b", None)
+    T.onehot_q = _p(oa[shift]) if oa is not None else None
+    T.onehot_kv = _p(ob[shift]) if (cross and ob is not None) else None
     T.n_win = _p(part.n_win[shift:shift + 1])
     T.small_end = _p(small_end(part, shift))
     T.mid_end = _p(mid_end(part, shift))
@@ -590,7 +660,7 @@ def encoder_layer_fwd(x, x_kv, params, T, lut, tau_min, eps, heads):
     return y, saved
 
 
-def encoder_layer_bwd(dy, x, x_kv, params, T, tau_min, heads, saved, want_dkv):
+def encoder_layer_bwd(dy, x, x_kv, params, T, lut, tau_min, heads, saved, want_dkv):
     """-> (dx, dx_kv or None, [13 parameter gradients])."""
     L = lib()
     m_q, c = x.shape
@@ -609,6 +679,6 @@ def encoder_layer_bwd(dy, x, x_kv, params, T, tau_min, heads, saved, want_dkv):
     scratch = _ws(nb, x.device)
     dx = torch.empty_like(x)
     dkv = torch.empty_like(x_kv) if (cross and want_dkv) else None
-    _call("encoder_layer_bwd", _p(dy, F32), _p(x, F32), _p(x_kv), ctypes.byref(P), ctypes.byref(T), float(tau_min), m_q, m_kv, c, ff, heads,
+    _call("encoder_layer_bwd", _p(dy, F32), _p(x, F32), _p(x_kv), ctypes.byref(P), ctypes.byref(T), _p(lut, F32), float(tau_min), m_q, m_kv, c, ff, heads,
           _state["precision"], _p(saved), saved.numel(), _p(dx), _p(dkv), ctypes.byref(G), _p(scratch), nb, _stream())
     return dx, dkv, grads

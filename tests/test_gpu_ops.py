@@ -451,6 +451,89 @@ def _attention_core_case(C, cross, tol):
     assert_close(dtau, mha.tau.grad, tol or 1e-4, (tol or 1e-4) * mha.tau.grad.abs().item(), "dtau")
 
 
+def test_window_attention_packed_strides():
+    """q, k, v as column blocks of one packed (rows, 3C) projection output (row pitch 3C), gradients written into the
+    same packed layout: identical results to separate contiguous tensors."""
+    C, H, B, g = 128, 8, 2, 64
+    _, _, levels = _levels("pretrain")
+    ca = _coords(3, 1800, B, g)
+    P = ops.window_partition(ca.to(DEV), B, g, g, levels)
+    m = ca.shape[0]
+    gen = torch.Generator().manual_seed(5)
+    qkv = torch.randn(m, 3 * C, generator=gen).to(DEV)
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    tau = torch.tensor([[[0.4]]], device=DEV)
+    args = (P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), ops.mid_end(P, 0), min(P.wcap, m), tau, 0.01, H)
+    for tc in (0, 1):
+        ops.set_option("attn_tc", tc)
+        try:
+            o1, l1 = ops.window_attention_fwd(q, k, v, *args, False)
+            o2, l2 = ops.window_attention_fwd(q.contiguous(), k.contiguous(), v.contiguous(), *args, False)
+            assert torch.equal(o1, o2) and torch.equal(l1, l2)
+            do = torch.randn(m, C, generator=gen).to(DEV)
+            t1, t2 = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+            g1 = ops.window_attention_bwd(do, q, k, v, o1, l1, *args, t1, False)
+            g2 = ops.window_attention_bwd(do, q.contiguous(), k.contiguous(), v.contiguous(), o2, l2, *args, t2, False)
+            assert g1[0].stride(0) == 3 * C, "gradients of a packed projection come back packed"
+            for a, b in zip(g1, g2):
+                assert torch.equal(a, b)
+        finally:
+            ops.set_option("attn_tc", 0)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("m,c,parts", [(3000, 128, 3), (1700, 256, 3), (900, 128, 1), (5, 256, 2)])
+def test_packed_projection_with_position_table(m, c, parts, prec):
+    """y = x W^T + (pos_lut W_pos^T + b)[posidx] against (x + pos) W^T + b in float64, and its backward pieces:
+    binned column sum, bias / position-term weight gradient."""
+    gen = torch.Generator().manual_seed(m + c)
+    n = parts * c
+    n_pos = min(2, parts) * c if parts != 1 else c
+    x = torch.randn(m, c, generator=gen)
+    w = torch.randn(n, c, generator=gen) / c ** .5
+    b = torch.randn(n, generator=gen) * 0.1
+    lut = torch.randn(64, c, generator=gen)
+    pi = torch.randint(0, 64, (m,), generator=gen, dtype=torch.uint8)
+    xd, wd, ld = x.double(), w.double(), lut.double()
+    pos = ld[pi.long()]
+    ref = xd @ wd.T + b.double()
+    ref[:, :n_pos] += pos @ wd[:n_pos].T
+    ops.set_precision(prec)
+    try:
+        table, table_t = ops.pos_table(lut.to(DEV), w.to(DEV), b.to(DEV), n_pos)
+        tref = b.double()[None, :].repeat(64, 1)
+        tref[:, :n_pos] += ld @ wd[:n_pos].T
+        assert_close(table, tref, 1e-5, 1e-5, "position table"), assert_close(table_t, tref.T, 1e-5, 1e-5, "position table (transposed)")
+        y = ops.linear_fwd_lut(x.to(DEV), w.to(DEV), table, pi.to(DEV))
+        onehot = ops.onehot64(pi.to(DEV))
+        assert torch.equal(onehot.cpu(), torch.nn.functional.one_hot(pi.long(), 64).float())
+        y2 = ops.linear_fwd_dual(x.to(DEV), w.to(DEV), onehot, table_t)
+        dy_ = torch.randn(m, n, generator=gen)
+        dtt = torch.empty(n, 64, device=DEV)
+        ops.linear_bwd_weight(dy_.to(DEV), onehot, dtt)
+    finally:
+        ops.set_precision("fp32")
+    tol = 1e-5 if prec == "fp32" else 3e-3
+    assert_close(y, ref, 1e-5, 3e-5, "packed projection, table-bias epilogue (fp32 SIMT)")
+    assert_close(y2, ref, tol, tol * 3, f"packed projection, dual-source GEMM ({prec})")
+    dref_t = torch.zeros(64, n, dtype=torch.float64).index_add_(0, pi.long(), dy_.double()).T
+    assert_close(dtt, dref_t, tol * 2, tol * 2 * m ** .5, f"dy^T onehot ({prec})")
+    dw1 = torch.zeros(n, c, device=DEV)
+    db1 = ops.pos_table_bwd(dtt, lut.to(DEV), dw1, n_pos, transposed=True)
+    assert_close(db1, dy_.double().sum(0), tol * 2, tol * 2 * m ** .5, "bias gradient from the transposed table gradient")
+    dy = torch.randn(m, n, generator=gen)
+    dt = ops.binned_colsum(dy.to(DEV), pi.to(DEV))
+    dref = torch.zeros(64, n, dtype=torch.float64).index_add_(0, pi.long(), dy.double())
+    assert_close(dt, dref, 1e-5, 1e-4, "binned column sum")
+    dw0 = torch.randn(n, c, generator=gen)
+    dw = dw0.clone().to(DEV)
+    db = ops.pos_table_bwd(dt, lut.to(DEV), dw, n_pos)
+    assert_close(db, dy.double().sum(0), 1e-5, 1e-4 * m ** .5, "bias gradient")
+    wref = dw0.double()
+    wref[:n_pos] += dref[:, :n_pos].T @ ld
+    assert_close(dw, wref, 1e-5, 1e-4 * m ** .5, "position term of the weight gradient")
+
+
 # ------------------------------------------------------------------------------------ loss
 def test_gt_group_and_chamfer():
     pts, _ = cases.small_points(4, 2500, 2)
