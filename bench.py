@@ -217,6 +217,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     host_ms = []
+    host_out = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(max(args.steps, 1))]
 
     def timed(from_host):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -235,12 +236,11 @@ def run_ours(args):
                     out = step(a, b)
                 else:
                     out = step(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True))
-                if w["train"]:
-                    out.item()  # loss read-back
-                    d2h = 4
-                else:
-                    out.mean().item()
-                    d2h = 4
+                # device->host read of this step's result (loss / mean feature) into pinned memory, enqueued in-stream every
+                # step and complete before the closing synchronize of the timed region; the host does not stall on it
+                # (a training loop logs the loss the same way)
+                host_out[i % len(host_out)].copy_((out if w["train"] else out.float().mean()).detach().reshape(1), non_blocking=True)
+                d2h = 4
             else:
                 out = step(*resident[i % len(resident)])
             ev[i + 1].record()
@@ -259,7 +259,11 @@ def run_ours(args):
     with ClockSampler(local) as cs:
         total, per, launches, _ = timed(False)
     clocks = cs.summary()
+    steps_saved, args.steps = args.steps, 2   # untimed pass over the host-input path (its device buffers are new allocator sizes)
+    timed(True)
+    args.steps = steps_saved
     e_total, e_per, _, d2h = timed(True)
+    assert all(torch.isfinite(t).all() for t in host_out), "non-finite step result"
 
     def maxr(x):
         if world == 1:

@@ -314,6 +314,9 @@ bool tc_linear_bwd_data_ok(int64_t m, int64_t n, int64_t k);
 int tc_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int accumulate, cudaStream_t s);
 bool tc_linear_bwd_weight_ok(int64_t m, int64_t n, int64_t k);
 int tc_linear_bwd_weight(const float* dy, const float* x, float* dw, int64_t m, int64_t n, int64_t k, cudaStream_t s);
+bool tma_sparse_conv_ok(const float* x, const float* w, const float* y, int cin, int cout);
+int tma_sparse_conv_fwd(const float* x, const int* table, const float* w, float* y, int64_t rows_out, int taps, int cin, int cout, int accumulate,
+                        cudaStream_t s);
 bool tc_sparse_conv_ok(int cin, int cout);
 int tc_sparse_conv_fwd(const float* x, const int* table, const float* w, float* y, int64_t rows_out, int taps, int cin, int cout,
                        int accumulate, cudaStream_t s);
@@ -325,6 +328,7 @@ int tc_sparse_conv_bwd_weight(const float* dy, const float* x, const int* table,
 using namespace tmae;
 
 namespace tmae { extern bool g_attn_tc; }  // attention.cu
+static bool g_conv_async = true;  // tmae_set_option("conv_async", 0): sparse-conv forward / backward-data on the thread-staged bf16 kernel
 static bool g_use_tma = true;  // tmae_set_option("tma", 0) keeps every tensor-core GEMM on the thread-staged bf16 kernel
 
 #define TMAE_CHECK_PREC(p) TMAE_CHECK_ARG((p) == TMAE_PREC_FP32 || (p) == TMAE_PREC_BF16, "precision must be TMAE_PREC_FP32 or TMAE_PREC_BF16")
@@ -334,6 +338,7 @@ extern "C" {
 int tmae_set_option(const char* name, int32_t value) {
   if (name && !strcmp(name, "tma")) { g_use_tma = value != 0; return 0; }
   if (name && !strcmp(name, "attn_tc")) { g_attn_tc = value != 0; return 0; }
+  if (name && !strcmp(name, "conv_async")) { g_conv_async = value != 0; return 0; }
   set_error("tmae_set_option: unknown option");
   return TMAE_ERR_INVALID_ARG;
 }
@@ -518,6 +523,10 @@ int tmae_gelu_bwd(const float* dy, const float* preact, float* dx, int64_t n, vo
 int tmae_sparse_conv_fwd(const float* x, const int32_t* table, const float* w, float* y, int64_t rows_out, int32_t taps,
                          int32_t cin, int32_t cout, int32_t accumulate, int32_t precision, void* stream) {
   TMAE_CHECK_PREC(precision);
+  if (precision == TMAE_PREC_BF16 && g_use_tma && g_conv_async && rows_out > 0 && tma_sparse_conv_ok(x, w, y, cin, cout)) {
+    if (tma_sparse_conv_fwd(x, table, w, y, rows_out, taps, cin, cout, accumulate, (cudaStream_t)stream)) { set_error("tmae_sparse_conv_fwd: TMA/cp.async launch failed"); return TMAE_ERR_CUDA; }
+    return 0;
+  }
   if (precision == TMAE_PREC_BF16 && tc_sparse_conv_ok(cin, cout)) {
     if (tc_sparse_conv_fwd(x, table, w, y, rows_out, taps, cin, cout, accumulate, (cudaStream_t)stream)) { set_error("tmae_sparse_conv_fwd: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
     return 0;

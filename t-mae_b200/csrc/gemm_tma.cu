@@ -32,6 +32,7 @@ struct TmaArgs {
   int64_t M, N, K;
   const float* bias;
   int64_t k_split;                   // NT dual source: k-blocks at k >= k_split come from the second pair of tensor maps
+  const float* gsrc; const int* gtab; int gtaps, gcin;   // GATHER: A rows come through a neighbour table (sparse conv)
   float* C; float* P; int64_t ldc;   // output, optional pre-activation copy
   const float* gelu_pre;             // optional: multiply the result by gelu'(gelu_pre[m,n])  (fused GELU backward)
   int act, reduce_add, has_preact;
@@ -133,8 +134,18 @@ __device__ __forceinline__ void bar_arrive(uint64_t* b) {
 //   K-major operand (rows x 32 fp32): ONE box {32, rows}; 8-row groups 1024 B apart (SBO), k-step = +32 B.
 //   MN-major operand (32 k-rows x cols): cols/32 boxes {32, 32} of 4096 B each (LBO between boxes), 4-row K atoms 512 B
 //   apart (SBO), k-step (8 rows) = +1024 B.
-template <int MODE, int BN, int STAGES>
-__global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+// 16-byte cp.async with zero fill (src_bytes = 0 writes zeros): the gathered A operand of the sparse convolution
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the executing thread's prior cp.async operations arrive on the mbarrier when they complete (no pending-count change)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+constexpr int GATHER_WARPS = 2;   // extra producer warps of the GATHER variant (warps 6, 7)
+
+template <int MODE, int BN, int STAGES, bool GATHER = false>
+__global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0), 1) tma_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_b,
                                                                   const __grid_constant__ CUtensorMap map_a2,
                                                                   const __grid_constant__ CUtensorMap map_b2, TmaArgs g) {
@@ -148,7 +159,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
   const int total = m_tiles * n_tiles * z_tiles;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { bar_init(&bar_full[s], 1); bar_init(&bar_empty[s], 1); }
+    // GATHER: the stage is full when the TMA bytes of B have landed (1 arrival + tx) and every gather thread's cp.asyncs of A have
+    for (int s = 0; s < STAGES; ++s) { bar_init(&bar_full[s], GATHER ? 1 + GATHER_WARPS * 32 : 1); bar_init(&bar_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { bar_init(&bar_acc_full[b], 1); bar_init(&bar_acc_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -186,8 +198,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
           uint8_t* a = smem + s * STAGE;
           uint8_t* b = a + A_BYTES;
           const int k0 = (int)(kbeg + (int64_t)kb * KB);
-          bar_expect_tx(&bar_full[s], STAGE);
-          if (MODE == T_TN) {
+          bar_expect_tx(&bar_full[s], GATHER ? B_BYTES : STAGE);
+          if (GATHER) {
+            // A comes from the gather warps
+          } else if (MODE == T_TN) {
 #pragma unroll
             for (int j = 0; j < UM / 32; ++j) tma_load_2d(a + j * 4096, &map_a, m0 + j * 32, k0, &bar_full[s]);
           } else if (MODE == T_NT && k0 >= g.k_split) {   // second source pair: C = A1 B1^T + A2 B2^T
@@ -225,6 +239,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
           const int s = it % STAGES, use = it / STAGES;
           bar_wait(&bar_full[s], use & 1);
           trace_ev(tb, tn, g.trace_cap / 4, 3, it);
+          if (GATHER) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) writes -> UMMA (async proxy) reads
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_addr = s_u32(smem + s * STAGE), b_addr = a_addr + A_BYTES;
 #pragma unroll
@@ -236,6 +251,49 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) tma_gemm_kernel(const __grid_c
           commit_to(&bar_empty[s]);
         }
         commit_to(&bar_acc_full[buf]);
+      }
+    }
+  } else if (GATHER && warp >= 6) {
+    // ---------------- gather producers (sparse convolution): A[m][tap*cin + c] = src[tab[m][tap]][c], absent neighbours
+    // are zero-filled.  One k-block (32 fp32 = 128 bytes of one tap) of the 128 tile rows = 1024 16-byte pieces written
+    // with cp.async straight into the SWIZZLE_128B K-major layout the UMMA descriptor expects (row r at (r/8)*1024 +
+    // (r%8)*128, 16-byte chunk c at ((c ^ (r%8))*16); a thread owns 2 rows x 8 chunks and looks its two source rows up
+    // one k-block ahead.
+    const int gt = (warp - 6) * 32 + lane;          // 0 .. 63
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      int m0, n0, nkb; int64_t kbeg;
+      decode(t, m0, n0, kbeg, nkb);
+      const int64_t rowa = m0 + gt, rowb = m0 + 64 + gt;
+      const int* ta = rowa < g.M ? g.gtab + rowa * g.gtaps : nullptr;
+      const int* tb2 = rowb < g.M ? g.gtab + rowb * g.gtaps : nullptr;
+      int tap = (int)(kbeg / g.gcin);
+      int sa = ta ? __ldg(ta + tap) : -1, sb = tb2 ? __ldg(tb2 + tap) : -1;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES, use = it / STAGES;
+        const int k0 = (int)(kbeg + (int64_t)kb * KB);
+        const int c0 = k0 - tap * g.gcin;
+        // look ahead: source rows of the next k-block (same tap unless the k-block crosses into the next one)
+        int tap_n = tap, sa_n = sa, sb_n = sb;
+        if (kb + 1 < nkb && c0 + KB >= g.gcin) {
+          tap_n = tap + 1;
+          sa_n = ta ? __ldg(ta + tap_n) : -1;
+          sb_n = tb2 ? __ldg(tb2 + tap_n) : -1;
+        }
+        if (use > 0) bar_wait(&bar_empty[s], (use - 1) & 1);
+        const uint32_t abase = s_u32(smem + s * STAGE);
+        const float* pa = g.gsrc + (int64_t)(sa < 0 ? 0 : sa) * g.gcin + c0;
+        const float* pb = g.gsrc + (int64_t)(sb < 0 ? 0 : sb) * g.gcin + c0;
+        const uint32_t da = abase + (uint32_t)((gt >> 3) * 1024 + (gt & 7) * 128);
+        const uint32_t db = da + 8 * 1024;           // row + 64
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t off = (uint32_t)((c ^ (gt & 7)) * 16);
+          cp_async16_zfill(da + off, pa + c * 4, sa < 0 ? 0u : 16u);
+          cp_async16_zfill(db + off, pb + c * 4, sb < 0 ? 0u : 16u);
+        }
+        cp_async_arrive_noinc(&bar_full[s]);
+        tap = tap_n; sa = sa_n; sb = sb_n;
       }
     }
   } else {
@@ -350,7 +408,7 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 struct DualSrc { const float* A2; const float* B2; int64_t K2; };  // optional second source pair of an NT GEMM (K-major, pitch K2)
 
-template <int MODE, int BN>
+template <int MODE, int BN, bool GATHER = false>
 static int tma_launch(const float* A, const float* B, float* C, float* preact, int64_t lda, int64_t ldb, int64_t ldc, TmaArgs g, int splits,
                       cudaStream_t s, DualSrc d2 = DualSrc{nullptr, nullptr, 0}) {
   constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
@@ -380,18 +438,19 @@ static int tma_launch(const float* A, const float* B, float* C, float* preact, i
   g.trace = g_trace_buf; g.trace_cap = (int)g_trace_cap;
   g.C = C; g.P = preact; g.ldc = ldc;
   size_t smem = (size_t)STAGES * (UM * KB * 4 + BN * KB * 4) + 1024;
-  auto kern = tma_gemm_kernel<MODE, BN, STAGES>;
+  auto kern = tma_gemm_kernel<MODE, BN, STAGES, GATHER>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TMAE_ERR_CUDA;
     attr_set = true;
   }
-  static const char* names[3] = {"tma_gemm_nt", "tma_gemm_nn", "tma_gemm_tn"};
+  static const char* names[4] = {"tma_gemm_nt", "tma_gemm_nn", "tma_gemm_tn", "tma_gemm_nt_gather"};
   double c_el = (double)g.M * g.N * (1.0 + (g.reduce_add && z == 1 ? 1.0 : 0.0) + (preact ? 1.0 : 0.0));
-  ProfScope prof(names[MODE], 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + c_el), s);
+  ProfScope prof(names[GATHER ? 3 : MODE], 2.0 * g.M * g.N * g.K,
+                 4.0 * ((GATHER ? (double)g.M * g.gcin : (double)g.M * g.K) + (double)g.N * g.K + c_el), s);
   int64_t tiles = (int64_t)cdiv(g.N, BN) * cdiv(g.M, UM) * z;
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
-  kern<<<grid, TMA_THREADS, smem, s>>>(ma, mb, ma2, mb2, g);
+  kern<<<grid, TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0), smem, s>>>(ma, mb, ma2, mb2, g);
   return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
 }
 
@@ -434,6 +493,20 @@ int tma_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, i
   TmaArgs g{};
   g.M = m; g.N = k; g.K = n; g.reduce_add = accumulate; g.gelu_pre = gelu_pre;
   return tma_dispatch<T_NN>(dy, w, dx, nullptr, n, k, k, g, 1, s);
+}
+// sparse convolution forward / backward-data as a gathered NT GEMM: y[o, :] = sum_tap x[table[o, tap], :] w[:, tap, :]^T
+bool tma_sparse_conv_ok(const float* x, const float* w, const float* y, int cin, int cout) {
+  return cin % KB == 0 && cout % 4 == 0 && aligned16(x) && aligned16(w) && aligned16(y);
+}
+int tma_sparse_conv_fwd(const float* x, const int* table, const float* w, float* y, int64_t rows_out, int taps, int cin, int cout, int accumulate,
+                        cudaStream_t s) {
+  TmaArgs g{};
+  g.M = rows_out; g.N = cout; g.K = (int64_t)taps * cin; g.reduce_add = accumulate;
+  g.gsrc = x; g.gtab = table; g.gtaps = taps; g.gcin = cin;
+  // the A tensor map is unused by the GATHER variant: describe w twice so that both maps are valid
+  if (cout > 128) return tma_launch<T_NT, 256, true>(w, w, y, nullptr, g.K, g.K, cout, g, 1, s);
+  if (cout > 64) return tma_launch<T_NT, 128, true>(w, w, y, nullptr, g.K, g.K, cout, g, 1, s);
+  return tma_launch<T_NT, 64, true>(w, w, y, nullptr, g.K, g.K, cout, g, 1, s);
 }
 bool tma_linear_bwd_weight_ok(const float* dy, const float* x, const float* dw, int64_t m, int64_t n, int64_t k) {
   return n % 4 == 0 && k % 4 == 0 && aligned16(dy) && aligned16(x) && aligned16(dw);

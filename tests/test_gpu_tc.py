@@ -86,19 +86,29 @@ def _coords(seed, m, B, g):
 
 
 @pytest.mark.parametrize("seed,m,B,g,cin,cout", [(0, 1500, 2, 96, 128, 128), (1, 700, 2, 47, 128, 256), (2, 3000, 1, 90, 256, 256)])
-def test_tc_sparse_conv(seed, m, B, g, cin, cout):
-    bf = lambda t: t.to(torch.bfloat16).double()  # noqa: E731  the gathered GEMMs always stage bf16
+def test_tc_sparse_conv(seed, m, B, g, cin, cout, _tc_mode):
+    """Forward and backward-data: cp.async-gathered TF32 tcgen05 GEMM in the default tensor-core mode (operands stay
+    fp32 in shared memory, the tensor core drops the low 13 bits: tolerance = one TF32 ulp per product, as for the
+    dense TMA GEMMs), thread-staged bf16 kernel otherwise (exact products of rounded operands: 1e-4).  The weight
+    gradient always runs on the thread-staged bf16 kernel."""
     c = _coords(seed, m, B, g)
     m = c.shape[0]
     gen = torch.Generator().manual_seed(seed)
     x = torch.randn(m, cin, generator=gen)
+    async_path = _tc_mode == "tma_tf32"
+    rnd = tf32 if async_path else bf
+    tol_f = (2e-3, 2e-3 * (9 * cin) ** .5 * 0.1) if async_path else (1e-4, 1e-4)
     for subm in (True, False):
         conv = restated.SparseConv(cin, cout, 3, 1 if subm else 2, 1, subm).double()
-        with torch.no_grad():
-            conv.weight.copy_(bf(conv.weight.float()))
-        xr = bf(x).requires_grad_()
-        ref = conv(restated.SparseTensor(xr, c, [g, g], B))
-        w = conv.weight.detach().float().to(DEV)
+        w32 = conv.weight.detach().float()
+        refs = {}
+        for name, r in (("f", rnd), ("w", bf)):   # reference for forward / dx, and for the (bf16-staged) weight gradient
+            cv = restated.SparseConv(cin, cout, 3, 1 if subm else 2, 1, subm).double()
+            with torch.no_grad():
+                cv.weight.copy_(r(w32))
+            xr = r(x).requires_grad_()
+            refs[name] = (cv, xr, cv(restated.SparseTensor(xr, c, [g, g], B)))
+        w = w32.to(DEV)
         if subm:
             table = ops.subm_table(c.to(DEV), B, g, g)
             table_t, flip, rows_out = table, True, m
@@ -107,10 +117,11 @@ def test_tc_sparse_conv(seed, m, B, g, cin, cout):
             rows_out = int(n_out)
             table, flip = table[:rows_out], False
         y = ops.sparse_conv_fwd(x.to(DEV), table, w, rows_out)
-        assert_close(y, ref.features.detach(), 1e-4, 1e-4, f"tc sparse conv fwd subm={subm}")
+        assert_close(y, refs["f"][2].features.detach(), *tol_f, f"tc sparse conv fwd subm={subm}")
         dy = torch.randn(rows_out, cout, generator=gen)
-        ref.features.backward(bf(dy))
+        refs["f"][2].features.backward(rnd(dy))
+        refs["w"][2].features.backward(bf(dy))
         dx = ops.sparse_conv_fwd(dy.to(DEV), table_t, ops.transpose_taps(w, flip), m)
-        assert_close(dx, xr.grad, 1e-4, 1e-4, f"tc sparse conv dx subm={subm}")
+        assert_close(dx, refs["f"][1].grad, *tol_f, f"tc sparse conv dx subm={subm}")
         dw = ops.sparse_conv_bwd_weight(dy.to(DEV), x.to(DEV), table, w.shape)
-        assert_close(dw, conv.weight.grad, 1e-4, 1e-4 * m ** .5, f"tc sparse conv dw subm={subm}")
+        assert_close(dw, refs["w"][0].weight.grad, 1e-4, 1e-4 * m ** .5, f"tc sparse conv dw subm={subm}")
