@@ -14,6 +14,7 @@ the public module API from pinned HOST buffers (H2D copies and the loss read-bac
 not exist on the GPU box) on a bounded sample of the same workload.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -56,7 +57,7 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index, period=0.25):
+    def __init__(self, index, period=float(os.environ.get("TMAE_CLOCK_PERIOD", "0.25"))):
         self.index, self.period = index, period
         self.sm, self.mx, self.reasons, self.stop, self.t, self.proc, self.lines = [], 0, set(), False, None, None, []
 
@@ -222,11 +223,16 @@ def run_ours(args):
     def timed(from_host):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         d2h = 0
+        gc.collect()
+        gc.disable()   # a generation-2 collection of the Python heap is a 50-250 ms host pause (seen as one slow step in ~half the runs)
         barrier()
         c0 = ops.launch_count()
         host_t0 = time.perf_counter()
         ev[0].record()
         for i in range(args.steps):
+            if i >= 2:
+                ev[i - 1].synchronize()  # bounded run-ahead: the host stays at most two steps in front of the GPU, so blocks
+                                         # recorded on two streams return to the allocator pool before it has to grow
             if from_host:
                 a, b = host[i % len(host)]
                 if side is not None:  # input pipeline: the H2D copies of this step's scans are issued on the side stream
@@ -246,20 +252,29 @@ def run_ours(args):
             ev[i + 1].record()
         host_ms.append((time.perf_counter() - host_t0) * 1e3 / args.steps)  # host time to ENQUEUE the steps (no sync when resident)
         barrier()
+        gc.enable()
         per = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-        print(f"[bench] {'e2e' if from_host else 'resident'} per-step ms: " + " ".join(f"{p:.1f}" for p in per), file=sys.stderr)
+        ms = torch.cuda.memory_stats(dev)
+        print(f"[bench] {'e2e' if from_host else 'resident'} per-step ms: " + " ".join(f"{p:.1f}" for p in per) +
+              f" | cudaMalloc calls so far {ms.get('num_device_alloc', 0)}, frees {ms.get('num_device_free', 0)}, retries {ms.get('num_alloc_retries', 0)}, "
+              f"reserved {ms.get('reserved_bytes.all.current', 0) / 2**30:.1f} GiB", file=sys.stderr)
         total = ev[0].elapsed_time(ev[-1])
         return total, per, ops.launch_count() - c0, d2h
 
-    # every distinct batch twice: its row counts are new sizes for the caching allocator (cudaMalloc stalls otherwise
-    # land in the first timed steps)
-    args.warmup = max(args.warmup, 2 * len(resident))
+    # every distinct batch four times: its row counts are new sizes for the caching allocator, and with the host running a
+    # step ahead of the GPU (no sync in the loop) blocks recorded on two streams return to the pool late, so the pool keeps
+    # growing (cudaMalloc stalls of 50-250 ms) for ~14 steps before it is stationary
+    args.warmup = max(args.warmup, 4 * len(resident))
     for i in range(args.warmup):
         step(*resident[i % len(resident)])
-    with ClockSampler(local) as cs:
+    if args.clock_sampler:
+        with ClockSampler(local) as cs:
+            total, per, launches, _ = timed(False)
+        clocks = cs.summary()
+    else:
         total, per, launches, _ = timed(False)
-    clocks = cs.summary()
-    steps_saved, args.steps = args.steps, 2   # untimed pass over the host-input path (its device buffers are new allocator sizes)
+        clocks = None
+    steps_saved, args.steps = args.steps, len(host)   # untimed pass over the host-input path: every distinct batch once (new allocator sizes)
     timed(True)
     args.steps = steps_saved
     e_total, e_per, _, d2h = timed(True)
@@ -425,6 +440,7 @@ def main():
     ap.add_argument("--decoder", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clock-sampler", dest="clock_sampler", action="store_false")
     ap.add_argument("--ddp", action="store_true", help="wrap the step in torch DistributedDataParallel instead of the flat gradient all-reduce")
     ap.add_argument("--no-side-stream", dest="side_stream", action="store_false",
                     help="run the coordinate-only pre-pass (voxelise, mask, plans) on the main stream instead of the library's side stream")

@@ -317,6 +317,9 @@ int tc_linear_bwd_weight(const float* dy, const float* x, float* dw, int64_t m, 
 bool tma_sparse_conv_ok(const float* x, const float* w, const float* y, int cin, int cout);
 int tma_sparse_conv_fwd(const float* x, const int* table, const float* w, float* y, int64_t rows_out, int taps, int cin, int cout, int accumulate,
                         cudaStream_t s);
+bool tma_sparse_conv_bwd_weight_ok(const float* dy, const float* x, const float* dw, int cin, int cout);
+int tma_sparse_conv_bwd_weight(const float* dy, const float* x, const int* table, float* dw, int64_t rows_out, int taps, int cin, int cout,
+                               cudaStream_t s);
 bool tc_sparse_conv_ok(int cin, int cout);
 int tc_sparse_conv_fwd(const float* x, const int* table, const float* w, float* y, int64_t rows_out, int taps, int cin, int cout,
                        int accumulate, cudaStream_t s);
@@ -546,7 +549,10 @@ int tmae_sparse_conv_bwd_weight(const float* dy, const float* x, const int32_t* 
   int64_t kk = (int64_t)taps * cin;
   TMAE_CUDA(cudaMemsetAsync(dw, 0, (size_t)cout * kk * sizeof(float), s));
   if (rows_out <= 0) return 0;
-  if (precision == TMAE_PREC_BF16 && tc_sparse_conv_ok(cin, cout) && cin % 8 == 0) {
+  if (precision == TMAE_PREC_BF16 && g_use_tma && g_conv_async && rows_out > 0 && tma_sparse_conv_bwd_weight_ok(dy, x, dw, cin, cout)) {
+    if (tma_sparse_conv_bwd_weight(dy, x, table, dw, rows_out, taps, cin, cout, s)) { set_error("tmae_sparse_conv_bwd_weight: TMA/cp.async launch failed"); return TMAE_ERR_CUDA; }
+    return 0;
+  } else if (precision == TMAE_PREC_BF16 && tc_sparse_conv_ok(cin, cout) && cin % 8 == 0) {
     if (tc_sparse_conv_bwd_weight(dy, x, table, dw, rows_out, taps, cin, cout, s)) { set_error("tmae_sparse_conv_bwd_weight: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
     return 0;
   }

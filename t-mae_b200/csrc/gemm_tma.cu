@@ -198,8 +198,9 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
           uint8_t* a = smem + s * STAGE;
           uint8_t* b = a + A_BYTES;
           const int k0 = (int)(kbeg + (int64_t)kb * KB);
-          bar_expect_tx(&bar_full[s], GATHER ? B_BYTES : STAGE);
-          if (GATHER) {
+          constexpr bool GA = GATHER && MODE == T_NT, GB = GATHER && MODE == T_TN;  // which operand the gather warps write
+          bar_expect_tx(&bar_full[s], GA ? B_BYTES : (GB ? A_BYTES : STAGE));
+          if (GA) {
             // A comes from the gather warps
           } else if (MODE == T_TN) {
 #pragma unroll
@@ -213,6 +214,8 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
             tma_load_2d(b, &map_b2, k0 - (int)g.k_split, n0, &bar_full[s]);
           } else if (MODE == T_NT) {
             tma_load_2d(b, &map_b, k0, n0, &bar_full[s]);
+          } else if (GB) {
+            // B comes from the gather warps
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 32; ++j) tma_load_2d(b + j * 4096, &map_b, n0 + j * 32, k0, &bar_full[s]);
@@ -251,6 +254,43 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
           commit_to(&bar_empty[s]);
         }
         commit_to(&bar_acc_full[buf]);
+      }
+    }
+  } else if (GATHER && MODE == T_TN && warp >= 6) {
+    // ---------------- gather producers, weight gradient of the sparse convolution:
+    //   dW[co][tap*cin + c] = sum_r dy[r][co] * src[tab[r][tap]][c]        (TN: A = dy by TMA, B gathered, reduction over r)
+    // One k-block = 32 reduction rows x BN columns of B in the MN-major SWIZZLE_128B_ATOM_32B layout (boxes of 32 columns,
+    // 4096 B each; row k at +128 k; 32-byte chunk j of the row at (j ^ (k % 4)) * 32).  A thread owns one half (BN/2
+    // columns, inside one tap because cin % (BN/2) == 0) of one row and looks its source row up one k-block ahead.
+    const int gt = (warp - 6) * 32 + lane;          // 0 .. 63
+    const int kr = gt >> 1, half = gt & 1;          // reduction row inside the k-block, column half
+    constexpr int HALF = BN / 2, PIECES = HALF / 4; // 16-byte pieces per thread per k-block
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      int m0, n0, nkb; int64_t kbeg;
+      decode(t, m0, n0, kbeg, nkb);
+      const int64_t kend = kbeg + g.k_chunk < g.K ? kbeg + g.k_chunk : g.K;
+      const int col0 = n0 + half * HALF;            // first B column (= tap * cin + c) of this thread's half
+      const bool col_ok = col0 < g.N;
+      const int tap = col_ok ? col0 / g.gcin : 0, c0 = col_ok ? col0 - tap * g.gcin : 0;
+      int64_t r = kbeg + kr;
+      int srow = (col_ok && r < kend) ? __ldg(g.gtab + r * g.gtaps + tap) : -1;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES, use = it / STAGES;
+        const int64_t rn = r + KB;
+        const int srow_n = (col_ok && kb + 1 < nkb && rn < kend) ? __ldg(g.gtab + rn * g.gtaps + tap) : -1;
+        if (use > 0) bar_wait(&bar_empty[s], (use - 1) & 1);
+        const uint32_t bbase = s_u32(smem + s * STAGE + A_BYTES) + (uint32_t)(kr * 128);
+        const float* p = g.gsrc + (int64_t)(srow < 0 ? 0 : srow) * g.gcin + c0;
+        const uint32_t nbytes = srow < 0 ? 0u : 16u;
+#pragma unroll 8
+        for (int q = 0; q < PIECES; ++q) {
+          const int c16 = half * PIECES + q;        // 16-byte piece index inside the BN-column row
+          const uint32_t dst = bbase + (uint32_t)((c16 >> 3) * 4096 + ((((c16 >> 1) & 3) ^ (kr & 3)) * 32) + (c16 & 1) * 16);
+          cp_async16_zfill(dst, p + q * 4, nbytes);
+        }
+        cp_async_arrive_noinc(&bar_full[s]);
+        r = rn; srow = srow_n;
       }
     }
   } else if (GATHER && warp >= 6) {
@@ -444,10 +484,11 @@ static int tma_launch(const float* A, const float* B, float* C, float* preact, i
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TMAE_ERR_CUDA;
     attr_set = true;
   }
-  static const char* names[4] = {"tma_gemm_nt", "tma_gemm_nn", "tma_gemm_tn", "tma_gemm_nt_gather"};
+  static const char* names[5] = {"tma_gemm_nt", "tma_gemm_nn", "tma_gemm_tn", "tma_gemm_nt_gather", "tma_gemm_tn_gather"};
   double c_el = (double)g.M * g.N * (1.0 + (g.reduce_add && z == 1 ? 1.0 : 0.0) + (preact ? 1.0 : 0.0));
-  ProfScope prof(names[GATHER ? 3 : MODE], 2.0 * g.M * g.N * g.K,
-                 4.0 * ((GATHER ? (double)g.M * g.gcin : (double)g.M * g.K) + (double)g.N * g.K + c_el), s);
+  const double a_el = (GATHER && MODE == T_NT) ? (double)g.M * g.gcin : (double)g.M * g.K;
+  const double b_el = (GATHER && MODE == T_TN) ? (double)g.K * g.gcin : (double)g.N * g.K;
+  ProfScope prof(names[GATHER ? (MODE == T_TN ? 4 : 3) : MODE], 2.0 * g.M * g.N * g.K, 4.0 * (a_el + b_el + c_el), s);
   int64_t tiles = (int64_t)cdiv(g.N, BN) * cdiv(g.M, UM) * z;
   dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
   kern<<<grid, TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0), smem, s>>>(ma, mb, ma2, mb2, g);
@@ -507,6 +548,22 @@ int tma_sparse_conv_fwd(const float* x, const int* table, const float* w, float*
   if (cout > 128) return tma_launch<T_NT, 256, true>(w, w, y, nullptr, g.K, g.K, cout, g, 1, s);
   if (cout > 64) return tma_launch<T_NT, 128, true>(w, w, y, nullptr, g.K, g.K, cout, g, 1, s);
   return tma_launch<T_NT, 64, true>(w, w, y, nullptr, g.K, g.K, cout, g, 1, s);
+}
+// dw (cout, taps*cin), zero-filled by the caller: gathered TN GEMM, split over the output rows
+bool tma_sparse_conv_bwd_weight_ok(const float* dy, const float* x, const float* dw, int cin, int cout) {
+  return cin % 128 == 0 && cout % 4 == 0 && aligned16(dy) && aligned16(x) && aligned16(dw);
+}
+int tma_sparse_conv_bwd_weight(const float* dy, const float* x, const int* table, float* dw, int64_t rows_out, int taps, int cin, int cout,
+                               cudaStream_t s) {
+  TmaArgs g{};
+  const int64_t kk = (int64_t)taps * cin;
+  g.M = cout; g.N = kk; g.K = rows_out; g.reduce_add = 1;
+  g.gsrc = x; g.gtab = table; g.gtaps = taps; g.gcin = cin;
+  int64_t tiles = (int64_t)cdiv(cout, UM) * cdiv(kk, 256);
+  int64_t want = (kNumSMs + tiles - 1) / tiles, maxs = (rows_out + 8 * KB - 1) / (8 * KB);
+  if (want > maxs) want = maxs;
+  // the B tensor map is unused by the gather variant: describe dy twice
+  return tma_launch<T_TN, 256, true>(dy, dy, dw, nullptr, cout, kk, kk, g, (int)(want < 1 ? 1 : want), s);
 }
 bool tma_linear_bwd_weight_ok(const float* dy, const float* x, const float* dw, int64_t m, int64_t n, int64_t k) {
   return n % 4 == 0 && k % 4 == 0 && aligned16(dy) && aligned16(x) && aligned16(dw);

@@ -90,7 +90,7 @@ def test_tc_sparse_conv(seed, m, B, g, cin, cout, _tc_mode):
     """Forward and backward-data: cp.async-gathered TF32 tcgen05 GEMM in the default tensor-core mode (operands stay
     fp32 in shared memory, the tensor core drops the low 13 bits: tolerance = one TF32 ulp per product, as for the
     dense TMA GEMMs), thread-staged bf16 kernel otherwise (exact products of rounded operands: 1e-4).  The weight
-    gradient always runs on the thread-staged bf16 kernel."""
+    gradient takes the same two paths (gathered TN GEMM, split over the output rows)."""
     c = _coords(seed, m, B, g)
     m = c.shape[0]
     gen = torch.Generator().manual_seed(seed)
@@ -102,7 +102,7 @@ def test_tc_sparse_conv(seed, m, B, g, cin, cout, _tc_mode):
         conv = restated.SparseConv(cin, cout, 3, 1 if subm else 2, 1, subm).double()
         w32 = conv.weight.detach().float()
         refs = {}
-        for name, r in (("f", rnd), ("w", bf)):   # reference for forward / dx, and for the (bf16-staged) weight gradient
+        for name, r in (("f", rnd), ("w", rnd)):   # references on the operands as the tensor core consumes them
             cv = restated.SparseConv(cin, cout, 3, 1 if subm else 2, 1, subm).double()
             with torch.no_grad():
                 cv.weight.copy_(r(w32))
@@ -120,8 +120,9 @@ def test_tc_sparse_conv(seed, m, B, g, cin, cout, _tc_mode):
         assert_close(y, refs["f"][2].features.detach(), *tol_f, f"tc sparse conv fwd subm={subm}")
         dy = torch.randn(rows_out, cout, generator=gen)
         refs["f"][2].features.backward(rnd(dy))
-        refs["w"][2].features.backward(bf(dy))
+        refs["w"][2].features.backward(rnd(dy))
         dx = ops.sparse_conv_fwd(dy.to(DEV), table_t, ops.transpose_taps(w, flip), m)
         assert_close(dx, refs["f"][1].grad, *tol_f, f"tc sparse conv dx subm={subm}")
         dw = ops.sparse_conv_bwd_weight(dy.to(DEV), x.to(DEV), table, w.shape)
-        assert_close(dw, refs["w"][0].weight.grad, 1e-4, 1e-4 * m ** .5, f"tc sparse conv dw subm={subm}")
+        tol_w = (2e-3, 2e-3 * m ** .5) if async_path else (1e-4, 1e-4 * m ** .5)
+        assert_close(dw, refs["w"][0].weight.grad, *tol_w, f"tc sparse conv dw subm={subm}")
