@@ -287,7 +287,7 @@ TMAE_API size_t tmae_encoder_layer_saved_bytes(int64_t m_q, int64_t m_kv, int32_
 TMAE_API size_t tmae_encoder_layer_scratch_bytes(int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t cross);
 TMAE_API int tmae_encoder_layer_fwd(const float* x, const float* x_kv, const tmae_layer_params* P, const tmae_layer_tables* T, const float* pos_lut,
                            float tau_min, float eps, int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t precision,
-                           float* y, void* saved, size_t saved_size, void* stream);
+                           int32_t need_backward, float* y, void* saved, size_t saved_size, void* stream);
 TMAE_API int tmae_encoder_layer_bwd(const float* dy, const float* x, const float* x_kv, const tmae_layer_params* P, const tmae_layer_tables* T,
                            const float* pos_lut, float tau_min, int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t precision,
                            const void* saved, size_t saved_size, float* dx, float* dx_kv, const tmae_layer_params* G, void* scratch,

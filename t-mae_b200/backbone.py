@@ -79,7 +79,8 @@ class _LayerFn(torch.autograd.Function):
         if x_kv is not None:
             x_kv = x_kv.contiguous()
         T = ops.layer_tables(part, shift, x_kv is not None, x.shape[0], x_kv.shape[0] if x_kv is not None else 0)
-        y, saved = ops.encoder_layer_fwd(x, x_kv, params, T, lut, tau_min, eps, heads)
+        need_bwd = any(ctx.needs_input_grad)
+        y, saved = ops.encoder_layer_fwd(x, x_kv, params, T, lut, tau_min, eps, heads, need_bwd)
         ctx.save_for_backward(x, x_kv, saved, lut, *params)
         ctx.misc = (T, part, heads, tau_min)  # part keeps the device tables alive
         return y

@@ -83,7 +83,7 @@ size_t tmae_encoder_layer_scratch_bytes(int64_t m_q, int64_t m_kv, int32_t c, in
 
 int tmae_encoder_layer_fwd(const float* x, const float* x_kv, const tmae_layer_params* P, const tmae_layer_tables* T, const float* pos_lut,
                            float tau_min, float eps, int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t precision,
-                           float* y, void* saved, size_t saved_size, void* stream) {
+                           int32_t need_backward, float* y, void* saved, size_t saved_size, void* stream) {
   const bool cross = x_kv != nullptr;
   if (!cross) { m_kv = m_q; x_kv = x; }
   TMAE_CHECK_ARG(saved_size >= saved_bytes(m_q, m_kv, c, ff, heads, cross), "saved buffer too small");
@@ -126,7 +126,8 @@ int tmae_encoder_layer_fwd(const float* x, const float* x_kv, const tmae_layer_p
                                 P->tau, tau_min, c, heads, ldq, ldkv, ldkv, stream));
   TRY(tmae_linear_fwd(s.o, P->out_w, P->out_b, nullptr, s.a, nullptr, m_q, c, c, TMAE_ACT_NONE, precision, stream));
   TRY(tmae_add_layernorm_fwd(x, s.a, T->rowmask, P->ln1_g, P->ln1_b, s.x1, s.m1, s.r1, m_q, c, eps, stream));
-  TRY(tmae_linear_fwd(s.x1, P->w1, P->b1, nullptr, s.h, s.hpre, m_q, ff, c, TMAE_ACT_GELU, precision, stream));
+  // the pre-activation copy exists only for the GELU backward: inference skips that write (2 FF-wide rows per voxel)
+  TRY(tmae_linear_fwd(s.x1, P->w1, P->b1, nullptr, s.h, need_backward ? s.hpre : nullptr, m_q, ff, c, TMAE_ACT_GELU, precision, stream));
   TRY(tmae_linear_fwd(s.h, P->w2, P->b2, nullptr, s.f, nullptr, m_q, c, ff, TMAE_ACT_NONE, precision, stream));
   TRY(tmae_add_layernorm_fwd(s.x1, s.f, nullptr, P->ln2_g, P->ln2_b, y, s.m2, s.r2, m_q, c, eps, stream));
   return 0;

@@ -644,7 +644,7 @@ def _layer_params(tensors):
     return P
 
 
-def encoder_layer_fwd(x, x_kv, params, T, lut, tau_min, eps, heads):
+def encoder_layer_fwd(x, x_kv, params, T, lut, tau_min, eps, heads, need_backward=True):
     """params: the 13 tensors in tmae_layer_params order.  -> (y, saved buffer)."""
     L = lib()
     m_q, c = x.shape
@@ -656,7 +656,7 @@ def encoder_layer_fwd(x, x_kv, params, T, lut, tau_min, eps, heads):
     y = torch.empty_like(x)
     P = _layer_params(params)
     _call("encoder_layer_fwd", _p(x, F32), _p(x_kv), ctypes.byref(P), ctypes.byref(T), _p(lut, F32), float(tau_min), float(eps), m_q, m_kv,
-          c, ff, heads, _state["precision"], _p(y), _p(saved), nb, _stream())
+          c, ff, heads, _state["precision"], int(need_backward), _p(y), _p(saved), nb, _stream())
     return y, saved
 
 

@@ -29,7 +29,7 @@ elif what == "nt":
     for _ in range(4):
         ops.linear_fwd(x, w, b)
 else:
-    M, C, g, B = {"attn": (50000, 256, 234, 4), "attn1": (56000, 128, 468, 4), "attn1s": (14000, 128, 468, 4)}[what]
+    M, C, g, B = {"attn": (50000, 256, 234, 4), "attn1": (56000, 128, 468, 4), "attn1s": (14000, 128, 468, 4), "attn3": (28000, 256, 117, 4)}[what]
     ops.set_option("attn_tc", 1)
     rng = np.random.default_rng(0)
     cells = np.unique(np.clip((rng.normal(0, g / 5, (M * 3, 2)) + g / 2).astype(np.int64), 0, g - 1) @ np.array([g, 1]))
