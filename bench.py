@@ -342,7 +342,11 @@ def roofline(ops, step, resident, args):
         roof = {"kernel": name, "bound": "tensor", "achieved": round(tf, 3), "peak": pk["tensor"], "unit": "TFLOP/s", "frac": round(tf / pk["tensor"], 5)}
     else:
         roof = {"kernel": name, "bound": "hbm", "achieved": round(gb, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(gb / pk["hbm"], 5)}
-    roof.update(traffic=None, arithmetic_intensity_flop_per_byte=round(ai, 1) if r["bytes"] else None, ridge_flop_per_byte=round(ridge, 1),
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):  # dram__bytes_read + dram__bytes_write per launch of this kernel family from the committed ncu --set full capture
+        traffic = json.load(open(tp)).get(name, {}).get("traffic_bytes_per_launch")
+    roof.update(traffic=traffic, algorithmic_bytes_per_launch=round(r["bytes"] / r["calls"]) if r["calls"] else None, arithmetic_intensity_flop_per_byte=round(ai, 1) if r["bytes"] else None, ridge_flop_per_byte=round(ridge, 1),
                 tensor_tflops=round(tf, 2), peak_source=pk["src"], avg_launch_us=round(r["ms"] * 1e3 / r["calls"], 2),
                 launches_per_step=r["calls"] // n, share_of_library_time=round(r["ms"] / tot, 4))
     short = {k: {"ms_per_step": round(v["ms"] / n, 3), "launches_per_step": v["calls"] // n,
