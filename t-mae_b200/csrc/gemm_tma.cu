@@ -369,6 +369,18 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
       decode(t, m0, n0, kbeg, nkb);
       const int buf = i & 1, round = i >> 1;
       const int64_t row = m0 + q * 32 + lane;
+      // fused GELU backward: the pre-activation row segment of chunk c+1 is loaded while chunk c is processed (and the
+      // first one while this warp still waits for the accumulator) -- a load issued next to its use costs a DRAM round
+      // trip per 32-column chunk in the four warps that pace the whole kernel
+      float4 hn[8];
+      auto load_pre = [&](int ch) {
+        const int col0 = n0 + ch * 32;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          hn[c] = (row < g.M && col0 + 4 * c < g.N) ? __ldg(reinterpret_cast<const float4*>(g.gelu_pre + row * g.ldc + col0 + 4 * c))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      if (g.gelu_pre) load_pre(0);
       trace_ev(tb, tn, g.trace_cap / 4, 4, i);
       bar_wait(&bar_acc_full[buf], round & 1);
       trace_ev(tb, tn, g.trace_cap / 4, 5, i);
@@ -398,13 +410,12 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
             if (col0 + 4 * c < g.N) *reinterpret_cast<float4*>(prow + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
         if (g.gelu_pre) {
-          const float* hrow = g.gelu_pre + row * g.ldc + col0;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            if (col0 + 4 * c >= g.N) break;
-            float4 h = __ldg(reinterpret_cast<const float4*>(hrow + 4 * c));
+            const float4 h = hn[c];
             v[4 * c] *= gelu_grad_t(h.x); v[4 * c + 1] *= gelu_grad_t(h.y); v[4 * c + 2] *= gelu_grad_t(h.z); v[4 * c + 3] *= gelu_grad_t(h.w);
           }
+          if (ch + 1 < CHUNKS) load_pre(ch + 1);
         }
         if (g.act == TMAE_ACT_GELU) {
 #pragma unroll
