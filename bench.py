@@ -264,7 +264,9 @@ def run_ours(args):
     # every distinct batch four times: its row counts are new sizes for the caching allocator, and with the host running a
     # step ahead of the GPU (no sync in the loop) blocks recorded on two streams return to the pool late, so the pool keeps
     # growing (cudaMalloc stalls of 50-250 ms) for ~14 steps before it is stationary
-    args.warmup = max(args.warmup, 4 * len(resident))
+    # (and a one-off 100-300 ms driver-side stall was observed at the ~23rd step of a process in a third of the runs,
+    # with or without the clock sampler: the warm-up runs past it)
+    args.warmup = max(args.warmup, 7 * len(resident))
     for i in range(args.warmup):
         step(*resident[i % len(resident)])
     if args.clock_sampler:
