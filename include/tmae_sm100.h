@@ -249,6 +249,23 @@ TMAE_API int tmae_window_attention_bwd(const float* dout, const float* q, const 
                               const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min, int32_t channels,
                               int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, void* stream);
 
+/* ---- N2 / N3 (the step in front of the VFE): batch assembly of one frame set on the GPU ---------------
+ * raw (n_points, feats) fp32 [x, y, z, feat...] = the samples' point arrays back to back, sample_offsets (batch + 1) i64.
+ * Per point: remove_ego_points (once_utils.py:43-45; |x| < r and |y| < r on the RAW coordinates, r = 2:
+ * once_temporal_dataset.py:167-168), convert_prv_frame_to_cur (once_utils.py:4-29) as two float64 affine maps per sample
+ * (xform (batch, 2, 3, 4) row-major: prev -> global, global -> current = the reference's np.linalg.inv result, computed
+ * on the host; xform_flags (batch, 2): 0 skips a map, which is what the reference does for an all-zero pose; both NULL
+ * for the current frame), mask_points_by_range (common_utils.py:124-127; closed interval, compared in float64 like the
+ * reference), collate_batch (dataset.py:203-208; sample index in column 0) and the final .float().  Stable compaction:
+ * out (capacity n_points, 1 + feats) holds the kept points in input order, *count (device i64) how many; rows
+ * [count, n_points) are set to the out-of-range sentinel [0, 1e6, 1e6, 1e6, 0...] which tmae_voxelize's range test drops,
+ * so a caller may pass all n_points rows on without reading *count.  Two launches, no atomics; workspace = one i32 per
+ * 512 points. */
+TMAE_API size_t tmae_assemble_frames_workspace_bytes(int64_t n_points);
+TMAE_API int tmae_assemble_frames(const float* raw, const int64_t* sample_offsets, int32_t batch, int32_t feats, const double* xform,
+                         const uint8_t* xform_flags, float ego_radius, const float* crop_xyxy, float* out, int64_t* count,
+                         int64_t n_points, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- A10-A11 reconstruction target + Chamfer loss ------------------------------------------------
  * Replaces sst_ops_cuda.group_inner_inds_wrapper (pcdet/ops/sst_ops/src/sst_ops_api.cpp:8, sst_ops_gpu.cu:22-39),
  * the GT gather / centre subtraction (SiamWCA_MAE.py:132-139) and pytorch3d chamfer_distance (SiamWCA_MAE.py:163). */

@@ -66,3 +66,30 @@ def fixed_mask(voxel_coords, batch_size, ratio, seed):
         m[ids] = 0
         out.append(m)
     return torch.cat(out)
+
+
+def raw_samples(seed, n_points=3000, kind="once"):
+    """Four raw samples for the batch-assembly tests (tmae_b200.synth.raw_scan_pair): moving vehicle; all-zero poses
+    (static vehicle: no transformation, once_utils.py:5-10); zero previous pose with a non-zero current pose (only the
+    second map applies); and frame_id == frame_id_prev (alignment skipped, once_temporal_dataset.py:169).  Ragged sizes;
+    a few hand-placed points sit exactly on the ego radius and on the crop bounds (both tests are strict / closed)."""
+    import tmae_b200  # noqa: F401
+    from tmae_b200 import synth
+    rng32 = np.asarray(synth.SHAPES[kind]["range"], np.float32)
+    out = []
+    for i, n in enumerate([n_points, n_points // 2 + 7, n_points // 3 + 1, n_points // 4 + 3]):
+        s = synth.raw_scan_pair(seed + i, n, kind, static=(i == 1))
+        if i == 2:
+            s["pose_prev"] = np.zeros(7)
+            s["pose"][4:] = [1.5, -0.7, 0.1]   # keeps the mapped points inside the crop
+        if i == 3:
+            s["frame_id_prev"] = s["frame_id"]
+        for key in ("points", "points_prev"):
+            p = s[key]
+            p[0, :2] = [2.0, 0.5]             # |x| == r: not an ego point (strict <)
+            p[1, :2] = [-1.999, 1.999]        # ego point
+            p[2, :2] = [rng32[0], rng32[4]]   # on the crop bounds: kept (closed interval)
+            p[3, :2] = [np.nextafter(rng32[3], np.float32(np.inf)), 0.0]   # one ulp outside
+            p[4, :2] = [np.nan, 0.0]          # NaN fails the range test
+        out.append(s)
+    return out

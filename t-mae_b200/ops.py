@@ -184,6 +184,22 @@ def voxelize(points, pc_range, voxel_size, grid_size, batch_size):
     return out
 
 
+def assemble_frames(raw, sample_offsets, batch, xform, xform_flags, ego_radius, crop_xyxy):
+    """raw (n, F) f32 device rows [x,y,z,feat...] of `batch` samples back to back, sample_offsets (batch+1,) i64 device,
+    xform (batch,2,3,4) f64 / xform_flags (batch,2) u8 device or None -> (out (n, 1+F) f32, count (1,) i64 device)."""
+    L = lib()
+    n, feats = raw.shape
+    dev = raw.device
+    out = torch.empty(n, feats + 1, dtype=F32, device=dev)
+    count = torch.empty(1, dtype=I64, device=dev)
+    wsb = L.assemble_frames_workspace_bytes(n)
+    ws = _ws(wsb, dev)
+    crop = (ctypes.c_float * 4)(*[float(v) for v in crop_xyxy])
+    _call("assemble_frames", _p(raw, F32), _p(sample_offsets, I64), batch, feats, _p(xform, torch.float64), _p(xform_flags, U8),
+          float(ego_radius), crop, _p(out), _p(count), n, _p(ws), wsb, _stream())
+    return out, count
+
+
 def vfe_point_features(points_kept, point_coords, inverse, voxel_mean, pc_range, voxel_size):
     n, stride = points_kept.shape
     x = torch.empty(n, stride - 1 + 6, dtype=F32, device=points_kept.device)

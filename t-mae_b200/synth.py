@@ -108,3 +108,55 @@ def batch(first_seed, batch_size, n_points=60000, kind="once"):
     """(points, points_prev) collated float32 arrays for scan indices first_seed .. +batch_size-1."""
     pairs = [scan_pair(first_seed + i, n_points, kind) for i in range(batch_size)]
     return collate([p[0] for p in pairs]), collate([p[1] for p in pairs])
+
+
+def _quat_pose(rng, yaw_deg, trans):
+    """ONCE pose vector [qx, qy, qz, qw, tx, ty, tz] (vehicle -> global; once_utils.py:12-13 reads it so) with small roll/pitch."""
+    yaw, pitch, roll = np.deg2rad(yaw_deg), np.deg2rad(rng.uniform(-0.5, 0.5)), np.deg2rad(rng.uniform(-0.5, 0.5))
+    cy, sy, cp, sp, cr, sr = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(roll / 2), np.sin(roll / 2)
+    q = [sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy]
+    return np.array(q + list(trans), np.float64)
+
+
+def _quat_matrix(q):
+    x, y, z, w = q / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def raw_scan_pair(seed, n_points=60000, kind="once", static=False):
+    """One RAW sample as the ONCE temporal dataset reads it before any processing (once_temporal_dataset.py:159-165):
+    dict(points, points_prev (n_points, F) float32 in their OWN sensor frames, not cropped (returns out to 120 m), with
+    ~1 % ego-vehicle returns inside |x|,|y| < 2 m; pose, pose_prev (7,) float64 [qx,qy,qz,qw,tx,ty,tz]).  static=True gives
+    the all-zero poses ONCE stores for a parked vehicle (once_utils.py:5-6)."""
+    shape = SHAPES[kind]
+    rng = np.random.default_rng(seed + 77000)
+    scene = _scene(rng)
+
+    def frame():
+        xyz = _cast(rng, shape, n_points, scene)
+        xyz = xyz[rng.permutation(xyz.shape[0])[:n_points]]
+        k = max(1, xyz.shape[0] // 100)
+        xyz[:k] = np.stack([rng.uniform(-1.9, 1.9, k), rng.uniform(-1.9, 1.9, k), rng.uniform(-1.0, 0.5, k)], 1)
+        return xyz[rng.permutation(xyz.shape[0])]
+
+    cur, prev = frame(), frame()
+    if static:
+        pose = pose_prev = np.zeros(7)
+    else:
+        base_yaw, base_t = rng.uniform(-180, 180), np.append(rng.uniform(-500, 500, 2), rng.uniform(-2, 2))
+        pose = _quat_pose(rng, base_yaw, base_t)
+        pose_prev = _quat_pose(rng, base_yaw + rng.uniform(-2, 2), base_t + np.append(rng.uniform(-2, 2, 2), rng.uniform(-0.1, 0.1)))
+        # the previous scan sees the same scene from its own pose: current frame -> global -> previous frame
+        Rc, Rp = _quat_matrix(pose[:4]), _quat_matrix(pose_prev[:4])
+        prev = (prev @ Rc.T + pose[4:] - pose_prev[4:]) @ Rp
+    out = {}
+    for key, xyz in (("points", cur), ("points_prev", prev)):
+        feats = [rng.uniform(0, 1, (xyz.shape[0], 1))]
+        if shape["feats"] == 5:
+            feats = [np.tanh(feats[0] * 3.0), rng.uniform(0, 1.5, (xyz.shape[0], 1))]
+        out[key] = np.concatenate([xyz] + feats, 1).astype(np.float32)
+    out["pose"], out["pose_prev"] = pose, pose_prev
+    out["frame_id"], out["frame_id_prev"] = str(seed), str(seed) + "p"
+    return out
