@@ -23,6 +23,7 @@ enum TmaMode { T_NT = 0, T_NN = 1, T_TN = 2 };
 
 // Optional timeline of CTA 0 (diagnostics, tmae_debug_set_trace): records (event id << 56 | index << 40 | clock) words.
 unsigned long long* g_trace_buf = nullptr;
+bool g_wide_st = true;   // tmae_set_option("wide_st", 0): 128-bit epilogue stores (A/B measurement)
 long long g_trace_cap = 0;
 __device__ __forceinline__ void trace_ev(unsigned long long* buf, int& n, int cap, int ev, int idx) {
   if (buf && n < cap) buf[n++] = ((unsigned long long)ev << 56) | ((unsigned long long)(idx & 0xffff) << 40) | (clock64() & 0xffffffffffull);
@@ -36,6 +37,7 @@ struct TmaArgs {
   float* C; float* P; int64_t ldc;   // output, optional pre-activation copy
   const float* gelu_pre;             // optional: multiply the result by gelu'(gelu_pre[m,n])  (fused GELU backward)
   int act, reduce_add, has_preact;
+  int wide_st;                       // 1: rows of C (and P) are 32-byte aligned and N % 8 == 0 -> 256-bit epilogue stores
   int64_t k_chunk;
   unsigned long long* trace; int trace_cap;
 };
@@ -141,6 +143,12 @@ __device__ __forceinline__ float gelu_grad_t(float x) {
   return fmaf(x, pdf, cdf);
 }
 
+// 256-bit store (sm_100+): one full 32-byte sector per lane and instruction, so the L2 never sees a partial-sector write
+// and the epilogue issues half as many store instructions as with 128-bit stores
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
+               "f"(v[6]), "f"(v[7]) : "memory");
+}
 __device__ __forceinline__ void bar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory");
 }
@@ -405,9 +413,15 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
         float* crow = g.C + row * g.ldc + col0;
         if (g.has_preact) {
           float* prow = g.P + row * g.ldc + col0;
+          if (g.wide_st) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (col0 + 4 * c < g.N) *reinterpret_cast<float4*>(prow + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            for (int c = 0; c < 4; ++c)
+              if (col0 + 8 * c < g.N) st_global_v8(prow + 8 * c, v + 8 * c);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (col0 + 4 * c < g.N) *reinterpret_cast<float4*>(prow + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
         }
         if (g.gelu_pre) {
 #pragma unroll
@@ -428,6 +442,10 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             if (col0 + 4 * c < g.N) atomicAdd(reinterpret_cast<float4*>(crow + 4 * c), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+        } else if (g.wide_st) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (col0 + 8 * c < g.N) st_global_v8(crow + 8 * c, v + 8 * c);
         } else {
 #pragma unroll
           for (int c = 0; c < 8; ++c)
@@ -506,6 +524,7 @@ static int tma_launch(const float* A, const float* B, float* C, float* preact, i
   g.has_preact = preact != nullptr;
   g.trace = g_trace_buf; g.trace_cap = (int)g_trace_cap;
   g.C = C; g.P = preact; g.ldc = ldc;
+  g.wide_st = g_wide_st && ldc % 8 == 0 && g.N % 8 == 0 && ((uintptr_t)C & 31) == 0 && ((uintptr_t)preact & 31) == 0;
   size_t smem = (size_t)STAGES * (UM * KB * 4 + BN * KB * 4) + 1024;
   auto kern = tma_gemm_kernel<MODE, BN, STAGES, GATHER>;
   static bool attr_set = false;

@@ -54,6 +54,9 @@ def timeit_queue(fns, reps=3):
 
 def gemm(prec):
     ops.set_precision(prec)
+    for key, val in os.environ.items():   # TMAE_OPT_<name>=<int> -> tmae_set_option (A/B runs)
+        if key.startswith("TMAE_OPT_"):
+            ops.set_option(key[9:].lower(), int(val))
     print(f"--- linear ({prec}) : m n k | fwd us TFLOP/s GB/s | bwd_data us GB/s | bwd_weight us GB/s")
     for m, n, k in [(56000, 128, 128), (56000, 384, 128), (56000, 256, 128), (56000, 128, 256), (50000, 256, 256), (50000, 768, 256), (50000, 512, 256),
                     (50000, 256, 512), (14000, 128, 128), (14000, 256, 256), (240000, 128, 64)]:
