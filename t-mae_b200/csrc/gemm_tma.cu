@@ -2,8 +2,9 @@
 // consumed as TF32 (kind::tf32, fp32 accumulate in TMEM), so no thread ever touches an operand byte:
 //   warp 0      TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B boxes) -> STAGES-deep shared ring, mbarrier tx
 //   warp 1      MMA issuer     tcgen05.mma.kind::tf32, M=128, N=BN, K=8 per instruction; tcgen05.commit frees stages
-//   warps 2..5  epilogue       tcgen05.ld (lane = row) -> bias / GELU / pre-activation copy -> 128-bit stores of the
-//                              lane's 128-byte row segment (vector atomics for C += and the split reduction of dW)
+//   warps 2..9  epilogue       tcgen05.ld (lane = row; two warps per TMEM lane quarter take alternate 32-column chunks)
+//                              -> bias / GELU / pre-activation copy -> 256-bit stores of the lane's 128-byte row
+//                              segment (vector atomics for C += and the split reduction of dW)
 // Modes: NT  C[m,n] = sum_k A[m,k] W[n,k]   (A, B K-major)            linear forward
 //        NN  C[m,n] = sum_k A[m,k] B[k,n]   (A K-major, B MN-major)   linear backward-data
 //        TN  C[m,n] = sum_k A[k,m] B[k,n]   (A, B MN-major)           linear backward-weight, split over k
@@ -17,7 +18,9 @@ namespace tmae {
 
 constexpr int UM = 128;        // UMMA M
 constexpr int KB = 32;         // fp32 elements per k-block = one 128-byte swizzle span
-constexpr int TMA_THREADS = 192;
+constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int TMA_THREADS = 64 + 32 * EPI_WARPS;  // producer + MMA issuer + epilogue warps
+constexpr int GW0 = 2 + EPI_WARPS;                // first gather warp of the GATHER variants
 
 enum TmaMode { T_NT = 0, T_NN = 1, T_TN = 2 };
 
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
   if (threadIdx.x == 0) {
     // GATHER: the stage is full when the TMA bytes of B have landed (1 arrival + tx) and every gather thread's cp.asyncs of A have
     for (int s = 0; s < STAGES; ++s) { bar_init(&bar_full[s], GATHER ? 1 + GATHER_WARPS * 32 : 1); bar_init(&bar_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { bar_init(&bar_acc_full[b], 1); bar_init(&bar_acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { bar_init(&bar_acc_full[b], 1); bar_init(&bar_acc_empty[b], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -282,13 +285,13 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
         commit_to(&bar_acc_full[buf]);
       }
     }
-  } else if (GATHER && MODE == T_TN && warp >= 6) {
+  } else if (GATHER && MODE == T_TN && warp >= GW0) {
     // ---------------- gather producers, weight gradient of the sparse convolution:
     //   dW[co][tap*cin + c] = sum_r dy[r][co] * src[tab[r][tap]][c]        (TN: A = dy by TMA, B gathered, reduction over r)
     // One k-block = 32 reduction rows x BN columns of B in the MN-major SWIZZLE_128B_ATOM_32B layout (boxes of 32 columns,
     // 4096 B each; row k at +128 k; 32-byte chunk j of the row at (j ^ (k % 4)) * 32).  A thread owns one half (BN/2
     // columns, inside one tap because cin % (BN/2) == 0) of one row and looks its source row up one k-block ahead.
-    const int gt = (warp - 6) * 32 + lane;          // 0 .. 63
+    const int gt = (warp - GW0) * 32 + lane;          // 0 .. 63
     const int kr = gt >> 1, half = gt & 1;          // reduction row inside the k-block, column half
     constexpr int HALF = BN / 2, PIECES = HALF / 4; // 16-byte pieces per thread per k-block
     int it = 0;
@@ -319,13 +322,13 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
         r = rn; srow = srow_n;
       }
     }
-  } else if (GATHER && warp >= 6) {
+  } else if (GATHER && warp >= GW0) {
     // ---------------- gather producers (sparse convolution): A[m][tap*cin + c] = src[tab[m][tap]][c], absent neighbours
     // are zero-filled.  One k-block (32 fp32 = 128 bytes of one tap) of the 128 tile rows = 1024 16-byte pieces written
     // with cp.async straight into the SWIZZLE_128B K-major layout the UMMA descriptor expects (row r at (r/8)*1024 +
     // (r%8)*128, 16-byte chunk c at ((c ^ (r%8))*16); a thread owns 2 rows x 8 chunks and looks its two source rows up
     // one k-block ahead.
-    const int gt = (warp - 6) * 32 + lane;          // 0 .. 63
+    const int gt = (warp - GW0) * 32 + lane;          // 0 .. 63
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       int m0, n0, nkb; int64_t kbeg;
@@ -368,7 +371,8 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
     // L2 merges the 16-byte pieces of a line, and there is no shared-memory staging, proxy fence or bulk-store wait on
     // the critical path (measured: the TMA-store variant spent ~2 us per 32x32 chunk waiting on them).
     const int q = warp & 3;
-    constexpr int CHUNKS = BN / 32;
+    constexpr int CHUNKS = BN / 32, CSTEP = EPI_WARPS / 4;
+    const int ch0 = (warp - 2) >> 2;   // this warp's first chunk; it takes every CSTEP-th
     int i = 0;
     unsigned long long* tb = blockIdx.x == 0 && g.trace && warp == 2 && lane == 0 ? g.trace + 2 * (g.trace_cap / 4) : nullptr;
     int tn = 0;
@@ -388,18 +392,18 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
           hn[c] = (row < g.M && col0 + 4 * c < g.N) ? __ldg(reinterpret_cast<const float4*>(g.gelu_pre + row * g.ldc + col0 + 4 * c))
                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
       };
-      if (g.gelu_pre) load_pre(0);
+      if (g.gelu_pre) load_pre(ch0);
       trace_ev(tb, tn, g.trace_cap / 4, 4, i);
       bar_wait(&bar_acc_full[buf], round & 1);
       trace_ev(tb, tn, g.trace_cap / 4, 5, i);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + buf * BN;
-      for (int ch = 0; ch < CHUNKS; ++ch) {
+      for (int ch = ch0; ch < CHUNKS; ch += CSTEP) {
         const int col0 = n0 + ch * 32;
         const float bl = (g.bias && col0 + lane < g.N) ? __ldg(g.bias + col0 + lane) : 0.f;  // in flight during the TMEM load
         uint32_t r[32];
         ld_tmem32(tmem_d + ((uint32_t)(q * 32) << 16) + ch * 32, r);
-        if (ch == CHUNKS - 1) {  // this warp has read everything it needs from the accumulator
+        if (ch + CSTEP >= CHUNKS) {  // this warp has read everything it needs from the accumulator
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) bar_arrive(&bar_acc_empty[buf]);
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
             const float4 h = hn[c];
             v[4 * c] *= gelu_grad_t(h.x); v[4 * c + 1] *= gelu_grad_t(h.y); v[4 * c + 2] *= gelu_grad_t(h.z); v[4 * c + 3] *= gelu_grad_t(h.w);
           }
-          if (ch + 1 < CHUNKS) load_pre(ch + 1);
+          if (ch + CSTEP < CHUNKS) load_pre(ch + CSTEP);
         }
         if (g.act == TMAE_ACT_GELU) {
 #pragma unroll
