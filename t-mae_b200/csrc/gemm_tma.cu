@@ -612,7 +612,9 @@ int tma_sparse_conv_bwd_weight(const float* dy, const float* x, const int* table
   g.M = cout; g.N = kk; g.K = rows_out; g.reduce_add = 1;
   g.gsrc = x; g.gtab = table; g.gtaps = taps; g.gcin = cin;
   int64_t tiles = (int64_t)cdiv(cout, UM) * cdiv(kk, 256);
-  int64_t want = (kNumSMs + tiles - 1) / tiles, maxs = (rows_out + 8 * KB - 1) / (8 * KB);
+  // split the reduction so that tiles x splits fills ONE wave of the persistent grid (rounding up instead -- 5 tiles x 30 =
+  // 150 work items on 148 CTAs -- makes two CTAs run two items each and doubles the kernel's makespan)
+  int64_t want = kNumSMs / tiles, maxs = (rows_out + 8 * KB - 1) / (8 * KB);
   if (want > maxs) want = maxs;
   // the B tensor map is unused by the gather variant: describe dy twice
   return tma_launch<T_TN, 256, true>(dy, dy, dw, nullptr, cout, kk, kk, g, (int)(want < 1 ? 1 : want), s);
@@ -626,7 +628,7 @@ int tma_linear_bwd_weight(const float* dy, const float* x, float* dw, int64_t m,
   g.M = n; g.N = k; g.K = m; g.reduce_add = 1;
   int bn = k > 128 ? 256 : (k > 64 ? 128 : 64);
   int64_t tiles = (int64_t)cdiv(n, UM) * cdiv(k, bn);
-  int64_t want = (kNumSMs + tiles - 1) / tiles, maxs = (m + 8 * KB - 1) / (8 * KB);
+  int64_t want = kNumSMs / tiles, maxs = (m + 8 * KB - 1) / (8 * KB);   // one wave: see tma_sparse_conv_bwd_weight
   if (want > maxs) want = maxs;
   return tma_dispatch<T_TN>(dy, x, dw, nullptr, n, k, k, g, (int)(want < 1 ? 1 : want), s);
 }
