@@ -326,43 +326,49 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
     // ---------------- gather producers (sparse convolution): A[m][tap*cin + c] = src[tab[m][tap]][c], absent neighbours
     // are zero-filled.  One k-block (32 fp32 = 128 bytes of one tap) of the 128 tile rows = 1024 16-byte pieces written
     // with cp.async straight into the SWIZZLE_128B K-major layout the UMMA descriptor expects (row r at (r/8)*1024 +
-    // (r%8)*128, 16-byte chunk c at ((c ^ (r%8))*16); a thread owns 2 rows x 8 chunks and looks its two source rows up
-    // one k-block ahead.
+    // (r%8)*128, 16-byte chunk c at ((c ^ (r%8))*16).  Eight lanes copy one row's 128 bytes, so a warp instruction reads 4 rows x
+    // 128 contiguous bytes (lane = row would touch 32 lines per instruction); a thread owns one chunk of 16 rows and looks
+    // their source rows up one k-block ahead.
     const int gt = (warp - GW0) * 32 + lane;          // 0 .. 63
+    const int rsub = gt >> 3, c16 = gt & 7;           // row inside an 8-row group, 16-byte chunk of the 128-byte k-block row
+    constexpr int RG = UM / 8;                        // 16 row groups: the thread copies chunk c16 of rows rsub + 8 j
+    const uint32_t doff = (uint32_t)(rsub * 128 + ((c16 ^ rsub) * 16));
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       int m0, n0, nkb; int64_t kbeg;
       decode(t, m0, n0, kbeg, nkb);
-      const int64_t rowa = m0 + gt, rowb = m0 + 64 + gt;
-      const int* ta = rowa < g.M ? g.gtab + rowa * g.gtaps : nullptr;
-      const int* tb2 = rowb < g.M ? g.gtab + rowb * g.gtaps : nullptr;
       int tap = (int)(kbeg / g.gcin);
-      int sa = ta ? __ldg(ta + tap) : -1, sb = tb2 ? __ldg(tb2 + tap) : -1;
+      int src[RG], src_n[RG];
+#pragma unroll
+      for (int j = 0; j < RG; ++j) {
+        const int64_t row = m0 + j * 8 + rsub;
+        src[j] = row < g.M ? __ldg(g.gtab + row * g.gtaps + tap) : -1;
+      }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % STAGES, use = it / STAGES;
         const int k0 = (int)(kbeg + (int64_t)kb * KB);
         const int c0 = k0 - tap * g.gcin;
         // look ahead: source rows of the next k-block (same tap unless the k-block crosses into the next one)
-        int tap_n = tap, sa_n = sa, sb_n = sb;
-        if (kb + 1 < nkb && c0 + KB >= g.gcin) {
-          tap_n = tap + 1;
-          sa_n = ta ? __ldg(ta + tap_n) : -1;
-          sb_n = tb2 ? __ldg(tb2 + tap_n) : -1;
+        const bool cross = kb + 1 < nkb && c0 + KB >= g.gcin;
+        if (cross) {
+#pragma unroll
+          for (int j = 0; j < RG; ++j) {
+            const int64_t row = m0 + j * 8 + rsub;
+            src_n[j] = row < g.M ? __ldg(g.gtab + row * g.gtaps + tap + 1) : -1;
+          }
         }
         if (use > 0) bar_wait(&bar_empty[s], (use - 1) & 1);
-        const uint32_t abase = s_u32(smem + s * STAGE);
-        const float* pa = g.gsrc + (int64_t)(sa < 0 ? 0 : sa) * g.gcin + c0;
-        const float* pb = g.gsrc + (int64_t)(sb < 0 ? 0 : sb) * g.gcin + c0;
-        const uint32_t da = abase + (uint32_t)((gt >> 3) * 1024 + (gt & 7) * 128);
-        const uint32_t db = da + 8 * 1024;           // row + 64
+        const uint32_t dst = s_u32(smem + s * STAGE) + doff;
+        const float* base = g.gsrc + c0 + c16 * 4;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t off = (uint32_t)((c ^ (gt & 7)) * 16);
-          cp_async16_zfill(da + off, pa + c * 4, sa < 0 ? 0u : 16u);
-          cp_async16_zfill(db + off, pb + c * 4, sb < 0 ? 0u : 16u);
-        }
+        for (int j = 0; j < RG; ++j)   // one instruction = 4 rows x 128 contiguous bytes (8 lanes per row)
+          cp_async16_zfill(dst + j * 1024, base + (int64_t)(src[j] < 0 ? 0 : src[j]) * g.gcin, src[j] < 0 ? 0u : 16u);
         cp_async_arrive_noinc(&bar_full[s]);
-        tap = tap_n; sa = sa_n; sb = sb_n;
+        if (cross) {
+          ++tap;
+#pragma unroll
+          for (int j = 0; j < RG; ++j) src[j] = src_n[j];
+        }
       }
     }
   } else {
