@@ -289,37 +289,39 @@ __global__ void __launch_bounds__(TMA_THREADS + (GATHER ? GATHER_WARPS * 32 : 0)
     // ---------------- gather producers, weight gradient of the sparse convolution:
     //   dW[co][tap*cin + c] = sum_r dy[r][co] * src[tab[r][tap]][c]        (TN: A = dy by TMA, B gathered, reduction over r)
     // One k-block = 32 reduction rows x BN columns of B in the MN-major SWIZZLE_128B_ATOM_32B layout (boxes of 32 columns,
-    // 4096 B each; row k at +128 k; 32-byte chunk j of the row at (j ^ (k % 4)) * 32).  A thread owns one half (BN/2
-    // columns, inside one tap because cin % (BN/2) == 0) of one row and looks its source row up one k-block ahead.
-    const int gt = (warp - GW0) * 32 + lane;          // 0 .. 63
-    const int kr = gt >> 1, half = gt & 1;          // reduction row inside the k-block, column half
-    constexpr int HALF = BN / 2, PIECES = HALF / 4; // 16-byte pieces per thread per k-block
+    // 4096 B each; row k at +128 k; 32-byte chunk j of the row at (j ^ (k % 4)) * 32).  A thread owns one 16-byte piece
+    // column of all 32 reduction rows of the k-block.
+    static_assert(!(GATHER && MODE == T_TN) || BN == 4 * GATHER_WARPS * 32, "one 16-byte piece column per gather thread");
+    const int gt = (warp - GW0) * 32 + lane;          // 0 .. 63 = 16-byte piece of the BN-column row: a warp instruction
+                                                      // copies 512 contiguous bytes of ONE source row (4 lines, not 32)
+    const uint32_t poff = (uint32_t)((gt >> 3) * 4096 + (gt & 1) * 16);   // box of 32 columns, 16-byte half of the 32-byte chunk
+    const int jj = (gt >> 1) & 3;                     // 32-byte chunk inside the box row, XORed with (k % 4) below
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       int m0, n0, nkb; int64_t kbeg;
       decode(t, m0, n0, kbeg, nkb);
       const int64_t kend = kbeg + g.k_chunk < g.K ? kbeg + g.k_chunk : g.K;
-      const int col0 = n0 + half * HALF;            // first B column (= tap * cin + c) of this thread's half
-      const bool col_ok = col0 < g.N;
-      const int tap = col_ok ? col0 / g.gcin : 0, c0 = col_ok ? col0 - tap * g.gcin : 0;
-      int64_t r = kbeg + kr;
-      int srow = (col_ok && r < kend) ? __ldg(g.gtab + r * g.gtaps + tap) : -1;
+      const int col = n0 + gt * 4;                    // first B column (= tap * cin + c) of this thread's piece
+      const bool col_ok = col < g.N;
+      // cin % 128 == 0 and a warp spans 128 columns: the 32 lanes of a warp share one tap, so lane l looks up the source row
+      // of reduction row l (one k-block ahead) and the row loop broadcasts it with a shuffle
+      const int tap = col_ok ? col / g.gcin : 0, c0 = col_ok ? col - tap * g.gcin : 0;
+      int64_t r = kbeg + lane;
+      int srow_l = (col_ok && r < kend) ? __ldg(g.gtab + r * g.gtaps + tap) : -1;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % STAGES, use = it / STAGES;
         const int64_t rn = r + KB;
         const int srow_n = (col_ok && kb + 1 < nkb && rn < kend) ? __ldg(g.gtab + rn * g.gtaps + tap) : -1;
         if (use > 0) bar_wait(&bar_empty[s], (use - 1) & 1);
-        const uint32_t bbase = s_u32(smem + s * STAGE + A_BYTES) + (uint32_t)(kr * 128);
-        const float* p = g.gsrc + (int64_t)(srow < 0 ? 0 : srow) * g.gcin + c0;
-        const uint32_t nbytes = srow < 0 ? 0u : 16u;
+        const uint32_t bbase = s_u32(smem + s * STAGE + A_BYTES) + poff;
+        const float* p = g.gsrc + c0;
 #pragma unroll 8
-        for (int q = 0; q < PIECES; ++q) {
-          const int c16 = half * PIECES + q;        // 16-byte piece index inside the BN-column row
-          const uint32_t dst = bbase + (uint32_t)((c16 >> 3) * 4096 + ((((c16 >> 1) & 3) ^ (kr & 3)) * 32) + (c16 & 1) * 16);
-          cp_async16_zfill(dst, p + q * 4, nbytes);
+        for (int kr = 0; kr < KB; ++kr) {
+          const int srow = __shfl_sync(0xffffffffu, srow_l, kr);
+          cp_async16_zfill(bbase + (uint32_t)(kr * 128 + ((jj ^ (kr & 3)) * 32)), p + (int64_t)(srow < 0 ? 0 : srow) * g.gcin, srow < 0 ? 0u : 16u);
         }
         cp_async_arrive_noinc(&bar_full[s]);
-        r = rn; srow = srow_n;
+        r = rn; srow_l = srow_n;
       }
     }
   } else if (GATHER && warp >= GW0) {
