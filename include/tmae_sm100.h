@@ -191,6 +191,11 @@ TMAE_API int tmae_add_layernorm_fwd(const float* x, const float* res, const uint
 TMAE_API int tmae_add_layernorm_bwd(const float* dy, const float* x, const float* res, const uint8_t* rowmask, const float* gamma,
                            const float* mean, const float* rstd, float* dv, float* dres, float* dgamma, float* dbeta, int64_t rows,
                            int32_t c, void* stream);
+/* same, and dcolsum[c] (nullable; overwritten) = column sums of dres when dres is written, else of dv: the bias gradient of the
+ * linear layer that produced res (out_proj / linear2, sst_basic_block.py:78-83), folded into the pass that computes it */
+TMAE_API int tmae_add_layernorm_bwd_colsum(const float* dy, const float* x, const float* res, const uint8_t* rowmask, const float* gamma,
+                                  const float* mean, const float* rstd, float* dv, float* dres, float* dgamma, float* dbeta, float* dcolsum,
+                                  int64_t rows, int32_t c, void* stream);
 /* BatchNorm1d (+ReLU) over rows: network_utils.py:31 (VFE), spconv_utils.py:50-54 (after sparse convs) */
 TMAE_API size_t tmae_bn_workspace_bytes(int32_t c);
 TMAE_API int tmae_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,

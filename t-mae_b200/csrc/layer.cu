@@ -162,15 +162,18 @@ int tmae_encoder_layer_bwd(const float* dy, const float* x, const float* x_kv, c
   float* g_ln2_b = (float*)G->ln2_b;
 
   // LN2 -> FFN -> LN1
-  TRY(tmae_add_layernorm_bwd(dy, s.x1, s.f, nullptr, P->ln2_g, s.m2, s.r2, dx1, nullptr, g_ln2_g, g_ln2_b, m_q, c, stream));
-  TRY(tmae_linear_bwd_weight(dx1, s.h, g_w2, g_b2, m_q, c, ff, precision, stream));
+  // the bias gradients of linear2 and out_proj are column sums of what the two LayerNorm backward passes write: they
+  // accumulate them on the way instead of a separate pass over the (m, c) gradient
+  TRY(tmae_add_layernorm_bwd_colsum(dy, s.x1, s.f, nullptr, P->ln2_g, s.m2, s.r2, dx1, nullptr, g_ln2_g, g_ln2_b, g_b2, m_q, c, stream));
+  TRY(tmae_linear_bwd_weight(dx1, s.h, g_w2, nullptr, m_q, c, ff, precision, stream));
   TRY(tmae_linear_bwd_data_gelu(dx1, P->w2, s.hpre, dh, m_q, c, ff, precision, stream));
   TRY(tmae_linear_bwd_weight(dh, s.x1, g_w1, g_b1, m_q, ff, c, precision, stream));
   TRY(tmae_linear_bwd_data(dh, P->w1, dx1, m_q, ff, c, 1, precision, stream));  // dx1 = grad wrt x1 (both branches)
-  TRY(tmae_add_layernorm_bwd(dx1, x, s.a, T->rowmask, P->ln1_g, s.m1, s.r1, dx, T->rowmask ? da : nullptr, g_ln1_g, g_ln1_b, m_q, c, stream));
+  TRY(tmae_add_layernorm_bwd_colsum(dx1, x, s.a, T->rowmask, P->ln1_g, s.m1, s.r1, dx, T->rowmask ? da : nullptr, g_ln1_g, g_ln1_b, g_out_b,
+                                    m_q, c, stream));
   const float* dap = T->rowmask ? da : dx;  // grad wrt the attention branch (masked rows contribute nothing)
   // out projection
-  TRY(tmae_linear_bwd_weight(dap, s.o, g_out_w, g_out_b, m_q, c, c, precision, stream));
+  TRY(tmae_linear_bwd_weight(dap, s.o, g_out_w, nullptr, m_q, c, c, precision, stream));
   TRY(tmae_linear_bwd_data(dap, P->out_w, dob, m_q, c, c, 0, precision, stream));
   // attention core: gradients land in the packed layout of the projections
   const int ldq = cross ? c : 3 * c, ldkv = cross ? 2 * c : 3 * c;

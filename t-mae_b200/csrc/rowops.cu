@@ -171,23 +171,26 @@ __global__ void __launch_bounds__(256) add_ln_fwd_vec_kernel(const float* __rest
   }
 }
 
-template <int VPL>
+// COLSUM: also accumulates the column sums of the kernel's own output (of dres when it is written, else of dv) into
+// dcol -- the bias gradient of the linear layer that produced `res`, which would otherwise re-read the output from HBM.
+template <int VPL, bool COLSUM>
 __global__ void __launch_bounds__(256) add_ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                              const float* __restrict__ res, const uint8_t* __restrict__ rowmask,
                                                              const float* __restrict__ gamma, const float* __restrict__ mean_in,
                                                              const float* __restrict__ rstd_in, float* __restrict__ dv,
                                                              float* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                             int64_t rows) {
+                                                             float* __restrict__ dcol, int64_t rows) {
   constexpr int C = VPL * 128;
-  __shared__ float red[2][8][C];
+  __shared__ float red[COLSUM ? 3 : 2][8][C];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float4 g[VPL], dg[VPL], db[VPL];
+  float4 g[VPL], dg[VPL], db[VPL], dc[COLSUM ? VPL : 1];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     g[k] = ld4(gamma + k * 128 + lane * 4);
     dg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (COLSUM) dc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int64_t r0 = warp * 2; r0 < rows; r0 += nwarps * 2) {
     float4 v[2][VPL], d[2][VPL];
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_vec_kernel(const float* __rest
         const int64_t off = r * C + k * 128 + lane * 4;
         *reinterpret_cast<float4*>(dv + off) = o;
         if (dres) *reinterpret_cast<float4*>(dres + off) = use[u] ? o : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (COLSUM && (use[u] || !dres)) { dc[k].x += o.x; dc[k].y += o.y; dc[k].z += o.z; dc[k].w += o.w; }
       }
     }
   }
@@ -245,14 +249,16 @@ __global__ void __launch_bounds__(256) add_ln_bwd_vec_kernel(const float* __rest
   for (int k = 0; k < VPL; ++k) {
     *reinterpret_cast<float4*>(&red[0][wib][k * 128 + lane * 4]) = dg[k];
     *reinterpret_cast<float4*>(&red[1][wib][k * 128 + lane * 4]) = db[k];
+    if (COLSUM) *reinterpret_cast<float4*>(&red[2][wib][k * 128 + lane * 4]) = dc[k];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += 256) {
-    float a = 0.f, b = 0.f;
+    float a = 0.f, b = 0.f, e = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { a += red[0][w][c]; b += red[1][w][c]; }
+    for (int w = 0; w < 8; ++w) { a += red[0][w][c]; b += red[1][w][c]; if (COLSUM) e += red[2][w][c]; }
     atomicAdd(dgamma + c, a);
     atomicAdd(dbeta + c, b);
+    if (COLSUM) atomicAdd(dcol + c, e);
   }
 }
 
@@ -373,10 +379,21 @@ int tmae_add_layernorm_fwd(const float* x, const float* res, const uint8_t* rowm
 int tmae_add_layernorm_bwd(const float* dy, const float* x, const float* res, const uint8_t* rowmask, const float* gamma,
                            const float* mean, const float* rstd, float* dv, float* dres, float* dgamma, float* dbeta, int64_t rows,
                            int32_t c, void* stream) {
+  return tmae_add_layernorm_bwd_colsum(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, nullptr, rows, c, stream);
+}
+
+int tmae_add_layernorm_bwd_colsum(const float* dy, const float* x, const float* res, const uint8_t* rowmask, const float* gamma,
+                                  const float* mean, const float* rstd, float* dv, float* dres, float* dgamma, float* dbeta, float* dcolsum,
+                                  int64_t rows, int32_t c, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   TMAE_CUDA(cudaMemsetAsync(dgamma, 0, c * sizeof(float), s));
   TMAE_CUDA(cudaMemsetAsync(dbeta, 0, c * sizeof(float), s));
+  if (dcolsum) TMAE_CUDA(cudaMemsetAsync(dcolsum, 0, c * sizeof(float), s));
   if (rows <= 0) return 0;
+  if (dcolsum && c != 128 && c != 256) {   // the fused column sum exists for the vectorised 128 / 256-channel kernels
+    int rc = tmae_add_layernorm_bwd_colsum(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, nullptr, rows, c, stream);
+    return rc ? rc : tmae_colsum(dres ? dres : dv, dcolsum, rows, c, stream);
+  }
   int rpw = 16;
   int64_t warps = (rows + rpw - 1) / rpw;
   int grid = cdiv(warps * 32, 256);
@@ -385,9 +402,15 @@ int tmae_add_layernorm_bwd(const float* dy, const float* x, const float* res, co
   int vgrid = (int)(vb < (int64_t)kNumSMs * 6 ? vb : (int64_t)kNumSMs * 6);
   switch (c) {
     case 64: add_ln_bwd_kernel<2><<<grid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows, rpw); break;
-    case 128: add_ln_bwd_vec_kernel<1><<<vgrid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows); break;
-    case 256: add_ln_bwd_vec_kernel<2><<<vgrid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows); break;
-    case 512: add_ln_bwd_vec_kernel<4><<<vgrid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows); break;
+    case 128:
+      if (dcolsum) add_ln_bwd_vec_kernel<1, true><<<vgrid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, dcolsum, rows);
+      else add_ln_bwd_vec_kernel<1, false><<<vgrid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, nullptr, rows);
+      break;
+    case 256:
+      if (dcolsum) add_ln_bwd_vec_kernel<2, true><<<vgrid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, dcolsum, rows);
+      else add_ln_bwd_vec_kernel<2, false><<<vgrid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, nullptr, rows);
+      break;
+    case 512: add_ln_bwd_vec_kernel<4, false><<<vgrid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, nullptr, rows); break;
     default: set_error("tmae_add_layernorm_bwd: channels must be 64/128/256/512"); return TMAE_ERR_UNSUPPORTED;
   }
   TMAE_CHECK_LAUNCH();

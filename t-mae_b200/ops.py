@@ -424,12 +424,14 @@ def add_layernorm_fwd(x, res, rowmask, gamma, beta, eps):
     return y, mean, rstd
 
 
-def add_layernorm_bwd(dy, x, res, rowmask, gamma, mean, rstd, dgamma, dbeta, want_dres=False):
+def add_layernorm_bwd(dy, x, res, rowmask, gamma, mean, rstd, dgamma, dbeta, want_dres=False, dcolsum=None):
+    """dcolsum (c,) optional: receives the column sums of dres (when want_dres) or of dv -- the bias gradient of the linear
+    layer that produced `res`."""
     rows, c = x.shape
     dv = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dres else None
-    _call("add_layernorm_bwd", _p(dy, F32), _p(x, F32), _p(res), _p(rowmask), _p(gamma, F32), _p(mean), _p(rstd), _p(dv), _p(dres),
-          _p(dgamma, F32), _p(dbeta, F32), rows, c, _stream())
+    _call("add_layernorm_bwd_colsum", _p(dy, F32), _p(x, F32), _p(res), _p(rowmask), _p(gamma, F32), _p(mean), _p(rstd), _p(dv), _p(dres),
+          _p(dgamma, F32), _p(dbeta, F32), _p(dcolsum, F32), rows, c, _stream())
     return dv, dres
 
 

@@ -257,8 +257,10 @@ def test_add_layernorm(rows, C):
         y, mean, rstd = ops.add_layernorm_fwd(x.to(DEV), r.to(DEV), mk, ga.to(DEV), be.to(DEV), 1e-5)
         assert_close(y, ref.detach(), 1e-5, 1e-5, "LN fwd")
         dg, db = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
-        dv, dres = ops.add_layernorm_bwd(dy.to(DEV), x.to(DEV), r.to(DEV), mk, ga.to(DEV), mean, rstd, dg, db, want_dres=use_mask)
+        dc = torch.full((C,), 7.0, device=DEV)   # overwritten: column sums of dres (masked case) or dv = the producer's bias gradient
+        dv, dres = ops.add_layernorm_bwd(dy.to(DEV), x.to(DEV), r.to(DEV), mk, ga.to(DEV), mean, rstd, dg, db, want_dres=use_mask, dcolsum=dc)
         assert_close(dv, xd.grad, 1e-4, 1e-5, "LN dx")
+        assert_close(dc, (rd.grad if use_mask else xd.grad).sum(0), 1e-4, 1e-4 * rows ** .5, "LN fused column sum")
         if use_mask:
             assert_close(dres, rd.grad, 1e-4, 1e-5, "LN dres (masked)")
         assert_close(dg, gd.grad, 1e-4, 1e-4 * rows ** .5, "LN dgamma")
