@@ -1,0 +1,45 @@
+"""DRAM traffic per launch of a kernel family from an `ncu --set full` capture (read here, no GPU):
+
+    python tools/traffic_json.py capture.ncu-rep <family name in bench.py's kernel table> "<how it was captured>"
+
+Merges {family: {traffic_bytes_per_launch, launches_captured, per_launch: [{us, read, write}], how}} into
+profiles/r01_traffic.json, which bench.py reads for `roofline.traffic`.
+"""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def to_bytes(v, unit):
+    return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+
+
+def to_us(v, unit):
+    return float(v.replace(",", "")) * {"ns": 1e-3, "us": 1, "usecond": 1, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3}[unit]
+
+
+def main():
+    rep, family, how = sys.argv[1], sys.argv[2], sys.argv[3]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], dict(zip(rows[0], rows[1]))
+    per = []
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        per.append({"kernel": d["Kernel Name"][:60], "us": round(to_us(d["gpu__time_duration.sum"], units["gpu__time_duration.sum"]), 3),
+                    "read": to_bytes(d["dram__bytes_read.sum"], units["dram__bytes_read.sum"]),
+                    "write": to_bytes(d["dram__bytes_write.sum"], units["dram__bytes_write.sum"])})
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[family] = {"traffic_bytes_per_launch": round(sum(p["read"] + p["write"] for p in per) / max(1, len(per))),
+                    "launches_captured": len(per), "per_launch": per, "how": how}
+    json.dump(data, open(path, "w"), indent=1)
+    print(json.dumps(data[family], indent=1))
+
+
+if __name__ == "__main__":
+    main()
