@@ -93,3 +93,11 @@ def raw_samples(seed, n_points=3000, kind="once"):
             p[4, :2] = [np.nan, 0.0]          # NaN fails the range test
         out.append(s)
     return out
+
+
+def bev_input(seed, B=2, C=128, Y=40, X=40):
+    """A seeded BEV map shaped like `spatial_features`: non-negative (it follows a ReLU) and ~70 % empty."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, Y, X, generator=g).clamp_min(0)
+    occ = (torch.rand(B, 1, Y, X, generator=g) < 0.3).float()
+    return x * occ

@@ -92,3 +92,16 @@ def build(kind, grid_size, voxel_size, pc_range, num_point_features=5, seed=0):
     with contextlib.redirect_stdout(io.StringIO()):  # WCABlock prints a warning per block
         bb = cls(cfg.BACKBONE_3D, vfe.get_output_feature_dim(), np.asarray(grid_size), voxel_size, pc_range)
     return vfe, bb
+
+
+def build_bev(seed=0):
+    """The reference's own SSTBEVBackbone (pcdet/models/backbones_2d/sst_bev_backbone.py, loaded by file path: it imports
+    numpy and torch only) with cfg.MODEL.BACKBONE_2D of t_mae.yaml."""
+    import importlib.util
+    import torch
+    root = ref_root()
+    spec = importlib.util.spec_from_file_location("_tmae_ref_sst_bev", os.path.join(root, "pcdet", "models", "backbones_2d", "sst_bev_backbone.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(seed)
+    return mod.SSTBEVBackbone(load_cfg("finetune").BACKBONE_2D)

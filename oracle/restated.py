@@ -710,6 +710,35 @@ def model_cfg(kind):
     return {"VFE": vfe, "BACKBONE_3D": bb}
 
 
+BEV_CFG = {"NAME": "SSTBEVBackbone", "NUM_FILTER": 128, "CONV_SHORTCUT": [0, 1, 2],   # t_mae.yaml:197-206
+           "CONV_KWARGS": [{"out_channels": 128, "kernel_size": 3, "dilation": d, "padding": d, "stride": 1} for d in (1, 1, 2, 1)]}
+
+
+class SSTBEVBackbone(nn.Module):
+    """Restatement of pcdet/models/backbones_2d/sst_bev_backbone.py:6-44: Conv2d(no bias) ->
+    BatchNorm2d(eps 1e-3, momentum 0.01) -> ReLU per entry of CONV_KWARGS; the result is added to its input where the
+    shapes agree and the layer index is in CONV_SHORTCUT."""
+
+    def __init__(self, model_cfg, **kwargs):
+        super().__init__()
+        cin, blocks = model_cfg["NUM_FILTER"], []
+        for kw in model_cfg["CONV_KWARGS"]:
+            blocks.append(nn.Sequential(nn.Conv2d(cin, bias=False, **dict(kw)), nn.BatchNorm2d(kw["out_channels"], eps=1e-3, momentum=0.01),
+                                        nn.ReLU()))
+            cin = kw["out_channels"]
+        self.conv_layer = nn.ModuleList(blocks)
+        self.shortcut = set(model_cfg["CONV_SHORTCUT"])
+        self.num_bev_features = cin
+
+    def forward(self, data_dict):
+        x = data_dict["spatial_features"]
+        for i, blk in enumerate(self.conv_layer):
+            y = blk(x)
+            x = y + x if (i in self.shortcut and y.shape == x.shape) else y
+        data_dict["spatial_features_2d"] = x
+        return data_dict
+
+
 def build(kind, grid_size, voxel_size, pc_range, num_point_features=5, seed=0):
     cfg = model_cfg(kind)
     torch.manual_seed(seed)

@@ -9,7 +9,8 @@ compute modules without the built library, or with CPU tensors, raises.
     vfe, backbone = build_model("pretrain", grid_size, voxel_size, point_cloud_range)
 
 `vfe_registry` / `backbone_registry` have the shape of pcdet's `vfe.__all__` / `backbones_3d.__all__`
-(pcdet/models/backbones_3d/vfe/__init__.py:8-14, pcdet/models/backbones_3d/__init__.py:7-12).
+(pcdet/models/backbones_3d/vfe/__init__.py:8-14, pcdet/models/backbones_3d/__init__.py:7-12); `backbone_2d_registry`
+that of `backbones_2d.__all__` (pcdet/models/backbones_2d/__init__.py) for `SSTBEVBackbone`.
 """
 __version__ = "0.1.0"
 
@@ -23,6 +24,9 @@ def __getattr__(name):  # lazy: `import tmae_b200.synth` must work without torch
         from . import backbone
         reg = {"SiamWCA": backbone.SiamWCA, "SiamWCA_MAE": backbone.SiamWCA_MAE}
         return reg if name == "backbone_registry" else reg[name]
+    if name in ("SSTBEVBackbone", "backbone_2d_registry"):
+        from . import bev
+        return {"SSTBEVBackbone": bev.SSTBEVBackbone} if name == "backbone_2d_registry" else bev.SSTBEVBackbone
     if name == "build_model":
         return _build_model
     raise AttributeError(name)

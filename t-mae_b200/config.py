@@ -35,4 +35,9 @@ def model_cfg(kind):
                              "DIS_THRESH": 0.3, "NUM_ABOVE_GROUND": 0}
     vfe = {"NAME": "TemporalDynVFE", "TYPE": "mean", "WITH_DISTANCE": False, "USE_ABSLOTE_XYZ": True,
            "USE_CLUSTER_XYZ": True, "MLPS": [[64, 128]], "FT": kind == "finetune"}
-    return {"VFE": vfe, "BACKBONE_3D": bb}
+    cfg = {"VFE": vfe, "BACKBONE_3D": bb}
+    if kind == "finetune":   # t_mae.yaml:197-206
+        conv = lambda d: {"out_channels": 128, "kernel_size": 3, "dilation": d, "padding": d, "stride": 1}  # noqa: E731
+        cfg["BACKBONE_2D"] = {"NAME": "SSTBEVBackbone", "NUM_FILTER": 128, "CONV_KWARGS": [conv(1), conv(1), conv(2), conv(1)],
+                              "CONV_SHORTCUT": [0, 1, 2]}
+    return cfg

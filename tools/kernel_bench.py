@@ -106,6 +106,33 @@ def attn(tc=1):
     ops.set_option("attn_tc", 0)
 
 
+def bev(batch=8):
+    """SSTBEVBackbone forward (eval) and forward+backward (train) on a finetune-sized bf16 channels-last map."""
+    from tmae_b200 import config
+    m = tmae_b200.SSTBEVBackbone(config.model_cfg("finetune")["BACKBONE_2D"]).to(DEV)
+    torch.backends.cudnn.benchmark = True
+    xs = [(torch.randn(batch, 128, 468, 468, device=DEV).clamp_min(0) * (torch.rand(batch, 1, 468, 468, device=DEV) < 0.3)).to(torch.bfloat16)
+          .contiguous(memory_format=torch.channels_last) for _ in range(2)]
+    nbytes = xs[0].numel() * 2
+    for train in (False, True):
+        m.train(train)
+
+        def run(x):
+            if not train:
+                with torch.no_grad():
+                    return m(dict(spatial_features=x))["spatial_features_2d"]
+            x = x.detach().requires_grad_()
+            y = m(dict(spatial_features=x))["spatial_features_2d"]
+            y.backward(y.detach())
+            return y
+        t = timeit_queue([lambda x=x: run(x) for x in xs] * 2)
+        tab = ops.lib_profile(lambda: [run(x) for x in xs])
+        ours = sum(v["ms"] for v in tab.values()) / len(xs)
+        print(f"SSTBEVBackbone batch {batch} 468x468x128 bf16 {'fwd+bwd (train)' if train else 'fwd (eval)'}: {t:.2f} ms per call "
+              f"({batch / t * 1e3:.0f} scans/s); library BatchNorm kernels {ours:.2f} ms of it; one map = {nbytes / 1e6:.0f} MB")
+        print("     " + "  ".join(f"{k} {v['ms'] / v['calls'] * 1e3:.0f}us x{v['calls'] // len(xs)} ({v['bytes'] / v['ms'] / 1e6:.0f} GB/s)" for k, v in tab.items() if v["ms"] > 0))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("gemm", "all"):
@@ -114,3 +141,5 @@ if __name__ == "__main__":
         gemm("fp32")
     if what in ("attn", "all"):
         attn()
+    if what == "bev":
+        bev()
