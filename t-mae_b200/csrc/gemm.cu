@@ -178,6 +178,29 @@ static int launch(GemmArgs& g, int splits, cudaStream_t s) {
   return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
 }
 
+// y[m, n] = x[m, k] w[n, k]^T (+ bias) for k <= 16: thread = (row, 4 adjacent outputs), w transposed in shared memory
+// (conflict-free float4 reads), the k inputs of a row are read once per thread (16 threads of a row share them through
+// L1), 16-byte coalesced stores.  fp32 FMA chain over k in ascending order.
+__global__ void __launch_bounds__(256) thin_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ y, int64_t m, int n, int k) {
+  extern __shared__ float wt[];   // [k][n]
+  for (int i = threadIdx.x; i < n * k; i += blockDim.x) wt[(i % k) * n + i / k] = w[i];
+  __syncthreads();
+  const int n4 = n >> 2;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m * n4) return;
+  const int64_t row = t / n4;
+  const int c = (int)(t - row * n4) * 4;
+  float4 acc = bias ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* xr = x + row * k;
+  for (int kk = 0; kk < k; ++kk) {
+    const float xv = __ldg(xr + kk);
+    const float4 wv = *reinterpret_cast<const float4*>(wt + kk * n + c);
+    acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(y + row * n + c) = acc;
+}
+
 __global__ void colsum_kernel(const float* __restrict__ x, int64_t rows, int cols, const int* __restrict__ row_count,
                               float* __restrict__ out, int rows_per_block) {
   // block: 256 threads = 8 row-lanes x 32 column-lanes; grid.x over column groups of 32, grid.y over row chunks
@@ -350,6 +373,14 @@ int tmae_set_option(const char* name, int32_t value) {
 int tmae_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact,
                     int64_t m, int64_t n, int64_t k, int32_t act, int32_t precision, void* stream) {
   TMAE_CHECK_PREC(precision);
+  if (k <= 16 && n <= 256 && n % 4 == 0 && !residual && !preact && act == TMAE_ACT_NONE && m > 0 && (((uintptr_t)y) & 15) == 0 &&
+      (((uintptr_t)bias) & 15) == 0) {
+    // thin reduction (the VFE's first layer, k = 10): a tile kernel would run 16-wide k-blocks that are mostly padding
+    ProfScope prof("linear_thin_k", 2.0 * m * n * k, 4.0 * ((double)m * k + (double)n * k + (double)m * n), (cudaStream_t)stream);
+    thin_linear_fwd_kernel<<<cdiv(m * (n / 4), 256), 256, (size_t)n * k * sizeof(float), (cudaStream_t)stream>>>(x, w, bias, y, m, (int)n, (int)k);
+    TMAE_CHECK_LAUNCH();
+    return 0;
+  }
   if (precision == TMAE_PREC_BF16 && g_use_tma && tma_linear_fwd_ok(x, w, y, residual, m, n, k)) {
     if (tma_linear_fwd(x, w, bias, y, preact, m, n, k, act, (cudaStream_t)stream)) { set_error("tmae_linear_fwd: TMA launch failed"); return TMAE_ERR_CUDA; }
     return 0;

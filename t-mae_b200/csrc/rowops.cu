@@ -283,6 +283,40 @@ __global__ void segmax_fwd_kernel(const float* __restrict__ x, const int* __rest
   }
 }
 
+// C % 128 == 0: a lane owns 4 adjacent channels (one 512-byte row = one coalesced warp access), the point loop is
+// unrolled by 4 so four independent row loads are in flight; same comparison sequence as the scalar kernel.
+__global__ void __launch_bounds__(256) segmax_fwd_vec_kernel(const float* __restrict__ x, const int* __restrict__ offset,
+                                                             const int* __restrict__ order, int64_t m, int C, float* __restrict__ out,
+                                                             int* __restrict__ arg) {
+  const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (v >= m) return;
+  const int beg = offset[v], end = offset[v + 1];
+  for (int c = lane * 4; c < C; c += 128) {
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int bi[4] = {-1, -1, -1, -1};
+    auto take = [&](const float4& t, int p) {
+      const float val[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (val[j] > best[j] || bi[j] < 0) { best[j] = val[j]; bi[j] = p; }
+    };
+    int k = beg;
+    for (; k + 4 <= end; k += 4) {
+      const int p0 = order[k], p1 = order[k + 1], p2 = order[k + 2], p3 = order[k + 3];
+      const float4 t0 = ld4(x + (int64_t)p0 * C + c), t1 = ld4(x + (int64_t)p1 * C + c);
+      const float4 t2 = ld4(x + (int64_t)p2 * C + c), t3 = ld4(x + (int64_t)p3 * C + c);
+      take(t0, p0); take(t1, p1); take(t2, p2); take(t3, p3);
+    }
+    for (; k < end; ++k) {
+      const int p = order[k];
+      take(ld4(x + (int64_t)p * C + c), p);
+    }
+    *reinterpret_cast<float4*>(out + v * C + c) = make_float4(best[0], best[1], best[2], best[3]);
+    *reinterpret_cast<int4*>(arg + v * C + c) = make_int4(bi[0], bi[1], bi[2], bi[3]);
+  }
+}
+
 __global__ void segmax_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ arg, int64_t n, int C, float* __restrict__ dx) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -420,7 +454,10 @@ int tmae_add_layernorm_bwd_colsum(const float* dy, const float* x, const float* 
 int tmae_segment_max_fwd(const float* x, const int32_t* voxel_offset, const int32_t* pt_order, int64_t n_voxels, int32_t c, float* out,
                          int32_t* argmax, void* stream) {
   if (n_voxels <= 0) return 0;
-  segmax_fwd_kernel<<<cdiv(n_voxels * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, voxel_offset, pt_order, n_voxels, c, out, argmax);
+  if (c % 128 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)argmax & 15) == 0)
+    segmax_fwd_vec_kernel<<<cdiv(n_voxels * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, voxel_offset, pt_order, n_voxels, c, out, argmax);
+  else
+    segmax_fwd_kernel<<<cdiv(n_voxels * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, voxel_offset, pt_order, n_voxels, c, out, argmax);
   TMAE_CHECK_LAUNCH();
   return 0;
 }

@@ -240,6 +240,22 @@ def test_linear_fwd_bwd(m, n, k):
     assert_close(ops.gelu_bwd(dy.to(DEV), pre.to(DEV)), p.grad, 1e-5, 1e-6, "gelu'")
 
 
+@pytest.mark.parametrize("m,n,k,with_bias", [(1, 64, 10, False), (777, 64, 10, False), (5000, 128, 16, True), (240001, 64, 10, False)])
+def test_linear_fwd_thin_k(m, n, k, with_bias):
+    """The VFE's first layer (k = 10, no bias, no activation) takes the thin-reduction kernel in both precision modes."""
+    g = torch.Generator().manual_seed(m + n)
+    x, w = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k ** .5
+    b = torch.randn(n, generator=g) if with_bias else None
+    ref = x.double() @ w.double().T + (b.double() if with_bias else 0)
+    for prec in ("fp32", "bf16"):
+        ops.set_precision(prec)
+        try:
+            y = ops.linear_fwd(x.to(DEV), w.to(DEV), b.to(DEV) if with_bias else None)
+        finally:
+            ops.set_precision("fp32")
+        assert_close(y, ref, 1e-5, 1e-5, f"thin-k linear ({prec})")
+
+
 @pytest.mark.parametrize("rows,C", [(1, 128), (1000, 128), (4097, 256)])
 def test_add_layernorm(rows, C):
     g = torch.Generator().manual_seed(rows)
