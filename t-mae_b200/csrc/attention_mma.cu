@@ -210,8 +210,10 @@ __global__ void __launch_bounds__(TCAP * 2) attn_mma_fwd_kernel(AttnMmaArgs a) {
   }
 }
 
-template <int HD, int TCAP>
-__global__ void __launch_bounds__(TCAP * 2, TCAP == 64 ? 4 : 8) attn_mma_bwd_kernel(AttnMmaArgs a) {
+// OCC: CTAs per SM the register allocation targets.  The kernel is bound by fixed-latency dependency stalls and CTA
+// barriers with 4 warps per scheduler (profiles/r01_ncu_attn_mma_v2.txt), so one more resident CTA per SM buys issue slots.
+template <int HD, int TCAP, int OCC>
+__global__ void __launch_bounds__(TCAP * 2, OCC) attn_mma_bwd_kernel(AttnMmaArgs a) {
   constexpr int KS = HD + 4, VS = HD + 8, NT = TCAP / 8, THREADS = TCAP * 2;
   __shared__ __align__(16) float Qs[TCAP * KS], Ks[TCAP * KS], Vs[TCAP * VS], Ds[TCAP * KS];  // Ds = dO
   __shared__ float qinv[TCAP], kinv[TCAP], lse_s[TCAP], dsum[TCAP];
@@ -347,13 +349,29 @@ __global__ void __launch_bounds__(TCAP * 2, TCAP == 64 ? 4 : 8) attn_mma_bwd_ker
   if (lane == 0 && a.dtau && tau_raw > a.tau_min && dtau_acc != 0.f) atomicAdd(a.dtau, dtau_acc * inv_tau);
 }
 
+int g_attn_occ = 1;   // 1: the <= 32-token backward kernels are compiled for 10 CTAs per SM instead of 8 (measured 245 -> 220 us on a
+                      // stage-2-like window mix; the 64-token class lost 8 % at 5 instead of 4 and stays at 4); 0 for A/B runs
+
+template <typename K>
+static void max_carveout(K kern) {   // static shared memory only: ask for the largest shared-memory carveout once per kernel
+  static bool done = false;
+  if (!done) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); done = true; }
+}
+
 template <int HD, int TCAP>
 static void launch_mma(bool bwd, const AttnMmaArgs& a, int64_t max_windows, cudaStream_t s) {
   int64_t items = max_windows * a.H;
-  const int per_sm = bwd ? (TCAP == 32 ? 10 : 4) : (TCAP == 32 ? 14 : 7);
+  constexpr int OCC0 = TCAP == 64 ? 4 : 8, OCC1 = TCAP == 64 ? 4 : 10;
+  const int per_sm = bwd ? (g_attn_occ ? OCC1 : (TCAP == 32 ? 10 : 4)) : (TCAP == 32 ? 14 : 7);
   int grid = (int)(items < (int64_t)per_sm * kNumSMs ? items : (int64_t)per_sm * kNumSMs);
-  if (bwd) attn_mma_bwd_kernel<HD, TCAP><<<grid, TCAP * 2, 0, s>>>(a);
-  else attn_mma_fwd_kernel<HD, TCAP><<<grid, TCAP * 2, 0, s>>>(a);
+  if (bwd && g_attn_occ) {
+    max_carveout(attn_mma_bwd_kernel<HD, TCAP, OCC1>);
+    attn_mma_bwd_kernel<HD, TCAP, OCC1><<<grid, TCAP * 2, 0, s>>>(a);
+  } else if (bwd) {
+    attn_mma_bwd_kernel<HD, TCAP, OCC0><<<grid, TCAP * 2, 0, s>>>(a);
+  } else {
+    attn_mma_fwd_kernel<HD, TCAP><<<grid, TCAP * 2, 0, s>>>(a);
+  }
 }
 
 static int attn_mma_run(bool bwd, AttnMmaArgs a, int hd, int64_t max_windows, cudaStream_t s) {

@@ -73,6 +73,9 @@ def gemm(prec):
 def attn(tc=1):
     import numpy as np
     ops.set_option("attn_tc", tc)
+    for key, val in os.environ.items():   # TMAE_OPT_<name>=<int> -> tmae_set_option (A/B runs)
+        if key.startswith("TMAE_OPT_"):
+            ops.set_option(key[9:].lower(), int(val))
     print(f"--- window attention (attn_tc={tc}) : M C | fwd us (GB/s of 4*M*C*4) | bwd us (GB/s of 8*M*C*4)")
     for M, C, g, B in [(56000, 128, 468, 4), (14000, 128, 468, 4), (50000, 256, 234, 4), (28000, 256, 117, 4)]:
         rng = np.random.default_rng(0)
