@@ -154,6 +154,14 @@ def run_ours(args):
     w = WORKLOADS[args.workload]
     shape = synth.ONCE
     grid = synth.grid_size(shape).tolist()
+    # One slab for the caching allocator: the step's tensor sizes change with every batch (row counts), and blocks recorded
+    # on two streams return to the pool late, so a pool made of many cudaMalloc'd segments sized to past requests keeps
+    # hitting a size nothing fits -- a cudaMalloc in the middle of a step synchronises the device (one 70-100 ms step in
+    # about a quarter of the runs).  A single large cached segment is split and re-merged on demand instead.
+    slab_gib = min(64, int(torch.cuda.mem_get_info(dev)[0] * 0.45) >> 30)
+    if slab_gib > 0:
+        del_me = torch.empty(slab_gib << 30, dtype=torch.uint8, device=dev)
+        del del_me
     torch.manual_seed(0)
     vfe, bb = tmae_b200.build_model(w["kind"], grid, shape["voxel"], shape["range"])
     ops.set_precision(args.precision)
@@ -308,7 +316,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32/bf16 tensor-core operands, f32 accumulate+storage", "data": "synthetic",
             "config": {"workload": w["name"], "precision": f"encoder kernels {args.precision}; cuDNN decoder {args.decoder}",
                        "parallelism": f"dp{world} (scan-pair sharding" + ((", DistributedDataParallel NCCL gradient all-reduce)" if args.ddp else ", one flat NCCL gradient all-reduce per step)") if w["train"] else ", no collective)"),
-                       "l2": f"inputs cycle over {args.batches} distinct batches; per-step activation working set >> 126 MB L2"},
+                       "l2": f"inputs cycle over {args.batches} distinct batches; per-step activation working set >> 126 MB L2",
+                       "allocator": f"torch caching allocator over one pre-reserved {slab_gib} GiB slab"},
             "clocks": clocks,
             "e2e": {"value": round(e_value, 3), "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e_total / args.steps, 3)},

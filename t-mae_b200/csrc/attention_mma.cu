@@ -145,8 +145,8 @@ __device__ __forceinline__ void strip_pz(const float p[NT][4], const float* Z, i
 }
 
 // windows [*a.begin, *a.end) of the level-sorted list hold at most TCAP tokens per side; CTA = TCAP/16 warps
-template <int HD, int TCAP>
-__global__ void __launch_bounds__(TCAP * 2) attn_mma_fwd_kernel(AttnMmaArgs a) {
+template <int HD, int TCAP, int OCC = 0>
+__global__ void __launch_bounds__(TCAP * 2, OCC) attn_mma_fwd_kernel(AttnMmaArgs a) {
   constexpr int KS = HD + 4, VS = HD + 8, NT = TCAP / 8, THREADS = TCAP * 2;
   __shared__ __align__(16) float Qs[TCAP * KS], Ks[TCAP * KS], Vs[TCAP * VS];
   __shared__ int qt[TCAP];
@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(TCAP * 2, OCC) attn_mma_bwd_kernel(AttnMmaArgs
   if (lane == 0 && a.dtau && tau_raw > a.tau_min && dtau_acc != 0.f) atomicAdd(a.dtau, dtau_acc * inv_tau);
 }
 
+int g_attn_occ_fwd = 1;   // 0: forward kernels with the compiler's default register allocation (A/B runs)
 int g_attn_occ = 1;   // 1: the <= 32-token backward kernels are compiled for 10 CTAs per SM instead of 8 (measured 245 -> 220 us on a
                       // stage-2-like window mix; the 64-token class lost 8 % at 5 instead of 4 and stays at 4); 0 for A/B runs
 
@@ -369,6 +370,12 @@ static void launch_mma(bool bwd, const AttnMmaArgs& a, int64_t max_windows, cuda
     attn_mma_bwd_kernel<HD, TCAP, OCC1><<<grid, TCAP * 2, 0, s>>>(a);
   } else if (bwd) {
     attn_mma_bwd_kernel<HD, TCAP, OCC0><<<grid, TCAP * 2, 0, s>>>(a);
+  } else if (g_attn_occ_fwd) {
+    // 72 registers: 7 resident 4-warp CTAs (64-token class) / 14 resident 2-warp CTAs (32-token class) per SM instead of 5 / 10
+    // (measured: 88.4 -> 74.4 us on a stage-3-like and 107.4 -> 92.3 us on a stage-2-like window mix)
+    constexpr int O = TCAP == 64 ? 7 : 14;
+    max_carveout(attn_mma_fwd_kernel<HD, TCAP, O>);
+    attn_mma_fwd_kernel<HD, TCAP, O><<<grid, TCAP * 2, 0, s>>>(a);
   } else {
     attn_mma_fwd_kernel<HD, TCAP><<<grid, TCAP * 2, 0, s>>>(a);
   }
