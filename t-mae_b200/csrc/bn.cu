@@ -22,6 +22,10 @@ template <> struct Vec<float> {
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
   __device__ static void store(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+  typedef float4 Raw;   // a load kept as it came from memory; unpacked where it is used (register pressure of the unrolled loops)
+  __device__ static Raw load_raw(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ static Raw zero_raw() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ static void unpack(const Raw& t, float* v) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
 };
 template <> struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
@@ -37,6 +41,14 @@ template <> struct Vec<__nv_bfloat16> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     *reinterpret_cast<uint4*>(p) = t;
+  }
+  typedef uint4 Raw;
+  __device__ static Raw load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ static Raw zero_raw() { return make_uint4(0u, 0u, 0u, 0u); }
+  __device__ static void unpack(const Raw& t, float* v) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
   }
 };
 
@@ -54,46 +66,44 @@ __global__ void __launch_bounds__(BN_THREADS) bn_colsum_kernel(const T* __restri
   const int tpr = C / V;               // threads per row
   const int rpb = BN_THREADS / tpr;    // rows per block iteration
   const int ch = (threadIdx.x % tpr) * V, rg = threadIdx.x / tpr;
-  float a0[V], a1[V], m[V], rs[V], sc[V], sh[V];
+  float a0[V], a1[V], m[V], sc[V], sh[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
   if (MODE == 1) {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      m[j] = mean[ch + j]; rs[j] = rstd[ch + j];
-      sc[j] = rs[j] * gamma[ch + j];
+      m[j] = mean[ch + j];
+      sc[j] = rstd[ch + j] * gamma[ch + j];
       sh[j] = (beta ? beta[ch + j] : 0.f) - m[j] * sc[j];   // same expressions as the forward: identical ReLU mask
     }
   }
   const int64_t stride = (int64_t)gridDim.x * rpb;
   for (int64_t r = (int64_t)blockIdx.x * rpb + rg; r < rows; r += stride * BN_UNROLL) {
-    float xv[BN_UNROLL][V], dv[BN_UNROLL][V];
+    typename Vec<T>::Raw xr[BN_UNROLL], dr[BN_UNROLL];   // all loads of the iteration in flight, unpacked one row at a time
 #pragma unroll
     for (int u = 0; u < BN_UNROLL; ++u) {
       const int64_t rr = r + u * stride;
-      if (rr < rows) {
-        Vec<T>::load(x + rr * ldx + ch, xv[u]);
-        if (MODE == 1) Vec<T>::load(dy + rr * ldd + ch, dv[u]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < V; ++j) { xv[u][j] = MODE == 1 ? m[j] : 0.f; dv[u][j] = 0.f; }
-      }
+      xr[u] = rr < rows ? Vec<T>::load_raw(x + rr * ldx + ch) : Vec<T>::zero_raw();
+      if (MODE == 1) dr[u] = rr < rows ? Vec<T>::load_raw(dy + rr * ldd + ch) : Vec<T>::zero_raw();   // dy' = 0: the row adds nothing
     }
 #pragma unroll
-    for (int u = 0; u < BN_UNROLL; ++u)
+    for (int u = 0; u < BN_UNROLL; ++u) {
+      float xv[V], dv[V];
+      Vec<T>::unpack(xr[u], xv);
+      if (MODE == 1) Vec<T>::unpack(dr[u], dv);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         if (MODE == 0) {
-          a0[j] += xv[u][j];
-          a1[j] = fmaf(xv[u][j], xv[u][j], a1[j]);
+          a0[j] += xv[j];
+          a1[j] = fmaf(xv[j], xv[j], a1[j]);
         } else {
-          const float xh = (xv[u][j] - m[j]) * rs[j];
-          float d = dv[u][j];
-          if (relu && !(fmaf(xv[u][j], sc[j], sh[j]) > 0.f)) d = 0.f;
+          float d = dv[j];
+          if (relu && !(fmaf(xv[j], sc[j], sh[j]) > 0.f)) d = 0.f;
           a0[j] += d;
-          a1[j] = fmaf(d, xh, a1[j]);
+          a1[j] = fmaf(d, xv[j] - m[j], a1[j]);   // sum of dy' (x - mean); the common factor rstd is applied once per block below
         }
       }
+    }
   }
 #pragma unroll
   for (int j = 0; j < V; ++j) { red[0][threadIdx.x][j] = a0[j]; red[1][threadIdx.x][j] = a1[j]; }
@@ -103,6 +113,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_colsum_kernel(const T* __restri
     const int t0 = c / V, j = c % V;
     float u0 = 0.f, u1 = 0.f;
     for (int g = 0; g < rpb; ++g) { u0 += red[0][g * tpr + t0][j]; u1 += red[1][g * tpr + t0][j]; }
+    if (MODE == 1) u1 *= rstd[c];
     atomicAdd(s0 + c, (double)u0);
     atomicAdd(s1 + c, (double)u1);
   }
@@ -130,7 +141,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
 //         = gamma rstd (dy' - [train] (mean(dy') + xhat mean(dy' xhat))),  dy' = dy [x sc + sh > 0]
 // Four per-channel constants per thread keep the register count low enough for 2+ blocks per SM.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(BN_THREADS) bn_rows_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t ldd,
+__global__ void __launch_bounds__(BN_THREADS, sizeof(T) == 2 ? 3 : 0) bn_rows_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t ldd,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                                                               int training, const double* __restrict__ s_dy, const double* __restrict__ s_dyx,
