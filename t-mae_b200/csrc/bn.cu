@@ -171,28 +171,28 @@ __global__ void __launch_bounds__(BN_THREADS, sizeof(T) == 2 ? 3 : 0) bn_rows_ke
   }
   const int64_t stride = (int64_t)gridDim.x * rpb;
   for (int64_t r = (int64_t)blockIdx.x * rpb + rg; r < rows; r += stride * U) {
-    float xv[U][V], dv[U][V];
+    typename Vec<T>::Raw xr[U], dr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t rr = r + u * stride;
-      if (rr < rows) {
-        Vec<T>::load(x + rr * ldx + ch, xv[u]);
-        if (MODE == 1) Vec<T>::load(dy + rr * ldd + ch, dv[u]);
-      }
+      xr[u] = rr < rows ? Vec<T>::load_raw(x + rr * ldx + ch) : Vec<T>::zero_raw();
+      if (MODE == 1) dr[u] = rr < rows ? Vec<T>::load_raw(dy + rr * ldd + ch) : Vec<T>::zero_raw();
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t rr = r + u * stride;
       if (rr >= rows) continue;
-      float o[V];
+      float xv[V], dv[V], o[V];
+      Vec<T>::unpack(xr[u], xv);
+      if (MODE == 1) Vec<T>::unpack(dr[u], dv);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        const float v = fmaf(xv[u][j], sc[j], sh[j]);
+        const float v = fmaf(xv[j], sc[j], sh[j]);
         if (MODE == 0) {
           o[j] = relu ? fmaxf(v, 0.f) : v;
         } else {
-          const float d = (relu && !(v > 0.f)) ? 0.f : dv[u][j];
-          o[j] = fmaf(sc[j], d, fmaf(xv[u][j], kb[j], kc[j]));
+          const float d = (relu && !(v > 0.f)) ? 0.f : dv[j];
+          o[j] = fmaf(sc[j], d, fmaf(xv[j], kb[j], kc[j]));
         }
       }
       Vec<T>::store(out + rr * ldo + ch, o);
