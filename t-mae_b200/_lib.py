@@ -54,6 +54,9 @@ class _Lib:
                 setattr(self, name[5:], self._checked(fn, name))
             else:
                 setattr(self, name[5:], fn)
+        for key, val in os.environ.items():   # TMAE_OPT_<NAME>=<int> -> tmae_set_option (A/B measurements)
+            if key.startswith("TMAE_OPT_"):
+                self.set_option(key[9:].lower().encode(), int(val))
 
     def _checked(self, fn, name):
         err = self.cdll.tmae_last_error_string

@@ -205,10 +205,15 @@ static bool bn_shape_ok(int c) {
   constexpr int V = Vec<T>::N;
   return c % V == 0 && c / V <= BN_THREADS && BN_THREADS % (c / V) == 0;
 }
-static int bn_grid(int64_t rows, int c, int vec) {
+// Blocks per SM of the column-sum kernels.  Every block ends with 2 C double atomics onto the same 2 C addresses, and with
+// 16 blocks per SM that serialised tail cost more than the streaming part on the 36-61 MB sparse-conv tensors (57.7 us at
+// 16, 43.4 at 8, 35.3 at 4, 33.0 at 2 for 70k x 128 fp32; tools/kernel_bench.py bn).  0 = automatic: 2, or 4 for maps of
+// more than 64 Mi elements (the decoder's BEV maps); tmae_set_option("bn_colsum_cap", n) forces n.
+int g_bn_colsum_cap = 0;
+static int bn_grid(int64_t rows, int c, int vec, int per_sm = 16) {
   int rpb = BN_THREADS / (c / vec);
   int64_t blocks = (rows + (int64_t)rpb * BN_UNROLL - 1) / ((int64_t)rpb * BN_UNROLL);
-  int64_t cap = (int64_t)kNumSMs * 16;
+  int64_t cap = (int64_t)kNumSMs * per_sm;
   return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
@@ -219,7 +224,7 @@ static int bn_fwd_impl(const T* x, int64_t ldx, const float* gamma, const float*
   const int grid = bn_grid(rows, c, Vec<T>::N);
   if (train) {
     if (cudaMemsetAsync(ws, 0, 2 * c * sizeof(double), s) != cudaSuccess) return TMAE_ERR_CUDA;
-    bn_colsum_kernel<T, 0><<<grid, BN_THREADS, 0, s>>>(x, ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, rows, c, ws, ws + c);
+    bn_colsum_kernel<T, 0><<<bn_grid(rows, c, Vec<T>::N, g_bn_colsum_cap > 0 ? g_bn_colsum_cap : (rows * c > ((int64_t)64 << 20) ? 4 : 2)), BN_THREADS, 0, s>>>(x, ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, rows, c, ws, ws + c);
     bn_finalize_kernel<<<cdiv(c, 128), 128, 0, s>>>(ws, ws + c, rows, c, eps, momentum, mean, rstd, running_mean, running_var);
   }
   bn_rows_kernel<T, 0><<<grid, BN_THREADS, 0, s>>>(x, ldx, nullptr, 0, mean, rstd, gamma, beta, relu, 0, nullptr, nullptr, y, ldy, nullptr,
@@ -233,7 +238,7 @@ static int bn_bwd_impl(const T* dy, int64_t ldd, const T* x, int64_t ldx, const 
                        double* ws, cudaStream_t s) {
   const int grid = bn_grid(rows, c, Vec<T>::N);
   if (cudaMemsetAsync(ws, 0, 2 * c * sizeof(double), s) != cudaSuccess) return TMAE_ERR_CUDA;
-  bn_colsum_kernel<T, 1><<<grid, BN_THREADS, 0, s>>>(x, ldx, dy, ldd, mean, rstd, gamma, beta, relu, rows, c, ws, ws + c);
+  bn_colsum_kernel<T, 1><<<bn_grid(rows, c, Vec<T>::N, g_bn_colsum_cap > 0 ? g_bn_colsum_cap : (rows * c > ((int64_t)64 << 20) ? 4 : 2)), BN_THREADS, 0, s>>>(x, ldx, dy, ldd, mean, rstd, gamma, beta, relu, rows, c, ws, ws + c);
   bn_rows_kernel<T, 1><<<grid, BN_THREADS, 0, s>>>(x, ldx, dy, ldd, mean, rstd, gamma, beta, relu, training, ws, ws + c, dx, ldo, dgamma, dbeta,
                                                    rows, c);
   return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;

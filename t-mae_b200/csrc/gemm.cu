@@ -353,7 +353,7 @@ int tc_sparse_conv_bwd_weight(const float* dy, const float* x, const int* table,
 
 using namespace tmae;
 
-namespace tmae { extern bool g_attn_tc; extern bool g_wide_st; extern int g_attn_occ; extern int g_attn_occ_fwd; }  // attention.cu, gemm_tma.cu
+namespace tmae { extern bool g_attn_tc; extern bool g_wide_st; extern int g_attn_occ; extern int g_attn_occ_fwd; extern int g_bn_colsum_cap; extern int g_ln_bwd_cap; }  // attention.cu, gemm_tma.cu
 static bool g_conv_async = true;  // tmae_set_option("conv_async", 0): sparse-conv forward / backward-data on the thread-staged bf16 kernel
 static bool g_use_tma = true;  // tmae_set_option("tma", 0) keeps every tensor-core GEMM on the thread-staged bf16 kernel
 
@@ -364,6 +364,8 @@ extern "C" {
 int tmae_set_option(const char* name, int32_t value) {
   if (name && !strcmp(name, "tma")) { g_use_tma = value != 0; return 0; }
   if (name && !strcmp(name, "attn_tc")) { g_attn_tc = value != 0; return 0; }
+  if (name && !strcmp(name, "bn_colsum_cap")) { g_bn_colsum_cap = value < 0 ? 0 : value; return 0; }
+  if (name && !strcmp(name, "ln_bwd_cap")) { g_ln_bwd_cap = value < 1 ? 1 : value; return 0; }
   if (name && !strcmp(name, "attn_occ_fwd")) { g_attn_occ_fwd = value; return 0; }
   if (name && !strcmp(name, "attn_occ")) { g_attn_occ = value; return 0; }   // 1: mma attention backward at one more CTA per SM
   if (name && !strcmp(name, "wide_st")) { g_wide_st = value != 0; return 0; }   // 0: 128-bit epilogue stores in the TMA GEMM (A/B measurement)

@@ -173,6 +173,8 @@ __global__ void __launch_bounds__(256) add_ln_fwd_vec_kernel(const float* __rest
 
 // COLSUM: also accumulates the column sums of the kernel's own output (of dres when it is written, else of dv) into
 // dcol -- the bias gradient of the linear layer that produced `res`, which would otherwise re-read the output from HBM.
+int g_ln_bwd_cap = 6;   // blocks per SM of the vectorised LayerNorm backward (each block ends with 2-3 C atomics); tmae_set_option("ln_bwd_cap", n)
+
 template <int VPL, bool COLSUM>
 __global__ void __launch_bounds__(256) add_ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                              const float* __restrict__ res, const uint8_t* __restrict__ rowmask,
@@ -433,7 +435,7 @@ int tmae_add_layernorm_bwd_colsum(const float* dy, const float* x, const float* 
   int grid = cdiv(warps * 32, 256);
   ProfScope prof("add_layernorm_bwd", 0, 4.0 * rows * c * (res ? 4 : 3) + (dres ? 4.0 * rows * c : 0), s);
   int64_t vb = (rows + 63) / 64;  // vectorised kernels: every warp walks >= 8 rows so the per-block reduction amortises
-  int vgrid = (int)(vb < (int64_t)kNumSMs * 6 ? vb : (int64_t)kNumSMs * 6);
+  int vgrid = (int)(vb < (int64_t)kNumSMs * g_ln_bwd_cap ? vb : (int64_t)kNumSMs * g_ln_bwd_cap);
   switch (c) {
     case 64: add_ln_bwd_kernel<2><<<grid, 256, 0, s>>>(dy, x, res, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, rows, rpw); break;
     case 128:

@@ -109,6 +109,22 @@ def attn(tc=1):
     ops.set_option("attn_tc", 0)
 
 
+def bn():
+    """BatchNorm1d + ReLU over sparse-conv rows (fp32) and over a decoder map (bf16): forward (train) and backward."""
+    for key, val in os.environ.items():
+        if key.startswith("TMAE_OPT_"):
+            ops.set_option(key[9:].lower(), int(val))
+    for rows, C in [(70000, 128), (60000, 256), (240000, 64)]:
+        g, b = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+        rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        sets = [(torch.randn(rows, C, device=DEV), torch.randn(rows, C, device=DEV)) for _ in range(4)]
+        t = timeit_queue([lambda s=s: ops.bn_train_fwd(s[0], g, b, rm, rv, 0.01, 1e-3, True) for s in sets] * 2)
+        _, mean, rstd = ops.bn_train_fwd(sets[0][0], g, b, rm, rv, 0.01, 1e-3, True)
+        t2 = timeit_queue([lambda s=s: ops.bn_bwd(s[1], s[0], b, mean, rstd, g, True, True) for s in sets] * 2)
+        by = rows * C * 4
+        print(f"bn fp32 {rows:7d} x {C:3d} | fwd {t * 1e3:7.1f} us ({3 * by / t / 1e6:.0f} GB/s) | bwd {t2 * 1e3:7.1f} us ({5 * by / t2 / 1e6:.0f} GB/s)")
+
+
 def bev(batch=8):
     """SSTBEVBackbone forward (eval) and forward+backward (train) on a finetune-sized bf16 channels-last map."""
     from tmae_b200 import config
@@ -146,3 +162,5 @@ if __name__ == "__main__":
         attn()
     if what == "bev":
         bev()
+    if what == "bn":
+        bn()
