@@ -129,7 +129,12 @@ TMAE_API int tmae_window_partition(const int32_t* coords_a, int64_t m_a, const i
  * network_utils.py:30, SiamWCA_MAE.py:117-119 and their autograd backward.  w is (n, k) row-major
  * (torch Linear layout).  y = act(x w^T + bias) + residual ; preact (nullable) receives x w^T + bias. */
 /* options: "tma" (default 1) -- 0 routes the dense tensor-core GEMMs to the thread-staged bf16 kernel;
- * "attn_tc" (default 0; the layer entry points set it from `precision`) -- windows above 16 tokens on mma.sync TF32 */
+ * "conv_async" (default 1) -- 0 keeps the sparse convolutions on the thread-staged bf16 gather kernel;
+ * "attn_tc" (default 0; the layer entry points set it from `precision`) -- windows above 16 tokens on mma.sync TF32;
+ * measurement switches (A/B runs; defaults are the measured best): "wide_st" (1: 256-bit epilogue stores in the TMA GEMM),
+ * "attn_occ" / "attn_occ_fwd" (1: mma attention kernels compiled for more resident CTAs per SM), "bn_colsum_cap" (0 = automatic
+ * blocks per SM of the BatchNorm column sums), "ln_bwd_cap" (6 blocks per SM of the LayerNorm backward).
+ * The Python binding applies TMAE_OPT_<NAME>=<int> environment variables through this call when the library is loaded. */
 TMAE_API int tmae_set_option(const char* name, int32_t value);
 /* Diagnostics: when device_u64 is non-null, CTA 0 of every following TMA GEMM launch writes a timeline of its TMA
  * producer, MMA issuer and epilogue (four equal slices of `capacity` 64-bit words: event << 56 | index << 40 | SM clock).
