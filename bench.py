@@ -304,6 +304,12 @@ def run_ours(args):
     roof, prof_table = None, None
     if rank == 0:
         roof, prof_table = roofline(ops, step_local, resident, args)
+    counts = None
+    if rank == 0:
+        try:
+            counts = workload_counts(bb, resident)
+        except Exception as e:  # diagnostics only: never lose the measurement over them
+            counts = {"error": repr(e)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(w, args)
@@ -322,11 +328,28 @@ def run_ours(args):
             "e2e": {"value": round(e_value, 3), "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e_total / args.steps, 3)},
             "gpu_launches": launches, "host_enqueue_ms_per_step": round(host_ms[0], 2),
-            "roofline": roof, "cpu_baseline": cpu, "kernel_time_table": prof_table,
+            "roofline": roof, "cpu_baseline": cpu, "kernel_time_table": prof_table, "counts": counts,
         }
         emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def workload_counts(bb, resident):
+    """Row counts of the last step that ran (SURVEY.md section 8: log N, M per stage and the window counts with every run);
+    read from the backbone's geometry plan after the timed region."""
+    plans, _ = bb.last_plan
+    names = ["current (visible)" if bb.__class__.__name__ == "SiamWCA_MAE" else "current", "previous", "both frames (Siamese-batched set)"]
+    out = {"points_per_frame_set_first_batch": [int(resident[0][0].shape[0]), int(resident[0][1].shape[0])],
+           "pillars_per_stage": {n: [int(st.m) for st in fp.stages] for n, fp in zip(names, plans)}}
+    win = {}
+    for s, st in enumerate(plans[-1].stages):   # the set that runs through the SST blocks carries the partition tables
+        if st.part is not None:
+            lb = st.part.level_base.cpu().tolist()   # (2 shifts, levels + 1): windows in front of each level, last = all
+            win[f"stage{s + 1}"] = {"windows_shift0": int(lb[0][-1]), "windows_shift1": int(lb[1][-1]), "windows_by_level_shift0":
+                                    [int(lb[0][i + 1] - lb[0][i]) for i in range(len(lb[0]) - 1)], "level_max_tokens": list(st.part.tokens)}
+    out["windows"] = win
+    return out
 
 
 def roofline(ops, step, resident, args):
