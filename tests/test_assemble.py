@@ -76,6 +76,34 @@ def test_pose_affines_host_logic():
         pose_affines(np.array([0, 0, 0, 0, 1.0, 2, 3]), np.zeros(7))   # zero-norm quaternion, like scipy in the reference
 
 
+def test_oracle_properties():
+    """Size-independent properties of the path (the GPU tests check the same on the CUDA output through the oracle):
+    every kept point is outside the ego box in its RAW coordinates and inside the crop after alignment; the order of the
+    kept points is the input order; samples are independent (assembling a sub-batch gives the same rows up to the sample
+    index); a second pass with zero poses and no ego box is the identity."""
+    kind = "once"
+    rng = synth.SHAPES[kind]["range"]
+    samples = cases.raw_samples(77, 2500, kind)
+    p, q = assemble_ref.assemble(samples, rng)
+    r32 = np.asarray(rng, np.float32)
+    for out in (p, q):
+        ok = np.isfinite(out[:, 1])
+        assert ok.all()
+        assert ((out[:, 1] >= r32[0]) & (out[:, 1] <= r32[3]) & (out[:, 2] >= r32[1]) & (out[:, 2] <= r32[4])).all()
+        assert (np.diff(out[:, 0]) >= 0).all()                       # samples back to back
+    for b, s in enumerate(samples):                                  # current frame: rows are a subsequence of the raw rows
+        mine = p[p[:, 0] == b][:, 1:]
+        raw = s["points"]
+        keep = ~((np.abs(raw[:, 0]) < 2) & (np.abs(raw[:, 1]) < 2)) & assemble_ref.mask_points_by_range(raw, r32)
+        assert np.array_equal(mine, raw[keep], equal_nan=True)
+    sub_p, sub_q = assemble_ref.assemble(samples[2:3], rng)          # sample independence
+    assert np.array_equal(sub_p[:, 1:], p[p[:, 0] == 2][:, 1:]) and np.array_equal(sub_q[:, 1:], q[q[:, 0] == 2][:, 1:])
+    again = [dict(points=p[p[:, 0] == b][:, 1:], points_prev=q[q[:, 0] == b][:, 1:], pose=np.zeros(7), pose_prev=np.zeros(7))
+             for b in range(len(samples))]
+    p2, q2 = assemble_ref.assemble(again, rng, ego_radius=0)
+    assert np.array_equal(p2, p) and np.array_equal(q2, q)
+
+
 def test_assembler_refuses_cpu():
     from tmae_b200.assemble import FrameAssembler
     with pytest.raises(RuntimeError):
