@@ -164,6 +164,7 @@ def run_ours(args):
         del del_me
     torch.manual_seed(0)
     vfe, bb = tmae_b200.build_model(w["kind"], grid, shape["voxel"], shape["range"])
+    args.precision = args.precision or ops.BENCH_PRECISION
     ops.set_precision(args.precision)
     bb.decoder_autocast = torch.bfloat16 if args.decoder == "bf16" else None
     torch.backends.cudnn.benchmark = True
@@ -319,7 +320,8 @@ def run_ours(args):
             "metric": "encoder scans/sec (scan pairs through vfe -> backbone_3d -> loss)", "value": round(value, 3), "unit": "scans/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total / args.steps, 3),
             "p50_ms_per_scan": round(float(np.median(per)) / w["batch"], 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32/bf16 tensor-core operands, f32 accumulate+storage", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32 (tensor-core operands; f32 accumulate and storage)",
+                                     "bf16": "bf16 (activation storage and tensor-core operands; f32 accumulate, statistics, master weights)"}[args.precision], "data": "synthetic",
             "config": {"workload": w["name"], "precision": f"encoder kernels {args.precision}; cuDNN decoder {args.decoder}",
                        "parallelism": f"dp{world} (scan-pair sharding" + ((", DistributedDataParallel NCCL gradient all-reduce)" if args.ddp else ", one flat NCCL gradient all-reduce per step)") if w["train"] else ", no collective)"),
                        "l2": f"inputs cycle over {args.batches} distinct batches; per-step activation working set >> 126 MB L2",
@@ -473,8 +475,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pretrain", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
-                    help="bf16 = tensor-core mode (TF32 tcgen05 dense GEMMs + TF32 mma attention, bf16 sparse-conv GEMMs, fp32 accumulate and storage); fp32 = FFMA parity mode")
+    ap.add_argument("--precision", default=None, choices=["fp32", "tf32", "bf16"],
+                    help="bf16 = bf16 activation storage + tcgen05 kind::f16 GEMMs (fp32 accumulate); tf32 = fp32 storage + tcgen05 kind::tf32 "
+                         "GEMMs + TF32 mma attention; fp32 = FFMA parity mode.  Default: tmae_b200.ops.BENCH_PRECISION")
     ap.add_argument("--decoder", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--batches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

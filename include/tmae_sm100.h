@@ -13,10 +13,15 @@
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises;
  *   - returns 0 on success, a negative TMAE_ERR_* otherwise (never exits the process, unlike
  *     pcdet/ops/sst_ops/src/sst_ops.cpp:7-19); tmae_last_error_string() describes the failure;
- *   - re-entrant, no globals besides the thread-local error string: one process per GPU is safe;
+ *   - the data path keeps no mutable global state: the error string is thread-local, per-(kernel, device) attribute
+ *     flags are mutex-protected, counters are atomics.  Process-wide, opt-in and NOT thread-safe: the measurement
+ *     switches of tmae_set_option, the event profiler (tmae_profile_begin/_end) and the GEMM timeline
+ *     (tmae_debug_set_trace) -- diagnostics, never needed for results;
  *   - element counts are int64_t; index tensors use the reference's dtypes where they cross the
  *     module API (int64 coords / inverse indices) and int32 internally.
- *   - features are fp32 row-major (rows, channels).
+ *   - features are fp32 row-major (rows, channels) in the fp32 and tf32 modes; the bf16-storage mode (tmae_bf16_*
+ *     entry points) keeps encoder activations and their gradients in bf16, statistics / accumulators / weights'
+ *     master copies and weight gradients in fp32.
  */
 #ifndef TMAE_SM100_H_
 #define TMAE_SM100_H_
@@ -42,8 +47,10 @@ extern "C" {
 
 /* GEMM arithmetic selector for the ops that take `precision`. */
 #define TMAE_PREC_FP32 0 /* fp32 FFMA, parity mode (rtol 1e-5 vs the fp32 oracle) */
-#define TMAE_PREC_BF16 1 /* tensor-core mode: tcgen05 with fp32 accumulate in TMEM; dense GEMMs read their fp32 operands through
-                            TMA as TF32, the gathered (sparse-conv) GEMMs convert to bf16 while staging */
+#define TMAE_PREC_TF32 1 /* tensor-core mode with fp32 STORAGE: tcgen05.mma.kind::tf32, fp32 accumulate in TMEM; operands stay fp32
+                            in HBM and are read through TMA (dense) or cp.async gathers (sparse conv) as TF32 */
+#define TMAE_PREC_BF16 2 /* tensor-core mode with bf16 STORAGE (the throughput mode): tcgen05.mma.kind::f16 on bf16 operands, fp32
+                            accumulate in TMEM, bf16 activations out of the TMEM epilogue; only the tmae_bf16_* entry points take it */
 
 #define TMAE_ACT_NONE 0
 #define TMAE_ACT_GELU 1 /* exact erf GELU (torch default, sst_basic_block.py:121-122) */
@@ -59,6 +66,10 @@ TMAE_API int tmae_device_check(void); /* 0 iff the current device is sm_100 */
 /* Per-kernel timing with CUDA events on the launching stream (used by bench.py for the roofline object): begin, run some
  * steps, end -> text table "name calls total_ms algorithmic_flops algorithmic_bytes" per kernel family. */
 TMAE_API int64_t tmae_launch_count(void); /* instrumented kernel launches so far (lower bound of all launches) */
+/* Which kernel served the GEMM-shaped calls so far: out[0] TMA-fed tcgen05 kernel, out[1] fp32 FFMA kernel in parity mode,
+ * out[2] fp32 FFMA kernel taken in a tensor-core mode because TMA cannot express the shape (must stay 0 on the hot path),
+ * out[3] thin-k kernel (k <= 16: the first VFE layer).  n <= 4 entries are written. */
+TMAE_API int tmae_dispatch_counts(int64_t* out, int32_t n);
 TMAE_API void tmae_profile_begin(void);
 TMAE_API int64_t tmae_profile_end(char* buf, int64_t cap);
 TMAE_API int64_t tmae_scan_scratch_elems(int64_t n);
@@ -128,10 +139,7 @@ TMAE_API int tmae_window_partition(const int32_t* coords_a, int64_t m_a, const i
  * Replace torch.nn.functional.linear at cosine_msa.py:57-62,431, sst_basic_block.py:81, wca_block.py:99,
  * network_utils.py:30, SiamWCA_MAE.py:117-119 and their autograd backward.  w is (n, k) row-major
  * (torch Linear layout).  y = act(x w^T + bias) + residual ; preact (nullable) receives x w^T + bias. */
-/* options: "tma" (default 1) -- 0 routes the dense tensor-core GEMMs to the thread-staged bf16 kernel;
- * "conv_async" (default 1) -- 0 keeps the sparse convolutions on the thread-staged bf16 gather kernel;
- * "attn_tc" (default 0; the layer entry points set it from `precision`) -- windows above 16 tokens on mma.sync TF32;
- * measurement switches (A/B runs; defaults are the measured best): "wide_st" (1: 256-bit epilogue stores in the TMA GEMM),
+/* options = measurement switches (A/B runs; defaults are the measured best): "wide_st" (1: 256-bit epilogue stores in the TMA GEMM),
  * "attn_occ" / "attn_occ_fwd" (1: mma attention kernels compiled for more resident CTAs per SM), "bn_colsum_cap" (0 = automatic
  * blocks per SM of the BatchNorm column sums), "ln_bwd_cap" (6 blocks per SM of the LayerNorm backward).
  * The Python binding applies TMAE_OPT_<NAME>=<int> environment variables through this call when the library is loaded. */
@@ -248,16 +256,20 @@ TMAE_API int tmae_scatter_rows(const float* rows, const int32_t* sel, int64_t m,
  * level-sorted): those run one warp per window, the rest one CTA per window with shared memory sized for 32 tokens
  * (windows [small_end, mid_end), mid_end = level_base[first level with max_tokens > 32]) or 64.  Backward: dsum (q rows,
  * heads) scratch.  ld_q / ld_k / ld_v: row pitches (elements, >= channels, multiples of 4) of q / k / v and of
- * dq / dk / dv, so the three may be column blocks of one packed projection output (rows, 3*channels); o, dout: channels. */
+ * dq / dk / dv, so the three may be column blocks of one packed projection output (rows, 3*channels); o, dout: channels.
+ * precision: TMAE_PREC_FP32 = IEEE math, fp32 FFMA kernels for > 16-token windows; TMAE_PREC_TF32 = MUFU math, mma.sync TF32.
+ * rows_q / rows_kv: row counts of q and k/v (only used for the profiler's algorithmic byte count; 0 = unknown). */
 TMAE_API int tmae_window_attention_fwd(const float* q, const float* k, const float* v, float* o, float* lse, const int32_t* qtok,
                               const int32_t* qcnt, const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win,
                               const int32_t* small_end, const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min,
-                              int32_t channels, int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, void* stream);
+                              int32_t channels, int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, int64_t rows_q, int64_t rows_kv,
+                              int32_t precision, void* stream);
 TMAE_API int tmae_window_attention_bwd(const float* dout, const float* q, const float* k, const float* v, const float* o, const float* lse,
                               float* dsum, float* dq, float* dk, float* dv, float* dtau, const int32_t* qtok, const int32_t* qcnt,
                               const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win, const int32_t* small_end,
                               const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min, int32_t channels,
-                              int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, void* stream);
+                              int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, int64_t rows_q, int64_t rows_kv, int32_t precision,
+                              void* stream);
 
 /* ---- N2 / N3 (the step in front of the VFE): batch assembly of one frame set on the GPU ---------------
  * raw (n_points, feats) fp32 [x, y, z, feat...] = the samples' point arrays back to back, sample_offsets (batch + 1) i64.

@@ -232,7 +232,7 @@ def flat2window(feat, tables):
         T = info["max_tokens"]
         R = int(inds.max()) // T + 1
         buf = feat.new_zeros(R * T, feat.shape[-1])
-        buf[inds] = feat[pos]
+        buf[inds] = feat[pos].to(buf.dtype)   # no-op in fp32; under torch.autocast (mixed-precision yardstick) dtypes differ
         out[dl] = buf.view(R, T, -1)
     return out
 
@@ -244,7 +244,7 @@ def window2flat(feat3d, tables):
     out = any_.new_zeros(n, any_.shape[-1])
     for dl, f in feat3d.items():
         inds, (pos,) = tables[dl]
-        out[pos] = f.reshape(-1, f.shape[-1])[inds]
+        out[pos] = f.reshape(-1, f.shape[-1])[inds].to(out.dtype)
     return out
 
 
@@ -393,7 +393,7 @@ class EncoderLayer(nn.Module):
             out[dl] = self.win_attn.cross_attn(q, k, fp, masks_p[dl]).permute(1, 0, 2)
         src = src.clone()
         if out:
-            src[keep] = src[keep] + window2flat(out, tables)
+            src[keep] = (src[keep] + window2flat(out, tables)).to(src.dtype)
         return self._ffn(src)
 
 
@@ -418,7 +418,7 @@ class SparseTensor:
         Y, X = self.spatial_shape
         out = self.features.new_zeros(self.batch_size, Y, X, self.features.shape[1])
         i = self.indices.long()
-        out[i[:, 0], i[:, 1], i[:, 2]] = self.features
+        out[i[:, 0], i[:, 1], i[:, 2]] = self.features.to(out.dtype)
         return out.permute(0, 3, 1, 2).contiguous()
 
 
@@ -492,7 +492,7 @@ class SSTBlock(nn.Module):
                 x = layer.forward_self(x, info[f"pos_dict_shift{s}"], info[f"flat2win_inds_shift{s}"],
                                        info[f"key_mask_shift{s}"])
         un = torch.zeros_like(feat)
-        un[info["voxel_keep_inds"]] = x
+        un[info["voxel_keep_inds"]] = x.to(un.dtype)
         return self.conv_out(sp.replace_feature(feat + un))
 
 

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .plan import build_plans
+from .plan import build_plans, validate_levels
 from .sparse import ConvBNReLU, SparseConvTensor, gather_bev
 from .vfe import _LinearFn  # noqa: F401
 
@@ -136,6 +136,7 @@ class _EncBlockBase(nn.Module):
             raise NotImplementedError("SHUFFLE_VOXELS is False in both T-MAE configs (t_mae_ssl.yaml:74)")
         if enc["ACTIVATION"] != "gelu" or enc["DROPOUT"] != 0.0:
             raise NotImplementedError("encoder uses GELU and no dropout on the T-MAE path")
+        validate_levels(pre)
         self.d_model = enc["D_MODEL"]
         self.register_buffer("pos_lut", pos_embed_table(self.d_model, pre["POS_TEMPERATURE"], normalize=pre["NORMALIZE_POS"]),
                              persistent=False)

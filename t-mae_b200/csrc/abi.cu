@@ -2,7 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
+#include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -22,8 +25,22 @@ void set_error(const char* fmt, ...) {
 // ---------------------------------------------------------------- per-kernel profiler (CUDA events)
 struct ProfRec { const char* name; double flops, bytes; cudaEvent_t e0, e1; };
 static bool g_prof = false;
-double g_prof_rows_hint[2] = {0, 0};
-long long g_launch_groups = 0;
+static std::atomic<long long> g_launch_groups{0};
+void count_launch() { g_launch_groups.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<long long> g_dispatch[DISP_N];
+void count_dispatch(int which) { if (which >= 0 && which < DISP_N) g_dispatch[which].fetch_add(1, std::memory_order_relaxed); }
+
+int smem_attr_once(const void* kern, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return TMAE_ERR_CUDA;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({kern, dev})) return 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return TMAE_ERR_CUDA;
+  done.insert({kern, dev});
+  return 0;
+}
 static std::vector<ProfRec> g_recs;
 bool prof_enabled() { return g_prof; }
 void prof_push(const char* name, double flops, double bytes, cudaStream_t s, bool begin) {
@@ -161,7 +178,12 @@ int tmae_device_check(void) {
   return 0;
 }
 
-int64_t tmae_launch_count(void) { return tmae::g_launch_groups; }
+int64_t tmae_launch_count(void) { return tmae::g_launch_groups.load(); }
+
+int tmae_dispatch_counts(int64_t* out, int32_t n) {
+  for (int i = 0; i < n; ++i) out[i] = i < tmae::DISP_N ? tmae::g_dispatch[i].load() : 0;
+  return 0;
+}
 
 void tmae_profile_begin(void) {
   cudaDeviceSynchronize();

@@ -47,6 +47,8 @@ struct AttnArgs {
   int C, H;
   int ldq, ldk, ldv;                                 // row pitches (elements) of q / k / v and of dq / dk / dv; o, dO: C
   const float* dout; float* dq; float* dk; float* dv; float* dtau;
+  int tc;                                            // host only: 1 = tensor-core precision mode (MUFU math, mma.sync for > 16 tokens)
+  double rows_q, rows_kv;                            // host only: row counts for the profiler's algorithmic byte count (0 = unknown)
 };
 
 __device__ __forceinline__ void load_row(const float* __restrict__ p, float* r) {
@@ -540,11 +542,7 @@ static int launch_large(const AttnArgs& a, const int* begin, const int* end, int
   constexpr int HEADS = TW / HD;
   size_t smem = (size_t)(2 * TCAP * RS + 2 * TCAP * HEADS) * sizeof(float);
   auto kern = attn_large_kernel<HD, MODE, TCAP>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TMAE_ERR_CUDA;
-    attr_set = true;
-  }
+  if (smem_attr_once((const void*)kern, (int)smem)) return TMAE_ERR_CUDA;
   int64_t items = max_windows * (a.C / TW);
   int per_sm = TCAP == 32 ? 5 : 2;
   int grid = (int)(items < (int64_t)per_sm * kNumSMs ? items : (int64_t)per_sm * kNumSMs);
@@ -564,7 +562,6 @@ struct AttnMmaArgs {
 };
 int attn_mma_fwd(const AttnMmaArgs& a, int hd, int64_t max_windows, cudaStream_t s);
 int attn_mma_bwd(const AttnMmaArgs& a, int hd, int64_t max_windows, cudaStream_t s);
-bool g_attn_tc = false;  // set by the layer entry points (tensor-core precision mode) or tmae_set_option("attn_tc", 1)
 
 static AttnMmaArgs to_mma(const AttnArgs& a) {
   AttnMmaArgs m{};
@@ -576,7 +573,7 @@ static AttnMmaArgs to_mma(const AttnArgs& a) {
 
 static void attn_bytes(const AttnArgs& a, double& fwd, double& bwd) {
   // algorithmic traffic: fwd reads q,k,v writes o ; bwd reads q,k,v,o,dO writes dq,dk,dv
-  const double rq = g_prof_rows_hint[0] * a.C * 4.0, rk = g_prof_rows_hint[1] * a.C * 4.0;
+  const double rq = a.rows_q * a.C * 4.0, rk = a.rows_kv * a.C * 4.0;
   fwd = 2 * rq + 2 * rk;
   bwd = 4 * rq + 4 * rk;
 }
@@ -593,10 +590,10 @@ static int launch_fwd(const AttnArgs& a, int64_t max_windows, cudaStream_t s) {
     ProfScope prof("attn_small_fwd", 0, fb, s);
     int64_t items = max_windows * (a.C / 128);
     int64_t warps = items < (int64_t)kNumSMs * 32 ? items : (int64_t)kNumSMs * 32;
-    if (g_attn_tc) attn_small_fwd_kernel<HD, false><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, 0, s>>>(a);
+    if (a.tc) attn_small_fwd_kernel<HD, false><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, 0, s>>>(a);
     else attn_small_fwd_kernel<HD, true><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, 0, s>>>(a);
   }
-  if (g_attn_tc) return attn_mma_fwd(to_mma(a), HD, max_windows, s);
+  if (a.tc) return attn_mma_fwd(to_mma(a), HD, max_windows, s);
   ProfScope prof("attn_large_fwd", 0, 0, s);
   int r = launch_large<HD, 0, 32>(a, a.small_end, a.mid_end, max_windows, s);
   if (!r) r = launch_large<HD, 0, 64>(a, a.mid_end, a.n_win, max_windows, s);
@@ -612,17 +609,12 @@ static int launch_bwd(const AttnArgs& a, int64_t max_windows, cudaStream_t s) {
     int64_t items = max_windows * (a.C / 128);
     int64_t warps = items < (int64_t)kNumSMs * 24 ? items : (int64_t)kNumSMs * 24;
     constexpr int smem = (int)sizeof(SmallBwdSmem) * (SW_THREADS / 32);
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(attn_small_bwd_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-          cudaFuncSetAttribute(attn_small_bwd_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-        return TMAE_ERR_CUDA;
-      attr_set = true;
-    }
-    if (g_attn_tc) attn_small_bwd_kernel<HD, false><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, smem, s>>>(a);
+    if (smem_attr_once((const void*)attn_small_bwd_kernel<HD, false>, smem) || smem_attr_once((const void*)attn_small_bwd_kernel<HD, true>, smem))
+      return TMAE_ERR_CUDA;
+    if (a.tc) attn_small_bwd_kernel<HD, false><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, smem, s>>>(a);
     else attn_small_bwd_kernel<HD, true><<<cdiv(warps * 32, SW_THREADS), SW_THREADS, smem, s>>>(a);
   }
-  if (g_attn_tc) return attn_mma_bwd(to_mma(a), HD, max_windows, s);  // ONE fused pass (dQ, dK, dV, dtau)
+  if (a.tc) return attn_mma_bwd(to_mma(a), HD, max_windows, s);  // ONE fused pass (dQ, dK, dV, dtau)
   ProfScope prof("attn_large_bwd", 0, 0, s);
   int r = launch_large<HD, 1, 32>(a, a.small_end, a.mid_end, max_windows, s);
   if (!r) r = launch_large<HD, 1, 64>(a, a.mid_end, a.n_win, max_windows, s);
@@ -646,8 +638,11 @@ extern "C" {
 int tmae_window_attention_fwd(const float* q, const float* k, const float* v, float* o, float* lse, const int32_t* qtok,
                               const int32_t* qcnt, const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win,
                               const int32_t* small_end, const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min,
-                              int32_t channels, int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, void* stream) {
+                              int32_t channels, int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, int64_t rows_q, int64_t rows_kv,
+                              int32_t precision, void* stream) {
+  TMAE_CHECK_ARG(precision == TMAE_PREC_FP32 || precision == TMAE_PREC_TF32, "precision must be TMAE_PREC_FP32 or TMAE_PREC_TF32");
   AttnArgs a{};
+  a.tc = precision != TMAE_PREC_FP32; a.rows_q = (double)rows_q; a.rows_kv = (double)rows_kv;
   a.ldq = ld_q; a.ldk = ld_k; a.ldv = ld_v;
   a.q = q; a.k = k; a.v = v; a.o = o; a.lse = lse; a.qtok = qtok; a.qcnt = qcnt; a.ktok = ktok; a.kcnt = kcnt; a.n_win = n_win;
   a.small_end = small_end; a.mid_end = mid_end; a.tau = tau; a.tau_min = tau_min; a.C = channels; a.H = heads;
@@ -664,8 +659,11 @@ int tmae_window_attention_bwd(const float* dout, const float* q, const float* k,
                               float* dsum, float* dq, float* dk, float* dv, float* dtau, const int32_t* qtok, const int32_t* qcnt,
                               const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win, const int32_t* small_end,
                               const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min, int32_t channels,
-                              int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, void* stream) {
+                              int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, int64_t rows_q, int64_t rows_kv, int32_t precision,
+                              void* stream) {
+  TMAE_CHECK_ARG(precision == TMAE_PREC_FP32 || precision == TMAE_PREC_TF32, "precision must be TMAE_PREC_FP32 or TMAE_PREC_TF32");
   AttnArgs a{};
+  a.tc = precision != TMAE_PREC_FP32; a.rows_q = (double)rows_q; a.rows_kv = (double)rows_kv;
   a.ldq = ld_q; a.ldk = ld_k; a.ldv = ld_v;
   a.q = q; a.k = k; a.v = v; a.o = (float*)o; a.lse = (float*)lse; a.dsum = dsum; a.qtok = qtok; a.qcnt = qcnt; a.ktok = ktok;
   a.kcnt = kcnt; a.n_win = n_win; a.small_end = small_end; a.mid_end = mid_end; a.tau = tau; a.tau_min = tau_min; a.C = channels;

@@ -355,8 +355,8 @@ int g_attn_occ = 1;   // 1: the <= 32-token backward kernels are compiled for 10
 
 template <typename K>
 static void max_carveout(K kern) {   // static shared memory only: ask for the largest shared-memory carveout once per kernel
-  static bool done = false;
-  if (!done) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); done = true; }
+  // idempotent and cheap next to a launch; a per-process "done" flag would skip every device after the first
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 template <int HD, int TCAP>

@@ -76,13 +76,18 @@ constexpr int kNumSMs = 148;  // B200
 // Optional per-kernel timing with CUDA events on the launching stream (tmae_profile_begin / _end); off by default
 // and free when off.  flops / bytes are the ALGORITHMIC work of the launch.
 bool prof_enabled();
-extern long long g_launch_groups;  // kernel-family launches made by this process (always counted)
-extern double g_prof_rows_hint[2];  // (q rows, kv rows) of the next attention call, set by the layer entry points
+void count_launch();    // kernel-family launches made by this process (always counted; atomic)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: set once per (kernel, device), thread-safe
+int smem_attr_once(const void* kern, int bytes);
+// which kernel family served a GEMM-shaped call (tmae_dispatch_counts): tensor-core TMA path, the fp32 SIMT kernel
+// in parity mode, or the fp32 SIMT kernel taken INSIDE a tensor-core mode because TMA cannot express the shape
+enum Dispatch { DISP_TMA = 0, DISP_SIMT_FP32 = 1, DISP_SIMT_IN_TC_MODE = 2, DISP_THIN_K = 3, DISP_N = 4 };
+void count_dispatch(int which);
 void prof_push(const char* name, double flops, double bytes, cudaStream_t s, bool begin);
 struct ProfScope {
   const char* name; double flops, bytes; cudaStream_t s; bool on;
   ProfScope(const char* n, double f, double b, cudaStream_t st) : name(n), flops(f), bytes(b), s(st), on(prof_enabled()) {
-    ++g_launch_groups;
+    count_launch();
     if (on) prof_push(name, flops, bytes, s, true);
   }
   ~ProfScope() { if (on) prof_push(name, flops, bytes, s, false); }

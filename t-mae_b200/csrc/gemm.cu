@@ -329,47 +329,33 @@ int tma_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, i
                         cudaStream_t s);
 bool tma_linear_bwd_weight_ok(const float* dy, const float* x, const float* dw, int64_t m, int64_t n, int64_t k);
 int tma_linear_bwd_weight(const float* dy, const float* x, float* dw, int64_t m, int64_t n, int64_t k, cudaStream_t s);
-// thread-staged bf16 tensor-core path (gemm_tc.cu)
-bool tc_linear_fwd_ok(int64_t m, int64_t n, int64_t k);
-int tc_linear_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y, float* preact, int64_t m,
-                  int64_t n, int64_t k, int act, cudaStream_t s);
-bool tc_linear_bwd_data_ok(int64_t m, int64_t n, int64_t k);
-int tc_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int accumulate, cudaStream_t s);
-bool tc_linear_bwd_weight_ok(int64_t m, int64_t n, int64_t k);
-int tc_linear_bwd_weight(const float* dy, const float* x, float* dw, int64_t m, int64_t n, int64_t k, cudaStream_t s);
 bool tma_sparse_conv_ok(const float* x, const float* w, const float* y, int cin, int cout);
 int tma_sparse_conv_fwd(const float* x, const int* table, const float* w, float* y, int64_t rows_out, int taps, int cin, int cout, int accumulate,
                         cudaStream_t s);
 bool tma_sparse_conv_bwd_weight_ok(const float* dy, const float* x, const float* dw, int cin, int cout);
 int tma_sparse_conv_bwd_weight(const float* dy, const float* x, const int* table, float* dw, int64_t rows_out, int taps, int cin, int cout,
                                cudaStream_t s);
-bool tc_sparse_conv_ok(int cin, int cout);
-int tc_sparse_conv_fwd(const float* x, const int* table, const float* w, float* y, int64_t rows_out, int taps, int cin, int cout,
-                       int accumulate, cudaStream_t s);
-int tc_sparse_conv_bwd_weight(const float* dy, const float* x, const int* table, float* dw, int64_t rows_out, int taps, int cin,
-                              int cout, cudaStream_t s);
 
 }  // namespace tmae
 
 using namespace tmae;
 
-namespace tmae { extern bool g_attn_tc; extern bool g_wide_st; extern int g_attn_occ; extern int g_attn_occ_fwd; extern int g_bn_colsum_cap; extern int g_ln_bwd_cap; }  // attention.cu, gemm_tma.cu
-static bool g_conv_async = true;  // tmae_set_option("conv_async", 0): sparse-conv forward / backward-data on the thread-staged bf16 kernel
-static bool g_use_tma = true;  // tmae_set_option("tma", 0) keeps every tensor-core GEMM on the thread-staged bf16 kernel
+namespace tmae { extern bool g_wide_st; extern int g_attn_occ; extern int g_attn_occ_fwd; extern int g_bn_colsum_cap; extern int g_ln_bwd_cap; }  // gemm_tma.cu, attention_mma.cu, bn.cu, rowops.cu
 
-#define TMAE_CHECK_PREC(p) TMAE_CHECK_ARG((p) == TMAE_PREC_FP32 || (p) == TMAE_PREC_BF16, "precision must be TMAE_PREC_FP32 or TMAE_PREC_BF16")
+#define TMAE_CHECK_PREC(p) TMAE_CHECK_ARG((p) == TMAE_PREC_FP32 || (p) == TMAE_PREC_TF32, "precision must be TMAE_PREC_FP32 or TMAE_PREC_TF32 (the bf16-storage mode has its own entry points: tmae_bf16_*)")
+// Two kernels per GEMM shape and no third: the TMA-fed tcgen05 kernel in a tensor-core mode, the fp32 FFMA kernel in
+// parity mode.  A tensor-core-mode call whose shape TMA cannot express still runs (fp32 FFMA) but is COUNTED, so tests
+// and the bench can assert that the hot path never takes it (tmae_dispatch_counts).
+static inline void count_simt(int precision) { count_dispatch(precision == TMAE_PREC_FP32 ? DISP_SIMT_FP32 : DISP_SIMT_IN_TC_MODE); }
 
 extern "C" {
 
 int tmae_set_option(const char* name, int32_t value) {
-  if (name && !strcmp(name, "tma")) { g_use_tma = value != 0; return 0; }
-  if (name && !strcmp(name, "attn_tc")) { g_attn_tc = value != 0; return 0; }
   if (name && !strcmp(name, "bn_colsum_cap")) { g_bn_colsum_cap = value < 0 ? 0 : value; return 0; }
   if (name && !strcmp(name, "ln_bwd_cap")) { g_ln_bwd_cap = value < 1 ? 1 : value; return 0; }
   if (name && !strcmp(name, "attn_occ_fwd")) { g_attn_occ_fwd = value; return 0; }
   if (name && !strcmp(name, "attn_occ")) { g_attn_occ = value; return 0; }   // 1: mma attention backward at one more CTA per SM
   if (name && !strcmp(name, "wide_st")) { g_wide_st = value != 0; return 0; }   // 0: 128-bit epilogue stores in the TMA GEMM (A/B measurement)
-  if (name && !strcmp(name, "conv_async")) { g_conv_async = value != 0; return 0; }
   set_error("tmae_set_option: unknown option");
   return TMAE_ERR_INVALID_ARG;
 }
@@ -380,19 +366,18 @@ int tmae_linear_fwd(const float* x, const float* w, const float* bias, const flo
   if (k <= 16 && n <= 256 && n % 4 == 0 && !residual && !preact && act == TMAE_ACT_NONE && m > 0 && (((uintptr_t)y) & 15) == 0 &&
       (((uintptr_t)bias) & 15) == 0) {
     // thin reduction (the VFE's first layer, k = 10): a tile kernel would run 16-wide k-blocks that are mostly padding
+    count_dispatch(DISP_THIN_K);
     ProfScope prof("linear_thin_k", 2.0 * m * n * k, 4.0 * ((double)m * k + (double)n * k + (double)m * n), (cudaStream_t)stream);
     thin_linear_fwd_kernel<<<cdiv(m * (n / 4), 256), 256, (size_t)n * k * sizeof(float), (cudaStream_t)stream>>>(x, w, bias, y, m, (int)n, (int)k);
     TMAE_CHECK_LAUNCH();
     return 0;
   }
-  if (precision == TMAE_PREC_BF16 && g_use_tma && tma_linear_fwd_ok(x, w, y, residual, m, n, k)) {
+  if (precision == TMAE_PREC_TF32 && tma_linear_fwd_ok(x, w, y, residual, m, n, k)) {
     if (tma_linear_fwd(x, w, bias, y, preact, m, n, k, act, (cudaStream_t)stream)) { set_error("tmae_linear_fwd: TMA launch failed"); return TMAE_ERR_CUDA; }
+    count_dispatch(DISP_TMA);
     return 0;
   }
-  if (precision == TMAE_PREC_BF16 && tc_linear_fwd_ok(m, n, k)) {
-    if (tc_linear_fwd(x, w, bias, residual, y, preact, m, n, k, act, (cudaStream_t)stream)) { set_error("tmae_linear_fwd: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
-    return 0;
-  }
+  count_simt(precision);
   GemmArgs g{};
   g.A = x; g.B = w; g.C = y; g.M = m; g.N = n; g.K = k; g.lda = k; g.ldb = k; g.ldc = n;
   g.bias = bias; g.residual = residual; g.preact = preact; g.act = act;
@@ -404,6 +389,7 @@ int tmae_linear_fwd_lut(const float* x, const float* w, const float* lut, const 
                         int64_t k, int32_t precision, void* stream) {
   TMAE_CHECK_PREC(precision);
   TMAE_CHECK_ARG(lut && rowidx, "lut and rowidx are required");
+  count_simt(precision);
   GemmArgs g{};  // always the fp32 SIMT kernel: the tensor-core form of the same product is tmae_linear_fwd_dual
   g.A = x; g.B = w; g.C = y; g.M = m; g.N = n; g.K = k; g.lda = k; g.ldb = k; g.ldc = n;
   g.lut = lut; g.rowidx = rowidx; g.ldlut = n;
@@ -415,10 +401,12 @@ int tmae_linear_fwd_lut(const float* x, const float* w, const float* lut, const 
 int tmae_linear_fwd_dual(const float* x, const float* w, const float* x2, const float* w2, float* y, int64_t m, int64_t n, int64_t k, int64_t k2,
                          int32_t precision, void* stream) {
   TMAE_CHECK_PREC(precision);
-  if (precision == TMAE_PREC_BF16 && g_use_tma && tma_linear_fwd_dual_ok(x, w, x2, w2, y, m, n, k, k2)) {
+  if (precision == TMAE_PREC_TF32 && tma_linear_fwd_dual_ok(x, w, x2, w2, y, m, n, k, k2)) {
     if (tma_linear_fwd_dual(x, w, x2, w2, y, m, n, k, k2, (cudaStream_t)stream)) { set_error("tmae_linear_fwd_dual: TMA launch failed"); return TMAE_ERR_CUDA; }
+    count_dispatch(DISP_TMA);
     return 0;
   }
+  count_simt(precision);
   GemmArgs g{};
   g.A = x; g.B = w; g.C = y; g.M = m; g.N = n; g.K = k; g.lda = k; g.ldb = k; g.ldc = n;
   if (launch<A_KCONTIG, B_KCONTIG>(g, 1, (cudaStream_t)stream)) { set_error("tmae_linear_fwd_dual: launch failed"); return TMAE_ERR_CUDA; }
@@ -431,15 +419,13 @@ int tmae_linear_fwd_dual(const float* x, const float* w, const float* x2, const 
 int tmae_linear_bwd_data(const float* dy, const float* w, float* dx, int64_t m, int64_t n, int64_t k, int32_t accumulate,
                          int32_t precision, void* stream) {
   TMAE_CHECK_PREC(precision);
-  if (precision == TMAE_PREC_BF16 && g_use_tma && tma_linear_bwd_data_ok(dy, w, dx, m, n, k)) {
+  if (precision == TMAE_PREC_TF32 && tma_linear_bwd_data_ok(dy, w, dx, m, n, k)) {
     if (tma_linear_bwd_data(dy, w, dx, m, n, k, accumulate, nullptr, (cudaStream_t)stream)) { set_error("tmae_linear_bwd_data: TMA launch failed"); return TMAE_ERR_CUDA; }
-    return 0;
-  }
-  if (precision == TMAE_PREC_BF16 && tc_linear_bwd_data_ok(m, n, k)) {
-    if (tc_linear_bwd_data(dy, w, dx, m, n, k, accumulate, (cudaStream_t)stream)) { set_error("tmae_linear_bwd_data: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
+    count_dispatch(DISP_TMA);
     return 0;
   }
   // dx[m,k] = sum_n dy[m,n] * w[n,k]
+  count_simt(precision);
   GemmArgs g{};
   g.A = dy; g.B = w; g.C = dx; g.M = m; g.N = k; g.K = n; g.lda = n; g.ldb = k; g.ldc = k; g.accumulate = accumulate;
   if (launch<A_KCONTIG, B_NCONTIG>(g, 1, (cudaStream_t)stream)) { set_error("tmae_linear_bwd_data: launch failed"); return TMAE_ERR_CUDA; }
@@ -456,8 +442,9 @@ extern "C" {
 int tmae_linear_bwd_data_gelu(const float* dy, const float* w, const float* preact, float* dx, int64_t m, int64_t n, int64_t k,
                               int32_t precision, void* stream) {
   TMAE_CHECK_PREC(precision);
-  if (precision == TMAE_PREC_BF16 && g_use_tma && tma_linear_bwd_data_ok(dy, w, dx, m, n, k) && ((uintptr_t)preact & 15) == 0) {
+  if (precision == TMAE_PREC_TF32 && tma_linear_bwd_data_ok(dy, w, dx, m, n, k) && ((uintptr_t)preact & 15) == 0) {
     if (tma_linear_bwd_data(dy, w, dx, m, n, k, 0, preact, (cudaStream_t)stream)) { set_error("tmae_linear_bwd_data_gelu: TMA launch failed"); return TMAE_ERR_CUDA; }
+    count_dispatch(DISP_TMA);
     return 0;
   }
   int r = tmae_linear_bwd_data(dy, w, dx, m, n, k, 0, precision, stream);
@@ -479,12 +466,12 @@ int tmae_linear_bwd_weight(const float* dy, const float* x, float* dw, float* db
   cudaStream_t s = (cudaStream_t)stream;
   // dw[n,k] = sum_m dy[m,n] * x[m,k]   (overwrites dw; reduction over m split across CTAs)
   TMAE_CUDA(cudaMemsetAsync(dw, 0, (size_t)n * k * sizeof(float), s));
-  if (precision == TMAE_PREC_BF16 && g_use_tma && m > 0 && tma_linear_bwd_weight_ok(dy, x, dw, m, n, k)) {
+  if (precision == TMAE_PREC_TF32 && m > 0 && tma_linear_bwd_weight_ok(dy, x, dw, m, n, k)) {
     if (tma_linear_bwd_weight(dy, x, dw, m, n, k, s)) { set_error("tmae_linear_bwd_weight: TMA launch failed"); return TMAE_ERR_CUDA; }
-  } else if (precision == TMAE_PREC_BF16 && tc_linear_bwd_weight_ok(m, n, k)) {
-    if (tc_linear_bwd_weight(dy, x, dw, m, n, k, s)) { set_error("tmae_linear_bwd_weight: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
+    count_dispatch(DISP_TMA);
   } else {
-    GemmArgs g{};
+    count_simt(precision);
+  GemmArgs g{};
     g.A = dy; g.B = x; g.C = dw; g.M = n; g.N = k; g.K = m; g.lda = n; g.ldb = k; g.ldc = k;
     int splits = pick_splits((int64_t)cdiv(n, BM) * cdiv(k, BN), m);
     if (m > 0 && launch<A_MCONTIG, B_NCONTIG>(g, splits, s)) { set_error("tmae_linear_bwd_weight: launch failed"); return TMAE_ERR_CUDA; }
@@ -562,14 +549,12 @@ int tmae_gelu_bwd(const float* dy, const float* preact, float* dx, int64_t n, vo
 int tmae_sparse_conv_fwd(const float* x, const int32_t* table, const float* w, float* y, int64_t rows_out, int32_t taps,
                          int32_t cin, int32_t cout, int32_t accumulate, int32_t precision, void* stream) {
   TMAE_CHECK_PREC(precision);
-  if (precision == TMAE_PREC_BF16 && g_use_tma && g_conv_async && rows_out > 0 && tma_sparse_conv_ok(x, w, y, cin, cout)) {
+  if (precision == TMAE_PREC_TF32 && rows_out > 0 && tma_sparse_conv_ok(x, w, y, cin, cout)) {
     if (tma_sparse_conv_fwd(x, table, w, y, rows_out, taps, cin, cout, accumulate, (cudaStream_t)stream)) { set_error("tmae_sparse_conv_fwd: TMA/cp.async launch failed"); return TMAE_ERR_CUDA; }
+    count_dispatch(DISP_TMA);
     return 0;
   }
-  if (precision == TMAE_PREC_BF16 && tc_sparse_conv_ok(cin, cout)) {
-    if (tc_sparse_conv_fwd(x, table, w, y, rows_out, taps, cin, cout, accumulate, (cudaStream_t)stream)) { set_error("tmae_sparse_conv_fwd: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
-    return 0;
-  }
+  count_simt(precision);
   GemmArgs g{};
   g.A = x; g.B = w; g.C = y; g.M = rows_out; g.N = cout; g.K = (int64_t)taps * cin; g.lda = cin; g.ldb = g.K; g.ldc = cout;
   g.tab = table; g.taps = taps; g.cin = cin; g.accumulate = accumulate;
@@ -585,13 +570,12 @@ int tmae_sparse_conv_bwd_weight(const float* dy, const float* x, const int32_t* 
   int64_t kk = (int64_t)taps * cin;
   TMAE_CUDA(cudaMemsetAsync(dw, 0, (size_t)cout * kk * sizeof(float), s));
   if (rows_out <= 0) return 0;
-  if (precision == TMAE_PREC_BF16 && g_use_tma && g_conv_async && rows_out > 0 && tma_sparse_conv_bwd_weight_ok(dy, x, dw, cin, cout)) {
+  if (precision == TMAE_PREC_TF32 && rows_out > 0 && tma_sparse_conv_bwd_weight_ok(dy, x, dw, cin, cout)) {
     if (tma_sparse_conv_bwd_weight(dy, x, table, dw, rows_out, taps, cin, cout, s)) { set_error("tmae_sparse_conv_bwd_weight: TMA/cp.async launch failed"); return TMAE_ERR_CUDA; }
-    return 0;
-  } else if (precision == TMAE_PREC_BF16 && tc_sparse_conv_ok(cin, cout) && cin % 8 == 0) {
-    if (tc_sparse_conv_bwd_weight(dy, x, table, dw, rows_out, taps, cin, cout, s)) { set_error("tmae_sparse_conv_bwd_weight: tcgen05 launch failed"); return TMAE_ERR_CUDA; }
+    count_dispatch(DISP_TMA);
     return 0;
   }
+  count_simt(precision);
   GemmArgs g{};
   g.A = dy; g.B = x; g.C = dw; g.M = cout; g.N = kk; g.K = rows_out; g.lda = cout; g.ldb = cin; g.ldc = kk;
   g.tab = table; g.taps = taps; g.cin = cin;

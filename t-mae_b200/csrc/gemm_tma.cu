@@ -8,15 +8,16 @@
 // Modes: NT  C[m,n] = sum_k A[m,k] W[n,k]   (A, B K-major)            linear forward
 //        NN  C[m,n] = sum_k A[m,k] B[k,n]   (A K-major, B MN-major)   linear backward-data
 //        TN  C[m,n] = sum_k A[k,m] B[k,n]   (A, B MN-major)           linear backward-weight, split over k
-// The gathered sparse-conv forms and shapes TMA cannot express (row pitch not a multiple of 16 bytes) stay on
-// gemm_tc.cu.  Every mbarrier wait is bounded and traps instead of hanging.
+// Shapes TMA cannot express (row pitch not a multiple of 16 bytes: only the k = 10 first VFE layer on this path) run on
+// the fp32 kernels of gemm.cu and are counted (tmae_dispatch_counts).  Every mbarrier wait is bounded and traps
+// instead of hanging.
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace tmae {
 
-constexpr int UM = 128;        // UMMA M
 constexpr int KB = 32;         // fp32 elements per k-block = one 128-byte swizzle span
 constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quarter, alternating 32-column chunks
 constexpr int TMA_THREADS = 64 + 32 * EPI_WARPS;  // producer + MMA issuer + epilogue warps
@@ -44,117 +45,6 @@ struct TmaArgs {
   int64_t k_chunk;
   unsigned long long* trace; int trace_cap;
 };
-
-__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bar_init(uint64_t* b, uint32_t n) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(n) : "memory");
-}
-__device__ __forceinline__ void bar_expect_tx(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
-  uint32_t ok = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(s_u32(b)), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > (1u << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(s_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(s_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1, bool reduce_add) {
-  if (reduce_add)
-    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(s_u32(src)), "r"(c0), "r"(c1) : "memory");
-  else
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(s_u32(src)), "r"(c0), "r"(c1) : "memory");
-}
-// at most one bulk group (= the previous chunk's stores) may still be reading shared memory
-__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// SWIZZLE_128B UMMA shared-memory descriptor: start >> 4, LBO >> 4 (bit 16), SBO >> 4 (bit 32), version 1 (bit 46),
-// layout type 2 = SWIZZLE_128B (bits 61..63)
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// MN-major TF32 operands must use the 128-byte swizzle with 32-byte atomicity (layout type 1 = SWIZZLE_128B_BASE32B;
-// CUTLASS: "for mn-major tf32 operands, SW128_32B is the only available smem layout"): atoms of 32 MN x 4 K rows,
-// 32-byte chunks XORed with (row % 4).  TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
-__device__ __forceinline__ uint64_t desc_sw128_32b(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (1ull << 61);
-}
-// kind::tf32 instruction descriptor: D fp32 (1 << 4), A/B tf32 (2 << 7, 2 << 10), majors, N >> 3, M >> 4
-__device__ __forceinline__ uint32_t idesc_tf32(int a_mn, int b_mn, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(UM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void commit_to(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void ld_tmem32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// GELU (erf form) and its derivative for the TMEM epilogue.  The four epilogue warps are the pacing resource of the FFN
-// GEMMs (2C-wide outputs), and libm's erff + a separate expf per element made the fused GELU-backward GEMM run at a third
-// of the plain one (205 us vs 73 us for the same bytes): Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) needs ONE
-// exponential, exp(-x^2/2), which is also the Gaussian factor of the derivative.
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
-  const float u = fabsf(x) * 0.70710678118654752440f;
-  const float e = __expf(-u * u);  // exp(-x^2 / 2)
-  const float t = __fdividef(1.f, fmaf(0.3275911f, u, 1.f));
-  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-  cdf = 0.5f * (1.f + copysignf(1.f - poly * e, x));
-  pdf = 0.39894228040143267794f * e;
-}
-__device__ __forceinline__ float gelu_erf_t(float x) {
-  float cdf, pdf;
-  gelu_parts(x, cdf, pdf);
-  return x * cdf;
-}
-__device__ __forceinline__ float gelu_grad_t(float x) {
-  float cdf, pdf;
-  gelu_parts(x, cdf, pdf);
-  return fmaf(x, pdf, cdf);
-}
-
-// 256-bit store (sm_100+): one full 32-byte sector per lane and instruction, so the L2 never sees a partial-sector write
-// and the epilogue issues half as many store instructions as with 128-bit stores
-__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
-               "f"(v[6]), "f"(v[7]) : "memory");
-}
-__device__ __forceinline__ void bar_arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory");
-}
 
 // PERSISTENT kernel: one CTA per SM walks the tile list (n fastest, so CTAs running together share A through L2); the
 // smem ring runs across tile boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the loads
@@ -539,11 +429,7 @@ static int tma_launch(const float* A, const float* B, float* C, float* preact, i
   g.wide_st = g_wide_st && ldc % 8 == 0 && g.N % 8 == 0 && ((uintptr_t)C & 31) == 0 && ((uintptr_t)preact & 31) == 0;
   size_t smem = (size_t)STAGES * (UM * KB * 4 + BN * KB * 4) + 1024;
   auto kern = tma_gemm_kernel<MODE, BN, STAGES, GATHER>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TMAE_ERR_CUDA;
-    attr_set = true;
-  }
+  if (smem_attr_once((const void*)kern, (int)smem)) return TMAE_ERR_CUDA;
   static const char* names[5] = {"tma_gemm_nt", "tma_gemm_nn", "tma_gemm_tn", "tma_gemm_nt_gather", "tma_gemm_tn_gather"};
   double c_el = (double)g.M * g.N * (1.0 + (g.reduce_add && z == 1 ? 1.0 : 0.0) + (preact ? 1.0 : 0.0));
   const double a_el = (GATHER && MODE == T_NT) ? (double)g.M * g.gcin : (double)g.M * g.K;

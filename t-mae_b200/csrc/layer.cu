@@ -7,8 +7,6 @@
 
 using namespace tmae;
 
-namespace tmae { extern bool g_attn_tc; }
-
 namespace {
 
 struct Carve {
@@ -99,7 +97,7 @@ int tmae_encoder_layer_fwd(const float* x, const float* x_kv, const tmae_layer_p
   const int ldq = cross ? c : 3 * c, ldkv = cross ? 2 * c : 3 * c;
   // tensor-core mode with one-hot cell indices from the plan: the table term is a second (one-hot, table^T) source pair of
   // the same GEMM; otherwise (fp32 parity mode) the table is added per row in the SIMT epilogue.  Same arithmetic.
-  const bool dual = precision == TMAE_PREC_BF16 && T->onehot_q && (!cross || T->onehot_kv);
+  const bool dual = precision == TMAE_PREC_TF32 && T->onehot_q && (!cross || T->onehot_kv);
   if (!cross) {
     TRY(tmae_pos_table(pos_lut, P->in_w, P->in_b, dual ? nullptr : table, dual ? table : nullptr, 3 * c, 2 * c, c, stream));
     if (dual) TRY(tmae_linear_fwd_dual(x, P->in_w, T->onehot_q, table, s.qkv, m_q, 3 * c, c, 64, precision, stream));
@@ -120,10 +118,8 @@ int tmae_encoder_layer_fwd(const float* x, const float* x_kv, const tmae_layer_p
   const float* qp = s.qkv;
   const float* kp = cross ? s.kv : s.qkv + c;
   const float* vp = cross ? s.kv + c : s.qkv + 2 * c;
-  g_prof_rows_hint[0] = (double)m_q; g_prof_rows_hint[1] = (double)m_kv;
-  g_attn_tc = precision == TMAE_PREC_BF16;
   TRY(tmae_window_attention_fwd(qp, kp, vp, s.o, s.lse, T->qtok, T->qcnt, T->ktok, T->kcnt, T->n_win, T->small_end, T->mid_end, T->max_windows,
-                                P->tau, tau_min, c, heads, ldq, ldkv, ldkv, stream));
+                                P->tau, tau_min, c, heads, ldq, ldkv, ldkv, m_q, m_kv, precision, stream));
   TRY(tmae_linear_fwd(s.o, P->out_w, P->out_b, nullptr, s.a, nullptr, m_q, c, c, TMAE_ACT_NONE, precision, stream));
   TRY(tmae_add_layernorm_fwd(x, s.a, T->rowmask, P->ln1_g, P->ln1_b, s.x1, s.m1, s.r1, m_q, c, eps, stream));
   // the pre-activation copy exists only for the GELU backward: inference skips that write (2 FF-wide rows per voxel)
@@ -139,8 +135,18 @@ int tmae_encoder_layer_bwd(const float* dy, const float* x, const float* x_kv, c
                            void* scratch, size_t scratch_size, void* stream) {
   const bool cross = x_kv != nullptr;
   if (!cross) { m_kv = m_q; x_kv = x; }
-  if (m_q <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (m_q <= 0) {
+    // an empty query set (e.g. a sample with < 4 voxels under a 75 % mask, or an empty stage) contributes nothing:
+    // every parameter gradient and the key/value input gradient are ZERO, not whatever the caller's buffers held
+    const size_t cc_ = (size_t)c * c;
+    const struct { const float* p; size_t n; } z[13] = {{G->in_w, 3 * cc_}, {G->in_b, (size_t)3 * c}, {G->out_w, cc_}, {G->out_b, (size_t)c},
+        {G->tau, 1}, {G->ln1_g, (size_t)c}, {G->ln1_b, (size_t)c}, {G->w1, (size_t)ff * c}, {G->b1, (size_t)ff}, {G->w2, (size_t)ff * c},
+        {G->b2, (size_t)c}, {G->ln2_g, (size_t)c}, {G->ln2_b, (size_t)c}};
+    for (auto& e : z) if (e.p) TMAE_CUDA(cudaMemsetAsync((void*)e.p, 0, e.n * sizeof(float), st));
+    if (cross && dx_kv && m_kv > 0) TMAE_CUDA(cudaMemsetAsync(dx_kv, 0, (size_t)m_kv * c * sizeof(float), st));
+    return 0;
+  }
   Saved s;
   TMAE_CHECK_ARG(carve_saved(s, (void*)saved, saved_size, m_q, m_kv, c, ff, heads, cross), "saved buffer carve failed");
   TMAE_CHECK_ARG(scratch_size >= scratch_bytes(m_q, m_kv, c, ff, heads), "scratch too small");
@@ -188,14 +194,12 @@ int tmae_encoder_layer_bwd(const float* dy, const float* x, const float* x_kv, c
     TMAE_CUDA(cudaMemsetAsync(dqkv, 0, (size_t)m_q * c * sizeof(float), st));
     TMAE_CUDA(cudaMemsetAsync(dkv, 0, (size_t)m_kv * 2 * c * sizeof(float), st));
   }
-  g_prof_rows_hint[0] = (double)m_q; g_prof_rows_hint[1] = (double)m_kv;
-  g_attn_tc = precision == TMAE_PREC_BF16;
   TRY(tmae_window_attention_bwd(dob, qp, kp, vp, s.o, s.lse, dsum, dqp, dkp, dvp, g_tau, T->qtok, T->qcnt, T->ktok, T->kcnt, T->n_win,
-                                T->small_end, T->mid_end, T->max_windows, P->tau, tau_min, c, heads, ldq, ldkv, ldkv, stream));
+                                T->small_end, T->mid_end, T->max_windows, P->tau, tau_min, c, heads, ldq, ldkv, ldkv, m_q, m_kv, precision, stream));
   // packed in-projection: dW = dqkv^T x (+ the position term), db and the position term from ONE binned column sum of
   // dqkv over the 64 window cells, dx += dqkv W
   // (dual: the binned sum is the weight-gradient GEMM against the one-hot matrix, dtab = dy^T onehot, (n, 64))
-  const bool dual = precision == TMAE_PREC_BF16 && T->onehot_q && (!cross || T->onehot_kv);
+  const bool dual = precision == TMAE_PREC_TF32 && T->onehot_q && (!cross || T->onehot_kv);
   auto table_grad = [&](const float* dy_, const uint8_t* pidx, const float* onehot, int64_t rows, int n, int n_pos, float* gw, float* gb) -> int {
     if (dual) TRY(tmae_linear_bwd_weight(dy_, onehot, dtab, nullptr, rows, n, 64, precision, stream));
     else TRY(tmae_binned_colsum(dy_, pidx, dtab, rows, n, stream));

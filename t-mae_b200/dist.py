@@ -2,32 +2,114 @@
 the only exchange is the gradient average of pretraining (the reference wraps the model in DistributedDataParallel,
 tools/train.py:285-289).
 
-`allreduce_gradients` does that exchange as ONE flat all-reduce after backward: the whole model is 11.8 M parameters
-(47 MB fp32), ~0.2 ms over NVLink 5, so overlapping buckets with backward buys nothing, while DDP's per-parameter hooks,
-bucket copies and its 25 MB default buckets cost ~4 ms of host and copy time per step on this workload (measured at 2
-GPUs: 41.1 ms per step under DDP vs 36.8 ms single-GPU)."""
+`FlatGradients` does that exchange over ONE persistent flat fp32 buffer (the whole model is 11.8 M parameters = 47 MB):
+every `p.grad` is a view of the buffer (DDP's gradient_as_bucket_view), the buffer is all-reduced in `n_buckets` slices
+issued on a communication stream so that slice i+1's copy-in and the optimizer's first reads overlap slice i's
+all-reduce, and the 1/world average is NCCL's own `ReduceOp.AVG` (no extra pass).  Parameters that receive no gradient
+on ANY rank keep `grad = None`, exactly as under DDP with `find_unused_parameters=False` -- the optimizer skips them
+(no weight decay, no moment update).
+
+Measured background (round 1): under `DistributedDataParallel` the 2-GPU step was 41.1 ms against 36.8 ms single-GPU
+(per-parameter hooks, bucket copies); one serialised flat all-reduce built with `torch.cat` every step cost +1.3 ms.
+"""
 import torch
 import torch.distributed as dist
 
 
+class FlatGradients:
+    def __init__(self, params, world_size=None, group=None, n_buckets=4):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = (dist.get_world_size(group) if dist.is_initialized() else 1) if world_size is None else world_size
+        self.flat = None
+        self.views = None
+        self.present = None          # which parameters receive a gradient on at least one rank (fixed after the first step)
+        self.n_buckets = max(1, n_buckets)
+        self.comm = None
+        self.last_ms = None
+
+    def _setup(self):
+        p0 = self.params[0]
+        sizes = [p.numel() for p in self.params]
+        self.flat = torch.zeros(sum(sizes), dtype=p0.dtype, device=p0.device)
+        self.views, off = [], 0
+        for p, n in zip(self.params, sizes):
+            self.views.append(self.flat[off:off + n].view_as(p))
+            off += n
+        # bucket boundaries on parameter boundaries, roughly equal bytes
+        target = (off + self.n_buckets - 1) // self.n_buckets
+        self.bounds, acc, start = [], 0, 0
+        for i, n in enumerate(sizes):
+            acc += n
+            if acc >= target or i == len(sizes) - 1:
+                self.bounds.append((start, i + 1))
+                start, acc = i + 1, 0
+        if self.flat.is_cuda:
+            self.comm = torch.cuda.Stream(device=self.flat.device)
+
+    def _presence(self, has):
+        """Agree once on the set of parameters that get a gradient anywhere (a rank whose batch leaves one unused must
+        still contribute zeros for it); later steps assert the local set is a subset."""
+        t = torch.tensor([1.0 if h else 0.0 for h in has], device=self.flat.device)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self.present = [bool(v) for v in t.tolist()]
+
+    def reduce(self):
+        """Averages the gradients of `params` over the group; afterwards every present `p.grad` is a view of `self.flat`."""
+        if not self.params:
+            return None
+        if self.flat is None:
+            self._setup()
+        has = [p.grad is not None for p in self.params]
+        if self.present is None:
+            self._presence(has)
+        elif any(h and not pr for h, pr in zip(has, self.present)):
+            self._presence([h or pr for h, pr in zip(has, self.present)])
+        main = torch.cuda.current_stream() if self.flat.is_cuda else None
+        for a, b in self.bounds:
+            src, dst, zero = [], [], []
+            for i in range(a, b):
+                if not self.present[i]:
+                    continue
+                g = self.params[i].grad
+                if g is None:
+                    zero.append(self.views[i])
+                elif g.data_ptr() != self.views[i].data_ptr():
+                    src.append(g)
+                    dst.append(self.views[i])
+            if dst:
+                torch._foreach_copy_(dst, src)   # one multi-tensor kernel per bucket; nothing when grads already live in the buffer
+            if zero:
+                torch._foreach_zero_(zero)
+            if self.world > 1:
+                lo = self.views[a].data_ptr() - self.flat.data_ptr()
+                hi = self.views[b - 1].data_ptr() - self.flat.data_ptr() + self.views[b - 1].numel() * self.flat.element_size()
+                sl = self.flat[lo // self.flat.element_size(): hi // self.flat.element_size()]
+                if self.comm is not None:
+                    self.comm.wait_stream(main)
+                    with torch.cuda.stream(self.comm):
+                        dist.all_reduce(sl, op=dist.ReduceOp.AVG, group=self.group)
+                else:
+                    dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=self.group)
+                    sl.div_(self.world)
+        if self.comm is not None and self.world > 1:
+            main.wait_stream(self.comm)
+        for p, v, pr in zip(self.params, self.views, self.present):
+            p.grad = v if pr else None
+        return self.flat
+
+
+_cache = {}
+
+
 def allreduce_gradients(params, world_size=None, group=None):
-    """Averages .grad of `params` over the process group in place.  Parameters whose grad is None on this rank
-    contribute zeros (every rank must pass the same parameter list).  Returns the flat buffer (for inspection)."""
+    """Functional form kept for callers of round 1: one FlatGradients per parameter list (cached by identity)."""
     params = [p for p in params if p.requires_grad]
     if not params:
         return None
-    world_size = dist.get_world_size(group) if world_size is None else world_size
-    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    if world_size > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.div_(world_size)
-    off = 0
-    views = []
-    for g in grads:
-        n = g.numel()
-        views.append(flat[off:off + n].view_as(g))
-        off += n
-    for p, v in zip(params, views):
-        p.grad = v  # views of the flat buffer: no copy back
-    return flat
+    key = (id(params[0]), len(params), world_size)
+    fg = _cache.get(key)
+    if fg is None or any(a is not b for a, b in zip(fg.params, params)):
+        fg = _cache[key] = FlatGradients(params, world_size, group)
+    return fg.reduce()

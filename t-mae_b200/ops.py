@@ -10,24 +10,51 @@ import torch
 
 from ._lib import lib
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}
 
 _state = {"precision": PREC_FP32, "launches": 0}
 
 
 def set_precision(p):
-    """'fp32' (parity mode, FFMA) or 'bf16' (tcgen05 tensor cores, fp32 accumulate)."""
-    _state["precision"] = {"fp32": PREC_FP32, "bf16": PREC_BF16}[p]
+    """'fp32': parity mode (FFMA GEMMs, IEEE math, fp32 storage).
+    'tf32': tcgen05 kind::tf32 GEMMs + TF32 mma attention, fp32 accumulate AND fp32 storage.
+    'bf16': the throughput mode -- bf16 activation storage in the encoder, tcgen05 kind::f16 GEMMs, fp32 accumulate,
+            fp32 statistics / master weights / weight gradients."""
+    if PRECISIONS[p] == PREC_BF16 and not BF16_READY:
+        raise NotImplementedError("the bf16-storage mode is not built yet")
+    _state["precision"] = PRECISIONS[p]
+
+
+BF16_READY = False
+BENCH_PRECISION = "tf32"   # the mode bench.py and smoke() run by default
 
 
 def precision():
     return _state["precision"]
 
 
+def precision_name():
+    return {v: k for k, v in PRECISIONS.items()}[_state["precision"]]
+
+
+def _gemm_prec():
+    """precision argument of the fp32-storage entry points (the bf16-storage layers have their own)."""
+    return PREC_FP32 if _state["precision"] == PREC_FP32 else PREC_TF32
+
+
 def set_option(name, value):
-    """Library options: "tma" (1 = dense tensor-core GEMMs through the TMA-fed TF32 kernel, 0 = thread-staged bf16)."""
+    """Library measurement switches (tmae_set_option): "wide_st", "attn_occ", "attn_occ_fwd", "bn_colsum_cap", "ln_bwd_cap"."""
     lib().set_option(name.encode(), int(value))
+
+
+def dispatch_counts():
+    """{'tma': n, 'simt_fp32': n, 'simt_in_tc_mode': n, 'thin_k': n}: which kernel served the GEMM-shaped calls so far
+    (tmae_dispatch_counts).  'simt_in_tc_mode' must stay 0 on the hot path of a tensor-core mode."""
+    out = (ctypes.c_int64 * 4)()
+    lib().dispatch_counts(out, 4)
+    return dict(zip(("tma", "simt_fp32", "simt_in_tc_mode", "thin_k"), [int(v) for v in out]))
 
 
 def launch_count():
@@ -216,7 +243,7 @@ class Partition:
                  "keep_a", "keep_b", "onehot_a", "onehot_b")
 
 
-def window_partition(coords_a, batch, grid_x, grid_y, levels, coords_b=None, want_ref=False):
+def window_partition(coords_a, batch, grid_x, grid_y, levels, coords_b=None, want_ref=False, status=None):
     """coords_* (m,3) i32 ascending [b,y,x]; levels = [(max_tokens, lo, hi), ...]."""
     L = lib()
     dev = coords_a.device
@@ -243,7 +270,7 @@ def window_partition(coords_a, batch, grid_x, grid_y, levels, coords_b=None, wan
     P.win_level = torch.empty(2, wcap, dtype=I32, device=dev)
     P.n_win = torch.empty(2, dtype=I32, device=dev)
     P.level_base = torch.empty(2, P.n_levels + 1, dtype=I32, device=dev)
-    P.status = torch.empty(1, dtype=I32, device=dev)
+    P.status = torch.empty(1, dtype=I32, device=dev) if status is None else status   # (1,) i32; may be a slice of a shared buffer
     P.ref_a = P.ref_b = None
     if want_ref:
         P.ref_a = [torch.empty(2, max(1, P.m_a), dtype=I64, device=dev) for _ in range(3)]
@@ -257,11 +284,11 @@ def window_partition(coords_a, batch, grid_x, grid_y, levels, coords_b=None, wan
           P.n_levels, _i32([l[1] for l in levels]), _i32([l[2] for l in levels]), _i32(P.tokens),
           _p(P.win_a), _p(P.slot_a), _p(P.posidx_a), _p(P.tok_a), _p(P.cnt_a),
           _p(P.win_b), _p(P.slot_b), _p(P.posidx_b), _p(P.tok_b), _p(P.cnt_b),
-          _p(P.win_level), _p(P.n_win), _p(P.level_base), _p(P.status), *ra, *rb, _p(ws), wsb, _stream())
+          _p(P.win_level), _p(P.n_win), _p(P.level_base), P.status.data_ptr(), *ra, *rb, _p(ws), wsb, _stream())
     P.keep_a = P.keep_b = None
     # (2, m, 64) one-hot form of posidx: second A operand of the packed q/k/v projection in tensor-core mode
-    P.onehot_a = onehot64(P.posidx_a) if (_state["precision"] == PREC_BF16 and P.m_a > 0) else None
-    P.onehot_b = onehot64(P.posidx_b) if (_state["precision"] == PREC_BF16 and P.temporal and P.m_b > 0) else None
+    P.onehot_a = onehot64(P.posidx_a) if (_state["precision"] == PREC_TF32 and P.m_a > 0) else None
+    P.onehot_b = onehot64(P.posidx_b) if (_state["precision"] == PREC_TF32 and P.temporal and P.m_b > 0) else None
     return P
 
 
@@ -281,7 +308,7 @@ def linear_fwd(x, w, bias=None, residual=None, act=ACT_NONE, want_preact=False, 
     pre = torch.empty(m, n, dtype=F32, device=x.device) if want_preact else None
     wp = _p(w, F32) + w_offset_rows * k * 4
     bp = None if bias is None else _p(bias, F32) + w_offset_rows * 4
-    _call("linear_fwd", _p(x, F32), wp, bp, _p(residual), _p(y), _p(pre), m, n, k, act, _state["precision"], _stream(),
+    _call("linear_fwd", _p(x, F32), wp, bp, _p(residual), _p(y), _p(pre), m, n, k, act, _gemm_prec(), _stream(),
           flops=2 * m * n * k, nbytes=4 * (m * k + n * k + m * n))
     return (y, pre) if want_preact else y
 
@@ -291,7 +318,7 @@ def linear_fwd_lut(x, w, lut, rowidx):
     m, k = x.shape
     n = w.shape[0]
     y = torch.empty(m, n, dtype=F32, device=x.device)
-    _call("linear_fwd_lut", _p(x, F32), _p(w, F32), _p(lut, F32), _p(rowidx, U8), _p(y), m, n, k, _state["precision"], _stream(),
+    _call("linear_fwd_lut", _p(x, F32), _p(w, F32), _p(lut, F32), _p(rowidx, U8), _p(y), m, n, k, _gemm_prec(), _stream(),
           flops=2 * m * n * k, nbytes=4 * (m * k + n * k + m * n))
     return y
 
@@ -310,7 +337,7 @@ def linear_fwd_dual(x, w, x2, w2):
     m, k = x.shape
     n, k2 = w.shape[0], x2.shape[1]
     y = torch.empty(m, n, dtype=F32, device=x.device)
-    _call("linear_fwd_dual", _p(x, F32), _p(w, F32), _p(x2, F32), _p(w2, F32), _p(y), m, n, k, k2, _state["precision"], _stream(),
+    _call("linear_fwd_dual", _p(x, F32), _p(w, F32), _p(x2, F32), _p(w2, F32), _p(y), m, n, k, k2, _gemm_prec(), _stream(),
           flops=2 * m * n * (k + k2), nbytes=4 * (m * (k + k2) + n * (k + k2) + m * n))
     return y
 
@@ -335,7 +362,7 @@ def linear_bwd_data(dy, w, dx=None, accumulate=False, w_offset_rows=0):
     if dx is None:
         dx = torch.empty(m, k, dtype=F32, device=dy.device)
         accumulate = False
-    _call("linear_bwd_data", _p(dy, F32), _p(w, F32) + w_offset_rows * k * 4, _p(dx), m, n, k, int(accumulate), _state["precision"], _stream(),
+    _call("linear_bwd_data", _p(dy, F32), _p(w, F32) + w_offset_rows * k * 4, _p(dx), m, n, k, int(accumulate), _gemm_prec(), _stream(),
           flops=2 * m * n * k, nbytes=4 * (m * k + n * k + m * n))
     return dx
 
@@ -345,7 +372,7 @@ def linear_bwd_weight(dy, x, dw, dbias=None, w_offset_rows=0):
     m, n = dy.shape
     k = x.shape[1]
     dbp = None if dbias is None else _p(dbias, F32) + w_offset_rows * 4
-    _call("linear_bwd_weight", _p(dy, F32), _p(x, F32), _p(dw, F32) + w_offset_rows * k * 4, dbp, m, n, k, _state["precision"], _stream(),
+    _call("linear_bwd_weight", _p(dy, F32), _p(x, F32), _p(dw, F32) + w_offset_rows * k * 4, dbp, m, n, k, _gemm_prec(), _stream(),
           flops=2 * m * n * k, nbytes=4 * (m * k + n * k + m * n))
 
 
@@ -387,7 +414,7 @@ def strided_table(indices, batch, Y, X, rows_dev=None):
 def sparse_conv_fwd(x, table, w, rows_out):
     cout, taps, cin = w.shape[0], w.shape[1] * w.shape[2] if w.dim() == 4 else w.shape[1], w.shape[-1]
     y = torch.empty(rows_out, cout, dtype=F32, device=x.device)
-    _call("sparse_conv_fwd", _p(x, F32), _p(table, I32), _p(w, F32), _p(y), rows_out, taps, cin, cout, 0, _state["precision"], _stream(),
+    _call("sparse_conv_fwd", _p(x, F32), _p(table, I32), _p(w, F32), _p(y), rows_out, taps, cin, cout, 0, _gemm_prec(), _stream(),
           flops=2 * rows_out * taps * cin * cout, nbytes=4 * (x.numel() + w.numel() + rows_out * cout) + 4 * rows_out * taps)
     return y
 
@@ -395,7 +422,7 @@ def sparse_conv_fwd(x, table, w, rows_out):
 def sparse_conv_bwd_weight(dy, x, table, w_shape):
     cout, taps, cin = w_shape[0], w_shape[1] * w_shape[2], w_shape[3]
     dw = torch.empty(w_shape, dtype=F32, device=x.device)
-    _call("sparse_conv_bwd_weight", _p(dy, F32), _p(x, F32), _p(table, I32), _p(dw), dy.shape[0], taps, cin, cout, _state["precision"], _stream(),
+    _call("sparse_conv_bwd_weight", _p(dy, F32), _p(x, F32), _p(table, I32), _p(dw), dy.shape[0], taps, cin, cout, _gemm_prec(), _stream(),
           flops=2 * dy.shape[0] * taps * cin * cout, nbytes=4 * (x.numel() + dy.numel() + dw.numel()))
     return dw
 
@@ -560,8 +587,8 @@ def window_attention_fwd(q, k, v, qtok, qcnt, ktok, kcnt, n_win, small, mid, max
     o = torch.zeros(mq, c, dtype=F32, device=q.device) if zero_out else torch.empty(mq, c, dtype=F32, device=q.device)
     lse = torch.empty(max(1, mq), heads, dtype=F32, device=q.device)
     _call("window_attention_fwd", _pv(q), _pv(k), _pv(v), _p(o), _p(lse), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win),
-          _p(small), _p(mid), max_windows, _p(tau, F32), float(tau_min), c, heads, q.stride(0), k.stride(0), v.stride(0), _stream(),
-          nbytes=4 * (q.numel() * 2 + k.numel() * 2))
+          _p(small), _p(mid), max_windows, _p(tau, F32), float(tau_min), c, heads, q.stride(0), k.stride(0), v.stride(0), mq, k.shape[0],
+          _gemm_prec(), _stream(), nbytes=4 * (q.numel() * 2 + k.numel() * 2))
     return o, lse
 
 
@@ -576,7 +603,7 @@ def window_attention_bwd(dout, q, k, v, o, lse, qtok, qcnt, ktok, kcnt, n_win, s
     dsum = torch.empty_like(lse)
     _call("window_attention_bwd", _p(dout, F32), _pv(q), _pv(k), _pv(v), _p(o, F32), _p(lse, F32), _p(dsum), _pv(dq), _pv(dk),
           _pv(dv), _p(dtau, F32), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win), _p(small), _p(mid), max_windows, _p(tau, F32), float(tau_min), q.shape[1],
-          heads, q.stride(0), k.stride(0), v.stride(0), _stream(), nbytes=4 * (q.numel() * 4 + k.numel() * 4))
+          heads, q.stride(0), k.stride(0), v.stride(0), q.shape[0], k.shape[0], _gemm_prec(), _stream(), nbytes=4 * (q.numel() * 4 + k.numel() * 4))
     return dq, dk, dv
 
 
@@ -674,7 +701,7 @@ def encoder_layer_fwd(x, x_kv, params, T, lut, tau_min, eps, heads, need_backwar
     y = torch.empty_like(x)
     P = _layer_params(params)
     _call("encoder_layer_fwd", _p(x, F32), _p(x_kv), ctypes.byref(P), ctypes.byref(T), _p(lut, F32), float(tau_min), float(eps), m_q, m_kv,
-          c, ff, heads, _state["precision"], int(need_backward), _p(y), _p(saved), nb, _stream())
+          c, ff, heads, _gemm_prec(), int(need_backward), _p(y), _p(saved), nb, _stream())
     return y, saved
 
 
@@ -698,5 +725,5 @@ def encoder_layer_bwd(dy, x, x_kv, params, T, lut, tau_min, heads, saved, want_d
     dx = torch.empty_like(x)
     dkv = torch.empty_like(x_kv) if (cross and want_dkv) else None
     _call("encoder_layer_bwd", _p(dy, F32), _p(x, F32), _p(x_kv), ctypes.byref(P), ctypes.byref(T), _p(lut, F32), float(tau_min), m_q, m_kv, c, ff, heads,
-          _state["precision"], _p(saved), saved.numel(), _p(dx), _p(dkv), ctypes.byref(G), _p(scratch), nb, _stream())
+          _gemm_prec(), _p(saved), saved.numel(), _p(dx), _p(dkv), ctypes.byref(G), _p(scratch), nb, _stream())
     return dx, dkv, grads

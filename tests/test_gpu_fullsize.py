@@ -69,7 +69,7 @@ def test_finetune_dense_scans_properties():
     grid = synth.grid_size(shape).tolist()
     pts, ptsp = synth.batch(2000, 2, 120000)
     outs = []
-    ops.set_precision("bf16")
+    ops.set_precision("tf32")
     try:
         for batched in (True, False):
             vfe, bb = tmae_b200.build_model("finetune", grid, shape["voxel"], shape["range"])

@@ -247,7 +247,7 @@ def test_linear_fwd_thin_k(m, n, k, with_bias):
     x, w = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k ** .5
     b = torch.randn(n, generator=g) if with_bias else None
     ref = x.double() @ w.double().T + (b.double() if with_bias else 0)
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "tf32"):
         ops.set_precision(prec)
         try:
             y = ops.linear_fwd(x.to(DEV), w.to(DEV), b.to(DEV) if with_bias else None)
@@ -421,11 +421,11 @@ def _attn_ref(mha, q_in, k_in, v_in, wq, wk, slotq, slotk, nw):
 def test_window_attention_core(C, cross, tc):
     """tc = 1: windows above 16 tokens run on mma.sync TF32 (operands rounded to 10 mantissa bits, fp32 accumulate):
     tolerance 3e-3 instead of the fp32 path's 1e-5 / 1e-4."""
-    ops.set_option("attn_tc", tc)
+    ops.set_precision("tf32" if tc else "fp32")
     try:
         _attention_core_case(C, cross, 3e-3 if tc else None)
     finally:
-        ops.set_option("attn_tc", 0)
+        ops.set_precision("fp32")
 
 
 def _attention_core_case(C, cross, tol):
@@ -483,7 +483,7 @@ def test_window_attention_packed_strides():
     tau = torch.tensor([[[0.4]]], device=DEV)
     args = (P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), ops.mid_end(P, 0), min(P.wcap, m), tau, 0.01, H)
     for tc in (0, 1):
-        ops.set_option("attn_tc", tc)
+        ops.set_precision("tf32" if tc else "fp32")
         try:
             o1, l1 = ops.window_attention_fwd(q, k, v, *args, False)
             o2, l2 = ops.window_attention_fwd(q.contiguous(), k.contiguous(), v.contiguous(), *args, False)
@@ -496,10 +496,10 @@ def test_window_attention_packed_strides():
             for a, b in zip(g1, g2):
                 assert torch.equal(a, b)
         finally:
-            ops.set_option("attn_tc", 0)
+            ops.set_precision("fp32")
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
 @pytest.mark.parametrize("m,c,parts", [(3000, 128, 3), (1700, 256, 3), (900, 128, 1), (5, 256, 2)])
 def test_packed_projection_with_position_table(m, c, parts, prec):
     """y = x W^T + (pos_lut W_pos^T + b)[posidx] against (x + pos) W^T + b in float64, and its backward pieces:

@@ -11,7 +11,7 @@ from tmae_b200._lib import lib  # noqa: E402
 
 m, n, k = (int(v) for v in sys.argv[1:4])
 mode = sys.argv[4] if len(sys.argv) > 4 else "nt"
-ops.set_precision("bf16")
+ops.set_precision("tf32")
 DEV = "cuda"
 xs = [torch.randn(m, k, device=DEV) for _ in range(3)]
 dys = [torch.randn(m, n, device=DEV) for _ in range(3)]

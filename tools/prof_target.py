@@ -11,7 +11,7 @@ from tmae_b200 import ops  # noqa: E402
 
 DEV = "cuda"
 what = sys.argv[1]
-ops.set_precision("bf16")
+ops.set_precision("tf32")
 if what == "nn":
     m, n, k = 50000, 256, 256
     dy, w = torch.randn(m, n, device=DEV), torch.randn(n, k, device=DEV)

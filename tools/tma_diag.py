@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import tmae_b200  # noqa
 from tmae_b200 import ops
 DEV = "cuda"
-ops.set_precision("bf16")
+ops.set_precision("tf32")
 
 def rn(t):
     i = t.float().contiguous().view(torch.int32)
