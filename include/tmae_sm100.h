@@ -332,6 +332,75 @@ TMAE_API int tmae_encoder_layer_bwd(const float* dy, const float* x, const float
                            const void* saved, size_t saved_size, float* dx, float* dx_kv, const tmae_layer_params* G, void* scratch,
                            size_t scratch_size, void* stream);
 
+/* ==== bf16-STORAGE mode (TMAE_PREC_BF16) ==========================================================================
+ * Same reference functions as above (file:line cited there), for callers that keep encoder activations and their gradients
+ * as bf16 rows (rows, channels) in HBM: what the reference itself does under its fp16 autocast
+ * (tools/train_utils/train_utils.py:73-77; normalisation, softmax and LayerNorm statistics stay fp32: cosine_msa.py:151-176).
+ * `void*` activation pointers are bf16 and must be 32-byte aligned; weights are bf16 copies of the fp32 master parameters
+ * (tmae_cast_f32_bf16 / _multi); biases, LayerNorm / BatchNorm parameters, statistics and EVERY parameter gradient are fp32.
+ * All GEMMs run on the TMA-fed tcgen05.mma.kind::f16 kernel (gemm_bf16.cu); there is no other implementation to fall back to. */
+TMAE_API int tmae_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+TMAE_API int tmae_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
+/* segs: DEVICE array of n_seg records {const float* src; void* dst; int64_t n} (24 bytes each): every cast in ONE launch */
+TMAE_API int tmae_cast_f32_bf16_multi(const void* segs, int32_t n_seg, void* stream);
+/* F.linear (cosine_msa.py:57-62,431; sst_basic_block.py:81): y = act(x w^T + bias) [+= y]; preact (nullable) = x w^T + bias */
+TMAE_API int tmae_bf16_linear_fwd(const void* x, const void* w, const float* bias, void* y, void* preact, int64_t m, int64_t n, int64_t k,
+                         int32_t act, int32_t accumulate, void* stream);
+/* packed q/k/v projection (cosine_msa.py:57-62 with q = k = x + pos, sst_basic_block.py:44): y = x w^T + table[posidx], the first
+ * norm_cols columns (q, k) L2-normalised per head of width hd (F.normalize eps 1e-12, cosine_msa.py:151-152);
+ * inv (m, norm_cols / hd) fp32 = 1 / max(|.|, 1e-12).  table (64, n) fp32 from tmae_pos_table. */
+TMAE_API int tmae_bf16_qkv_fwd(const void* x, const void* w, const float* table, const uint8_t* posidx, void* y, float* inv, int64_t m, int64_t n,
+                      int64_t k, int32_t norm_cols, int32_t hd, void* stream);
+/* out_proj / linear2 + residual + LayerNorm in one pass (sst_basic_block.py:78,83; wca_block.py:96-102):
+ * v = res + (rowmask == NULL || rowmask[row] ? a w^T + bias : 0); y = LayerNorm(v) * gamma + beta; n in {128, 256}; v nullable */
+TMAE_API int tmae_bf16_linear_ln_fwd(const void* a, const void* w, const float* bias, const void* res, const uint8_t* rowmask, const float* gamma,
+                            const float* beta, float eps, void* v, void* y, float* mean, float* rstd, int64_t m, int64_t n, int64_t k,
+                            void* stream);
+/* dx = dy w [* gelu'(gelu_pre)] [+= dx] ;  dw (n, k) fp32 = dy^T x (overwrites) */
+TMAE_API int tmae_bf16_linear_bwd_data(const void* dy, const void* w, const void* gelu_pre, void* dx, int64_t m, int64_t n, int64_t k,
+                              int32_t accumulate, void* stream);
+/* onehot (m, 64) bf16 = tmae_onehot64_bf16(posidx), nullable: also dtab_t (n, 64) fp32 = dy^T onehot from the same pass over dy = the
+ * binned column sums behind the position-table gradient (tmae_pos_table_bwd with transposed = 1); needs k % 64 == 0 */
+TMAE_API int tmae_bf16_linear_bwd_weight(const void* dy, const void* x, float* dw, const void* onehot, float* dtab_t, int64_t m, int64_t n,
+                                int64_t k, void* stream);
+TMAE_API int tmae_onehot64_bf16(const uint8_t* idx, void* out, int64_t m, void* stream);
+/* LayerNorm backward from the saved pre-norm sum v: dv = grad wrt v; dres (nullable) = dv on rows with rowmask != 0 else 0;
+ * dcolsum (nullable, fp32) = column sums of dres when written, else of dv (the bias gradient of the producing linear layer) */
+TMAE_API int tmae_bf16_layernorm_bwd(const void* dy, const void* v, const uint8_t* rowmask, const float* gamma, const float* mean, const float* rstd,
+                            void* dv, void* dres, float* dgamma, float* dbeta, float* dcolsum, int64_t rows, int32_t c, void* stream);
+TMAE_API int tmae_bf16_colsum(const void* x, float* out, int64_t rows, int32_t cols, void* stream);
+TMAE_API int tmae_bf16_binned_colsum(const void* dy, const uint8_t* rowidx, float* dtable, int64_t rows, int32_t n, void* stream);
+/* sparse convolution (spconv_utils.py:37-56) on bf16 rows: gathered tcgen05 GEMMs; w (cout, taps, cin) bf16; dw fp32 */
+TMAE_API int tmae_bf16_sparse_conv_fwd(const void* x, const int32_t* table, const void* w, void* y, int64_t rows_out, int32_t taps, int32_t cin,
+                              int32_t cout, void* stream);
+TMAE_API int tmae_bf16_sparse_conv_bwd_weight(const void* dy, const void* x, const int32_t* table, float* dw, int64_t rows_out, int32_t taps,
+                                     int32_t cin, int32_t cout, void* stream);
+TMAE_API int tmae_transpose_taps_bf16(const float* w, void* wt, int32_t cout, int32_t taps, int32_t cin, int32_t flip, void* stream);
+/* SparseConvTensor.dense() / the BEV gather with 16-bit rows AND a 16-bit map */
+TMAE_API int tmae_densify_nhwc_b16(const void* rows, const int32_t* indices, int64_t m, int32_t c, int32_t batch, int32_t y, int32_t x, void* dense,
+                          int32_t zero_fill, void* stream);
+TMAE_API int tmae_gather_nhwc_b16(const void* dense, const int32_t* indices, int64_t m, int32_t c, int32_t y, int32_t x, void* rows, void* stream);
+/* dst = bf16(src * (col < norm_cols ? scale[row, col / hd] : 1)) */
+TMAE_API int tmae_scale_cast_bf16(const float* src, const float* scale, void* dst, int64_t rows, int32_t n, int32_t norm_cols, int32_t hd, void* stream);
+/* whole encoder layer (see tmae_encoder_layer_fwd): x, x_kv, y, dy, dx, dx_kv are bf16; P = fp32 master parameters (biases, LayerNorm,
+ * tau and the weights behind the position table), W = bf16 copies of the four weight matrices, G = fp32 gradient buffers. */
+typedef struct tmae_bf16_weights {
+  const void *in_w, *out_w, *w1, *w2;
+} tmae_bf16_weights;
+TMAE_API size_t tmae_bf16_encoder_layer_saved_bytes(int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t cross);
+TMAE_API size_t tmae_bf16_encoder_layer_scratch_bytes(int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t cross);
+TMAE_API int tmae_bf16_encoder_layer_fwd(const void* x, const void* x_kv, const tmae_layer_params* P, const tmae_bf16_weights* W,
+                                const tmae_layer_tables* T, const float* pos_lut, float tau_min, float eps, int64_t m_q, int64_t m_kv, int32_t c,
+                                int32_t ff, int32_t heads, int32_t need_backward, void* y, void* saved, size_t saved_size, void* stream);
+TMAE_API int tmae_bf16_encoder_layer_bwd(const void* dy, const void* x, const void* x_kv, const tmae_layer_params* P, const tmae_bf16_weights* W,
+                                const tmae_layer_tables* T, const float* pos_lut, float tau_min, int64_t m_q, int64_t m_kv, int32_t c, int32_t ff,
+                                int32_t heads, const void* saved, size_t saved_size, void* dx, void* dx_kv, const tmae_layer_params* G,
+                                void* scratch, size_t scratch_size, void* stream);
+/* which attention core the bf16 layers use: 1 = tcgen05 window kernel (attention_tc.cu), 0 = cast bridge to the fp32-I/O mma.sync
+ * kernels (kept as the checker of the former; measurement switch, process-wide) */
+TMAE_API int tmae_bf16_set_attention_impl(int32_t impl);
+TMAE_API int tmae_bf16_attention_tc_available(void); /* 1 iff the tcgen05 window-attention kernel is built into this library */
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,31 @@ class _LayerFn(torch.autograd.Function):
         return (dx, dkv, None, None, None, None, None, None, *grads)
 
 
+class _LayerFnBF16(torch.autograd.Function):
+    """_LayerFn in the bf16-storage mode (tmae_bf16_encoder_layer_fwd / _bwd): bf16 rows in and out, fp32 master parameters and
+    parameter gradients, bf16 weight copies from ops.shadows."""
+
+    @staticmethod
+    def forward(ctx, x, x_kv, part, shift, lut, heads, tau_min, eps, *params):
+        x = x.contiguous()
+        if x_kv is not None:
+            x_kv = x_kv.contiguous()
+        T = ops.layer_tables(part, shift, x_kv is not None, x.shape[0], x_kv.shape[0] if x_kv is not None else 0)
+        need_bwd = any(ctx.needs_input_grad)
+        y, saved = ops.encoder_layer_fwd_bf16(x, x_kv, params, T, lut, tau_min, eps, heads, need_bwd)
+        ctx.save_for_backward(x, x_kv, saved, lut, *params)
+        ctx.misc = (T, part, heads, tau_min)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, x_kv, saved, lut, *params = ctx.saved_tensors
+        T, _, heads, tau_min = ctx.misc
+        dx, dkv, grads = ops.encoder_layer_bwd_bf16(dy.contiguous(), x, x_kv, params, T, lut, tau_min, heads, saved,
+                                                    x_kv is not None and ctx.needs_input_grad[1])
+        return (dx, dkv, None, None, None, None, None, None, *grads)
+
+
 class EncoderLayer(nn.Module):
     def __init__(self, C, H, FF, layer_cfg, cross):
         super().__init__()
@@ -113,10 +138,12 @@ class EncoderLayer(nn.Module):
                 self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias, self.norm2.weight, self.norm2.bias)
 
     def forward_self(self, x, part, shift, lut):
-        return _LayerFn.apply(x, None, part, shift, lut, self.nhead, self.tau_min, self.norm1.eps, *self._params())
+        fn = _LayerFnBF16 if x.dtype == torch.bfloat16 else _LayerFn
+        return fn.apply(x, None, part, shift, lut, self.nhead, self.tau_min, self.norm1.eps, *self._params())
 
     def forward_cross(self, x, xprev, tp, shift, lut):
-        return _LayerFn.apply(x, xprev, tp, shift, lut, self.nhead, self.tau_min, self.norm1.eps, *self._params())
+        fn = _LayerFnBF16 if x.dtype == torch.bfloat16 else _LayerFn
+        return fn.apply(x, xprev, tp, shift, lut, self.nhead, self.tau_min, self.norm1.eps, *self._params())
 
 
 class ShiftBlock(nn.Module):
@@ -290,9 +317,17 @@ class SiamWCA(nn.Module):
         # host-to-device copy and a sync per call)
         return torch.stack((coords[:, 0], coords[:, 2], coords[:, 3]), 1).int()
 
+    def _bf16(self):
+        """bf16-storage mode (ops.set_precision("bf16")): encoder rows travel as bf16 from the VFE output to the BEV map."""
+        if ops.precision() != ops.PREC_BF16:
+            return False
+        if self.decoder_autocast != torch.bfloat16:
+            raise RuntimeError("the bf16-storage mode needs the bf16 decoder (decoder_autocast = torch.bfloat16)")
+        return True
+
     def _encode(self, feats, fp):
         hidden = []
-        x = feats
+        x = feats.to(torch.bfloat16) if self._bf16() else feats
         for blk, st in zip(self.sst_blocks, fp.stages):
             x = blk(x, st)
             hidden.append(x)
@@ -305,6 +340,8 @@ class SiamWCA(nn.Module):
         reference (SiamWCA_MAE.py:265-284 / SiamWCA.py:630-640).  Halves the launches of the encoder."""
         hid, hid_prev = [], []
         x = torch.cat([feats, feats_prev], 0)
+        if self._bf16():
+            x = x.to(torch.bfloat16)
         for blk, st, st_cur in zip(self.sst_blocks, fp_all.stages, fp_cur.stages):
             x = blk(x, st, (0, st_cur.m, st.m), (1, 0))
             hid.append(x[:st_cur.m])
@@ -382,6 +419,18 @@ class SiamWCA(nn.Module):
         B = int(bd["batch_size"])
         plans, tparts = self._prepass(bd, lambda: self._geometry(bd, coords, coords_prev)) if geom is None else geom
         self.last_plan = (plans, tparts)
+        if self._bf16():
+            # bf16 copies of the tensor-core weight operands: all registered up front so that every copy whose fp32 master
+            # changed (an optimizer step) is refreshed by ONE launch here
+            ws = []
+            for m in self.modules():
+                if isinstance(m, EncoderLayer):
+                    p = m._params()
+                    ws += [p[0], p[2], p[7], p[9]]
+                elif isinstance(m, ConvBNReLU):
+                    ws.append(m._modules["0"].weight)
+            ops.shadows.register(ws)
+            ops.shadows.refresh()
         if self.siamese_batched:
             hid, hid_prev = self._encode_siamese(feats, feats_prev, plans[2], plans[0])
         else:

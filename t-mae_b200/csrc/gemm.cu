@@ -470,8 +470,9 @@ int tmae_linear_bwd_weight(const float* dy, const float* x, float* dw, float* db
     if (tma_linear_bwd_weight(dy, x, dw, m, n, k, s)) { set_error("tmae_linear_bwd_weight: TMA launch failed"); return TMAE_ERR_CUDA; }
     count_dispatch(DISP_TMA);
   } else {
-    count_simt(precision);
-  GemmArgs g{};
+    // k <= 16 (the first VFE layer, k = 10: a 40-byte row pitch no tensor map can describe) is the thin-k family in every mode
+    if (k <= 16) count_dispatch(DISP_THIN_K); else count_simt(precision);
+    GemmArgs g{};
     g.A = dy; g.B = x; g.C = dw; g.M = n; g.N = k; g.K = m; g.lda = n; g.ldb = k; g.ldc = k;
     int splits = pick_splits((int64_t)cdiv(n, BM) * cdiv(k, BN), m);
     if (m > 0 && launch<A_MCONTIG, B_NCONTIG>(g, splits, s)) { set_error("tmae_linear_bwd_weight: launch failed"); return TMAE_ERR_CUDA; }

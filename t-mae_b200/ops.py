@@ -27,8 +27,8 @@ def set_precision(p):
     _state["precision"] = PRECISIONS[p]
 
 
-BF16_READY = False
-BENCH_PRECISION = "tf32"   # the mode bench.py and smoke() run by default
+BF16_READY = True
+BENCH_PRECISION = "bf16"   # the mode bench.py and smoke() run by default
 
 
 def precision():
@@ -179,7 +179,7 @@ def _ws(nbytes, device):
     return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
 
 
-F32, I32, I64, U8 = torch.float32, torch.int32, torch.int64, torch.uint8
+F32, I32, I64, U8, BF16 = torch.float32, torch.int32, torch.int64, torch.uint8, torch.bfloat16
 
 
 # ------------------------------------------------------------------------------------ voxelise
@@ -287,8 +287,11 @@ def window_partition(coords_a, batch, grid_x, grid_y, levels, coords_b=None, wan
           _p(P.win_level), _p(P.n_win), _p(P.level_base), P.status.data_ptr(), *ra, *rb, _p(ws), wsb, _stream())
     P.keep_a = P.keep_b = None
     # (2, m, 64) one-hot form of posidx: second A operand of the packed q/k/v projection in tensor-core mode
-    P.onehot_a = onehot64(P.posidx_a) if (_state["precision"] == PREC_TF32 and P.m_a > 0) else None
-    P.onehot_b = onehot64(P.posidx_b) if (_state["precision"] == PREC_TF32 and P.temporal and P.m_b > 0) else None
+    # (2, m, 64) one-hot form of posidx: second operand of the packed q/k/v projection (tf32 mode, fp32) / of its weight-gradient
+    # GEMM (bf16 mode, bf16)
+    oh = onehot64 if _state["precision"] == PREC_TF32 else (onehot64_bf16 if _state["precision"] == PREC_BF16 else None)
+    P.onehot_a = oh(P.posidx_a) if (oh and P.m_a > 0) else None
+    P.onehot_b = oh(P.posidx_b) if (oh and P.temporal and P.m_b > 0) else None
     return P
 
 
@@ -340,6 +343,13 @@ def linear_fwd_dual(x, w, x2, w2):
     _call("linear_fwd_dual", _p(x, F32), _p(w, F32), _p(x2, F32), _p(w2, F32), _p(y), m, n, k, k2, _gemm_prec(), _stream(),
           flops=2 * m * n * (k + k2), nbytes=4 * (m * (k + k2) + n * (k + k2) + m * n))
     return y
+
+
+def onehot64_bf16(idx):
+    """idx (..., m) u8 -> (..., m, 64) bf16 one-hot."""
+    out = torch.empty(*idx.shape, 64, dtype=BF16, device=idx.device)
+    _call("onehot64_bf16", _p(idx, U8), out.data_ptr(), idx.numel(), _stream())
+    return out
 
 
 def binned_colsum(dy, rowidx):
@@ -495,9 +505,6 @@ def bn_bwd(dy, x, beta, mean, rstd, gamma, relu, training, out=None):
     return dx, dgamma, dbeta
 
 
-BF16 = torch.bfloat16
-
-
 def bn_bf16_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, relu, training, out, mean=None, rstd=None):
     """x (rows, C) bf16 contiguous; out (rows, C) bf16 view with any row pitch (a column slice of the concat buffer)."""
     L = lib()
@@ -514,13 +521,13 @@ def bn_bf16_fwd(x, gamma, beta, running_mean, running_var, momentum, eps, relu, 
     return mean, rstd
 
 
-def bn_bf16_bwd(dy, x, mean, rstd, gamma, beta, relu, training):
+def bn_bf16_bwd(dy, x, mean, rstd, gamma, beta, relu, training, out=None):
     """dy (rows, C) bf16 view with any row pitch; x (rows, C) bf16 contiguous -> dx bf16 contiguous, dgamma, dbeta."""
     L = lib()
     rows, c = x.shape
     if not (dy.dtype == BF16 and x.dtype == BF16 and dy.stride(1) == 1 and x.stride(1) == 1):
         raise RuntimeError("bn_bf16_bwd needs bf16 tensors with unit column stride")
-    dx = torch.empty(rows, c, dtype=BF16, device=x.device)
+    dx = torch.empty(rows, c, dtype=BF16, device=x.device) if out is None else out
     dgamma = torch.empty(c, dtype=F32, device=x.device)
     dbeta = torch.empty(c, dtype=F32, device=x.device)
     wsb = L.bn_workspace_bytes(c)
@@ -726,4 +733,249 @@ def encoder_layer_bwd(dy, x, x_kv, params, T, lut, tau_min, heads, saved, want_d
     dkv = torch.empty_like(x_kv) if (cross and want_dkv) else None
     _call("encoder_layer_bwd", _p(dy, F32), _p(x, F32), _p(x_kv), ctypes.byref(P), ctypes.byref(T), _p(lut, F32), float(tau_min), m_q, m_kv, c, ff, heads,
           _gemm_prec(), _p(saved), saved.numel(), _p(dx), _p(dkv), ctypes.byref(G), _p(scratch), nb, _stream())
+    return dx, dkv, grads
+
+
+# ==================================================================================== bf16-storage mode
+def _pb(t):
+    """pointer of a contiguous bf16 CUDA tensor (32-byte aligned: the TMEM epilogues store 256-bit words)."""
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == BF16 and t.is_contiguous()):
+        raise RuntimeError("expected a contiguous bf16 CUDA tensor")
+    if t.data_ptr() % 32:
+        raise RuntimeError("bf16 activations must be 32-byte aligned")
+    return t.data_ptr()
+
+
+def cast_bf16(x):
+    """fp32 -> bf16 copy (round to nearest even)."""
+    y = torch.empty(x.shape, dtype=BF16, device=x.device)
+    _call("cast_f32_bf16", _p(x, F32), y.data_ptr(), x.numel(), _stream())
+    return y
+
+
+def cast_f32(x):
+    y = torch.empty(x.shape, dtype=F32, device=x.device)
+    _call("cast_bf16_f32", _p(x, BF16), y.data_ptr(), x.numel(), _stream())
+    return y
+
+
+class WeightShadows:
+    """bf16 copies of fp32 master weights (the tensor-core operands of the bf16 mode), refreshed when the master changes
+    (`Tensor._version` moves on every in-place optimizer update): ALL stale copies in one launch through a device-resident
+    segment table that is built once (the parameters and their shadows never move)."""
+
+    def __init__(self):
+        self.items = {}      # id(param) -> [param, shadow, version]
+        self.table = None    # (n, 3) int64 device: src ptr, dst ptr, numel
+        self.order = []
+
+    def _fresh(self, p):
+        it = self.items.get(id(p))
+        if it is None or it[0] is not p or it[3] != p.data_ptr():   # new parameter, or its storage moved (module.to(...), p.data = ...)
+            it = self.items[id(p)] = [p, torch.empty(p.shape, dtype=BF16, device=p.device), -1, p.data_ptr()]
+            self.table = None
+        return it
+
+    def get(self, p):
+        it = self._fresh(p)
+        if it[2] != p._version:
+            self.refresh()
+        return it[1]
+
+    def register(self, params):
+        for p in params:
+            self._fresh(p)
+
+    def refresh(self):
+        for key in [k for k, it in self.items.items() if it[3] != it[0].data_ptr()]:   # storage moved: re-create
+            self._fresh(self.items[key][0])
+        stale = [it for it in self.items.values() if it[2] != it[0]._version]
+        if not stale:
+            return
+        dev = stale[0][0].device
+        if len(stale) == len(self.items):
+            if self.table is None or self.table.device != dev:
+                self.order = list(self.items.values())
+                self.table = torch.tensor([[it[0].data_ptr(), it[1].data_ptr(), it[0].numel()] for it in self.order], dtype=I64, device=dev)
+            table, n = self.table, len(self.order)
+        else:
+            table = torch.tensor([[it[0].data_ptr(), it[1].data_ptr(), it[0].numel()] for it in stale], dtype=I64, device=dev)
+            n = len(stale)
+        _call("cast_f32_bf16_multi", table.data_ptr(), n, _stream())
+        for it in stale:
+            it[2] = it[0]._version
+        self._keep = table   # alive until the next refresh (the launch reads it asynchronously)
+
+
+shadows = WeightShadows()
+
+
+def bf16_linear_fwd(x, w, bias=None, act=ACT_NONE, want_preact=False, out=None, accumulate=False):
+    m, k = x.shape
+    n = w.shape[0]
+    y = torch.empty(m, n, dtype=BF16, device=x.device) if out is None else out
+    pre = torch.empty(m, n, dtype=BF16, device=x.device) if want_preact else None
+    _call("bf16_linear_fwd", _pb(x), _pb(w), _p(bias, F32), _pb(y), _pb(pre), m, n, k, act, int(accumulate), _stream())
+    return (y, pre) if want_preact else y
+
+
+def bf16_qkv_fwd(x, w, table, posidx, norm_cols, hd):
+    m, k = x.shape
+    n = w.shape[0]
+    y = torch.empty(m, n, dtype=BF16, device=x.device)
+    inv = torch.empty(m, norm_cols // hd, dtype=F32, device=x.device)
+    _call("bf16_qkv_fwd", _pb(x), _pb(w), _p(table, F32), _p(posidx, U8), _pb(y), _p(inv), m, n, k, norm_cols, hd, _stream())
+    return y, inv
+
+
+def bf16_linear_ln_fwd(a, w, bias, res, rowmask, gamma, beta, eps, want_v=True):
+    m, k = a.shape
+    n = w.shape[0]
+    y = torch.empty(m, n, dtype=BF16, device=a.device)
+    v = torch.empty(m, n, dtype=BF16, device=a.device) if want_v else None
+    mean = torch.empty(max(1, m), dtype=F32, device=a.device)
+    rstd = torch.empty(max(1, m), dtype=F32, device=a.device)
+    _call("bf16_linear_ln_fwd", _pb(a), _pb(w), _p(bias, F32), _pb(res), _p(rowmask, U8), _p(gamma, F32), _p(beta, F32), float(eps), _pb(v), _pb(y),
+          _p(mean), _p(rstd), m, n, k, _stream())
+    return y, v, mean, rstd
+
+
+def bf16_linear_bwd_data(dy, w, gelu_pre=None, dx=None, accumulate=False):
+    m, n = dy.shape
+    k = w.shape[1]
+    if dx is None:
+        dx = torch.empty(m, k, dtype=BF16, device=dy.device)
+        accumulate = False
+    _call("bf16_linear_bwd_data", _pb(dy), _pb(w), _pb(gelu_pre), _pb(dx), m, n, k, int(accumulate), _stream())
+    return dx
+
+
+def bf16_linear_bwd_weight(dy, x, onehot=None):
+    """-> dw (n, k) fp32 [, dtab_t (n, 64) fp32 = dy^T onehot when onehot (m, 64) bf16 is given]."""
+    m, n = dy.shape
+    k = x.shape[1]
+    dw = torch.empty(n, k, dtype=F32, device=dy.device)
+    dt = torch.empty(n, 64, dtype=F32, device=dy.device) if onehot is not None else None
+    _call("bf16_linear_bwd_weight", _pb(dy), _pb(x), _p(dw), _pb(onehot), _p(dt), m, n, k, _stream())
+    return dw if onehot is None else (dw, dt)
+
+
+def bf16_layernorm_bwd(dy, v, rowmask, gamma, mean, rstd, want_dres=False, want_colsum=False):
+    rows, c = v.shape
+    dv = torch.empty_like(v)
+    dres = torch.empty_like(v) if want_dres else None
+    dg = torch.empty(c, dtype=F32, device=v.device)
+    db = torch.empty(c, dtype=F32, device=v.device)
+    dc = torch.empty(c, dtype=F32, device=v.device) if want_colsum else None
+    _call("bf16_layernorm_bwd", _pb(dy), _pb(v), _p(rowmask, U8), _p(gamma, F32), _p(mean, F32), _p(rstd, F32), _pb(dv), _pb(dres), _p(dg), _p(db),
+          _p(dc), rows, c, _stream())
+    return dv, dres, dg, db, dc
+
+
+def bf16_colsum(x):
+    out = torch.empty(x.shape[1], dtype=F32, device=x.device)
+    _call("bf16_colsum", _pb(x), _p(out), x.shape[0], x.shape[1], _stream())
+    return out
+
+
+def bf16_binned_colsum(dy, rowidx):
+    t = torch.empty(64, dy.shape[1], dtype=F32, device=dy.device)
+    _call("bf16_binned_colsum", _pb(dy), _p(rowidx, U8), _p(t), dy.shape[0], dy.shape[1], _stream())
+    return t
+
+
+def bf16_sparse_conv_fwd(x, table, w, rows_out):
+    """x (rows_in, cin) bf16, w (cout, taps, cin) or (cout, kh, kw, cin) bf16 -> (rows_out, cout) bf16."""
+    cout, cin = w.shape[0], w.shape[-1]
+    taps = w.numel() // (cout * cin)
+    y = torch.empty(rows_out, cout, dtype=BF16, device=x.device)
+    _call("bf16_sparse_conv_fwd", _pb(x), _p(table, I32), _pb(w), _pb(y), rows_out, taps, cin, cout, _stream())
+    return y
+
+
+def bf16_sparse_conv_bwd_weight(dy, x, table, w_shape):
+    cout, taps, cin = w_shape[0], w_shape[1] * w_shape[2], w_shape[3]
+    dw = torch.empty(w_shape, dtype=F32, device=x.device)
+    _call("bf16_sparse_conv_bwd_weight", _pb(dy), _pb(x), _p(table, I32), _p(dw), dy.shape[0], taps, cin, cout, _stream())
+    return dw
+
+
+def transpose_taps_bf16(w, flip):
+    cout, taps, cin = w.shape[0], w.shape[1] * w.shape[2], w.shape[3]
+    wt = torch.empty(cin, taps, cout, dtype=BF16, device=w.device)
+    _call("transpose_taps_bf16", _p(w, F32), wt.data_ptr(), cout, taps, cin, int(flip), _stream())
+    return wt
+
+
+def densify_nhwc_b16(rows, indices, batch, Y, X):
+    m, c = rows.shape
+    dense = torch.empty(batch, Y, X, c, dtype=BF16, device=rows.device)
+    _call("densify_nhwc_b16", _pb(rows), _p(indices, I32), m, c, batch, Y, X, dense.data_ptr(), 1, _stream())
+    return dense
+
+
+def gather_nhwc_b16(dense, indices):
+    _, Y, X, c = dense.shape
+    m = indices.shape[0]
+    rows = torch.empty(m, c, dtype=BF16, device=dense.device)
+    _call("gather_nhwc_b16", _pb(dense), _p(indices, I32), m, c, Y, X, _pb(rows), _stream())
+    return rows
+
+
+class BF16Weights(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("in_w", "out_w", "w1", "w2")]
+
+
+def attention_tc_available():
+    return bool(lib().cdll.tmae_bf16_attention_tc_available())
+
+
+def set_attention_impl(impl):
+    """bf16 layers: 1 = tcgen05 window-attention kernel, 0 = cast bridge to the fp32-I/O mma.sync kernels (checker)."""
+    lib().bf16_set_attention_impl(int(impl))
+    _state["attn_impl"] = int(impl)
+
+
+def encoder_layer_fwd_bf16(x, x_kv, params, T, lut, tau_min, eps, heads, need_backward=True):
+    """bf16-storage form of encoder_layer_fwd: x, x_kv bf16; params = the 13 fp32 master tensors."""
+    L = lib()
+    m_q, c = x.shape
+    m_kv = x_kv.shape[0] if x_kv is not None else m_q
+    ff = params[7].shape[0]
+    cross = int(x_kv is not None)
+    nb = L.bf16_encoder_layer_saved_bytes(m_q, m_kv, c, ff, heads, cross)
+    saved = _ws(nb, x.device)
+    y = torch.empty_like(x)
+    P = _layer_params(params)
+    W = BF16Weights()
+    W.in_w, W.out_w, W.w1, W.w2 = (_pb(shadows.get(params[i])) for i in (0, 2, 7, 9))
+    _call("bf16_encoder_layer_fwd", _pb(x), _pb(x_kv), ctypes.byref(P), ctypes.byref(W), ctypes.byref(T), _p(lut, F32), float(tau_min), float(eps),
+          m_q, m_kv, c, ff, heads, int(need_backward), _pb(y), _p(saved), nb, _stream())
+    return y, saved
+
+
+def encoder_layer_bwd_bf16(dy, x, x_kv, params, T, lut, tau_min, heads, saved, want_dkv):
+    L = lib()
+    m_q, c = x.shape
+    m_kv = x_kv.shape[0] if x_kv is not None else m_q
+    ff = params[7].shape[0]
+    cross = int(x_kv is not None)
+    sizes = [t.numel() for t in params]
+    offs = [0]
+    for n in sizes:
+        offs.append(offs[-1] + (n + 63) // 64 * 64)
+    gbuf = torch.empty(offs[-1], dtype=F32, device=x.device)
+    grads = [gbuf[o:o + n].view(t.shape) for o, n, t in zip(offs, sizes, params)]
+    G = _layer_params(grads)
+    P = _layer_params(params)
+    W = BF16Weights()
+    W.in_w, W.out_w, W.w1, W.w2 = (_pb(shadows.get(params[i])) for i in (0, 2, 7, 9))
+    nb = L.bf16_encoder_layer_scratch_bytes(m_q, m_kv, c, ff, heads, cross)
+    scratch = _ws(nb, x.device)
+    dx = torch.empty_like(x)
+    dkv = torch.empty_like(x_kv) if (cross and want_dkv) else None
+    _call("bf16_encoder_layer_bwd", _pb(dy), _pb(x), _pb(x_kv), ctypes.byref(P), ctypes.byref(W), ctypes.byref(T), _p(lut, F32), float(tau_min),
+          m_q, m_kv, c, ff, heads, _p(saved), saved.numel(), _pb(dx), _pb(dkv), ctypes.byref(G), _p(scratch), nb, _stream())
     return dx, dkv, grads

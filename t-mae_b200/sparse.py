@@ -18,11 +18,19 @@ class _DensifyFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rows, indices, batch, Y, X, dtype):
         ctx.save_for_backward(indices)
+        ctx.b16 = rows.dtype == torch.bfloat16
+        if ctx.b16:   # bf16-storage mode: 16-bit rows into a 16-bit map, plain 16-byte copies
+            if dtype != torch.bfloat16:
+                raise RuntimeError("bf16 rows densify into a bf16 map (set decoder_autocast = torch.bfloat16)")
+            return ops.densify_nhwc_b16(rows.contiguous(), indices, batch, Y, X)
         return ops.densify_nhwc(rows.contiguous(), indices, batch, Y, X, dtype)
 
     @staticmethod
     def backward(ctx, d):
         (indices,) = ctx.saved_tensors
+        if ctx.b16:
+            d = d.contiguous()
+            return ops.gather_nhwc_b16(d if d.dtype == torch.bfloat16 else d.bfloat16(), indices), None, None, None, None, None
         return ops.gather_nhwc(d.contiguous(), indices), None, None, None, None, None
 
 
@@ -57,7 +65,7 @@ class SparseConvTensor:
         return SparseConvTensor(f, self.indices, self.spatial_shape, self.batch_size)
 
     def dense(self, dtype=torch.float32):
-        """(B, C, Y, X), stored channels-last; dtype fp32 or bf16 (features stay fp32)."""
+        """(B, C, Y, X), stored channels-last; dtype fp32 or bf16 (bf16 features need a bf16 map)."""
         Y, X = self.spatial_shape
         return _DensifyFn.apply(self.features, self.indices, self.batch_size, Y, X, dtype).permute(0, 3, 1, 2)
 
@@ -83,6 +91,27 @@ class _SparseConvFn(torch.autograd.Function):
         return dx, dw, None, None, None, None
 
 
+class _SparseConvFnBF16(torch.autograd.Function):
+    """_SparseConvFn in the bf16-storage mode: bf16 rows, bf16 copies of the fp32 master weight (ops.shadows), gathered
+    tcgen05 kind::f16 GEMMs, fp32 weight gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w, table, table_t, flip, rows_out):
+        ctx.save_for_backward(x, w, table, table_t)
+        ctx.flip = flip
+        return ops.bf16_sparse_conv_fwd(x, table, ops.shadows.get(w), rows_out)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, table, table_t = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.bf16_sparse_conv_fwd(dy, table_t, ops.transpose_taps_bf16(w, ctx.flip), x.shape[0])
+        dw = ops.bf16_sparse_conv_bwd_weight(dy, x, table, w.shape)
+        return dx, dw, None, None, None, None
+
+
 class SparseConvWeight(nn.Module):
     def __init__(self, cin, cout, k=3):
         super().__init__()
@@ -98,5 +127,6 @@ class ConvBNReLU(nn.Module):
         self.add_module("2", nn.ReLU())
 
     def forward(self, feats, table, table_t, flip, rows_out, bounds=None, order=None):
-        y = _SparseConvFn.apply(feats.contiguous(), self._modules["0"].weight, table, table_t, flip, rows_out)
+        fn = _SparseConvFnBF16 if feats.dtype == torch.bfloat16 else _SparseConvFn
+        y = fn.apply(feats.contiguous(), self._modules["0"].weight, table, table_t, flip, rows_out)
         return bn_relu(y, self._modules["1"], relu=True, bounds=bounds, order=order)

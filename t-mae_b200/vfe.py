@@ -96,6 +96,47 @@ class _BnReluSegFn(torch.autograd.Function):
         return dx, dg, db, None, None, None, None, None, None, None, None
 
 
+class _BnReluSegFnBF16(torch.autograd.Function):
+    """_BnReluSegFn on bf16 rows (the bf16-storage mode after the sparse convolutions): fp32 statistics and arithmetic,
+    bf16 in and out (tmae_bn_bf16_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, training, relu, bounds, order):
+        y = torch.empty_like(x)
+        stats = [None] * (len(bounds) - 1)
+        for i in order:
+            a, b = bounds[i], bounds[i + 1]
+            if b <= a:
+                continue
+            if training:
+                mean, rstd = ops.bn_bf16_fwd(x[a:b], gamma, beta, running_mean, running_var, momentum, eps, relu, True, y[a:b])
+            else:
+                mean, rstd = running_mean, torch.rsqrt(running_var + eps)
+                ops.bn_bf16_fwd(x[a:b], gamma, beta, None, None, 0.0, eps, relu, False, y[a:b], mean, rstd)
+            stats[i] = (mean, rstd)
+        ctx.save_for_backward(x, beta, gamma, *[t for s in stats if s is not None for t in s])
+        ctx.misc = (relu, training, bounds, [s is not None for s in stats])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, beta, gamma, *flat = ctx.saved_tensors
+        relu, training, bounds, present = ctx.misc
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dg = db = None
+        k = 0
+        for i, has in enumerate(present):
+            if not has:
+                continue
+            mean, rstd = flat[2 * k], flat[2 * k + 1]
+            k += 1
+            a, b = bounds[i], bounds[i + 1]
+            _, g, bb = ops.bn_bf16_bwd(dy[a:b], x[a:b], mean, rstd, gamma, beta, relu, training, out=dx[a:b])
+            dg, db = (g, bb) if dg is None else (dg + g, db + bb)
+        return dx, dg, db, None, None, None, None, None, None, None, None
+
+
 def bn_relu(x, bn, relu=True, bounds=None, order=None):
     """Applies an nn.BatchNorm1d's parameters/buffers with the library kernels (train or eval).  `bounds` = row
     boundaries [0, m0, m0+m1, ...] of segments normalised independently, visited in `order`."""
@@ -103,6 +144,11 @@ def bn_relu(x, bn, relu=True, bounds=None, order=None):
     n_seg = 1 if bounds is None else sum(1 for i in range(len(bounds) - 1) if bounds[i + 1] > bounds[i])
     if training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += n_seg
+    if x.dtype == torch.bfloat16:
+        bounds = (0, x.shape[0]) if bounds is None else bounds
+        order = list(range(len(bounds) - 1)) if order is None else order
+        return _BnReluSegFnBF16.apply(x.contiguous(), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, training, relu,
+                                      tuple(int(b) for b in bounds), tuple(order))
     if bounds is None:
         return _BnReluFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, training, relu)
     order = list(range(len(bounds) - 1)) if order is None else order

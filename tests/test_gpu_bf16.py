@@ -1,0 +1,281 @@
+"""GPU tests of the bf16-STORAGE kernels (gemm_bf16.cu, rowops_bf16.cu, layer_bf16.cu) against float64 references
+computed on the SAME bf16-rounded operands: products of bf16 values are exact in fp32 and the accumulator is fp32 (TMEM),
+so a result differs from float64 only by the accumulation order and by the final rounding of the OUTPUT to bf16
+(half an ulp = 2^-9 = 2e-3 relative) -- tolerance rtol 4e-3 + a small atol for bf16 outputs, 1e-4-class for fp32 outputs
+(weight gradients, statistics).  Every GEMM test asserts through tmae_dispatch_counts that the tcgen05 kernel ran."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import assert_close
+from oracle import restated
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import tmae_b200  # noqa: F401
+    from tmae_b200 import ops
+
+DEV = "cuda"
+BF = torch.bfloat16
+RT, AT = 4e-3, 2e-3
+
+
+def rb(t):
+    """fp32 -> bf16-rounded values as float64."""
+    return t.to(BF).double()
+
+
+def dev_bf(t):
+    return t.to(BF).to(DEV).contiguous()
+
+
+@pytest.fixture(autouse=True)
+def _counts():
+    before = ops.dispatch_counts()
+    yield
+    after = ops.dispatch_counts()
+    assert after["simt_in_tc_mode"] == before["simt_in_tc_mode"]
+
+
+def test_casts_and_shadows():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1000, 37, generator=g)
+    y = ops.cast_bf16(x.to(DEV))
+    assert torch.equal(y.cpu(), x.to(BF))
+    assert torch.equal(ops.cast_f32(y).cpu(), x.to(BF).float())
+    ps = [torch.nn.Parameter(torch.randn(n, generator=g).to(DEV)) for n in (5, 64, 1000, 12345)]
+    sh = ops.WeightShadows()
+    sh.register(ps)
+    sh.refresh()
+    for p in ps:
+        assert torch.equal(sh.get(p), p.detach().to(BF))
+    with torch.no_grad():
+        ps[2].add_(1.0)          # in-place update bumps _version: exactly that shadow is refreshed
+    assert torch.equal(sh.get(ps[2]), ps[2].detach().to(BF))
+    with torch.no_grad():
+        for p in ps:
+            p.mul_(0.5)
+    sh.refresh()
+    for p in ps:
+        assert torch.equal(sh.get(p), p.detach().to(BF))
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (1, 128, 64), (1000, 128, 128), (333, 256, 128), (2049, 256, 512), (4100, 512, 256),
+                                   (5000, 384, 128), (777, 768, 256), (130, 64, 96)])
+def test_bf16_linear_fwd_bwd(m, n, k):
+    g = torch.Generator().manual_seed(m + n + k)
+    x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k ** .5, torch.randn(n, generator=g)
+    xd, wd, bd = dev_bf(x), dev_bf(w), b.to(DEV)
+    before = ops.dispatch_counts()["tma"]
+    lin = rb(x) @ rb(w).T + b.double()
+    for act, f in ((ops.ACT_NONE, lambda t: t), (ops.ACT_GELU, F.gelu), (ops.ACT_RELU, F.relu)):
+        y, pre = ops.bf16_linear_fwd(xd, wd, bd, act=act, want_preact=True)
+        assert y.dtype == BF and pre.dtype == BF
+        assert_close(pre.float(), lin, RT, AT, f"preact m={m}")
+        assert_close(y.float(), f(lin), RT, AT, f"linear act={act}")
+    y0 = ops.bf16_linear_fwd(xd, wd, None)
+    y1 = ops.bf16_linear_fwd(xd, wd, bd, out=y0.clone(), accumulate=True)
+    assert_close(y1.float(), y0.double().cpu() + lin, RT, 2 * AT, "C +=")
+    dy = torch.randn(m, n, generator=g)
+    dyd = dev_bf(dy)
+    dx = ops.bf16_linear_bwd_data(dyd, wd)
+    assert_close(dx.float(), rb(dy) @ rb(w), RT, AT, "dx")
+    pre = torch.randn(m, k, generator=g)
+    p = rb(pre).requires_grad_()
+    F.gelu(p).backward(rb(dy) @ rb(w))
+    dxg = ops.bf16_linear_bwd_data(dyd, wd, gelu_pre=dev_bf(pre))
+    assert_close(dxg.float(), p.grad, RT, AT, "dx * gelu'")
+    dx2 = ops.bf16_linear_bwd_data(dyd, wd, dx=dx.clone(), accumulate=True)
+    assert_close(dx2.float(), dx.double().cpu() + rb(dy) @ rb(w), RT, 2 * AT, "dx accumulate")
+    dw = ops.bf16_linear_bwd_weight(dyd, xd)
+    assert dw.dtype == torch.float32
+    assert_close(dw, rb(dy).T @ rb(x), 1e-4, 1e-4 * max(1, m) ** .5, "dw")
+    assert_close(ops.bf16_colsum(dyd), rb(dy).sum(0), 1e-5, 1e-4 * max(1, m) ** .5, "colsum")
+    if k % 64 == 0:   # the same GEMM with one-hot extra columns: dW and the binned column sums (position-table gradient) at once
+        pi = torch.randint(0, 64, (m,), generator=g, dtype=torch.uint8)
+        oh = ops.onehot64_bf16(pi.to(DEV))
+        assert torch.equal(oh.float().cpu(), F.one_hot(pi.long(), 64).float())
+        dw2, dt = ops.bf16_linear_bwd_weight(dyd, xd, onehot=oh)
+        assert_close(dw2, rb(dy).T @ rb(x), 1e-4, 1e-4 * max(1, m) ** .5, "dw (one-hot form)")
+        ref = torch.zeros(64, n, dtype=torch.float64).index_add_(0, pi.long(), rb(dy))
+        assert_close(dt, ref.T, 1e-4, 1e-4 * max(1, m) ** .5, "dtable^T")
+    assert ops.dispatch_counts()["tma"] > before
+
+
+@pytest.mark.parametrize("m,c,parts,hd", [(3000, 128, 3, 16), (1700, 256, 3, 32), (900, 128, 1, 16), (5, 256, 2, 32), (129, 128, 2, 16)])
+def test_bf16_qkv_projection(m, c, parts, hd):
+    """Packed projection + position table + per-head normalisation of the q / k columns, against the reference op order
+    (x + pos) W^T + b -> F.normalize (cosine_msa.py:57-62,151-152) in float64."""
+    gen = torch.Generator().manual_seed(m + c)
+    n = parts * c
+    n_pos = min(2, parts) * c if parts != 1 else c
+    norm_cols = n_pos                       # q and k columns (cross kv: only k)
+    x = torch.randn(m, c, generator=gen)
+    w = torch.randn(n, c, generator=gen) / c ** .5
+    b = torch.randn(n, generator=gen) * 0.1
+    lut = torch.randn(64, c, generator=gen)
+    pi = torch.randint(0, 64, (m,), generator=gen, dtype=torch.uint8)
+    table, _ = ops.pos_table(lut.to(DEV), w.to(DEV), b.to(DEV), n_pos)
+    y, inv = ops.bf16_qkv_fwd(dev_bf(x), dev_bf(w), table, pi.to(DEV), norm_cols, hd)
+    ref = rb(x) @ rb(w).T + table.double().cpu()[pi.long()]
+    H = norm_cols // hd
+    heads = ref[:, :norm_cols].reshape(m, H, hd)
+    nrm = heads.norm(dim=-1).clamp_min(1e-12)
+    ref[:, :norm_cols] = (heads / nrm[..., None]).reshape(m, norm_cols)
+    assert_close(y.float(), ref, RT, AT, "qkv")
+    assert_close(inv, 1 / nrm, 1e-4, 1e-6, "1 / |.|")
+    # sanity against the un-rounded reference formulation
+    full = (x.double() + torch.cat([lut.double()[pi.long()]] * 1, 1)) @ w.double()[:n_pos].T + b.double()[:n_pos]
+    fh = full.reshape(m, H, hd)
+    fh = fh / fh.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    assert (y.float().cpu()[:, :norm_cols].double() - fh.reshape(m, norm_cols)).abs().max() < 3e-2
+
+
+@pytest.mark.parametrize("m,n,k,masked", [(1000, 128, 128, False), (4097, 256, 256, False), (777, 128, 256, True), (300, 256, 512, True), (1, 128, 128, False)])
+def test_bf16_linear_residual_layernorm(m, n, k, masked):
+    g = torch.Generator().manual_seed(m + n)
+    a, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k ** .5, torch.randn(n, generator=g) * 0.1
+    res = torch.randn(m, n, generator=g)
+    gamma, beta = 1 + 0.1 * torch.randn(n, generator=g), 0.1 * torch.randn(n, generator=g)
+    mask = (torch.rand(m, generator=g) < 0.6).to(torch.uint8) if masked else None
+    y, v, mean, rstd = ops.bf16_linear_ln_fwd(dev_bf(a), dev_bf(w), b.to(DEV), dev_bf(res), mask.to(DEV) if masked else None, gamma.to(DEV),
+                                              beta.to(DEV), 1e-5)
+    branch = rb(a) @ rb(w).T + b.double()
+    if masked:
+        branch = branch * mask.double()[:, None]
+    vref = rb(res) + branch
+    yref = F.layer_norm(vref, (n,), gamma.double(), beta.double(), 1e-5)
+    assert_close(v.float(), vref, RT, AT, "pre-norm sum")
+    assert_close(y.float(), yref, RT, 2 * AT, "LayerNorm output")
+    assert_close(mean[:m], vref.mean(1), 1e-4, 1e-5, "mean")
+    assert_close(rstd[:m], 1 / (vref.var(1, unbiased=False) + 1e-5).sqrt(), 1e-3, 1e-5, "rstd")
+    # backward from the saved (bf16) pre-norm sum
+    dy = torch.randn(m, n, generator=g)
+    vs = v.float().cpu().double().requires_grad_()
+    gd = gamma.double().requires_grad_()
+    bd_ = beta.double().requires_grad_()
+    F.layer_norm(vs, (n,), gd, bd_, 1e-5).backward(rb(dy))
+    dv, dres, dg, db, dc = ops.bf16_layernorm_bwd(dev_bf(dy), v, mask.to(DEV) if masked else None, gamma.to(DEV), mean, rstd, want_dres=masked,
+                                                  want_colsum=True)
+    assert_close(dv.float(), vs.grad, RT, AT, "dv")
+    s = m ** .5
+    assert_close(dg, gd.grad, 2e-3, 2e-3 * s, "dgamma"), assert_close(db, bd_.grad, 1e-4, 1e-4 * s, "dbeta")
+    if masked:
+        assert_close(dres.float(), vs.grad * mask.double()[:, None], RT, AT, "dres")
+        assert_close(dc, (vs.grad * mask.double()[:, None]).sum(0), 5e-3, 5e-3 * s, "colsum(dres)")
+    else:
+        assert_close(dc, vs.grad.sum(0), 5e-3, 5e-3 * s, "colsum(dv)")
+
+
+@pytest.mark.parametrize("rows,n", [(1, 128), (5000, 384), (777, 768), (3, 256)])
+def test_bf16_binned_colsum(rows, n):
+    g = torch.Generator().manual_seed(rows)
+    dy = torch.randn(rows, n, generator=g)
+    pi = torch.randint(0, 64, (rows,), generator=g, dtype=torch.uint8)
+    t = ops.bf16_binned_colsum(dev_bf(dy), pi.to(DEV))
+    ref = torch.zeros(64, n, dtype=torch.float64).index_add_(0, pi.long(), rb(dy))
+    assert_close(t, ref, 1e-4, 1e-4 * rows ** .5)
+
+
+def _coords(seed, m, B, g):
+    rng = np.random.default_rng(seed)
+    cells = np.sort(rng.choice(B * g * g, size=min(m, B * g * g), replace=False))
+    return torch.tensor(np.stack([cells // (g * g), (cells % (g * g)) // g, cells % g], 1), dtype=torch.int32)
+
+
+@pytest.mark.parametrize("seed,m,B,g,cin,cout", [(0, 1500, 2, 96, 128, 128), (1, 700, 2, 47, 128, 256), (2, 3000, 1, 90, 256, 256)])
+def test_bf16_sparse_conv(seed, m, B, g, cin, cout):
+    c = _coords(seed, m, B, g)
+    m = c.shape[0]
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(m, cin, generator=gen)
+    for subm in (True, False):
+        conv = restated.SparseConv(cin, cout, 3, 1 if subm else 2, 1, subm).double()
+        w32 = conv.weight.detach().float()
+        with torch.no_grad():
+            conv.weight.copy_(rb(w32))
+        xr = rb(x).requires_grad_()
+        out = conv(restated.SparseTensor(xr, c, [g, g], B))
+        if subm:
+            table = ops.subm_table(c.to(DEV), B, g, g)
+            table_t, flip, rows_out = table, True, m
+        else:
+            idx_out, n_out, table, table_t, _ = ops.strided_table(c.to(DEV), B, g, g)
+            rows_out = int(n_out)
+            table, flip = table[:rows_out], False
+        y = ops.bf16_sparse_conv_fwd(dev_bf(x), table, dev_bf(w32), rows_out)
+        scale = (9 * cin) ** .5 * 0.1
+        assert_close(y.float(), out.features.detach(), RT, AT * scale, f"sparse conv fwd subm={subm}")
+        dy = torch.randn(rows_out, cout, generator=gen)
+        out.features.backward(rb(dy))
+        dx = ops.bf16_sparse_conv_fwd(dev_bf(dy), table_t, ops.transpose_taps_bf16(w32.to(DEV), flip), m)
+        assert_close(dx.float(), xr.grad, RT, AT * scale, f"sparse conv dx subm={subm}")
+        dw = ops.bf16_sparse_conv_bwd_weight(dev_bf(dy), dev_bf(x), table, w32.shape)
+        assert_close(dw, conv.weight.grad, 1e-4, 1e-4 * m ** .5, f"sparse conv dw subm={subm}")
+
+
+def test_b16_dense_moves():
+    c = _coords(3, 900, 2, 40)
+    x = torch.randn(c.shape[0], 128)
+    d = ops.densify_nhwc_b16(dev_bf(x), c.to(DEV), 2, 40, 40)
+    ref = torch.zeros(2, 40, 40, 128, dtype=BF)
+    ref[c[:, 0].long(), c[:, 1].long(), c[:, 2].long()] = x.to(BF)
+    assert torch.equal(d.cpu(), ref)
+    assert torch.equal(ops.gather_nhwc_b16(d, c.to(DEV)).cpu(), x.to(BF))
+
+
+@pytest.mark.parametrize("C,cross", [(128, False), (256, False), (128, True), (256, True)])
+@pytest.mark.parametrize("impl", [0, 1])
+def test_bf16_encoder_layer_matches_fp32_layer(C, cross, impl):
+    """One whole encoder layer, forward and backward, in the bf16-storage mode against the SAME layer in the fp32 parity mode
+    (itself pinned to the oracle by test_gpu_ops.py / test_gpu_e2e.py): outputs within bf16 rounding of the layer's scale,
+    every parameter gradient within 3 % of its scale.  impl 0 = cast bridge to the fp32-I/O attention kernels, 1 = tcgen05."""
+    from tmae_b200 import backbone, config
+    from tmae_b200.plan import _levels
+    torch.manual_seed(C + cross)
+    H, FF, B, g = 8, 2 * C, 2, 64
+    cfg = config.model_cfg("pretrain")["BACKBONE_3D"]["SST_BLOCK_LIST"][0]
+    levels = _levels(cfg["PREPROCESS"])
+    layer = backbone.EncoderLayer(C, H, FF, cfg["ENCODER"]["LAYER_CFG"], cross).to(DEV)
+    with torch.no_grad():
+        at = layer.win_attn.cross_attn if cross else layer.win_attn.self_attn
+        at.in_proj_bias.normal_(0, 0.1), at.tau.fill_(0.4)
+    lut = backbone.pos_embed_table(C, 10000, normalize=False).to(DEV)
+    ca = _coords(0, 2500 if not cross else 700, B, g)
+    cb = _coords(5, 2200, B, g) if cross else None
+    P = ops.window_partition(ca.to(DEV), B, g, g, levels, coords_b=cb.to(DEV) if cross else None)
+    if cross:
+        P.keep_a = (P.win_a >= 0).to(torch.uint8)
+        P.keep_b = (P.win_b >= 0).to(torch.uint8)
+    x = torch.randn(ca.shape[0], C, device=DEV)
+    xp = torch.randn(cb.shape[0], C, device=DEV) if cross else None
+    dy = torch.randn(ca.shape[0], C, device=DEV)
+    outs = {}
+    for mode in ("fp32", "bf16"):
+        ops.set_precision(mode)
+        if mode == "bf16":
+            if impl == 1 and not ops.attention_tc_available():
+                ops.set_precision("fp32")
+                pytest.skip("tcgen05 attention kernel not built")
+            ops.set_attention_impl(impl)
+        try:
+            layer.zero_grad()
+            xi = (x.to(BF) if mode == "bf16" else x.clone()).requires_grad_()
+            xpi = None if not cross else (xp.to(BF) if mode == "bf16" else xp.clone()).requires_grad_()
+            y = layer.forward_cross(xi, xpi, P, 1, lut) if cross else layer.forward_self(xi, P, 1, lut)
+            y.backward(dy.to(y.dtype))
+            outs[mode] = (y.detach().float(), xi.grad.float(), None if not cross else xpi.grad.float(), {k: p.grad.clone() for k, p in layer.named_parameters()})
+        finally:
+            ops.set_precision("fp32")
+    (y0, dx0, dk0, g0), (y1, dx1, dk1, g1) = outs["fp32"], outs["bf16"]
+
+    def rel(a, b):
+        return (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
+    assert rel(y1, y0) < 2e-2, ("y", rel(y1, y0))
+    assert rel(dx1, dx0) < 4e-2, ("dx", rel(dx1, dx0))
+    if cross:
+        assert rel(dk1, dk0) < 4e-2, ("dx_kv", rel(dk1, dk0))
+    for k in g0:
+        assert rel(g1[k], g0[k]) < (8e-2 if k.endswith("tau") else 3e-2), (k, rel(g1[k], g0[k]))
