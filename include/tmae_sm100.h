@@ -382,6 +382,13 @@ TMAE_API int tmae_densify_nhwc_b16(const void* rows, const int32_t* indices, int
 TMAE_API int tmae_gather_nhwc_b16(const void* dense, const int32_t* indices, int64_t m, int32_t c, int32_t y, int32_t x, void* rows, void* stream);
 /* dst = bf16(src * (col < norm_cols ? scale[row, col / hd] : 1)) */
 TMAE_API int tmae_scale_cast_bf16(const float* src, const float* scale, void* dst, int64_t rows, int32_t n, int32_t norm_cols, int32_t hd, void* stream);
+/* window attention core on the tensor cores (attention_tc.cu; see tmae_window_attention_fwd for the tables): q, k are UNIT vectors per head
+ * (the output of tmae_bf16_qkv_fwd), q / k / v / o bf16 with row pitches ld_* (elements, multiples of 8), lse (rows_q, heads) fp32 */
+TMAE_API int tmae_bf16_window_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const int32_t* qtok,
+                                   const int32_t* qcnt, const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win,
+                                   const int32_t* small_end, const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min,
+                                   int32_t channels, int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, int64_t rows_q, int64_t rows_kv,
+                                   void* stream);
 /* whole encoder layer (see tmae_encoder_layer_fwd): x, x_kv, y, dy, dx, dx_kv are bf16; P = fp32 master parameters (biases, LayerNorm,
  * tau and the weights behind the position table), W = bf16 copies of the four weight matrices, G = fp32 gradient buffers. */
 typedef struct tmae_bf16_weights {

@@ -979,3 +979,20 @@ def encoder_layer_bwd_bf16(dy, x, x_kv, params, T, lut, tau_min, heads, saved, w
     _call("bf16_encoder_layer_bwd", _pb(dy), _pb(x), _pb(x_kv), ctypes.byref(P), ctypes.byref(W), ctypes.byref(T), _p(lut, F32), float(tau_min),
           m_q, m_kv, c, ff, heads, _p(saved), saved.numel(), _pb(dx), _pb(dkv), ctypes.byref(G), _p(scratch), nb, _stream())
     return dx, dkv, grads
+
+
+def _pvb(t):
+    """pointer of a (rows, C) bf16 view with unit column stride (a column block of a packed projection is allowed)."""
+    if not (t.is_cuda and t.dtype == BF16 and t.stride(1) == 1 and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0):
+        raise RuntimeError("expected a bf16 CUDA matrix with unit column stride, a row pitch that is a multiple of 8 and 16-byte alignment")
+    return t.data_ptr()
+
+
+def bf16_window_attention_fwd(q, k, v, qtok, qcnt, ktok, kcnt, n_win, small, mid, max_windows, tau, tau_min, heads, zero_out):
+    """tcgen05 window attention: q, k unit vectors per head (bf16), -> o (bf16), lse (fp32)."""
+    mq, c = q.shape
+    o = (torch.zeros if zero_out else torch.empty)(mq, c, dtype=BF16, device=q.device)
+    lse = torch.zeros(max(1, mq), heads, dtype=F32, device=q.device)
+    _call("bf16_window_attention_fwd", _pvb(q), _pvb(k), _pvb(v), _pb(o), _p(lse), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win), _p(small), _p(mid),
+          max_windows, _p(tau, F32), float(tau_min), c, heads, q.stride(0), k.stride(0), v.stride(0), mq, k.shape[0], _stream())
+    return o, lse

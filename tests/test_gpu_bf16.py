@@ -279,3 +279,59 @@ def test_bf16_encoder_layer_matches_fp32_layer(C, cross, impl):
         assert rel(dk1, dk0) < 4e-2, ("dx_kv", rel(dk1, dk0))
     for k in g0:
         assert rel(g1[k], g0[k]) < (8e-2 if k.endswith("tau") else 3e-2), (k, rel(g1[k], g0[k]))
+
+
+def _attn_ref64(q, k, v, P, shift, cross, tau, H):
+    """float64 window attention on GIVEN unit vectors (no re-normalisation): per window softmax(q k^T / tau) v over the valid keys."""
+    ma, C = q.shape
+    hd = C // H
+    nw = int(P.n_win[shift])
+    qt, qc = P.tok_a[shift].cpu().view(-1, 64), P.cnt_a[shift].cpu()
+    kt, kc = (P.tok_b[shift].cpu().view(-1, 64), P.cnt_b[shift].cpu()) if cross else (qt, qc)
+    o = torch.zeros(ma, C, dtype=torch.float64)
+    lse = torch.zeros(ma, H, dtype=torch.float64)
+    for w in range(nw):
+        qi, ki = qt[w, :qc[w]].long(), kt[w, :kc[w]].long()
+        if len(qi) == 0 or len(ki) == 0:
+            continue
+        Q, K, V = q[qi].view(-1, H, hd), k[ki].view(-1, H, hd), v[ki].view(-1, H, hd)
+        S = torch.einsum("qhd,khd->hqk", Q, K) / tau
+        o[qi] = torch.einsum("hqk,khd->qhd", S.softmax(-1), V).reshape(len(qi), C)
+        lse[qi] = torch.logsumexp(S, -1).T
+    return o, lse
+
+
+@pytest.mark.parametrize("C,cross", [(128, False), (256, False), (128, True), (256, True)])
+def test_bf16_window_attention_tcgen05_forward(C, cross):
+    from tmae_b200 import config
+    from tmae_b200.plan import _levels
+    H, B, g = 8, 2, 64
+    hd = C // H
+    levels = _levels(config.model_cfg("pretrain")["BACKBONE_3D"]["SST_BLOCK_LIST"][0]["PREPROCESS"])
+    ca = _coords(0, 2500 if not cross else 600, B, g)
+    cb = _coords(5, 2200, B, g) if cross else None
+    P = ops.window_partition(ca.to(DEV), B, g, g, levels, coords_b=cb.to(DEV) if cross else None)
+    gen = torch.Generator().manual_seed(C)
+    ma, mb = ca.shape[0], (cb.shape[0] if cross else ca.shape[0])
+
+    def unit(t):
+        t = t.view(-1, H, hd)
+        return (t / t.norm(dim=-1, keepdim=True)).reshape(-1, C)
+    # packed layouts as the layers use them: self (m, 3C) = [q | k | v]; cross q (mq, C), kv (mkv, 2C)
+    q, k, v = unit(torch.randn(ma, C, generator=gen)), unit(torch.randn(mb, C, generator=gen)), torch.randn(mb, C, generator=gen)
+    if cross:
+        qd = dev_bf(q)
+        kvd = dev_bf(torch.cat([k, v], 1))
+        kd, vd = kvd[:, :C], kvd[:, C:]
+    else:
+        qkv = dev_bf(torch.cat([q, k, v], 1))
+        qd, kd, vd = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    tau = torch.tensor([[[0.37]]])
+    for shift in (0, 1):
+        qt, qc = P.tok_a[shift], P.cnt_a[shift]
+        kt, kc = (P.tok_b[shift], P.cnt_b[shift]) if cross else (qt, qc)
+        o, lse = ops.bf16_window_attention_fwd(qd, kd, vd, qt, qc, kt, kc, P.n_win[shift:shift + 1], ops.small_end(P, shift), ops.mid_end(P, shift),
+                                               min(P.wcap, ma), tau.to(DEV), 0.01, H, zero_out=True)
+        oref, lref = _attn_ref64(rb(q), rb(k), rb(v), P, shift, cross, 0.37, H)
+        assert_close(o.float(), oref, RT, AT * 2, f"attention output shift {shift}")     # P is rounded to bf16 before P V
+        assert_close(lse, lref, 1e-4, 1e-4, f"log-sum-exp shift {shift}")
