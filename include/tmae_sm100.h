@@ -389,6 +389,15 @@ TMAE_API int tmae_bf16_window_attention_fwd(const void* q, const void* k, const 
                                    const int32_t* small_end, const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min,
                                    int32_t channels, int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, int64_t rows_q, int64_t rows_kv,
                                    void* stream);
+/* backward of the same: dq / dk / dv (bf16, pitches ld_q / ld_k / ld_v) are gradients wrt the UN-normalised projections: the kernel takes
+ * dq_hat, dk_hat back through the per-head L2 normalisation with inv_q / inv_k = 1 / |.| per (row, head) (row pitches ld_inv_*) as written
+ * by tmae_bf16_qkv_fwd; P is recomputed from lse; dtau (device, fp32) accumulates the temperature gradient. */
+TMAE_API int tmae_bf16_window_attention_bwd(const void* dout, const void* q, const void* k, const void* v, const float* lse, const float* inv_q,
+                                   int32_t ld_inv_q, const float* inv_k, int32_t ld_inv_k, void* dq, void* dk, void* dv, float* dtau,
+                                   const int32_t* qtok, const int32_t* qcnt, const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win,
+                                   const int32_t* small_end, const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min,
+                                   int32_t channels, int32_t heads, int32_t ld_q, int32_t ld_k, int32_t ld_v, int64_t rows_q, int64_t rows_kv,
+                                   void* stream);
 /* whole encoder layer (see tmae_encoder_layer_fwd): x, x_kv, y, dy, dx, dx_kv are bf16; P = fp32 master parameters (biases, LayerNorm,
  * tau and the weights behind the position table), W = bf16 copies of the four weight matrices, G = fp32 gradient buffers. */
 typedef struct tmae_bf16_weights {

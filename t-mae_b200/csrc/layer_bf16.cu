@@ -39,9 +39,9 @@ namespace tmae {
 // attention_tc.cu
 int attn_tc_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const tmae_layer_tables* T, const float* tau, float tau_min,
                 int64_t m_q, int64_t m_kv, int c, int heads, int ldq, int ldk, int ldv, cudaStream_t s);
-int attn_tc_bwd(const void* dout, const void* q, const void* k, const void* v, const void* o, const float* lse, const float* inv_q, const float* inv_k,
-                void* dq, void* dk, void* dv, float* dtau, const tmae_layer_tables* T, const float* tau, float tau_min, int64_t m_q, int64_t m_kv,
-                int c, int heads, int ldq, int ldk, int ldv, cudaStream_t s);
+int attn_tc_bwd(const void* dout, const void* q, const void* k, const void* v, const void* o, const float* lse, const float* inv_q, int ld_inv_q,
+                const float* inv_k, int ld_inv_k, void* dq, void* dk, void* dv, float* dtau, const tmae_layer_tables* T, const float* tau, float tau_min,
+                int64_t m_q, int64_t m_kv, int c, int heads, int ldq, int ldk, int ldv, cudaStream_t s);
 bool attn_tc_available();
 }  // namespace tmae
 
@@ -122,7 +122,7 @@ size_t scratch_bytes(int64_t mq, int64_t mkv, int c, int ff, int heads, bool cro
     if (rc__ != 0) return rc__; \
   } while (0)
 
-int g_attn_impl = 0;   // 1: tcgen05 window kernel (attention_tc.cu); 0: bridge to the fp32-I/O kernels (checker / A-B runs)
+int g_attn_impl = 1;   // 1: tcgen05 window kernel (attention_tc.cu); 0: bridge to the fp32-I/O kernels (checker / A-B runs)
 
 }  // namespace
 
@@ -264,7 +264,9 @@ int tmae_bf16_encoder_layer_bwd(const void* dy, const void* x, const void* x_kv,
   const float* inv_q = s.inv_q;
   const float* inv_k = cross ? s.inv_k : s.inv_q + heads;   // self: row r holds [q heads | k heads] at r * 2H
   if (g_attn_impl == 1) {
-    TRY(attn_tc_bwd(dob, qp, kp, vp, s.o, s.lse, inv_q, inv_k, dqp, dkp, dvp, g_tau, T, P->tau, tau_min, m_q, m_kv, c, heads, ldq, ldkv, ldkv, st));
+    const int ld_inv = cross ? heads : 2 * heads;
+    TRY(attn_tc_bwd(dob, qp, kp, vp, s.o, s.lse, inv_q, ld_inv, inv_k, ld_inv, dqp, dkp, dvp, g_tau, T, P->tau, tau_min, m_q, m_kv, c, heads, ldq, ldkv,
+                    ldkv, st));
   } else {
     float* q32 = (float*)cv.take((size_t)m_q * ldq * 4);
     float* kv32 = cross ? (float*)cv.take((size_t)m_kv * ldkv * 4) : nullptr;

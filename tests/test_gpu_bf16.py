@@ -302,7 +302,7 @@ def _attn_ref64(q, k, v, P, shift, cross, tau, H):
 
 
 @pytest.mark.parametrize("C,cross", [(128, False), (256, False), (128, True), (256, True)])
-def test_bf16_window_attention_tcgen05_forward(C, cross):
+def test_bf16_window_attention_tcgen05(C, cross):
     from tmae_b200 import config
     from tmae_b200.plan import _levels
     H, B, g = 8, 2, 64
@@ -332,6 +332,30 @@ def test_bf16_window_attention_tcgen05_forward(C, cross):
         kt, kc = (P.tok_b[shift], P.cnt_b[shift]) if cross else (qt, qc)
         o, lse = ops.bf16_window_attention_fwd(qd, kd, vd, qt, qc, kt, kc, P.n_win[shift:shift + 1], ops.small_end(P, shift), ops.mid_end(P, shift),
                                                min(P.wcap, ma), tau.to(DEV), 0.01, H, zero_out=True)
-        oref, lref = _attn_ref64(rb(q), rb(k), rb(v), P, shift, cross, 0.37, H)
-        assert_close(o.float(), oref, RT, AT * 2, f"attention output shift {shift}")     # P is rounded to bf16 before P V
-        assert_close(lse, lref, 1e-4, 1e-4, f"log-sum-exp shift {shift}")
+        qh, kh, vh = rb(q).requires_grad_(), rb(k).requires_grad_(), rb(v).requires_grad_()
+        tau64 = torch.tensor(0.37, dtype=torch.float64, requires_grad=True)
+        oref, lref = _attn_ref64(qh, kh, vh, P, shift, cross, tau64, H)
+        assert_close(o.float(), oref.detach(), RT, AT * 2, f"attention output shift {shift}")     # P is rounded to bf16 before P V
+        assert_close(lse, lref.detach(), 1e-4, 1e-4, f"log-sum-exp shift {shift}")
+        # backward: gradients wrt the un-normalised projections, through d(x / |x|) = (g - u (u . g)) / |x| per head with the given 1 / |x|
+        do = torch.randn(ma, C, generator=gen)
+        oref.backward(rb(do))
+        inv_q, inv_k = 0.5 + torch.rand(ma, H, generator=gen), 0.5 + torch.rand(mb, H, generator=gen)
+
+        def through_norm(g, u, inv):
+            g, u = g.view(-1, H, hd), u.detach().view(-1, H, hd)
+            return ((g - u * (u * g).sum(-1, keepdim=True)) * inv.double()[..., None]).reshape(-1, C)
+        dq_ref, dk_ref, dv_ref = through_norm(qh.grad, qh, inv_q), through_norm(kh.grad, kh, inv_k), vh.grad
+        dtau = torch.zeros(1, device=DEV)
+        if cross:
+            iq, ik = inv_q.to(DEV), inv_k.to(DEV)
+        else:   # self layers keep [q heads | k heads] per row
+            both = torch.cat([inv_q, inv_k], 1).to(DEV)
+            iq, ik = both[:, :H], both[:, H:]
+        dq, dk, dv = ops.bf16_window_attention_bwd(dev_bf(do), qd, kd, vd, lse, iq, ik, qt, qc, kt, kc, P.n_win[shift:shift + 1], ops.small_end(P, shift),
+                                                   ops.mid_end(P, shift), min(P.wcap, ma), tau.to(DEV), 0.01, H, dtau, zero=True)
+        assert dq.stride(0) == qd.stride(0) and dk.stride(0) == kd.stride(0), "gradients mirror the packed projection layout"
+        gs = max(dq_ref.abs().max().item(), 1e-6)
+        assert_close(dq.float(), dq_ref, 2e-2, 4e-3 * gs, "dq"), assert_close(dk.float(), dk_ref, 2e-2, 4e-3 * dk_ref.abs().max().item(), "dk")
+        assert_close(dv.float(), dv_ref, 2e-2, 4e-3 * dv_ref.abs().max().item(), "dv")
+        assert_close(dtau, tau64.grad.reshape(1), 2e-2, 2e-2 * abs(tau64.grad.item()), "dtau")
