@@ -391,8 +391,10 @@ TMAE_API int tmae_bf16_window_attention_fwd(const void* q, const void* k, const 
                                    void* stream);
 /* backward of the same: dq / dk / dv (bf16, pitches ld_q / ld_k / ld_v) are gradients wrt the UN-normalised projections: the kernel takes
  * dq_hat, dk_hat back through the per-head L2 normalisation with inv_q / inv_k = 1 / |.| per (row, head) (row pitches ld_inv_*) as written
- * by tmae_bf16_qkv_fwd; P is recomputed from lse; dtau (device, fp32) accumulates the temperature gradient. */
-TMAE_API int tmae_bf16_window_attention_bwd(const void* dout, const void* q, const void* k, const void* v, const float* lse, const float* inv_q,
+ * by tmae_bf16_qkv_fwd; P is recomputed from lse; dtau (device, fp32) accumulates the temperature gradient.  o = the forward output
+ * (bf16, pitch channels): the <= 16-token windows (warp kernels) take D = dO . O from it; NULL routes every window to the tcgen05 tiles,
+ * which form D from P and dP in registers. */
+TMAE_API int tmae_bf16_window_attention_bwd(const void* dout, const void* q, const void* k, const void* v, const void* o, const float* lse, const float* inv_q,
                                    int32_t ld_inv_q, const float* inv_k, int32_t ld_inv_k, void* dq, void* dk, void* dv, float* dtau,
                                    const int32_t* qtok, const int32_t* qcnt, const int32_t* ktok, const int32_t* kcnt, const int32_t* n_win,
                                    const int32_t* small_end, const int32_t* mid_end, int64_t max_windows, const float* tau, float tau_min,

@@ -998,7 +998,7 @@ def bf16_window_attention_fwd(q, k, v, qtok, qcnt, ktok, kcnt, n_win, small, mid
     return o, lse
 
 
-def bf16_window_attention_bwd(dout, q, k, v, lse, inv_q, inv_k, qtok, qcnt, ktok, kcnt, n_win, small, mid, max_windows, tau, tau_min, heads, dtau, zero):
+def bf16_window_attention_bwd(dout, q, k, v, o, lse, inv_q, inv_k, qtok, qcnt, ktok, kcnt, n_win, small, mid, max_windows, tau, tau_min, heads, dtau, zero):
     """-> dq, dk, dv (bf16, same packing as q / k / v): gradients wrt the UN-normalised projections (see tmae_bf16_window_attention_bwd)."""
     alloc = torch.zeros if zero else torch.empty
     C = q.shape[1]
@@ -1012,7 +1012,7 @@ def bf16_window_attention_bwd(dout, q, k, v, lse, inv_q, inv_k, qtok, qcnt, ktok
         dk, dv = buf[:, :C], buf[:, C:]
     else:
         dq, dk, dv = (alloc(t.shape[0], C, dtype=BF16, device=t.device) for t in (q, k, v))
-    _call("bf16_window_attention_bwd", _pb(dout), _pvb(q), _pvb(k), _pvb(v), _p(lse, F32), inv_q.data_ptr(), inv_q.stride(0), inv_k.data_ptr(), inv_k.stride(0),
+    _call("bf16_window_attention_bwd", _pb(dout), _pvb(q), _pvb(k), _pvb(v), _pb(o), _p(lse, F32), inv_q.data_ptr(), inv_q.stride(0), inv_k.data_ptr(), inv_k.stride(0),
           _pvb(dq), _pvb(dk), _pvb(dv), _p(dtau, F32), _p(qtok), _p(qcnt), _p(ktok), _p(kcnt), _p(n_win), _p(small), _p(mid), max_windows, _p(tau, F32),
           float(tau_min), C, heads, q.stride(0), k.stride(0), v.stride(0), q.shape[0], k.shape[0], _stream())
     return dq, dk, dv

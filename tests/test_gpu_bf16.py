@@ -301,8 +301,18 @@ def _attn_ref64(q, k, v, P, shift, cross, tau, H):
     return o, lse
 
 
+@pytest.mark.parametrize("small_warps", [1, 0])
 @pytest.mark.parametrize("C,cross", [(128, False), (256, False), (128, True), (256, True)])
-def test_bf16_window_attention_tcgen05(C, cross):
+def test_bf16_window_attention_tcgen05(C, cross, small_warps):
+    """small_warps = 1 (default): <= 16-token windows on the warp kernels, 17..64-token windows on tcgen05 tiles; 0: all on tcgen05."""
+    ops.set_option("attn_small_warps", small_warps)
+    try:
+        _attention_tc_case(C, cross)
+    finally:
+        ops.set_option("attn_small_warps", 1)
+
+
+def _attention_tc_case(C, cross):
     from tmae_b200 import config
     from tmae_b200.plan import _levels
     H, B, g = 8, 2, 64
@@ -352,7 +362,7 @@ def test_bf16_window_attention_tcgen05(C, cross):
         else:   # self layers keep [q heads | k heads] per row
             both = torch.cat([inv_q, inv_k], 1).to(DEV)
             iq, ik = both[:, :H], both[:, H:]
-        dq, dk, dv = ops.bf16_window_attention_bwd(dev_bf(do), qd, kd, vd, lse, iq, ik, qt, qc, kt, kc, P.n_win[shift:shift + 1], ops.small_end(P, shift),
+        dq, dk, dv = ops.bf16_window_attention_bwd(dev_bf(do), qd, kd, vd, o, lse, iq, ik, qt, qc, kt, kc, P.n_win[shift:shift + 1], ops.small_end(P, shift),
                                                    ops.mid_end(P, shift), min(P.wcap, ma), tau.to(DEV), 0.01, H, dtau, zero=True)
         assert dq.stride(0) == qd.stride(0) and dk.stride(0) == kd.stride(0), "gradients mirror the packed projection layout"
         gs = max(dq_ref.abs().max().item(), 1e-6)

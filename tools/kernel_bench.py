@@ -109,6 +109,61 @@ def attn(tc=1):
     ops.set_option("attn_tc", 0)
 
 
+def _lidar_partition(M, g, B, seed=0):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    cells = np.unique(np.clip((rng.normal(0, g / 5, (M * 3, 2)) + g / 2).astype(np.int64), 0, g - 1) @ np.array([g, 1]))
+    per = min(M // B, cells.shape[0])
+    cells = np.sort(rng.choice(cells, per, replace=False))
+    c = np.concatenate([np.stack([np.full(per, b), cells // g, cells % g], 1) for b in range(B)])
+    coords = torch.tensor(c, dtype=torch.int32, device=DEV)
+    return coords, ops.window_partition(coords, B, g, g, [(16, 0, 16), (32, 16, 32), (64, 32, 100000)])
+
+
+def attn_bf16(shapes=None):
+    """tcgen05 window attention (bf16 storage) at the bench's stage shapes: forward / backward us and GB/s of the algorithmic bytes."""
+    BF = torch.bfloat16
+    print("--- tcgen05 window attention (bf16) : M C | fwd us (GB/s of 4*M*C*2) | bwd us (GB/s of 7*M*C*2)")
+    for M, C, g, B in shapes or [(68000, 128, 468, 8), (14000, 128, 468, 4), (64000, 256, 234, 8), (35000, 256, 117, 8)]:
+        coords, P = _lidar_partition(M, g, B)
+        m = coords.shape[0]
+        tau = torch.ones(1, device=DEV)
+        H = 8
+        args = (P.tok_a[0], P.cnt_a[0], P.tok_a[0], P.cnt_a[0], P.n_win[0:1], ops.small_end(P, 0), ops.mid_end(P, 0), min(P.wcap, m), tau, 0.01, H)
+        sets = []
+        for _ in range(4):
+            qkv = torch.randn(m, 3 * C, device=DEV).to(BF)
+            q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+            o, lse = ops.bf16_window_attention_fwd(q, k, v, *args, False)
+            inv = torch.ones(m, 2 * H, device=DEV)
+            sets.append((q, k, v, o, lse, torch.randn(m, C, device=DEV).to(BF), inv))
+        dtau = torch.zeros(1, device=DEV)
+        t = timeit_queue([lambda s=s: ops.bf16_window_attention_fwd(s[0], s[1], s[2], *args, False) for s in sets] * 2)
+        t2 = timeit_queue([lambda s=s: ops.bf16_window_attention_bwd(s[5], s[0], s[1], s[2], s[3], s[4], s[6][:, :H], s[6][:, H:], *args, dtau, False) for s in sets] * 2)
+        nw = int(P.n_win[0])
+        lb = P.level_base[0].tolist()
+        print(f"{m:7d} {C:4d} windows {nw} levels {lb} | {t * 1e3:8.1f} ({4 * 2 * m * C / t / 1e6:.0f} GB/s) | {t2 * 1e3:8.1f} ({7 * 2 * m * C / t2 / 1e6:.0f} GB/s)")
+
+
+def gemm_bf16():
+    BF = torch.bfloat16
+    print("--- bf16 GEMMs : m n k | fwd us GB/s | ln-fused us GB/s | bwd_data us GB/s | bwd_weight us GB/s")
+    for m, n, k in [(68000, 128, 128), (68000, 384, 128), (68000, 256, 128), (68000, 128, 256), (64000, 256, 256), (64000, 768, 256), (64000, 512, 256),
+                    (64000, 256, 512), (35000, 256, 256), (14000, 128, 128)]:
+        w, b = torch.randn(n, k, device=DEV).to(BF), torch.randn(n, device=DEV)
+        sets = [(torch.randn(m, k, device=DEV).to(BF), torch.randn(m, n, device=DEV).to(BF)) for _ in range(4)]
+        t = timeit_queue([lambda s=s: ops.bf16_linear_fwd(s[0], w, b) for s in sets] * 2)
+        t2 = timeit_queue([lambda s=s: ops.bf16_linear_bwd_data(s[1], w) for s in sets] * 2)
+        t3 = timeit_queue([lambda s=s: ops.bf16_linear_bwd_weight(s[1], s[0]) for s in sets] * 2)
+        by = 2 * (m * k + m * n + n * k)
+        ln = ""
+        if n in (128, 256):
+            g_, be = torch.ones(n, device=DEV), torch.zeros(n, device=DEV)
+            t4 = timeit_queue([lambda s=s: ops.bf16_linear_ln_fwd(s[0], w, b, s[1], None, g_, be, 1e-5) for s in sets] * 2)
+            ln = f"{t4 * 1e3:8.1f} {(by + 2 * 2 * m * n) / t4 / 1e6:7.0f}"
+        print(f"{m:7d} {n:4d} {k:4d} | {t * 1e3:8.1f} {by / t / 1e6:7.0f} | {ln:>16s} | {t2 * 1e3:8.1f} {by / t2 / 1e6:7.0f} | {t3 * 1e3:8.1f} {(by + 2 * n * k) / t3 / 1e6:7.0f}")
+
+
 def bn():
     """BatchNorm1d + ReLU over sparse-conv rows (fp32) and over a decoder map (bf16): forward (train) and backward."""
     for key, val in os.environ.items():
@@ -154,6 +209,12 @@ def bev(batch=8):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("attn_bf16", "bf16"):
+        attn_bf16()
+    if what == "attn_bf16_one":
+        attn_bf16([(68000, 128, 468, 8)])
+    if what in ("gemm_bf16", "bf16"):
+        gemm_bf16()
     if what in ("gemm", "all"):
         gemm("bf16")
     if what in ("gemm32",):
