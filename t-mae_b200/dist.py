@@ -100,6 +100,100 @@ class FlatGradients:
         return self.flat
 
 
+class OverlappedGradients(FlatGradients):
+    """FlatGradients whose buckets are reduced WHILE backward is still running: every parameter gets a post-accumulate-grad hook
+    that counts its bucket down; the moment a bucket's last gradient exists, its gradients are copied into the flat buffer and the
+    bucket's all-reduce is issued on the communication stream (behind an event recorded on the compute stream).  `finish()` after
+    backward waits for the communication stream and re-points every `.grad` at the buffer.  This is what DDP's reducer does,
+    with one flat buffer, one multi-tensor copy per bucket and no bucket rebuilds.  Buckets are contiguous ranges of the parameter list
+    (module order); a bucket fires when its last gradient exists, whatever order backward produces them in."""
+
+    def __init__(self, params, world_size=None, group=None, n_buckets=6):
+        super().__init__(params, world_size, group, n_buckets)
+        self._handles = []
+        self._pending = None
+        self._fired = None
+
+    def attach(self):
+        if self.flat is None:
+            self._setup()
+        self.bucket_of = {}
+        for b, (lo, hi) in enumerate(self.bounds):
+            for i in range(lo, hi):
+                self.bucket_of[i] = b
+        self._reset()
+        for i, p in enumerate(self.params):
+            self._handles.append(p.register_post_accumulate_grad_hook(lambda _p, i=i: self._on_grad(i)))
+        return self
+
+    def detach(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    def _reset(self):
+        if self.present is None:
+            self._pending = [hi - lo for lo, hi in self.bounds]          # first step: every parameter is expected
+        else:
+            self._pending = [sum(1 for i in range(lo, hi) if self.present[i]) for lo, hi in self.bounds]
+        self._fired = [False] * len(self.bounds)
+
+    def _on_grad(self, i):
+        b = self.bucket_of[i]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and not self._fired[b] and self.present is not None:
+            self._fire(b)
+
+    def _fire(self, b):
+        lo, hi = self.bounds[b]
+        src, dst, zero = [], [], []
+        for i in range(lo, hi):
+            if not self.present[i]:
+                continue
+            g = self.params[i].grad
+            if g is None:
+                zero.append(self.views[i])
+            elif g.data_ptr() != self.views[i].data_ptr():
+                src.append(g)
+                dst.append(self.views[i])
+        if dst:
+            torch._foreach_copy_(dst, src)
+        if zero:
+            torch._foreach_zero_(zero)
+        self._fired[b] = True
+        if self.world > 1:
+            es = self.flat.element_size()
+            a = (self.views[lo].data_ptr() - self.flat.data_ptr()) // es
+            z = (self.views[hi - 1].data_ptr() - self.flat.data_ptr()) // es + self.views[hi - 1].numel()
+            sl = self.flat[a:z]
+            if self.comm is not None:
+                self.comm.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.comm):
+                    dist.all_reduce(sl, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=self.group)
+                sl.div_(self.world)
+
+    def finish(self):
+        """After backward: reduce whatever has not fired (first step, or parameters that got no gradient), wait, re-point .grad."""
+        has = [p.grad is not None for p in self.params]
+        if self.present is None:
+            self._presence(has)
+        elif any(h and not pr for h, pr in zip(has, self.present)):
+            self._presence([h or pr for h, pr in zip(has, self.present)])
+        for b in range(len(self.bounds)):
+            if not self._fired[b]:
+                self._fire(b)
+        if self.comm is not None and self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm)
+        for p, v, pr in zip(self.params, self.views, self.present):
+            p.grad = v if pr else None
+        self._reset()
+        return self.flat
+
+    reduce = finish
+
+
 _cache = {}
 
 

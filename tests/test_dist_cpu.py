@@ -69,3 +69,54 @@ def test_allreduce_gradients_gloo_world2():
         assert torch.equal(g0, torch.full((3, 4), 1.5))
         assert torch.equal(g1, torch.arange(5.0) * 1.5)
         assert torch.equal(g2, torch.full((2, 2), 0.5))
+
+
+def _overlap_worker(rank, world, port, out):
+    import importlib
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tdist = importlib.import_module("tmae_b200.dist")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 4), torch.nn.ReLU(), torch.nn.Linear(4, 3))
+    unused = torch.nn.Parameter(torch.zeros(7))          # never receives a gradient on any rank: must keep grad None
+    params = list(net.parameters()) + [unused]
+    og = tdist.OverlappedGradients(params, world, n_buckets=3).attach()
+    res = []
+    for it in range(3):                                   # first step (presence agreed in finish) and steady state (hooks fire buckets)
+        x = torch.full((2, 6), float(rank + 1 + it))
+        net(x).sum().backward()
+        og.finish()
+        res.append([None if p.grad is None else p.grad.clone() for p in params])
+        for p in params:
+            p.grad = None
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_overlapped_gradients_gloo_world2():
+    """OverlappedGradients (bucketed all-reduce fired from post-accumulate hooks during backward) == the mean of the ranks' gradients;
+    a parameter unused on every rank keeps grad None (as under DDP with find_unused_parameters=False)."""
+    import torch
+    import torch.multiprocessing as mp
+    import tmae_b200  # noqa: F401
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_overlap_worker, args=(2, 29537, out), nprocs=2, join=True)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 4), torch.nn.ReLU(), torch.nn.Linear(4, 3))
+    for it in range(3):
+        ref = None
+        for rank in range(2):
+            net.zero_grad()
+            net(torch.full((2, 6), float(rank + 1 + it))).sum().backward()
+            g = [p.grad.clone() for p in net.parameters()]
+            ref = g if ref is None else [a + b for a, b in zip(ref, g)]
+        ref = [r / 2 for r in ref]
+        for rank in range(2):
+            got = out[rank][it]
+            assert got[-1] is None
+            for a, b in zip(got[:-1], ref):
+                assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)

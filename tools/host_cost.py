@@ -22,7 +22,7 @@ dev = torch.device("cuda", 0)
 grid = synth.grid_size(synth.ONCE).tolist()
 torch.manual_seed(0)
 vfe, bb = tmae_b200.build_model("pretrain", grid, synth.ONCE["voxel"], synth.ONCE["range"])
-ops.set_precision("tf32")
+ops.set_precision(ops.BENCH_PRECISION)
 bb.decoder_autocast = torch.bfloat16
 torch.backends.cudnn.benchmark = True
 vfe.to(dev), bb.to(dev)

@@ -17,7 +17,7 @@ shape = synth.ONCE
 grid = synth.grid_size(shape).tolist()
 torch.manual_seed(0)
 vfe, bb = tmae_b200.build_model(w["kind"], grid, shape["voxel"], shape["range"])
-ops.set_precision("tf32")
+ops.set_precision(ops.BENCH_PRECISION)
 bb.decoder_autocast = torch.bfloat16
 torch.backends.cudnn.benchmark = True
 vfe.to(dev), bb.to(dev)
