@@ -171,6 +171,12 @@ def setup(args):
     if c.slab_gib > 0:
         del_me = torch.empty(c.slab_gib << 30, dtype=torch.uint8, device=c.dev)
         del del_me
+    # ... and one for the side stream's pool (the caching allocator keeps a pool per stream: the coordinate-only pre-pass allocates its
+    # tables there, with sizes that change every batch -- measured: one 40-90 ms cudaMalloc step in ~1 of 8 without it)
+    if args.side_stream and c.slab_gib > 8:
+        with torch.cuda.stream(ops.side_stream(c.dev)):
+            del_me = torch.empty(4 << 30, dtype=torch.uint8, device=c.dev)
+            del del_me
     args.precision = args.precision or ops.BENCH_PRECISION
     ops.set_precision(args.precision)
     torch.backends.cudnn.benchmark = True

@@ -413,7 +413,9 @@ TMAE_API int tmae_bf16_encoder_layer_fwd(const void* x, const void* x_kv, const 
 TMAE_API int tmae_bf16_encoder_layer_bwd(const void* dy, const void* x, const void* x_kv, const tmae_layer_params* P, const tmae_bf16_weights* W,
                                 const tmae_layer_tables* T, const float* pos_lut, float tau_min, int64_t m_q, int64_t m_kv, int32_t c, int32_t ff,
                                 int32_t heads, const void* saved, size_t saved_size, void* dx, void* dx_kv, const tmae_layer_params* G,
-                                void* scratch, size_t scratch_size, void* stream);
+                                void* g_base, size_t g_bytes, void* scratch, size_t scratch_size, void* stream);
+/* g_base / g_bytes (nullable): when the 13 gradient buffers of G are carved from ONE allocation, its extent -- the call then clears it with a
+ * single memset; NULL: every kernel clears its own target. */
 /* which attention core the bf16 layers use: 1 = tcgen05 window kernel (attention_tc.cu), 0 = cast bridge to the fp32-I/O mma.sync
  * kernels (kept as the checker of the former; measurement switch, process-wide) */
 TMAE_API int tmae_bf16_set_attention_impl(int32_t impl);

@@ -85,8 +85,8 @@ __device__ __forceinline__ void load_row32(const bf16* p, float* v) {
 //   ((c ^ (r % 8)) * 16); SBO = 1024 between 8-row groups, k-step (16 elements) = +32 B.
 //   MN-major operand (64 k-rows x cols): cols / 64 boxes {64, 64} of 8192 B each (LBO between boxes), k-row j of a box at
 //   j * 128 (same XOR swizzle), SBO = 1024 between 8-row k groups, k-step (16 rows) = +2048 B.
-template <int MODE, int BN, int STAGES, int EPI, bool GATHER>
-__global__ void __launch_bounds__(THREADS + (GATHER ? GATHER_WARPS * 32 : 0), 1) bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+template <int MODE, int BN, int STAGES, int EPI, bool GATHER, int OCC>
+__global__ void __launch_bounds__(THREADS + (GATHER ? GATHER_WARPS * 32 : 0), OCC) bf16_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                                                   const __grid_constant__ CUtensorMap map_b,
                                                                                                   const __grid_constant__ CUtensorMap map_b2, Args g) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -491,9 +491,11 @@ static const char* prof_name(int mode, int epi, bool gather) {
 
 struct SecondB { const bf16* B2; int64_t n2, ldb2; };   // TN: extra B columns [n_split, n_split + n2) from a second (K, n2) tensor
 
-template <int MODE, int BN, int EPI, bool GATHER = false>
+// OCC = 2 (BN <= 128 only: two CTAs need 2 x 2 BN TMEM columns and 2 x STAGES x stage bytes of shared memory): two co-resident CTAs per
+// SM with a 3-stage ring each -- one CTA's loads overlap the other's epilogue stores, and a launch has twice as many tiles in flight
+template <int MODE, int BN, int EPI, bool GATHER = false, int OCC = 1>
 static int launch(const bf16* A, const bf16* B, int64_t lda, int64_t ldb, Args g, int splits, cudaStream_t s, SecondB b2 = SecondB{nullptr, 0, 0}) {
-  constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  constexpr int STAGES = OCC == 2 ? (BN == 128 ? 3 : 4) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   if (g.M <= 0 || g.N <= 0) return 0;
   if (splits < 1) splits = 1;
   g.k_chunk = align_up((g.K + splits - 1) / splits, KB);
@@ -523,7 +525,7 @@ static int launch(const bf16* A, const bf16* B, int64_t lda, int64_t ldb, Args g
   else g.n_split = (int64_t)1 << 40;
   if (!ok) return TMAE_ERR_CUDA;
   size_t smem = (size_t)STAGES * (UM * KB * 2 + BN * KB * 2) + 1024;
-  auto kern = bf16_gemm_kernel<MODE, BN, STAGES, EPI, GATHER>;
+  auto kern = bf16_gemm_kernel<MODE, BN, STAGES, EPI, GATHER, OCC>;
   if (smem_attr_once((const void*)kern, (int)smem)) return TMAE_ERR_CUDA;
   const double out_el = (double)g.M * g.N;
   const double a_el = (GATHER && MODE == M_NT) ? (double)g.M * g.gcin : (double)g.M * g.K;
@@ -535,11 +537,14 @@ static int launch(const bf16* A, const bf16* B, int64_t lda, int64_t ldb, Args g
   ProfScope prof(prof_name(MODE, EPI, GATHER), 2.0 * g.M * g.N * g.K, bytes, s);
   count_dispatch(DISP_TMA);
   int64_t tiles = (int64_t)cdiv(g.N, BN) * cdiv(g.M, UM) * z;
-  dim3 grid((unsigned)(tiles < kNumSMs ? tiles : kNumSMs));
+  dim3 grid((unsigned)(tiles < OCC * kNumSMs ? tiles : OCC * kNumSMs));
   kern<<<grid, THREADS + (GATHER ? GATHER_WARPS * 32 : 0), smem, s>>>(ma, mb, mb2, g);
   return cudaGetLastError() == cudaSuccess ? 0 : TMAE_ERR_CUDA;
 }
 
+}  // namespace bfk
+int g_bf16_gemm_occ2 = 0;   // measurement switch (tmae_set_option "gemm_occ2")
+namespace bfk {
 static int pick_bn(int64_t n) {
   // N = 384 (packed q/k/v projection at 128 channels): three full 128-wide tiles instead of a full and a half-empty 256
   if (n > 128 && !(n % 256 != 0 && n % 128 == 0 && n <= 384)) return 256;
@@ -551,6 +556,10 @@ static int dispatch_bn(const bf16* A, const bf16* B, int64_t lda, int64_t ldb, c
                        SecondB b2 = SecondB{nullptr, 0, 0}) {
   const int bn = pick_bn(g.N);
   if (bn == 256) return launch<MODE, 256, EPI>(A, B, lda, ldb, g, splits, s, b2);
+  if (g_bf16_gemm_occ2 && EPI != E_F32) {
+    if (bn == 128) return launch<MODE, 128, EPI, false, 2>(A, B, lda, ldb, g, splits, s, b2);
+    return launch<MODE, 64, EPI, false, 2>(A, B, lda, ldb, g, splits, s, b2);
+  }
   if (bn == 128) return launch<MODE, 128, EPI>(A, B, lda, ldb, g, splits, s, b2);
   return launch<MODE, 64, EPI>(A, B, lda, ldb, g, splits, s, b2);
 }
@@ -569,6 +578,11 @@ using namespace tmae::bfk;
     int rc__ = (call);                                                       \
     if (rc__) { set_error("%s: tcgen05 launch failed", what); return rc__ < 0 ? rc__ : TMAE_ERR_CUDA; } \
   } while (0)
+
+namespace tmae {
+int bf16_linear_bwd_weight_impl(const void* dy, const void* x, float* dw, const void* onehot, float* dtab_t, int64_t m, int64_t n, int64_t k,
+                                bool zero, void* stream);
+}
 
 extern "C" {
 
@@ -607,7 +621,8 @@ int tmae_bf16_linear_ln_fwd(const void* a, const void* w, const float* bias, con
   Args g{};
   g.M = m; g.N = n; g.K = k; g.bias = bias; g.C = y; g.ldc = n; g.res = (const bf16*)res; g.rowmask = rowmask; g.gamma = gamma; g.beta = beta;
   g.eps = eps; g.V = (bf16*)v; g.mean = mean; g.rstd = rstd;
-  if (n == 128) BF_RUN((launch<M_NT, 128, E_LN>((const bf16*)a, (const bf16*)w, k, k, g, 1, (cudaStream_t)stream)), "tmae_bf16_linear_ln_fwd");
+  if (n == 128 && g_bf16_gemm_occ2) BF_RUN((launch<M_NT, 128, E_LN, false, 2>((const bf16*)a, (const bf16*)w, k, k, g, 1, (cudaStream_t)stream)), "tmae_bf16_linear_ln_fwd");
+  else if (n == 128) BF_RUN((launch<M_NT, 128, E_LN>((const bf16*)a, (const bf16*)w, k, k, g, 1, (cudaStream_t)stream)), "tmae_bf16_linear_ln_fwd");
   else BF_RUN((launch<M_NT, 256, E_LN>((const bf16*)a, (const bf16*)w, k, k, g, 1, (cudaStream_t)stream)), "tmae_bf16_linear_ln_fwd");
   return 0;
 }
@@ -629,12 +644,23 @@ int tmae_bf16_linear_bwd_data(const void* dy, const void* w, const void* gelu_pr
  * sums behind the position-table gradient (tmae_pos_table_bwd, transposed form); needs k % 64 == 0. */
 int tmae_bf16_linear_bwd_weight(const void* dy, const void* x, float* dw, const void* onehot, float* dtab_t, int64_t m, int64_t n, int64_t k,
                                 void* stream) {
+  return tmae::bf16_linear_bwd_weight_impl(dy, x, dw, onehot, dtab_t, m, n, k, true, stream);
+}
+
+}  // extern "C"
+
+namespace tmae {
+// zero = false: dw (and dtab_t) were zero-filled by the caller (the split reduction adds into them)
+int bf16_linear_bwd_weight_impl(const void* dy, const void* x, float* dw, const void* onehot, float* dtab_t, int64_t m, int64_t n, int64_t k,
+                                bool zero, void* stream) {
   BF_CHECK(n % 8 == 0 && k % 8 == 0, "n and k must be multiples of 8");
   BF_CHECK(al32(dy) && al32(x) && al32(dw) && al32(onehot) && al32(dtab_t), "pointers must be 32-byte aligned");
   BF_CHECK(!onehot || (dtab_t && k % 64 == 0), "the one-hot form needs dtab_t and k % 64 == 0");
   cudaStream_t s = (cudaStream_t)stream;
-  TMAE_CUDA(cudaMemsetAsync(dw, 0, (size_t)n * k * sizeof(float), s));
-  if (onehot) TMAE_CUDA(cudaMemsetAsync(dtab_t, 0, (size_t)n * 64 * sizeof(float), s));
+  if (zero) {
+    TMAE_CUDA(cudaMemsetAsync(dw, 0, (size_t)n * k * sizeof(float), s));
+    if (onehot) TMAE_CUDA(cudaMemsetAsync(dtab_t, 0, (size_t)n * 64 * sizeof(float), s));
+  }
   if (m <= 0) return 0;
   Args g{};
   g.M = n; g.N = onehot ? k + 64 : k; g.K = m; g.accumulate = 1; g.C = dw; g.ldc = k;
@@ -647,6 +673,9 @@ int tmae_bf16_linear_bwd_weight(const void* dy, const void* x, float* dw, const 
                                    SecondB{(const bf16*)onehot, 64, 64})), "tmae_bf16_linear_bwd_weight");
   return 0;
 }
+}  // namespace tmae
+
+extern "C" {
 
 /* sparse convolution forward / backward-data as a gathered NT GEMM: y[o, :] = sum_tap x[table[o, tap], :] w[:, tap, :]^T
  * x (rows_in, cin), w (cout, taps, cin), y (rows_out, cout): bf16 */

@@ -297,13 +297,20 @@ int tmae_cast_f32_bf16_multi(const void* segs, int32_t n_seg, void* stream) {
   return 0;
 }
 
-int tmae_bf16_layernorm_bwd(const void* dy, const void* v, const uint8_t* rowmask, const float* gamma, const float* mean, const float* rstd,
-                            void* dv, void* dres, float* dgamma, float* dbeta, float* dcolsum, int64_t rows, int32_t c, void* stream) {
+}  // extern "C"
+
+// `zero` = false: the caller has already zero-filled the fp32 accumulation targets (the layer entry points clear all parameter
+// gradients of a layer with ONE memset instead of one per target)
+namespace tmae {
+int bf16_layernorm_bwd_impl(const void* dy, const void* v, const uint8_t* rowmask, const float* gamma, const float* mean, const float* rstd,
+                            void* dv, void* dres, float* dgamma, float* dbeta, float* dcolsum, int64_t rows, int32_t c, bool zero, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   TMAE_CHECK_ARG(c == 128 || c == 256, "channels must be 128 or 256");
-  TMAE_CUDA(cudaMemsetAsync(dgamma, 0, c * sizeof(float), s));
-  TMAE_CUDA(cudaMemsetAsync(dbeta, 0, c * sizeof(float), s));
-  if (dcolsum) TMAE_CUDA(cudaMemsetAsync(dcolsum, 0, c * sizeof(float), s));
+  if (zero) {
+    TMAE_CUDA(cudaMemsetAsync(dgamma, 0, c * sizeof(float), s));
+    TMAE_CUDA(cudaMemsetAsync(dbeta, 0, c * sizeof(float), s));
+    if (dcolsum) TMAE_CUDA(cudaMemsetAsync(dcolsum, 0, c * sizeof(float), s));
+  }
   if (rows <= 0) return 0;
   ProfScope prof("bf16_layernorm_bwd", 0, 2.0 * rows * c * (3 + (dres ? 1 : 0)), s);
   int64_t vb = (rows + 63) / 64;
@@ -321,10 +328,10 @@ int tmae_bf16_layernorm_bwd(const void* dy, const void* v, const uint8_t* rowmas
   return 0;
 }
 
-int tmae_bf16_colsum(const void* x, float* out, int64_t rows, int32_t cols, void* stream) {
+int bf16_colsum_impl(const void* x, float* out, int64_t rows, int32_t cols, bool zero, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   TMAE_CHECK_ARG(cols % 8 == 0, "cols must be a multiple of 8");
-  TMAE_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), s));
+  if (zero) TMAE_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), s));
   if (rows <= 0) return 0;
   const int rpb = 1024;
   dim3 grid((unsigned)cdiv(cols / 8, 16), (unsigned)cdiv(rows, rpb));
@@ -332,6 +339,18 @@ int tmae_bf16_colsum(const void* x, float* out, int64_t rows, int32_t cols, void
   colsum_bf16_kernel<false><<<grid, 256, 0, s>>>((const bf16*)x, nullptr, out, rows, cols, rpb);
   TMAE_CHECK_LAUNCH();
   return 0;
+}
+}  // namespace tmae
+
+extern "C" {
+
+int tmae_bf16_layernorm_bwd(const void* dy, const void* v, const uint8_t* rowmask, const float* gamma, const float* mean, const float* rstd,
+                            void* dv, void* dres, float* dgamma, float* dbeta, float* dcolsum, int64_t rows, int32_t c, void* stream) {
+  return tmae::bf16_layernorm_bwd_impl(dy, v, rowmask, gamma, mean, rstd, dv, dres, dgamma, dbeta, dcolsum, rows, c, true, stream);
+}
+
+int tmae_bf16_colsum(const void* x, float* out, int64_t rows, int32_t cols, void* stream) {
+  return tmae::bf16_colsum_impl(x, out, rows, cols, true, stream);
 }
 
 /* dtable (64, n) fp32 = sum over rows with rowidx == p of dy[row, :] */

@@ -240,7 +240,7 @@ class Partition:
     """Device tables of one window partition (both shifts); see tmae_window_partition."""
     __slots__ = ("m_a", "m_b", "wcap", "n_levels", "tokens", "win_a", "slot_a", "posidx_a", "tok_a", "cnt_a", "win_b", "slot_b",
                  "posidx_b", "tok_b", "cnt_b", "win_level", "n_win", "level_base", "status", "ref_a", "ref_b", "temporal",
-                 "keep_a", "keep_b", "onehot_a", "onehot_b")
+                 "keep_a", "keep_b", "onehot_a", "onehot_b", "tcache")
 
 
 def window_partition(coords_a, batch, grid_x, grid_y, levels, coords_b=None, want_ref=False, status=None):
@@ -666,8 +666,15 @@ class LayerTables(ctypes.Structure):
 
 
 def layer_tables(part, shift, cross, m_q, m_kv):
-    """tmae_layer_tables for one shift of a partition (self: frame a on both sides; cross: a = current, b = previous)."""
-    T = LayerTables()
+    """tmae_layer_tables for one shift of a partition (self: frame a on both sides; cross: a = current, b = previous).  Built once
+    per (partition, shift): the 2-4 layers that share a partition reuse the struct."""
+    cache = getattr(part, "tcache", None)
+    if cache is None:
+        cache = part.tcache = {}
+    key = (shift, cross, m_q, m_kv)
+    if key in cache:
+        return cache[key]
+    T = cache[key] = LayerTables()
     T.posidx_q = _p(part.posidx_a[shift])
     T.qtok, T.qcnt = _p(part.tok_a[shift]), _p(part.cnt_a[shift])
     if cross:
@@ -694,6 +701,20 @@ def _layer_params(tensors):
     for (name, _), t in zip(LayerParams._fields_, tensors):
         setattr(P, name, _p(t, F32))
     return P
+
+
+_param_structs = {}
+
+
+def _layer_params_cached(params):
+    """LayerParams of a layer's 13 parameter tensors, rebuilt only when their storage moves (module.to(...), load_state_dict with
+    assign): 13 pointer checks per call otherwise."""
+    key = id(params[0])
+    hit = _param_structs.get(key)
+    ptrs = tuple(t.data_ptr() for t in params)
+    if hit is None or hit[0] != ptrs:
+        hit = _param_structs[key] = (ptrs, _layer_params(params))
+    return hit[1]
 
 
 def encoder_layer_fwd(x, x_kv, params, T, lut, tau_min, eps, heads, need_backward=True):
@@ -948,9 +969,9 @@ def encoder_layer_fwd_bf16(x, x_kv, params, T, lut, tau_min, eps, heads, need_ba
     nb = L.bf16_encoder_layer_saved_bytes(m_q, m_kv, c, ff, heads, cross)
     saved = _ws(nb, x.device)
     y = torch.empty_like(x)
-    P = _layer_params(params)
+    P = _layer_params_cached(params)
     W = BF16Weights()
-    W.in_w, W.out_w, W.w1, W.w2 = (_pb(shadows.get(params[i])) for i in (0, 2, 7, 9))
+    W.in_w, W.out_w, W.w1, W.w2 = (shadows.get(params[i]).data_ptr() for i in (0, 2, 7, 9))
     _call("bf16_encoder_layer_fwd", _pb(x), _pb(x_kv), ctypes.byref(P), ctypes.byref(W), ctypes.byref(T), _p(lut, F32), float(tau_min), float(eps),
           m_q, m_kv, c, ff, heads, int(need_backward), _pb(y), _p(saved), nb, _stream())
     return y, saved
@@ -968,16 +989,20 @@ def encoder_layer_bwd_bf16(dy, x, x_kv, params, T, lut, tau_min, heads, saved, w
         offs.append(offs[-1] + (n + 63) // 64 * 64)
     gbuf = torch.empty(offs[-1], dtype=F32, device=x.device)
     grads = [gbuf[o:o + n].view(t.shape) for o, n, t in zip(offs, sizes, params)]
-    G = _layer_params(grads)
-    P = _layer_params(params)
+    G = LayerParams()
+    base = gbuf.data_ptr()
+    for (name, _), o in zip(LayerParams._fields_, offs):
+        setattr(G, name, base + 4 * o)
+    P = _layer_params_cached(params)
     W = BF16Weights()
-    W.in_w, W.out_w, W.w1, W.w2 = (_pb(shadows.get(params[i])) for i in (0, 2, 7, 9))
+    W.in_w, W.out_w, W.w1, W.w2 = (shadows.get(params[i]).data_ptr() for i in (0, 2, 7, 9))
     nb = L.bf16_encoder_layer_scratch_bytes(m_q, m_kv, c, ff, heads, cross)
     scratch = _ws(nb, x.device)
     dx = torch.empty_like(x)
     dkv = torch.empty_like(x_kv) if (cross and want_dkv) else None
     _call("bf16_encoder_layer_bwd", _pb(dy), _pb(x), _pb(x_kv), ctypes.byref(P), ctypes.byref(W), ctypes.byref(T), _p(lut, F32), float(tau_min),
-          m_q, m_kv, c, ff, heads, _p(saved), saved.numel(), _pb(dx), _pb(dkv), ctypes.byref(G), _p(scratch), nb, _stream())
+          m_q, m_kv, c, ff, heads, _p(saved), saved.numel(), _pb(dx), _pb(dkv), ctypes.byref(G), gbuf.data_ptr(), gbuf.numel() * 4, _p(scratch), nb,
+          _stream())
     return dx, dkv, grads
 
 
