@@ -288,6 +288,18 @@ TMAE_API int tmae_assemble_frames(const float* raw, const int64_t* sample_offset
                          const uint8_t* xform_flags, float ego_radius, const float* crop_xyxy, float* out, int64_t* count,
                          int64_t n_points, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the reference's native op, 1:1 (pcdet/ops/sst_ops/src/sst_ops_api.cpp:6-8) ------------------------------------------------------
+ * Same tensors as sst_ops_cuda.ingroup_inds_wrapper(group_inds i64 (N,), out_inds i64 (N,)) and
+ * sst_ops_cuda.group_inner_inds_wrapper(inverse_inds i64 (N,), group_inds i64 (M,K)) (sst_ops.cpp:21-48), so sst_ops_utils.py:5-27 binds
+ * them unchanged.  Results are the CANONICAL ones (what a serial run of sst_ops_gpu.cu:14-39 yields): out_inds[i] = number of earlier
+ * elements with the same group id; group_inds[g] = the first K element indices of group g in ascending order, cyclically padded
+ * (group_inds[g][i] = group_inds[g][i mod cnt]); rows of groups without elements are left untouched (the reference pre-fills -1).
+ * No host sync, no allocation: workspace from tmae_sst_ops_workspace_bytes(N).  N < 2^31. */
+TMAE_API size_t tmae_sst_ops_workspace_bytes(int64_t n);
+TMAE_API int tmae_ingroup_inds(const int64_t* group_inds, int64_t* out_inds, int64_t n, void* workspace, size_t workspace_bytes, void* stream);
+TMAE_API int tmae_group_inner_inds(const int64_t* inverse_inds, int64_t n, int64_t* group_inds, int64_t m, int32_t k, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* ---- A10-A11 reconstruction target + Chamfer loss ------------------------------------------------
  * Replaces sst_ops_cuda.group_inner_inds_wrapper (pcdet/ops/sst_ops/src/sst_ops_api.cpp:8, sst_ops_gpu.cu:22-39),
  * the GT gather / centre subtraction (SiamWCA_MAE.py:132-139) and pytorch3d chamfer_distance (SiamWCA_MAE.py:163). */

@@ -614,6 +614,30 @@ def window_attention_bwd(dout, q, k, v, o, lse, qtok, qcnt, ktok, kcnt, n_win, s
     return dq, dk, dv
 
 
+# ------------------------------------------------------------------------------------ the reference's native op, 1:1
+def get_inner_win_inds(group_inds):
+    """pcdet/ops/sst_ops/sst_ops_utils.py:5-12 with the canonical (stable, deterministic) slot order."""
+    L = lib()
+    g = group_inds.contiguous()
+    out = torch.zeros_like(g) - 1
+    wsb = L.sst_ops_workspace_bytes(g.numel())
+    ws = _ws(wsb, g.device)
+    _call("ingroup_inds", _p(g, I64), _p(out, I64), g.numel(), _p(ws), wsb, _stream())
+    return out
+
+
+def group_inner_inds(points, inverse_inds, K, n_groups=None):
+    """pcdet/ops/sst_ops/sst_ops_utils.py:15-27.  n_groups (= number of voxels) skips the reference's .max().item() host sync."""
+    L = lib()
+    inv = inverse_inds.contiguous()
+    m = int(inv.max().item()) + 1 if n_groups is None else int(n_groups)
+    group_inds = torch.full((m, K), -1, dtype=I64, device=points.device)
+    wsb = L.sst_ops_workspace_bytes(inv.numel())
+    ws = _ws(wsb, inv.device)
+    _call("group_inner_inds", _p(inv, I64), inv.numel(), _p(group_inds, I64), m, K, _p(ws), wsb, _stream())
+    return points[group_inds]
+
+
 # ------------------------------------------------------------------------------------ loss
 def gt_group(points_kept, voxel_offset, pt_order, voxel_coords, pc_range, voxel_size, n_voxels, k, want_inds=False):
     dev = points_kept.device

@@ -578,3 +578,25 @@ def test_gt_group_and_chamfer():
         assert_close(dp, pr.grad, 1e-4, 1e-8, f"chamfer dpred fused={fused}")
     loss0, _ = ops.chamfer_fwd(pred.to(DEV), gt, torch.zeros(nv, device=DEV))
     assert float(loss0) == 0.0
+
+
+@pytest.mark.parametrize("n,groups,K", [(1, 1, 4), (5000, 37, 8), (60000, 14000, 64), (777, 2000, 3)])
+def test_sst_ops_one_to_one_seam(n, groups, K):
+    """tmae_ingroup_inds / tmae_group_inner_inds take the reference's own tensors (sst_ops_api.cpp:6-8) and return the canonical
+    result of sst_ops_gpu.cu:14-39 (what a serial run of the reference kernels yields), bit for bit: unsorted group ids, groups
+    larger than K (first K indices kept), groups smaller than K (cyclic padding), absent groups (row left at -1)."""
+    from oracle import shims
+    g = torch.Generator().manual_seed(n + groups)
+    gid = torch.randint(0, groups, (n,), generator=g)
+    ref = torch.zeros_like(gid) - 1
+    shims.ingroup_inds_wrapper(gid, ref)
+    out = ops.get_inner_win_inds(gid.to(DEV))
+    assert_equal_int(out, ref, "ingroup_inds")
+    m = int(gid.max()) + 1
+    gref = torch.full((m, K), -1, dtype=torch.long)
+    shims.group_inner_inds_wrapper(gid, gref)
+    pts = torch.randn(n, 3, generator=g)
+    got = ops.group_inner_inds(pts.to(DEV), gid.to(DEV), K)
+    assert torch.equal(got.cpu(), pts[gref]), "group_inner_inds"
+    got2 = ops.group_inner_inds(pts.to(DEV), gid.to(DEV), K, n_groups=m)   # no host sync form
+    assert torch.equal(got2.cpu(), pts[gref])
