@@ -344,6 +344,25 @@ TMAE_API int tmae_encoder_layer_bwd(const float* dy, const float* x, const float
                            const void* saved, size_t saved_size, float* dx, float* dx_kv, const tmae_layer_params* G, void* scratch,
                            size_t scratch_size, void* stream);
 
+/* ---- N4: CenterHead box decoding + rotated BEV NMS ------------------------------------------------------------------------
+ * Replaces centernet_utils.decode_bbox_from_heatmap (pcdet/models/model_utils/centernet_utils.py:154-220) after its top-K selection,
+ * iou3d_nms_cuda.boxes_iou_bev_gpu / nms_gpu (pcdet/ops/iou3d_nms/src/iou3d_nms_api.cpp, iou3d_nms_kernel.cu:236-311, iou3d_nms.cpp:90-135)
+ * and the [:NMS_POST_MAXSIZE] cut of model_nms_utils.class_agnostic_nms (:6-25).  Boxes are (.., 7) f32 [x, y, z, dx, dy, dz, heading].
+ * Unlike the reference, the suppression sweep runs on the device (no mask copy to the host, no cudaMalloc per call), batched over samples. */
+TMAE_API int tmae_boxes_iou_bev(const float* boxes_a, int64_t na, const float* boxes_b, int64_t nb, float* ans_iou, void* stream);
+TMAE_API size_t tmae_nms_bev_workspace_bytes(int32_t samples, int64_t cap);
+/* boxes (samples, cap, 7): each sample's first counts[s] rows in descending score order -> keep (samples, cap) i64 = kept row indices (the
+ * first num_keep[s] <= post_max entries are valid), num_keep (samples) i32 */
+TMAE_API int tmae_nms_bev(const float* boxes, const int32_t* counts, int32_t samples, int64_t cap, float thresh, int32_t post_max, int64_t* keep,
+                 int32_t* num_keep, void* workspace, size_t workspace_bytes, void* stream);
+/* one head: scores / inds (batch, k) = top-k of sigmoid(hm).flatten(1) (descending; index = class * h * w + y * w + x); head maps NCHW f32
+ * (dim = log sizes, rot = [cos, sin], iou nullable); class_map (ncls) i64 nullable; voxel_size / range_lo HOST float[2+], limit_range HOST
+ * float[6].  Outputs at capacity k per sample, the first counts[b] rows valid, score order preserved. */
+TMAE_API int tmae_centerhead_decode(const float* scores, const int64_t* inds, const float* center, const float* center_z, const float* dim,
+                           const float* rot, const float* iou, const int64_t* class_map, int32_t batch, int32_t k, int32_t h, int32_t w,
+                           int32_t ncls, float feature_map_stride, const float* voxel_size, const float* range_lo, const float* limit_range,
+                           float score_thresh, float* boxes, float* out_scores, int64_t* labels, float* ious, int32_t* counts, void* stream);
+
 /* ==== bf16-STORAGE mode (TMAE_PREC_BF16) ==========================================================================
  * Same reference functions as above (file:line cited there), for callers that keep encoder activations and their gradients
  * as bf16 rows (rows, channels) in HBM: what the reference itself does under its fp16 autocast
