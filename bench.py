@@ -220,26 +220,42 @@ def measure(w, args, c, steps, n_batches, full):
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
     params = [p for p in model.parameters() if p.requires_grad]
     # gradient exchange: persistent flat buffer, buckets all-reduced on a communication stream WHILE backward runs (tmae_b200/dist.py)
-    flat = tdist.OverlappedGradients(params, world).attach() if (w["train"] and world > 1 and not args.ddp) else None
+    flat = None
+    if w["train"] and world > 1 and not args.ddp:
+        flat = tdist.OverlappedGradients(params, world).attach() if args.grad_sync == "overlap" else tdist.FlatGradients(params, world)
     if world > 1:  # same initial weights on every rank (DDP broadcasts them; the flat all-reduce path does it here)
         for p in list(model.parameters()) + list(model.buffers()):
             torch.distributed.broadcast(p.data, 0)
     bb.mask_generator = torch.Generator(device=dev).manual_seed(2000 + rank)
 
-    host = make_batches(w, n_batches, rank)
+    host = make_batches(w, n_batches, rank + int(os.environ.get("TMAE_BENCH_RANK_OFFSET", "0")))   # debugging aid: another rank's scans on one GPU
     resident = [(a.to(dev), b.to(dev)) for a, b in host]
     h2d = sum(t.numel() * 4 for t in host[0])
     side = ops.side_stream(dev) if args.side_stream else None
 
     def step(pts, ptsp, module=None):
         m = net if module is None else module
+        if flat is not None and args.grad_sync == "overlap":
+            flat.enabled = module is None   # the rank-local profiling pass must not enter collectives
         if w["train"]:
+            dbg = os.environ.get("TMAE_SYNC_DEBUG")
+
+            def chk(tag):
+                if dbg:
+                    torch.cuda.synchronize()
+                    print(f"[dbg rank {rank}] {tag} ok", file=sys.stderr, flush=True)
             loss = m(pts, ptsp, side)
+            chk("forward")
             loss.backward()
+            chk("backward")
             if flat is not None and module is None:
-                flat.finish()   # buckets whose gradients were complete have been in flight since; wait for the communication stream
+                # overlap: buckets whose gradients were complete have been in flight since, wait for the communication stream;
+                # flat: copy into the persistent flat buffer and all-reduce its buckets now
+                (flat.finish if args.grad_sync == "overlap" else flat.reduce)()
+                chk("finish")
             opt.step()
             opt.zero_grad(set_to_none=True)
+            chk("step")
             return loss
         with torch.no_grad():
             return m(pts, ptsp, side)
@@ -338,7 +354,7 @@ def measure(w, args, c, steps, n_batches, full):
             out["counts"] = workload_counts(bb, resident)
         except Exception as e:  # diagnostics only: never lose the measurement over them
             out["counts"] = {"error": repr(e)}
-    if flat is not None:
+    if flat is not None and args.grad_sync == "overlap":
         flat.detach()
     del model, net, opt, params, flat, resident, host, vfe, bb
     gc.collect()
@@ -595,6 +611,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-core and the stock-PyTorch-on-GPU baselines")
     ap.add_argument("--no-extra", dest="extra", action="store_false", help="skip the short finetune / Waymo-shaped lines (extra_workloads)")
     ap.add_argument("--no-clock-sampler", dest="clock_sampler", action="store_false")
+    ap.add_argument("--grad-sync", default="flat", choices=["flat", "overlap"],
+                    help="gradient exchange of the multi-GPU pretraining step: 'flat' = after backward, the persistent flat buffer is all-reduced in buckets "
+                         "on a communication stream; 'overlap' = buckets are all-reduced from post-accumulate hooks while backward runs")
     ap.add_argument("--ddp", action="store_true", help="wrap the step in torch DistributedDataParallel instead of the flat gradient all-reduce")
     ap.add_argument("--no-side-stream", dest="side_stream", action="store_false",
                     help="run the coordinate-only pre-pass (voxelise, mask, plans) on the main stream instead of the library's side stream")

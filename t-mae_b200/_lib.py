@@ -57,6 +57,8 @@ class _Lib:
         for key, val in os.environ.items():   # TMAE_OPT_<NAME>=<int> -> tmae_set_option (A/B measurements)
             if key.startswith("TMAE_OPT_"):
                 self.set_option(key[9:].lower().encode(), int(val))
+        if "TMAE_BF16_ATTN_IMPL" in os.environ:
+            self.bf16_set_attention_impl(int(os.environ["TMAE_BF16_ATTN_IMPL"]))
 
     def _checked(self, fn, name):
         err = self.cdll.tmae_last_error_string

@@ -15,6 +15,7 @@
 // The backward kernel uses 64-channel groups (TMEM: S, dP, dQ, dK, dV accumulators) and recomputes P from the saved
 // log-sum-exp; D_i = sum_j P_ij dP_ij is taken from the registers that hold both, so O is never re-read.
 #include <cuda_bf16.h>
+#include <cstring>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -27,6 +28,23 @@ typedef __nv_bfloat16 bf16;
 constexpr int TILE_BYTES = 128 * 128 * 2;     // one operand tile of a 128-channel group: 128 rows x 256 bytes (two 64-element spans)
 constexpr int SPAN_BYTES = 128 * 128;         // one 64-element span of 128 rows
 
+#ifdef TMAE_ATTN_CHECK
+__device__ int* g_chk = nullptr;   // host-mapped: [0] = count, then 8 ints per record
+__device__ __noinline__ bool chk_fail(int code, long long v0, long long v1, long long v2, long long v3) {
+  if (!g_chk) return true;
+  const int i = atomicAdd(g_chk, 1);
+  if (i < 60) {
+    volatile int* p = g_chk + 8 + i * 8;
+    p[0] = code; p[1] = blockIdx.x; p[2] = threadIdx.x; p[3] = (int)v0; p[4] = (int)v1; p[5] = (int)v2; p[6] = (int)v3; p[7] = (int)(v3 >> 32);
+  }
+  __threadfence_system();
+  return true;
+}
+#define CHK(cond, code, v0, v1, v2, v3) ((cond) ? false : chk_fail(code, v0, v1, v2, v3))
+#else
+#define CHK(cond, code, v0, v1, v2, v3) false
+#endif
+
 struct Args {
   const bf16* q; const bf16* k; const bf16* v;
   bf16* o; float* lse;
@@ -38,6 +56,7 @@ struct Args {
   const bf16* dout; const float* inv_q; const float* inv_k; int ld_inv_q, ld_inv_k;
   bf16* dq; bf16* dk; bf16* dv; float* dtau;
   int skip_small;   // 1: the <= 16-token windows run on the warp kernels, the tcgen05 tile list starts at the 32-token class
+  int64_t mq, mkv, max_windows;   // bounds (debug checks)
 };
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -56,6 +75,7 @@ __device__ __forceinline__ void tile_counts(const Args& a, int& se, int& me, int
   nw = __ldg(a.n_win);
   se = min(__ldg(a.small_end), nw);
   me = min(max(__ldg(a.mid_end), se), nw);
+  if (CHK(nw >= 0 && nw <= a.max_windows && se >= 0, 2, nw, a.max_windows, se, me)) { nw = 0; se = 0; me = 0; }
   t16 = a.skip_small ? 0 : (se + 7) / 8;
   t32 = (me - se + 3) / 4;
   t64 = (nw - me + 1) / 2;
@@ -114,12 +134,14 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
 // voxel row of every tile row (or -1): looked up ONCE per item into shared memory -- the per-copy lookups (two dependent global loads
 // in front of every cp.async) made the gather warps the slowest stage of the pipeline
 template <int NT>
-__device__ __forceinline__ void tile_rows(int* __restrict__ rows, const int* __restrict__ tok, const int* __restrict__ cnt, const TileInfo& ti, int gt) {
+__device__ __forceinline__ void tile_rows(int* __restrict__ rows, const int* __restrict__ tok, const int* __restrict__ cnt, const TileInfo& ti, int gt,
+                                          int64_t nmax = 0, int64_t wmax = 0) {
   const int tshift = ti.T == 16 ? 4 : (ti.T == 32 ? 5 : 6);
   for (int r = gt; r < 128; r += NT) {
     const int w = ti.w0 + (r >> tshift), slot = r & (ti.T - 1);
     const bool ok = w < ti.w_end && slot < __ldg(cnt + w);
     rows[r] = ok ? __ldg(tok + (int64_t)w * 64 + slot) : -1;
+    if (ok && CHK(rows[r] >= 0 && rows[r] < nmax && w >= 0 && w < wmax, 1, rows[r], nmax, w, slot)) rows[r] = -1;
   }
 }
 template <int NT>
@@ -199,8 +221,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(Args a) {
       const int col0 = (item % G) * 64;
       if (use > 0) bar_wait(&in_empty[buf], (use - 1) & 1);
       const uint32_t base = s_u32(smem + buf * 3 * BT_BYTES);
-      tile_rows<GATHER_WARPS * 32>(rows_q[buf], a.qtok, a.qcnt, ti, gt);
-      tile_rows<GATHER_WARPS * 32>(rows_k[buf], a.ktok, a.kcnt, ti, gt);
+      tile_rows<GATHER_WARPS * 32>(rows_q[buf], a.qtok, a.qcnt, ti, gt, a.mq, a.max_windows);
+      tile_rows<GATHER_WARPS * 32>(rows_k[buf], a.ktok, a.kcnt, ti, gt, a.mkv, a.max_windows);
       named_bar(3, GATHER_WARPS * 32);
       gather_tile64<GATHER_WARPS * 32>(base, a.q, a.ldq, col0, rows_q[buf], gt);
       gather_tile64<GATHER_WARPS * 32>(base + BT_BYTES, a.k, a.ldk, col0, rows_k[buf], gt);
@@ -435,8 +457,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(Args a) {
       const int col0 = (item % G) * 64;
       if (use > 0) bar_wait(&in_empty[buf], (use - 1) & 1);
       const uint32_t base = s_u32(smem + buf * 4 * BT_BYTES);
-      tile_rows<GATHER_WARPS * 32>(rows_q[buf], a.qtok, a.qcnt, ti, gt);
-      tile_rows<GATHER_WARPS * 32>(rows_k[buf], a.ktok, a.kcnt, ti, gt);
+      tile_rows<GATHER_WARPS * 32>(rows_q[buf], a.qtok, a.qcnt, ti, gt, a.mq, a.max_windows);
+      tile_rows<GATHER_WARPS * 32>(rows_k[buf], a.ktok, a.kcnt, ti, gt, a.mkv, a.max_windows);
       named_bar(3, GATHER_WARPS * 32);
       gather_tile64<GATHER_WARPS * 32>(base, a.q, a.ldq, col0, rows_q[buf], gt);
       gather_tile64<GATHER_WARPS * 32>(base + BT_BYTES, a.k, a.ldk, col0, rows_k[buf], gt);
@@ -513,11 +535,14 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(Args a) {
       const int tshift = ti.T == 16 ? 4 : (ti.T == 32 ? 5 : 6);
       const int w = ti.w0 + (r >> tshift), slot = r & (ti.T - 1);
       const bool w_ok = w < ti.w_end;
+      CHK(!w_ok || (w >= 0 && w < a.max_windows), 5, w, a.max_windows, ti.w0, ti.w_end);
       const int nk = w_ok ? __ldg(a.kcnt + w) : 0;
       const bool row_ok = w_ok && slot < __ldg(a.qcnt + w);     // this tile row is a query row
       const bool key_ok = w_ok && slot < nk;                    // ... and / or a key row
-      const int64_t qrow = row_ok ? __ldg(a.qtok + (int64_t)w * 64 + slot) : 0;
-      const int64_t krow = key_ok ? __ldg(a.ktok + (int64_t)w * 64 + slot) : 0;
+      int64_t qrow = row_ok ? __ldg(a.qtok + (int64_t)w * 64 + slot) : 0;
+      int64_t krow = key_ok ? __ldg(a.ktok + (int64_t)w * 64 + slot) : 0;
+      if (CHK(qrow >= 0 && qrow < a.mq, 3, qrow, a.mq, w, slot)) qrow = 0;
+      if (CHK(krow >= 0 && krow < a.mkv, 4, krow, a.mkv, w, slot)) krow = 0;
       const int L = ti.T < 32 ? 32 : ti.T;
       const int cb = (r / L) * L;
       const int koff = (r >> tshift) * ti.T - cb;              // this row's first key column inside its L-block (0, or 16 in the 16-class)
@@ -853,7 +878,9 @@ __global__ void __launch_bounds__(SW_THREADS, 2) attn_small_bf16_bwd_kernel(Args
     const int w = item / groups, col = (item - w * groups) * 128 + lane * 4;
     const int head = col / HD;
     const int nq = min(a.qcnt[w], SW_T), nk = min(a.kcnt[w], SW_T);
-    const int tokv = lane < SW_T ? a.ktok[w * MAXT + lane] : a.qtok[w * MAXT + lane - SW_T];
+    int tokv = lane < SW_T ? a.ktok[w * MAXT + lane] : a.qtok[w * MAXT + lane - SW_T];
+    CHK(w >= 0 && w < a.max_windows && nq >= 0 && nk >= 0, 6, w, a.max_windows, nq, nk);
+    if (lane < SW_T ? (lane < nk && CHK(tokv >= 0 && tokv < a.mkv, 7, tokv, a.mkv, w, (long long)a.ktok)) : (lane - SW_T < nq && CHK(tokv >= 0 && tokv < a.mq, 8, tokv, a.mq, w, lane))) tokv = 0;
 #pragma unroll
     for (int i = 0; i < SW_T; ++i) {
       const int t = __shfl_sync(0xffffffffu, tokv, SW_T + i);
@@ -889,6 +916,19 @@ static int check(const Args& a) {
 
 }  // namespace atc
 
+#ifdef TMAE_ATTN_CHECK
+static int* g_chk_host = nullptr;
+extern "C" __attribute__((visibility("default"))) int* tmae_debug_attn_check_buffer() {
+  if (!g_chk_host) {
+    cudaHostAlloc((void**)&g_chk_host, 4096, cudaHostAllocMapped);
+    memset(g_chk_host, 0, 4096);
+    int* dptr = nullptr;
+    cudaHostGetDevicePointer((void**)&dptr, g_chk_host, 0);
+    cudaMemcpyToSymbol(atc::g_chk, &dptr, sizeof(dptr));
+  }
+  return g_chk_host;
+}
+#endif
 int g_small_on_warps = 1;   // measurement switch (tmae_set_option "attn_small_warps"): 0 = every window class on the tcgen05 tiles
 using namespace atc;
 
@@ -898,6 +938,7 @@ int attn_tc_fwd(const void* q, const void* k, const void* v, void* o, float* lse
   a.q = (const bf16*)q; a.k = (const bf16*)k; a.v = (const bf16*)v; a.o = (bf16*)o; a.lse = lse;
   a.qtok = T->qtok; a.qcnt = T->qcnt; a.ktok = T->ktok; a.kcnt = T->kcnt; a.n_win = T->n_win; a.small_end = T->small_end; a.mid_end = T->mid_end;
   a.tau = tau; a.tau_min = tau_min; a.C = c; a.H = heads; a.hd = c / heads; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv;
+  a.mq = m_q; a.mkv = m_kv; a.max_windows = T->max_windows;
   if (check(a)) { set_error("attn_tc_fwd: channels must be a multiple of 128 with head_dim 16 or 32, row pitches multiples of 8"); return TMAE_ERR_INVALID_ARG; }
   if (T->max_windows <= 0 || m_q <= 0) return 0;
   const size_t smem = 2 * 3 * BT_BYTES + 2 * TILE_BYTES + 1024;
@@ -935,6 +976,7 @@ int attn_tc_bwd(const void* dout, const void* q, const void* k, const void* v, c
   a.inv_q = inv_q; a.inv_k = inv_k; a.ld_inv_q = ld_inv_q; a.ld_inv_k = ld_inv_k; a.dq = (bf16*)dq; a.dk = (bf16*)dk; a.dv = (bf16*)dv; a.dtau = dtau;
   a.qtok = T->qtok; a.qcnt = T->qcnt; a.ktok = T->ktok; a.kcnt = T->kcnt; a.n_win = T->n_win; a.small_end = T->small_end; a.mid_end = T->mid_end;
   a.tau = tau; a.tau_min = tau_min; a.C = c; a.H = heads; a.hd = c / heads; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv;
+  a.mq = m_q; a.mkv = m_kv; a.max_windows = T->max_windows;
   if (check(a)) { set_error("attn_tc_bwd: channels must be a multiple of 128 with head_dim 16 or 32, row pitches multiples of 8"); return TMAE_ERR_INVALID_ARG; }
   if (T->max_windows <= 0 || m_q <= 0) return 0;
   const size_t smem = 2 * 4 * BT_BYTES + 2 * TILE_BYTES + 1024;

@@ -134,7 +134,7 @@ int g_attn_impl = 1;   // 1: tcgen05 window kernel (attention_tc.cu); 0: bridge 
 extern "C" {
 
 int tmae_bf16_set_attention_impl(int32_t impl) {
-  g_attn_impl = impl ? 1 : 0;
+  g_attn_impl = impl;   // 0 bridge, 1 tcgen05; debug: 2 = tcgen05 forward only, 3 = tcgen05 backward only
   return 0;
 }
 int tmae_bf16_attention_tc_available(void) { return attn_tc_available() ? 1 : 0; }
@@ -180,7 +180,7 @@ int tmae_bf16_encoder_layer_fwd(const void* x, const void* x_kv, const tmae_laye
   const bf16* qp = s.qkv;
   const bf16* kp = cross ? s.kv : s.qkv + c;
   const bf16* vp = cross ? s.kv + c : s.qkv + 2 * c;
-  if (g_attn_impl == 1) {
+  if (g_attn_impl == 1 || g_attn_impl == 2) {
     TRY(attn_tc_fwd(qp, kp, vp, s.o, s.lse, T, P->tau, tau_min, m_q, m_kv, c, heads, ldq, ldkv, ldkv, st));
   } else {
     Carve br((char*)saved + sb, saved_size - sb);
@@ -273,7 +273,7 @@ int tmae_bf16_encoder_layer_bwd(const void* dy, const void* x, const void* x_kv,
   }
   const float* inv_q = s.inv_q;
   const float* inv_k = cross ? s.inv_k : s.inv_q + heads;   // self: row r holds [q heads | k heads] at r * 2H
-  if (g_attn_impl == 1) {
+  if (g_attn_impl == 1 || g_attn_impl == 3) {
     const int ld_inv = cross ? heads : 2 * heads;
     TRY(attn_tc_bwd(dob, qp, kp, vp, s.o, s.lse, inv_q, ld_inv, inv_k, ld_inv, dqp, dkp, dvp, g_tau, T, P->tau, tau_min, m_q, m_kv, c, heads, ldq, ldkv,
                     ldkv, st));

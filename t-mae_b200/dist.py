@@ -113,6 +113,7 @@ class OverlappedGradients(FlatGradients):
         self._handles = []
         self._pending = None
         self._fired = None
+        self.enabled = True          # False: the hooks do nothing (a rank stepping ALONE, e.g. a profiling pass, must not enter collectives)
 
     def attach(self):
         if self.flat is None:
@@ -139,6 +140,8 @@ class OverlappedGradients(FlatGradients):
         self._fired = [False] * len(self.bounds)
 
     def _on_grad(self, i):
+        if not self.enabled:
+            return
         b = self.bucket_of[i]
         self._pending[b] -= 1
         if self._pending[b] == 0 and not self._fired[b] and self.present is not None:

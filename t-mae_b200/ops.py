@@ -94,27 +94,36 @@ def side_stream(device=None):
     return _side[idx]
 
 
-def record_all(obj, stream, _depth=0):
+def record_all(obj, stream, _seen=None):
     """record_stream(stream) on every CUDA tensor reachable from obj (dicts, sequences, objects with __slots__ or
-    __dict__): tensors allocated on the side stream are consumed by kernels of the main stream."""
-    if obj is None or _depth > 6:
+    __dict__): tensors allocated on the side stream are consumed by kernels of the main stream.  No depth limit (a visited
+    set guards cycles): a tensor that is missed returns to the side stream's pool the moment its last reference dies and
+    is handed to the NEXT step's pre-pass while this step's backward still reads it."""
+    if obj is None:
         return
     if isinstance(obj, torch.Tensor):
         if obj.is_cuda:
             obj.record_stream(stream)
         return
+    if isinstance(obj, (str, bytes, int, float, bool, torch.nn.Module, ctypes.Structure)):
+        return
+    if _seen is None:
+        _seen = set()
+    if id(obj) in _seen:
+        return
+    _seen.add(id(obj))
     if isinstance(obj, dict):
         for v in obj.values():
-            record_all(v, stream, _depth + 1)
+            record_all(v, stream, _seen)
     elif isinstance(obj, (list, tuple)):
         for v in obj:
-            record_all(v, stream, _depth + 1)
+            record_all(v, stream, _seen)
     elif hasattr(obj, "__slots__"):
         for k in obj.__slots__:
-            record_all(getattr(obj, k, None), stream, _depth + 1)
-    elif hasattr(obj, "__dict__") and not isinstance(obj, (str, bytes, int, float, torch.nn.Module)):
+            record_all(getattr(obj, k, None), stream, _seen)
+    elif hasattr(obj, "__dict__"):
         for v in vars(obj).values():
-            record_all(v, stream, _depth + 1)
+            record_all(v, stream, _seen)
 
 
 def _f3(v):

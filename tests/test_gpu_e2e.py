@@ -220,6 +220,58 @@ def test_side_stream_prepass_is_equivalent():
         assert abs(l0.item() - l1.item()) <= 1e-5 * abs(l0.item())
 
 
+def test_side_stream_tables_are_all_recorded(monkeypatch):
+    """Every table the pre-pass allocates on the side stream is marked as used by the main stream (Tensor.record_stream), however
+    deep it sits in the plan objects.  Regression: the window-partition tables of the pre-training path sat one level below the walk's
+    old depth limit, returned to the side stream's pool as soon as the plan was dropped, and were handed to the NEXT step's pre-pass
+    while this step's backward was still reading them (an illegal address / silently wrong gradients, but only with the host running
+    ahead)."""
+    recorded = set()
+    orig = torch.Tensor.record_stream
+
+    def spy(self, stream):
+        recorded.add(self.untyped_storage().data_ptr())
+        return orig(self, stream)
+    monkeypatch.setattr(torch.Tensor, "record_stream", spy)
+    pts, ptsp = cases.small_points(81, 900, 2)
+    vfe, bb = tmae_b200.build_model("pretrain", S["grid"], S["voxel"], S["range"])
+    cases.fill_params(vfe), cases.fill_params(bb)
+    vfe.to(DEV), bb.to(DEV)
+    bb.mask_generator = torch.Generator(device=DEV).manual_seed(7)
+    side = ops.side_stream(DEV)
+    bd = dict(points=torch.from_numpy(pts).to(DEV), points_prev=torch.from_numpy(ptsp).to(DEV), batch_size=2, side_stream=side)
+    bd = bb(vfe(bd))
+    torch.cuda.synchronize()
+
+    found = []
+
+    def walk(obj, path, seen):
+        if obj is None or isinstance(obj, (str, bytes, int, float, bool, torch.nn.Module)) or id(obj) in seen:
+            return
+        seen.add(id(obj))
+        if isinstance(obj, torch.Tensor):
+            if obj.is_cuda:
+                found.append((path, obj))
+        elif isinstance(obj, dict):
+            for k, v in obj.items():
+                walk(v, f"{path}.{k}", seen)
+        elif isinstance(obj, (list, tuple)):
+            for i, v in enumerate(obj):
+                walk(v, f"{path}[{i}]", seen)
+        elif hasattr(obj, "__slots__"):
+            for k in obj.__slots__:
+                walk(getattr(obj, k, None), f"{path}.{k}", seen)
+        elif hasattr(obj, "__dict__"):
+            for k, v in vars(obj).items():
+                walk(v, f"{path}.{k}", seen)
+    walk(bb.last_plan, "plan", set())
+    assert len(found) > 50, "the walk must reach the partition tables"
+    missing = [path for path, t in found if t.untyped_storage().data_ptr() not in recorded]
+    assert not missing, f"side-stream tensors without record_stream: {missing[:8]}"
+    names = " ".join(path for path, _ in found)
+    assert ".part.tok_a" in names and ".tok_b" in names and ".subm" in names
+
+
 def test_fused_decoder_batchnorm_matches_torch():
     """Throughput mode: the decoder's BatchNorm2d + ReLU + concat on the library's bf16 kernels against the same
     decoder with torch's BatchNorm2d / ReLU / cat under autocast (both bf16): features, loss, gradients and
