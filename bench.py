@@ -318,7 +318,7 @@ def measure(w, args, c, steps, n_batches, full):
     # growing (cudaMalloc stalls of 50-250 ms) for ~14 steps before it is stationary
     # (and a one-off 100-300 ms driver-side stall was observed at the ~23rd step of a process in a third of the runs,
     # with or without the clock sampler: the warm-up runs past it)
-    warmup = max(args.warmup, 7 * len(resident))
+    warmup = args.warmup if args.profile_run else max(args.warmup, 28, 2 * len(resident))
     for i in range(warmup):
         step(*resident[i % len(resident)])
     clocks = None
@@ -607,9 +607,12 @@ def main():
                     help="bf16 = bf16 activation storage + tcgen05 kind::f16 GEMMs (fp32 accumulate); tf32 = fp32 storage + tcgen05 kind::tf32 "
                          "GEMMs + TF32 mma attention; fp32 = FFMA parity mode.  Default: tmae_b200.ops.BENCH_PRECISION")
     ap.add_argument("--decoder", default="bf16", choices=["fp32", "bf16"])
-    ap.add_argument("--batches", type=int, default=4)
+    ap.add_argument("--batches", type=int, default=16,
+                    help="distinct scan-pair batches per rank (the timed steps cycle over them): enough that every rank's mean step cost is the population's, "
+                         "not the luck of four scenes (measured: 21.1 .. 22.0 ms between ranks with 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-core and the stock-PyTorch-on-GPU baselines")
     ap.add_argument("--no-extra", dest="extra", action="store_false", help="skip the short finetune / Waymo-shaped lines (extra_workloads)")
+    ap.add_argument("--profile-run", action="store_true", help="for runs under ncu: warm up exactly --warmup steps (no allocator-stationarity minimum)")
     ap.add_argument("--no-clock-sampler", dest="clock_sampler", action="store_false")
     ap.add_argument("--grad-sync", default="flat", choices=["flat", "overlap"],
                     help="gradient exchange of the multi-GPU pretraining step: 'flat' = after backward, the persistent flat buffer is all-reduced in buckets "

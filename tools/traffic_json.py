@@ -1,9 +1,9 @@
 """DRAM traffic per launch of a kernel family from an `ncu --set full` capture (read here, no GPU):
 
-    python tools/traffic_json.py capture.ncu-rep <family name in bench.py's kernel table> "<how it was captured>"
+    python tools/traffic_json.py capture.ncu-rep <family name in bench.py's kernel table> "<how it was captured>" [kernel-name regex] [out.json]
 
 Merges {family: {traffic_bytes_per_launch, launches_captured, per_launch: [{us, read, write}], how}} into
-profiles/r01_traffic.json, which bench.py reads for `roofline.traffic`.
+profiles/r02_traffic.json (default; bench.py reads r02 first, then r01), which bench.py reads for `roofline.traffic`.
 """
 import csv
 import json
@@ -23,17 +23,23 @@ def to_us(v, unit):
 
 
 def main():
+    import re
     rep, family, how = sys.argv[1], sys.argv[2], sys.argv[3]
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
+    pat = re.compile(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4] else None
+    out_name = sys.argv[5] if len(sys.argv) > 5 else "r02_traffic.json"
+    # a .ncu-rep, or its `ncu -i rep --page raw --csv --print-units base` export
+    out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], dict(zip(rows[0], rows[1]))
     per = []
     for r in rows[2:]:
         d = dict(zip(hdr, r))
-        per.append({"kernel": d["Kernel Name"][:60], "us": round(to_us(d["gpu__time_duration.sum"], units["gpu__time_duration.sum"]), 3),
+        if pat is not None and not pat.search(d["Kernel Name"]):
+            continue
+        per.append({"kernel": d["Kernel Name"][:90], "us": round(to_us(d["gpu__time_duration.sum"], units["gpu__time_duration.sum"]), 3),
                     "read": to_bytes(d["dram__bytes_read.sum"], units["dram__bytes_read.sum"]),
                     "write": to_bytes(d["dram__bytes_write.sum"], units["dram__bytes_write.sum"])})
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    path = os.path.join(ROOT, "profiles", out_name)
     data = json.load(open(path)) if os.path.exists(path) else {}
     data[family] = {"traffic_bytes_per_launch": round(sum(p["read"] + p["write"] for p in per) / max(1, len(per))),
                     "launches_captured": len(per), "per_launch": per, "how": how}
