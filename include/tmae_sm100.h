@@ -55,6 +55,10 @@ extern "C" {
 #define TMAE_ACT_NONE 0
 #define TMAE_ACT_GELU 1 /* exact erf GELU (torch default, sst_basic_block.py:121-122) */
 #define TMAE_ACT_RELU 2
+#define TMAE_ACT_GELU_DERIV 3 /* bf16 mode only: y = GELU(.), and `preact` receives GELU'(x w^T + bias) instead of the pre-activation */
+/* flag bits of tmae_bf16_linear_bwd_data's `accumulate` argument */
+#define TMAE_BWD_ACCUMULATE 1          /* dx += */
+#define TMAE_BWD_PRE_IS_DERIVATIVE 2   /* gelu_pre holds GELU'(pre-activation) (a TMAE_ACT_GELU_DERIV forward wrote it): multiply, do not re-derive */
 
 #define TMAE_MAX_LEVELS 8
 #define TMAE_WIN_TOKENS 64 /* 8 x 8 x 1 windows (t_mae_ssl.yaml:61) */
@@ -382,12 +386,20 @@ TMAE_API int tmae_bf16_linear_fwd(const void* x, const void* w, const float* bia
  * inv (m, norm_cols / hd) fp32 = 1 / max(|.|, 1e-12).  table (64, n) fp32 from tmae_pos_table. */
 TMAE_API int tmae_bf16_qkv_fwd(const void* x, const void* w, const float* table, const uint8_t* posidx, void* y, float* inv, int64_t m, int64_t n,
                       int64_t k, int32_t norm_cols, int32_t hd, void* stream);
+/* the same projection with the position term inside the MMA: y = [x | onehot] wcat^T; onehot (m, 64) bf16 from tmae_onehot64_bf16,
+ * wcat (n, k + 64) bf16 = [w | table^T] from tmae_bf16_qkv_wcat (k a multiple of 64).  What the fused layer uses. */
+TMAE_API int tmae_bf16_qkv_fwd_onehot(const void* x, const void* onehot, const void* wcat, void* y, float* inv, int64_t m, int64_t n, int64_t k,
+                             int32_t norm_cols, int32_t hd, void* stream);
+TMAE_API int tmae_bf16_qkv_wcat(const float* pos_lut, const float* w, const float* bias, void* wcat, int32_t n, int32_t n_pos, int32_t c, void* stream);
+/* the same for every layer of a model in ONE launch (the operand depends on the weights only: once per optimizer step).  segs: DEVICE array of
+ * n_seg records {const float* pos_lut; const float* w; const float* bias; void* wcat; int64_t n, n_pos, c} (56 bytes); max_n = the largest n */
+TMAE_API int tmae_bf16_qkv_wcat_multi(const void* segs, int32_t n_seg, int32_t max_n, void* stream);
 /* out_proj / linear2 + residual + LayerNorm in one pass (sst_basic_block.py:78,83; wca_block.py:96-102):
  * v = res + (rowmask == NULL || rowmask[row] ? a w^T + bias : 0); y = LayerNorm(v) * gamma + beta; n in {128, 256}; v nullable */
 TMAE_API int tmae_bf16_linear_ln_fwd(const void* a, const void* w, const float* bias, const void* res, const uint8_t* rowmask, const float* gamma,
                             const float* beta, float eps, void* v, void* y, float* mean, float* rstd, int64_t m, int64_t n, int64_t k,
                             void* stream);
-/* dx = dy w [* gelu'(gelu_pre)] [+= dx] ;  dw (n, k) fp32 = dy^T x (overwrites) */
+/* dx = dy w [* gelu'(gelu_pre)] [+= dx] ;  dw (n, k) fp32 = dy^T x (overwrites); `accumulate` = TMAE_BWD_* flag bits */
 TMAE_API int tmae_bf16_linear_bwd_data(const void* dy, const void* w, const void* gelu_pre, void* dx, int64_t m, int64_t n, int64_t k,
                               int32_t accumulate, void* stream);
 /* onehot (m, 64) bf16 = tmae_onehot64_bf16(posidx), nullable: also dtab_t (n, 64) fp32 = dy^T onehot from the same pass over dy = the
@@ -435,6 +447,8 @@ TMAE_API int tmae_bf16_window_attention_bwd(const void* dout, const void* q, con
  * tau and the weights behind the position table), W = bf16 copies of the four weight matrices, G = fp32 gradient buffers. */
 typedef struct tmae_bf16_weights {
   const void *in_w, *out_w, *w1, *w2;
+  const void* in_wcat; /* nullable: (3C, C + 64) bf16 [in_w | table^T] with n_pos = 2C (tmae_bf16_qkv_wcat), kept by the caller across calls while
+                          the weights do not change; NULL: the layer rebuilds it per call inside `saved` */
 } tmae_bf16_weights;
 TMAE_API size_t tmae_bf16_encoder_layer_saved_bytes(int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t cross);
 TMAE_API size_t tmae_bf16_encoder_layer_scratch_bytes(int64_t m_q, int64_t m_kv, int32_t c, int32_t ff, int32_t heads, int32_t cross);

@@ -429,8 +429,11 @@ class SiamWCA(nn.Module):
                     ws += [p[0], p[2], p[7], p[9]]
                 elif isinstance(m, ConvBNReLU):
                     ws.append(m._modules["0"].weight)
+            # training: refresh unconditionally -- fused optimizers and `p.data` updates do not move Tensor._version (ops._weights_epoch)
+            force = self.training and torch.is_grad_enabled()
             ops.shadows.register(ws)
-            ops.shadows.refresh()
+            ops.shadows.refresh(force)
+            ops.qkv_operands.refresh(force)
         if self.siamese_batched:
             hid, hid_prev = self._encode_siamese(feats, feats_prev, plans[2], plans[0])
         else:

@@ -46,6 +46,7 @@ struct Args {
   bf16* P;                         // E_PLAIN: optional pre-activation copy (pitch ldc)
   const bf16* gelu_pre;            // E_PLAIN: optional, result *= gelu'(gelu_pre[m, n]) (pitch ldc)
   int act, accumulate;             // accumulate: C += (bf16 read-modify-write; fp32 vector atomics for E_F32)
+  int pre_deriv;                   // gelu_pre already holds gelu'(pre-activation) (written by a TMAE_ACT_GELU_DERIV forward)
   int64_t k_chunk;
   // TN only: B columns at n >= n_split come from a second tensor (map_b2, columns n - n_split) and land in C2 (pitch ldc2):
   // the weight gradient dy^T [x | onehot(posidx)] yields dW and the position-table gradient in one pass over dy
@@ -149,6 +150,8 @@ __global__ void __launch_bounds__(THREADS + (GATHER ? GATHER_WARPS * 32 : 0), OC
           } else if (MODE == M_TN) {
 #pragma unroll
             for (int j = 0; j < UM / 64; ++j) tma_load_2d(a + j * 8192, &map_a, m0 + j * 64, k0, &bar_full[s]);
+          } else if (MODE == M_NT && EPI == E_QKV && k0 >= g.n_split) {
+            tma_load_2d(a, &map_b2, k0 - (int)g.n_split, m0, &bar_full[s]);   // [x | onehot(cell)]: the position term rides the MMA
           } else {
             tma_load_2d(a, &map_a, k0, m0, &bar_full[s]);
           }
@@ -364,14 +367,14 @@ __global__ void __launch_bounds__(THREADS + (GATHER ? GATHER_WARPS * 32 : 0), OC
         if (row_ok && col0 < g.N) load_row32(g.gelu_pre + row * g.ldc + col0, hn);
       };
       if (EPI == E_PLAIN && g.gelu_pre) load_pre(ch0);
-      const int pidx = (EPI == E_QKV && row_ok) ? (int)__ldg(g.posidx + row) : 0;
+      const int pidx = (EPI == E_QKV && g.table && row_ok) ? (int)__ldg(g.posidx + row) : 0;
       bar_wait(&bar_acc_full[buf], round & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int ch = ch0; ch < CHUNKS; ch += CSTEP) {
         const int col0 = n0 + ch * 32;
         const float bl = (EPI != E_QKV && g.bias && col0 + lane < g.N) ? __ldg(g.bias + col0 + lane) : 0.f;
         float4 tb[8];
-        if (EPI == E_QKV && row_ok && col0 < g.N) {
+        if (EPI == E_QKV && g.table && row_ok && col0 < g.N) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) tb[c] = __ldg(reinterpret_cast<const float4*>(g.table + (int64_t)pidx * g.N + col0) + c);
         }
@@ -380,16 +383,26 @@ __global__ void __launch_bounds__(THREADS + (GATHER ? GATHER_WARPS * 32 : 0), OC
         if (ch + CSTEP >= CHUNKS) release_acc();   // this warp has read everything it needs from the accumulator
         if (col0 >= g.N) continue;            // warp-uniform
         float v[32];
-        if (EPI != E_QKV) {                   // every lane takes part in the bias broadcast
+        if (EPI != E_QKV) {
+          if (g.bias) {                       // every lane takes part in the bias broadcast
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          }
         }
         if (!row_ok) continue;
         if (EPI == E_QKV) {
+          if (g.table) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            v[4 * c] = __uint_as_float(r[4 * c]) + tb[c].x; v[4 * c + 1] = __uint_as_float(r[4 * c + 1]) + tb[c].y;
-            v[4 * c + 2] = __uint_as_float(r[4 * c + 2]) + tb[c].z; v[4 * c + 3] = __uint_as_float(r[4 * c + 3]) + tb[c].w;
+            for (int c = 0; c < 8; ++c) {
+              v[4 * c] = __uint_as_float(r[4 * c]) + tb[c].x; v[4 * c + 1] = __uint_as_float(r[4 * c + 1]) + tb[c].y;
+              v[4 * c + 2] = __uint_as_float(r[4 * c + 2]) + tb[c].z; v[4 * c + 3] = __uint_as_float(r[4 * c + 3]) + tb[c].w;
+            }
+          } else {   // the table row came through the MMA (one-hot second A operand)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           }
           if (col0 < g.norm_cols) {   // q / k columns: unit vectors per head (F.normalize eps 1e-12, cosine_msa.py:151-152)
             const int nh = g.norm_cols / g.hd;
@@ -428,10 +441,27 @@ __global__ void __launch_bounds__(THREADS + (GATHER ? GATHER_WARPS * 32 : 0), OC
           continue;
         }
         // E_PLAIN
-        if (g.P) store_row32(g.P + row * g.ldc + col0, v);
-        if (g.gelu_pre) {
+        if (g.act == TMAE_ACT_GELU_DERIV) {   // y = gelu(v); P = gelu'(v): the backward's epilogue multiplies instead of re-deriving
+          float d[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= gelu_grad_t(hn[j]);
+          for (int j = 0; j < 32; ++j) {
+            float cdf, pdf;
+            gelu_parts(v[j], cdf, pdf);
+            d[j] = fmaf(v[j], pdf, cdf);
+            v[j] *= cdf;
+          }
+          if (g.P) store_row32(g.P + row * g.ldc + col0, d);
+        } else if (g.P) {
+          store_row32(g.P + row * g.ldc + col0, v);
+        }
+        if (g.gelu_pre) {
+          if (g.pre_deriv) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= hn[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= gelu_grad_t(hn[j]);
+          }
           if (ch + CSTEP < CHUNKS) load_pre(ch + CSTEP);
         }
         if (g.act == TMAE_ACT_GELU) {
@@ -489,7 +519,7 @@ static const char* prof_name(int mode, int epi, bool gather) {
   return mode == M_NT ? "bf16_gemm_nt" : (mode == M_NN ? "bf16_gemm_nn" : "bf16_gemm_tn");
 }
 
-struct SecondB { const bf16* B2; int64_t n2, ldb2; };   // TN: extra B columns [n_split, n_split + n2) from a second (K, n2) tensor
+struct SecondB { const bf16* B2; int64_t n2, ldb2; };   // TN: extra B columns [n_split, n_split + n2) from a second (K, n2) tensor; NT (E_QKV): extra A columns k >= n_split from a second (M, n2) tensor
 
 // OCC = 2 (BN <= 128 only: two CTAs need 2 x 2 BN TMEM columns and 2 x STAGES x stage bytes of shared memory): two co-resident CTAs per
 // SM with a 3-stage ring each -- one CTA's loads overlap the other's epilogue stores, and a launch has twice as many tiles in flight
@@ -515,13 +545,15 @@ static int launch(const bf16* A, const bf16* B, int64_t lda, int64_t ldb, Args g
     mb = ma;
   } else {
     // A: NT/NN K-major (rows = M, inner = K) box {64, 128} ; TN MN-major (rows = K, inner = M) box {64, 64}
-    ok &= MODE == M_TN ? make_map(&ma, A, g.M, g.K, lda, 64, 64) : make_map(&ma, A, g.K, g.M, lda, KB, UM);
+    const int64_t ka = (MODE == M_NT && b2.B2) ? g.n_split : g.K;   // NT with a second A source: A covers k < n_split only
+    ok &= MODE == M_TN ? make_map(&ma, A, g.M, g.K, lda, 64, 64) : make_map(&ma, A, ka, g.M, lda, KB, UM);
     // B: NT K-major (rows = N, inner = K) box {64, BN} ; NN/TN MN-major (rows = K, inner = N) box {64, 64}
     const int64_t nb = (MODE == M_TN && b2.B2) ? g.n_split : g.N;
     ok &= MODE == M_NT ? make_map(&mb, B, g.K, g.N, ldb, KB, BN) : make_map(&mb, B, nb, g.K, ldb, 64, 64);
   }
   CUtensorMap mb2 = mb;
   if (MODE == M_TN && b2.B2) ok &= make_map(&mb2, b2.B2, b2.n2, g.K, b2.ldb2, 64, 64);
+  else if (MODE == M_NT && b2.B2) ok &= make_map(&mb2, b2.B2, b2.n2, g.M, b2.ldb2, KB, UM);   // second A source: (M, n2) K-major, k >= n_split
   else g.n_split = (int64_t)1 << 40;
   if (!ok) return TMAE_ERR_CUDA;
   size_t smem = (size_t)STAGES * (UM * KB * 2 + BN * KB * 2) + 1024;
@@ -611,6 +643,87 @@ int tmae_bf16_qkv_fwd(const void* x, const void* w, const float* table, const ui
   return 0;
 }
 
+/* The same projection with the position term inside the MMA: y = [x | onehot(cell)] wcat^T, wcat (n, k + 64) bf16 = [w | table^T] from
+ * tmae_bf16_qkv_wcat.  The epilogue is left with the per-head normalisation (the per-row gathers of the 64-row table kept the L1 at 82 %
+ * of its throughput: 51 us against 35 us for the plain kernel at m = 68k, n = 384, k = 128). */
+int tmae_bf16_qkv_fwd_onehot(const void* x, const void* onehot, const void* wcat, void* y, float* inv, int64_t m, int64_t n, int64_t k,
+                             int32_t norm_cols, int32_t hd, void* stream) {
+  BF_CHECK(k % 64 == 0 && n % 32 == 0 && norm_cols % 32 == 0 && norm_cols <= n && (hd == 16 || hd == 32), "shape not supported");
+  BF_CHECK(al32(x) && al32(onehot) && al32(wcat) && al32(y) && onehot && inv, "pointers must be 32-byte aligned and non-null");
+  if (m <= 0) return 0;
+  Args g{};
+  g.M = m; g.N = n; g.K = k + 64; g.n_split = k; g.C = y; g.ldc = n; g.norm_cols = norm_cols; g.hd = hd; g.inv = inv;
+  BF_RUN((dispatch_bn<M_NT, E_QKV>((const bf16*)x, (const bf16*)wcat, k, k + 64, g, 1, (cudaStream_t)stream, SecondB{(const bf16*)onehot, 64, 64})),
+         "tmae_bf16_qkv_fwd_onehot");
+  return 0;
+}
+
+namespace tmae {
+namespace bfk {
+// wcat[j][0 .. c) = bf16(w[j][:]) ; wcat[j][c + p] = bf16((j < n_pos ? pos_lut[p] . w[j] : 0) + bias[j]).  One warp per (j, p).
+__global__ void qkv_wcat_kernel(const float* __restrict__ lut, const float* __restrict__ w, const float* __restrict__ bias, bf16* __restrict__ wcat,
+                                int n, int n_pos, int c) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= 64 * n) return;
+  const int j = warp >> 6, p = warp & 63;
+  const float* wr = w + (int64_t)j * c;
+  bf16* out = wcat + (int64_t)j * (c + 64);
+  float s = 0.f;
+  if (j < n_pos)
+    for (int k = lane; k < c; k += 32) s = fmaf(lut[p * c + k], wr[k], s);
+  s = warp_sum(s);
+  if (lane == 0) out[c + p] = __float2bfloat16_rn(s + (bias ? bias[j] : 0.f));
+  if (p == 0)
+    for (int k = lane; k < c; k += 32) out[k] = __float2bfloat16_rn(wr[k]);
+}
+}  // namespace bfk
+}  // namespace tmae
+
+namespace tmae {
+namespace bfk {
+struct WcatSeg { const float* lut; const float* w; const float* bias; bf16* wcat; int64_t n, n_pos, c; };
+// every layer's [W | table^T] in ONE launch: blockIdx.y = segment
+__global__ void qkv_wcat_multi_kernel(const WcatSeg* __restrict__ segs) {
+  const WcatSeg sg = segs[blockIdx.y];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int n = (int)sg.n, c = (int)sg.c;
+  if (warp >= 64 * n) return;
+  const int j = warp >> 6, p = warp & 63;
+  const float* wr = sg.w + (int64_t)j * c;
+  bf16* out = sg.wcat + (int64_t)j * (c + 64);
+  float s = 0.f;
+  if (j < sg.n_pos)
+    for (int k = lane; k < c; k += 32) s = fmaf(sg.lut[p * c + k], wr[k], s);
+  s = warp_sum(s);
+  if (lane == 0) out[c + p] = __float2bfloat16_rn(s + (sg.bias ? sg.bias[j] : 0.f));
+  if (p == 0)
+    for (int k = lane; k < c; k += 32) out[k] = __float2bfloat16_rn(wr[k]);
+}
+}  // namespace bfk
+}  // namespace tmae
+
+/* segs: DEVICE array of n_seg records {const float* pos_lut; const float* w; const float* bias; void* wcat; int64 n, n_pos, c} (56 bytes):
+ * tmae_bf16_qkv_wcat for every layer of a model in one launch (the operand depends on the weights only: once per optimizer step) */
+int tmae_bf16_qkv_wcat_multi(const void* segs, int32_t n_seg, int32_t max_n, void* stream) {
+  if (n_seg <= 0 || max_n <= 0) return 0;
+  ProfScope prof("qkv_wcat_multi", 0, 0, (cudaStream_t)stream);
+  dim3 grid((unsigned)cdiv((int64_t)64 * max_n * 32, 256), (unsigned)n_seg);
+  qkv_wcat_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const WcatSeg*)segs);
+  TMAE_CHECK_LAUNCH();
+  return 0;
+}
+
+/* wcat (n, c + 64) bf16 = [w | table^T] of the packed projection: table[p][j] = (j < n_pos ? pos_lut[p] . w[j] : 0) + bias[j]
+ * (tmae_pos_table), from the fp32 master weights */
+int tmae_bf16_qkv_wcat(const float* pos_lut, const float* w, const float* bias, void* wcat, int32_t n, int32_t n_pos, int32_t c, void* stream) {
+  if (n <= 0) return 0;
+  BF_CHECK(c % 64 == 0 && al32(wcat), "c must be a multiple of 64, wcat 32-byte aligned");
+  ProfScope prof("qkv_wcat", 0, 0, (cudaStream_t)stream);
+  qkv_wcat_kernel<<<cdiv((int64_t)64 * n * 32, 256), 256, 0, (cudaStream_t)stream>>>(pos_lut, w, bias, (bf16*)wcat, n, n_pos, c);
+  TMAE_CHECK_LAUNCH();
+  return 0;
+}
+
 /* v = res + (rowmask[row] ? a w^T + bias : 0) ; y = LayerNorm(v) * gamma + beta.  n in {128, 256} (a CTA owns whole rows). */
 int tmae_bf16_linear_ln_fwd(const void* a, const void* w, const float* bias, const void* res, const uint8_t* rowmask, const float* gamma,
                             const float* beta, float eps, void* v, void* y, float* mean, float* rstd, int64_t m, int64_t n, int64_t k,
@@ -634,7 +747,8 @@ int tmae_bf16_linear_bwd_data(const void* dy, const void* w, const void* gelu_pr
   BF_CHECK(al32(dy) && al32(w) && al32(dx) && al32(gelu_pre), "pointers must be 32-byte aligned");
   if (m <= 0) return 0;
   Args g{};
-  g.M = m; g.N = k; g.K = n; g.accumulate = accumulate; g.gelu_pre = (const bf16*)gelu_pre; g.C = dx; g.ldc = k;
+  g.M = m; g.N = k; g.K = n; g.accumulate = accumulate & TMAE_BWD_ACCUMULATE; g.pre_deriv = (accumulate & TMAE_BWD_PRE_IS_DERIVATIVE) ? 1 : 0;
+  g.gelu_pre = (const bf16*)gelu_pre; g.C = dx; g.ldc = k;
   BF_RUN((dispatch_bn<M_NN, E_PLAIN>((const bf16*)dy, (const bf16*)w, n, k, g, 1, (cudaStream_t)stream)), "tmae_bf16_linear_bwd_data");
   return 0;
 }

@@ -67,6 +67,12 @@ struct Carve {
 };
 inline size_t csz(size_t bytes) { return (bytes + 255) / 256 * 256; }
 
+// fp32 (64, 3C) position table of the epilogue form, or the bf16 (3C, C + 64) [W | table^T] operand of the one-hot form
+inline size_t tab_bytes(int c) {
+  const size_t a = (size_t)64 * 3 * c * 4, b = (size_t)3 * c * (c + 64) * 2;
+  return a > b ? a : b;
+}
+
 struct Saved {
   bf16 *qkv, *kv, *o, *v1, *x1, *h, *hpre, *v2;
   float *inv_q, *inv_k, *tab, *lse, *m1, *r1, *m2, *r2;
@@ -76,7 +82,7 @@ size_t saved_bytes(int64_t mq, int64_t mkv, int c, int ff, int heads, bool cross
   size_t b = 0;
   b += csz((size_t)mq * c * (cross ? 1 : 3) * 2) + (cross ? csz((size_t)mkv * c * 2 * 2) : 0);        // q[kv], kv
   b += csz((size_t)mq * heads * (cross ? 1 : 2) * 4) + (cross ? csz((size_t)mkv * heads * 4) : 0);    // inv
-  b += csz((size_t)64 * 3 * c * 4);                                                                     // table
+  b += csz(tab_bytes(c));                                                                               // position table / [W | table] operand
   b += csz((size_t)mq * c * 2) * 4;                                                                     // o, v1, x1, v2
   b += csz((size_t)mq * heads * 4) + csz((size_t)mq * 4) * 4;                                           // lse, m1, r1, m2, r2
   b += csz((size_t)mq * ff * 2) * 2;                                                                    // h, hpre
@@ -89,7 +95,7 @@ bool carve_saved(Saved& s, void* buf, size_t bytes, int64_t mq, int64_t mkv, int
   s.kv = cross ? (bf16*)cv.take((size_t)mkv * c * 2 * 2) : nullptr;
   s.inv_q = (float*)cv.take((size_t)mq * heads * (cross ? 1 : 2) * 4);
   s.inv_k = cross ? (float*)cv.take((size_t)mkv * heads * 4) : s.inv_q;   // self: (m, 2H) holds q heads then k heads per row
-  s.tab = (float*)cv.take((size_t)64 * 3 * c * 4);
+  s.tab = (float*)cv.take(tab_bytes(c));
   s.o = (bf16*)cv.take((size_t)mq * c * 2);
   s.v1 = (bf16*)cv.take((size_t)mq * c * 2);
   s.x1 = (bf16*)cv.take((size_t)mq * c * 2);
@@ -166,7 +172,25 @@ int tmae_bf16_encoder_layer_fwd(const void* x, const void* x_kv, const tmae_laye
   const int ldq = cross ? c : 3 * c, ldkv = cross ? 2 * c : 3 * c;
   // q = (x + pos) Wq^T + bq, k = (x_kv + pos) Wk^T + bk, v = x_kv Wv^T + bv as ONE packed projection per source tensor with the
   // position term as a 64-row table (fp32, from the fp32 master weights) added in the TMEM epilogue; q, k leave as unit vectors
-  if (!cross) {
+  const bool onehot = T->onehot_q != nullptr && (!cross || T->onehot_kv != nullptr) && c % 64 == 0;
+  if (onehot) {
+    // ... as a 64-column one-hot second A operand: [x | onehot(cell)] [W | table^T]^T, K = C + 64 (the operand the weight-gradient GEMM
+    // already reads); [W | table^T] is rebuilt from the fp32 masters per call (147 KB at C = 128)
+    // rows [0, C) q, [C, 2C) k (position term applied), [2C, 3C) v (bias only): one operand for the self AND the cross form
+    const bf16* wcat = (const bf16*)W->in_wcat;
+    if (!wcat) {
+      TRY(tmae_bf16_qkv_wcat(pos_lut, P->in_w, P->in_b, s.tab, 3 * c, 2 * c, c, stream));
+      wcat = (const bf16*)s.tab;
+    }
+    if (!cross) {
+      TRY(tmae_bf16_qkv_fwd_onehot(x, T->onehot_q, wcat, s.qkv, s.inv_q, m_q, 3 * c, c, 2 * c, hd, stream));
+    } else {
+      const bf16* wkv = wcat + (size_t)c * (c + 64);
+      TRY(tmae_bf16_qkv_fwd_onehot(x, T->onehot_q, wcat, s.qkv, s.inv_q, m_q, c, c, c, hd, stream));
+      TRY(tmae_bf16_qkv_fwd_onehot(x_kv, T->onehot_kv, wkv, s.kv, s.inv_k, m_kv, 2 * c, c, c, hd, stream));
+      TMAE_CUDA(cudaMemsetAsync(s.o, 0, (size_t)m_q * c * 2, st));   // rows outside paired windows
+    }
+  } else if (!cross) {
     TRY(tmae_pos_table(pos_lut, P->in_w, P->in_b, table, nullptr, 3 * c, 2 * c, c, stream));
     TRY(tmae_bf16_qkv_fwd(x, in_w, table, T->posidx_q, s.qkv, s.inv_q, m_q, 3 * c, c, 2 * c, hd, stream));
   } else {
@@ -200,7 +224,8 @@ int tmae_bf16_encoder_layer_fwd(const void* x, const void* x_kv, const tmae_laye
   }
   TRY(tmae_bf16_linear_ln_fwd(s.o, W->out_w, P->out_b, x, T->rowmask, P->ln1_g, P->ln1_b, eps, need_backward ? s.v1 : nullptr, s.x1, s.m1, s.r1,
                               m_q, c, c, stream));
-  TRY(tmae_bf16_linear_fwd(s.x1, W->w1, P->b1, s.h, need_backward ? s.hpre : nullptr, m_q, ff, c, TMAE_ACT_GELU, 0, stream));
+  TRY(tmae_bf16_linear_fwd(s.x1, W->w1, P->b1, s.h, need_backward ? s.hpre : nullptr, m_q, ff, c, need_backward ? TMAE_ACT_GELU_DERIV : TMAE_ACT_GELU, 0,
+                           stream));   // hpre receives gelu'(pre-activation): the only thing the backward needs it for
   TRY(tmae_bf16_linear_ln_fwd(s.h, W->w2, P->b2, s.x1, nullptr, P->ln2_g, P->ln2_b, eps, need_backward ? s.v2 : nullptr, y, s.m2, s.r2, m_q, c, ff,
                               stream));
   return 0;
@@ -250,7 +275,7 @@ int tmae_bf16_encoder_layer_bwd(const void* dy, const void* x, const void* x_kv,
   // LN2 -> FFN -> LN1 (the bias gradients of linear2 and out_proj are column sums of what the LayerNorm backward passes write)
   TRY(bf16_layernorm_bwd_impl(dy, s.v2, nullptr, P->ln2_g, s.m2, s.r2, dx1, nullptr, g_ln2_g, g_ln2_b, g_b2, m_q, c, z, stream));
   TRY(bf16_linear_bwd_weight_impl(dx1, s.h, g_w2, nullptr, nullptr, m_q, c, ff, z, stream));
-  TRY(tmae_bf16_linear_bwd_data(dx1, W->w2, s.hpre, dh, m_q, c, ff, 0, stream));      // dh = (dx1 W2) * gelu'(hpre)
+  TRY(tmae_bf16_linear_bwd_data(dx1, W->w2, s.hpre, dh, m_q, c, ff, TMAE_BWD_PRE_IS_DERIVATIVE, stream));      // dh = (dx1 W2) * gelu'(hpre)
   TRY(bf16_linear_bwd_weight_impl(dh, s.x1, g_w1, nullptr, nullptr, m_q, ff, c, z, stream));
   TRY(bf16_colsum_impl(dh, g_b1, m_q, ff, z, stream));
   TRY(tmae_bf16_linear_bwd_data(dh, W->w1, nullptr, dx1, m_q, ff, c, 1, stream));     // dx1 += dh W1: grad wrt x1 (both branches)

@@ -12,6 +12,7 @@ from ._lib import lib
 
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ACT_GELU_DERIV = 3   # bf16 mode: y = GELU(.), the pre-activation output receives GELU'(.) (tmae_sm100.h TMAE_ACT_GELU_DERIV)
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}
 
 _state = {"precision": PREC_FP32, "launches": 0}
@@ -815,6 +816,28 @@ def cast_f32(x):
     return y
 
 
+# Fused / foreach optimizers update parameters WITHOUT moving `Tensor._version` (measured: torch.optim.AdamW(fused=True) leaves it
+# unchanged), and so does any update through `p.data`.  Derived weight operands (bf16 shadows, [W | table] projections) therefore also
+# key on an "epoch" that every torch optimizer step advances (global post-step hook), and training-mode forwards refresh unconditionally.
+_weights_epoch = [0]
+
+
+def _on_optimizer_step(*_args, **_kw):
+    _weights_epoch[0] += 1
+
+
+def weights_changed():
+    """Tell the library that parameters were modified by means it cannot see (`p.data` arithmetic, a custom optimizer)."""
+    _weights_epoch[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_hook
+    _reg_post_hook(_on_optimizer_step)
+except ImportError:   # very old torch: training-mode forwards still refresh unconditionally
+    pass
+
+
 class WeightShadows:
     """bf16 copies of fp32 master weights (the tensor-core operands of the bf16 mode), refreshed when the master changes
     (`Tensor._version` moves on every in-place optimizer update): ALL stale copies in one launch through a device-resident
@@ -824,6 +847,7 @@ class WeightShadows:
         self.items = {}      # id(param) -> [param, shadow, version]
         self.table = None    # (n, 3) int64 device: src ptr, dst ptr, numel
         self.order = []
+        self.epoch = -1      # _weights_epoch at the last full refresh
 
     def _fresh(self, p):
         it = self.items.get(id(p))
@@ -834,7 +858,7 @@ class WeightShadows:
 
     def get(self, p):
         it = self._fresh(p)
-        if it[2] != p._version:
+        if it[2] != p._version or self.epoch != _weights_epoch[0]:
             self.refresh()
         return it[1]
 
@@ -842,10 +866,13 @@ class WeightShadows:
         for p in params:
             self._fresh(p)
 
-    def refresh(self):
+    def refresh(self, force=False):
+        """force (or an optimizer step since the last refresh): every copy is stale, whatever the version counters say."""
         for key in [k for k, it in self.items.items() if it[3] != it[0].data_ptr()]:   # storage moved: re-create
             self._fresh(self.items[key][0])
-        stale = [it for it in self.items.values() if it[2] != it[0]._version]
+        force = force or self.epoch != _weights_epoch[0]
+        self.epoch = _weights_epoch[0]
+        stale = list(self.items.values()) if force else [it for it in self.items.values() if it[2] != it[0]._version]
         if not stale:
             return
         dev = stale[0][0].device
@@ -884,6 +911,24 @@ def bf16_qkv_fwd(x, w, table, posidx, norm_cols, hd):
     return y, inv
 
 
+def bf16_qkv_wcat(pos_lut, w, bias, n_pos):
+    """(n, c + 64) bf16 [w | table^T] from the fp32 masters: the B operand of bf16_qkv_fwd_onehot."""
+    n, c = w.shape
+    wcat = torch.empty(n, c + 64, dtype=BF16, device=w.device)
+    _call("bf16_qkv_wcat", _p(pos_lut, F32), _p(w, F32), _p(bias, F32), _pb(wcat), n, n_pos, c, _stream())
+    return wcat
+
+
+def bf16_qkv_fwd_onehot(x, onehot, wcat, norm_cols, hd):
+    """bf16_qkv_fwd with the position term inside the MMA: y = [x | onehot] wcat^T, then the per-head normalisation."""
+    m, k = x.shape
+    n = wcat.shape[0]
+    y = torch.empty(m, n, dtype=BF16, device=x.device)
+    inv = torch.empty(m, norm_cols // hd, dtype=F32, device=x.device)
+    _call("bf16_qkv_fwd_onehot", _pb(x), _pb(onehot), _pb(wcat), _pb(y), _p(inv), m, n, k, norm_cols, hd, _stream())
+    return y, inv
+
+
 def bf16_linear_ln_fwd(a, w, bias, res, rowmask, gamma, beta, eps, want_v=True):
     m, k = a.shape
     n = w.shape[0]
@@ -896,13 +941,14 @@ def bf16_linear_ln_fwd(a, w, bias, res, rowmask, gamma, beta, eps, want_v=True):
     return y, v, mean, rstd
 
 
-def bf16_linear_bwd_data(dy, w, gelu_pre=None, dx=None, accumulate=False):
+def bf16_linear_bwd_data(dy, w, gelu_pre=None, dx=None, accumulate=False, pre_is_derivative=False):
+    """dx = dy w [* gelu'(gelu_pre)] [+= dx]; pre_is_derivative: gelu_pre already holds GELU' (an ACT_GELU_DERIV forward wrote it)."""
     m, n = dy.shape
     k = w.shape[1]
     if dx is None:
         dx = torch.empty(m, k, dtype=BF16, device=dy.device)
         accumulate = False
-    _call("bf16_linear_bwd_data", _pb(dy), _pb(w), _pb(gelu_pre), _pb(dx), m, n, k, int(accumulate), _stream())
+    _call("bf16_linear_bwd_data", _pb(dy), _pb(w), _pb(gelu_pre), _pb(dx), m, n, k, int(accumulate) | (2 if pre_is_derivative else 0), _stream())
     return dx
 
 
@@ -979,7 +1025,54 @@ def gather_nhwc_b16(dense, indices):
 
 
 class BF16Weights(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in ("in_w", "out_w", "w1", "w2")]
+    _fields_ = [(n, ctypes.c_void_p) for n in ("in_w", "out_w", "w1", "w2", "in_wcat")]
+
+
+class QkvOperands:
+    """Per attention layer the (3C, C + 64) bf16 operand [in_proj_weight | table^T] of the packed projection (tmae_bf16_qkv_wcat): it
+    depends on the weights only, so it is kept across calls and ALL stale ones are rebuilt by one launch when the masters changed
+    (`Tensor._version`, as WeightShadows); an inference loop never rebuilds it."""
+
+    def __init__(self):
+        self.items = {}      # id(in_w) -> [in_w, in_b, lut, wcat, versions, pointers]
+        self.table = None
+        self.epoch = -1
+
+    def get(self, w, b, lut):
+        it = self.items.get(id(w))
+        ptrs = (w.data_ptr(), b.data_ptr(), lut.data_ptr())
+        if it is None or it[0] is not w or it[5] != ptrs:
+            n, c = w.shape
+            it = self.items[id(w)] = [w, b, lut, torch.empty(n, c + 64, dtype=BF16, device=w.device), None, ptrs]
+            self.table = None
+        if it[4] != (w._version, b._version) or self.epoch != _weights_epoch[0]:
+            self.refresh()
+        return it[3]
+
+    def refresh(self, force=False):
+        force = force or self.epoch != _weights_epoch[0]
+        self.epoch = _weights_epoch[0]
+        stale = list(self.items.values()) if force else [it for it in self.items.values() if it[4] != (it[0]._version, it[1]._version)]
+        if not stale:
+            return
+        dev = stale[0][0].device
+
+        def recs(items):
+            return torch.tensor([[it[2].data_ptr(), it[0].data_ptr(), it[1].data_ptr(), it[3].data_ptr(), it[0].shape[0], 2 * it[0].shape[1], it[0].shape[1]]
+                                 for it in items], dtype=I64, device=dev)
+        if len(stale) == len(self.items):
+            if self.table is None or self.table.device != dev:
+                self.table = recs(stale)
+            table = self.table
+        else:
+            table = recs(stale)
+        _call("bf16_qkv_wcat_multi", table.data_ptr(), len(stale), max(it[0].shape[0] for it in stale), _stream())
+        for it in stale:
+            it[4] = (it[0]._version, it[1]._version)
+        self._keep = table   # alive until the next refresh (the launch reads it asynchronously)
+
+
+qkv_operands = QkvOperands()
 
 
 def attention_tc_available():
@@ -1005,6 +1098,7 @@ def encoder_layer_fwd_bf16(x, x_kv, params, T, lut, tau_min, eps, heads, need_ba
     P = _layer_params_cached(params)
     W = BF16Weights()
     W.in_w, W.out_w, W.w1, W.w2 = (shadows.get(params[i]).data_ptr() for i in (0, 2, 7, 9))
+    W.in_wcat = qkv_operands.get(params[0], params[1], lut).data_ptr() if (c % 64 == 0 and T.onehot_q) else None
     _call("bf16_encoder_layer_fwd", _pb(x), _pb(x_kv), ctypes.byref(P), ctypes.byref(W), ctypes.byref(T), _p(lut, F32), float(tau_min), float(eps),
           m_q, m_kv, c, ff, heads, int(need_backward), _pb(y), _p(saved), nb, _stream())
     return y, saved

@@ -75,6 +75,12 @@ def test_bf16_linear_fwd_bwd(m, n, k):
         assert y.dtype == BF and pre.dtype == BF
         assert_close(pre.float(), lin, RT, AT, f"preact m={m}")
         assert_close(y.float(), f(lin), RT, AT, f"linear act={act}")
+    # GELU with the derivative in place of the pre-activation copy, and the backward that multiplies by it
+    lin_g = lin.clone().requires_grad_()
+    F.gelu(lin_g).sum().backward()
+    y, der = ops.bf16_linear_fwd(xd, wd, bd, act=ops.ACT_GELU_DERIV, want_preact=True)
+    assert_close(y.float(), F.gelu(lin), RT, AT, "gelu (derivative-saving form)")
+    assert_close(der.float(), lin_g.grad, RT, AT, "gelu'")
     y0 = ops.bf16_linear_fwd(xd, wd, None)
     y1 = ops.bf16_linear_fwd(xd, wd, bd, out=y0.clone(), accumulate=True)
     assert_close(y1.float(), y0.double().cpu() + lin, RT, 2 * AT, "C +=")
@@ -87,6 +93,9 @@ def test_bf16_linear_fwd_bwd(m, n, k):
     F.gelu(p).backward(rb(dy) @ rb(w))
     dxg = ops.bf16_linear_bwd_data(dyd, wd, gelu_pre=dev_bf(pre))
     assert_close(dxg.float(), p.grad, RT, AT, "dx * gelu'")
+    der = dev_bf(torch.rand(m, k, generator=g) * 1.2 - 0.1)
+    dxd = ops.bf16_linear_bwd_data(dyd, wd, gelu_pre=der, pre_is_derivative=True)
+    assert_close(dxd.float(), (rb(dy) @ rb(w)) * der.double().cpu(), RT, AT, "dx * saved gelu'")
     dx2 = ops.bf16_linear_bwd_data(dyd, wd, dx=dx.clone(), accumulate=True)
     assert_close(dx2.float(), dx.double().cpu() + rb(dy) @ rb(w), RT, 2 * AT, "dx accumulate")
     dw = ops.bf16_linear_bwd_weight(dyd, xd)
@@ -126,11 +135,73 @@ def test_bf16_qkv_projection(m, c, parts, hd):
     ref[:, :norm_cols] = (heads / nrm[..., None]).reshape(m, norm_cols)
     assert_close(y.float(), ref, RT, AT, "qkv")
     assert_close(inv, 1 / nrm, 1e-4, 1e-6, "1 / |.|")
+    # the form the fused layer uses: the table row arrives through the MMA as a one-hot second A operand, table rounded to bf16
+    if c % 64 == 0:
+        wcat = ops.bf16_qkv_wcat(lut.to(DEV), w.to(DEV), b.to(DEV), n_pos)
+        assert torch.equal(wcat[:, :c].cpu(), w.to(BF)), "[W | table]: weight part"
+        assert_close(wcat[:, c:].float().T, table.double().cpu(), 1e-2, 1e-2, "[W | table]: table part")
+        y2, inv2 = ops.bf16_qkv_fwd_onehot(dev_bf(x), ops.onehot64_bf16(pi.to(DEV)), wcat, norm_cols, hd)
+        ref2 = rb(x) @ rb(w).T + wcat[:, c:].double().cpu().T[pi.long()]
+        h2 = ref2[:, :norm_cols].reshape(m, H, hd)
+        n2 = h2.norm(dim=-1).clamp_min(1e-12)
+        ref2[:, :norm_cols] = (h2 / n2[..., None]).reshape(m, norm_cols)
+        assert_close(y2.float(), ref2, RT, AT, "qkv (one-hot form)")
+        assert_close(inv2, 1 / n2, 1e-4, 1e-6, "1 / |.| (one-hot form)")
+        assert_close(y2.float(), y.double().cpu(), 2e-2, 2e-2, "one-hot form vs table-epilogue form")
     # sanity against the un-rounded reference formulation
     full = (x.double() + torch.cat([lut.double()[pi.long()]] * 1, 1)) @ w.double()[:n_pos].T + b.double()[:n_pos]
     fh = full.reshape(m, H, hd)
     fh = fh / fh.norm(dim=-1, keepdim=True).clamp_min(1e-12)
     assert (y.float().cpu()[:, :norm_cols].double() - fh.reshape(m, norm_cols)).abs().max() < 3e-2
+
+
+def test_shadows_follow_a_fused_optimizer_step():
+    """torch.optim.AdamW(fused=True) updates parameters WITHOUT moving Tensor._version: the bf16 shadows and the [W | table] operands must
+    still follow (global optimizer post-step hook -> ops._weights_epoch), and so after ops.weights_changed() for `p.data` arithmetic."""
+    g = torch.Generator().manual_seed(3)
+    w = torch.nn.Parameter((torch.randn(384, 128, generator=g) / 11).to(DEV))
+    b = torch.nn.Parameter((torch.randn(384, generator=g) * 0.1).to(DEV))
+    lut = torch.randn(64, 128, generator=g).to(DEV)
+    sh, qo = ops.WeightShadows(), ops.QkvOperands()
+    assert torch.equal(sh.get(w), w.detach().to(BF))
+    first = qo.get(w, b, lut).clone()
+    opt = torch.optim.AdamW([w, b], lr=0.05, fused=True)
+    w.grad, b.grad = torch.randn_like(w), torch.randn_like(b)
+    v0 = w._version
+    opt.step()
+    assert torch.equal(sh.get(w), w.detach().to(BF)), f"stale bf16 shadow after a fused optimizer step (_version {v0} -> {w._version})"
+    got = qo.get(w, b, lut)
+    assert torch.equal(got, ops.bf16_qkv_wcat(lut, w.detach(), b.detach(), 256)) and not torch.equal(got, first)
+    w.data.mul_(2.0)                      # invisible to the version counter
+    ops.weights_changed()
+    assert torch.equal(sh.get(w), w.detach().to(BF))
+    assert torch.equal(qo.get(w, b, lut), ops.bf16_qkv_wcat(lut, w.detach(), b.detach(), 256))
+
+
+def test_qkv_operands_cache_rebuilds_all_stale_in_one_launch():
+    """ops.QkvOperands: the per-layer [W | table^T] operands equal the single-layer builder, are rebuilt when a master changes in place
+    (an optimizer step) and not otherwise."""
+    g = torch.Generator().manual_seed(5)
+    qo = ops.QkvOperands()
+    layers = []
+    for c in (128, 256, 128):
+        w = (torch.randn(3 * c, c, generator=g) / c ** .5).to(DEV)
+        b = (torch.randn(3 * c, generator=g) * 0.1).to(DEV)
+        lut = torch.randn(64, c, generator=g).to(DEV)
+        layers.append((w, b, lut))
+    first = [qo.get(*l) for l in layers]
+    for (w, b, lut), got in zip(layers, first):
+        assert torch.equal(got, ops.bf16_qkv_wcat(lut, w, b, 2 * w.shape[1]))
+    calls = ops.launch_count()
+    again = [qo.get(*l) for l in layers]
+    assert ops.launch_count() == calls and all(a.data_ptr() == b_.data_ptr() for a, b_ in zip(first, again)), "unchanged masters: no launch"
+    for w, b, _ in layers:
+        w.mul_(1.5), b.add_(0.25)
+    calls = ops.launch_count()
+    third = [qo.get(*l) for l in layers]
+    assert ops.launch_count() == calls + 1, "all stale operands in ONE launch"
+    for (w, b, lut), got in zip(layers, third):
+        assert torch.equal(got, ops.bf16_qkv_wcat(lut, w, b, 2 * w.shape[1]))
 
 
 @pytest.mark.parametrize("m,n,k,masked", [(1000, 128, 128, False), (4097, 256, 256, False), (777, 128, 256, True), (300, 256, 512, True), (1, 128, 128, False)])

@@ -200,6 +200,57 @@ def test_golden_case_in_throughput_mode(golden_case, mode):
     assert rep["grad_median"] <= tol["grad_median"], rep["grad_median"]
 
 
+def test_bf16_mode_forward_follows_fused_optimizer_steps(golden_case):
+    """Training in the bench configuration (bf16 mode, torch.optim.AdamW(fused=True)): the forward must see every optimizer step.
+    Regression: the fused optimizer does not move Tensor._version, so the bf16 weight shadows (keyed on it) stayed at their step-1
+    values for the rest of the run -- same timing, silently wrong training.  After three steps the trained modules and a FRESH pair
+    loaded from their state_dict must produce bit-identical eval outputs, and the loss must have moved."""
+    g, pts, ptsp, B, ms, mask, _ = golden_case
+    P = torch.from_numpy(pts).to(DEV), torch.from_numpy(ptsp).to(DEV)
+
+    def build(state=None):
+        vfe, bb = tmae_b200.build_model("pretrain", S["grid"], S["voxel"], S["range"])
+        if state is None:
+            cases.fill_params(vfe), cases.fill_params(bb)
+        else:
+            vfe.load_state_dict(state[0]), bb.load_state_dict(state[1])
+        vfe.to(DEV), bb.to(DEV)
+        bb.decoder_autocast = torch.bfloat16
+        return vfe, bb
+
+    def run(vfe, bb):
+        bd = vfe(dict(points=P[0], points_prev=P[1], batch_size=B))
+        bd["voxel_mae_mask_in"] = mask.to(DEV)
+        bd = bb(bd)
+        return bd, bb.get_loss()[0]
+
+    ops.set_precision("bf16")
+    try:
+        vfe, bb = build()
+        vfe.train(), bb.train()
+        opt = torch.optim.AdamW(list(vfe.parameters()) + list(bb.parameters()), lr=2e-3, weight_decay=0.01, fused=True)
+        losses = []
+        for _ in range(3):
+            _, loss = run(vfe, bb)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            losses.append(loss.item())
+        assert abs(losses[2] - losses[0]) > 1e-3 * abs(losses[0]), f"the loss did not move over three optimizer steps: {losses}"
+        vfe.eval(), bb.eval()
+        with torch.no_grad():
+            bd1, l1 = run(vfe, bb)
+        state = ({k: v.detach().cpu().clone() for k, v in vfe.state_dict().items()}, {k: v.detach().cpu().clone() for k, v in bb.state_dict().items()})
+        vfe2, bb2 = build(state)
+        vfe2.eval(), bb2.eval()
+        with torch.no_grad():
+            bd2, l2 = run(vfe2, bb2)
+        assert torch.equal(bd1["spatial_features"], bd2["spatial_features"]), "trained modules and a fresh copy of their weights disagree: stale derived weight operands"
+        assert l1.item() == l2.item()
+    finally:
+        ops.set_precision("fp32")
+
+
 @pytest.mark.parametrize("mode", ["tf32", "bf16"])
 @pytest.mark.parametrize("shape_name,n_points,npf", [("once", 60000, 5), ("waymo", 180000, 6)])
 def test_full_scan_pair_in_throughput_mode(shape_name, n_points, npf, mode):
