@@ -174,6 +174,7 @@ __device__ __forceinline__ void row_softmax(float* x, int nk, float scale, float
 
 template <int HD>
 __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(Args a) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: see tc_common.cuh pdl_trigger
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int HG = 64 / HD;                  // heads per 64-channel group (4 or 2): even, so head h uses slot h & 1 = its warpgroup
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_fwd_kernel(Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_wait();   // set-up above (barriers, zeroed P tiles, TMEM) may overlap the previous kernel; nothing below may
 
   int se, me, nw, t16, t32, t64;
   tile_counts(a, se, me, nw, t16, t32, t64);
@@ -411,6 +413,7 @@ __device__ __forceinline__ void bwd_row_part(float* x, float* dp, int j0, int nk
 
 template <int HD>
 __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(Args a) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: see tc_common.cuh pdl_trigger
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int HG = 64 / HD;
@@ -441,6 +444,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_tc_bwd_kernel(Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  pdl_wait();   // set-up above (barriers, zeroed P tiles, TMEM) may overlap the previous kernel; nothing below may
 
   int se, me, nw, t16, t32, t64;
   tile_counts(a, se, me, nw, t16, t32, t64);
@@ -776,6 +780,7 @@ __device__ __forceinline__ void small_fwd_window(const Args& a, const uint2 (*qs
 
 template <int HD>
 __global__ void __launch_bounds__(SW_THREADS, 4) attn_small_bf16_fwd_kernel(Args a) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: see tc_common.cuh pdl_trigger
   constexpr int HL = HD / 4;
   __shared__ uint2 q_s[SW_THREADS / 32][SW_T][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -863,6 +868,7 @@ __device__ __forceinline__ void small_bwd_chunk(const Args& a, const SmallBwdSme
 
 template <int HD>
 __global__ void __launch_bounds__(SW_THREADS, 2) attn_small_bf16_bwd_kernel(Args a, const bf16* __restrict__ o) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: see tc_common.cuh pdl_trigger
   constexpr int HL = HD / 4;
   extern __shared__ __align__(16) unsigned char sw_raw[];
   SmallBwdSmem& S = reinterpret_cast<SmallBwdSmem*>(sw_raw)[threadIdx.x >> 5];
@@ -929,6 +935,21 @@ extern "C" __attribute__((visibility("default"))) int* tmae_debug_attn_check_buf
   return g_chk_host;
 }
 #endif
+extern int g_bf16_gemm_pdl;
+namespace atc {
+// launch with programmatic stream serialization (the kernel's set-up overlaps the previous kernel's tail; see pdl_wait in the kernels)
+template <typename K>
+static void launch_pdl(K kern, int grid, int threads, size_t smem, cudaStream_t s, const Args& a) {
+  if (!g_bf16_gemm_pdl) { kern<<<grid, threads, smem, s>>>(a); return; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, a);
+}
+}  // namespace atc
 int g_small_on_warps = 1;   // measurement switch (tmae_set_option "attn_small_warps"): 0 = every window class on the tcgen05 tiles
 using namespace atc;
 
@@ -957,10 +978,10 @@ int attn_tc_fwd(const void* q, const void* k, const void* v, void* o, float* lse
   ProfScope prof("attn_tc_fwd", 0, bytes, s);
   if (a.hd == 16) {
     if (smem_attr_once((const void*)attn_tc_fwd_kernel<16>, (int)smem)) return TMAE_ERR_CUDA;
-    attn_tc_fwd_kernel<16><<<grid, THREADS, smem, s>>>(a);
+    launch_pdl(attn_tc_fwd_kernel<16>, grid, THREADS, smem, s, a);
   } else {
     if (smem_attr_once((const void*)attn_tc_fwd_kernel<32>, (int)smem)) return TMAE_ERR_CUDA;
-    attn_tc_fwd_kernel<32><<<grid, THREADS, smem, s>>>(a);
+    launch_pdl(attn_tc_fwd_kernel<32>, grid, THREADS, smem, s, a);
   }
   if (cudaGetLastError() != cudaSuccess) { set_error("attn_tc_fwd: launch failed"); return TMAE_ERR_CUDA; }
   return 0;
@@ -996,10 +1017,10 @@ int attn_tc_bwd(const void* dout, const void* q, const void* k, const void* v, c
   ProfScope prof("attn_tc_bwd", 0, bytes, s);
   if (a.hd == 16) {
     if (smem_attr_once((const void*)attn_tc_bwd_kernel<16>, (int)smem)) return TMAE_ERR_CUDA;
-    attn_tc_bwd_kernel<16><<<grid, THREADS, smem, s>>>(a);
+    launch_pdl(attn_tc_bwd_kernel<16>, grid, THREADS, smem, s, a);
   } else {
     if (smem_attr_once((const void*)attn_tc_bwd_kernel<32>, (int)smem)) return TMAE_ERR_CUDA;
-    attn_tc_bwd_kernel<32><<<grid, THREADS, smem, s>>>(a);
+    launch_pdl(attn_tc_bwd_kernel<32>, grid, THREADS, smem, s, a);
   }
   if (cudaGetLastError() != cudaSuccess) { set_error("attn_tc_bwd: launch failed"); return TMAE_ERR_CUDA; }
   return 0;

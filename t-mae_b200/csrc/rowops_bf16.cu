@@ -43,6 +43,7 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
 // many tensors in one launch (the layer weights' bf16 shadows after an optimizer step): segment table on the device
 struct CastSeg { const float* src; bf16* dst; int64_t n; };
 __global__ void cast_multi_kernel(const CastSeg* __restrict__ segs, int n_seg) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: see tc_common.cuh pdl_trigger
   const CastSeg sg = segs[blockIdx.y];
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < sg.n; i += (int64_t)gridDim.x * blockDim.x * 8) {
     if (i + 8 <= sg.n) {
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const bf16* __restrict
                                                           const float* __restrict__ gamma, const float* __restrict__ mean_in,
                                                           const float* __restrict__ rstd_in, bf16* __restrict__ dv, bf16* __restrict__ dres,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcol, int64_t rows) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: see tc_common.cuh pdl_trigger
   constexpr int LPR = C / 8, RPW = 32 / LPR, UNR = 2;
   __shared__ float red[COLSUM ? 3 : 2][8][C];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const bf16* __restrict
 template <bool BINNED>
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, const uint8_t* __restrict__ bin, float* __restrict__ out,
                                                           int64_t rows, int n, int rpb) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: see tc_common.cuh pdl_trigger
   // block = 16 column chunks (128 columns) x 16 row lanes
   const int chunks = n / 8;
   const int cx = threadIdx.x & 15, cl = cx + 16 * blockIdx.x;
@@ -172,7 +175,20 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
   if (cl < chunks) {
     if (!BINNED) {
       float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int64_t r = r_beg + rl; r < r_end; r += 16) {
+      int64_t r = r_beg + rl;
+      for (; r + 48 < r_end; r += 64) {     // four independent 16-byte loads in flight per thread
+        uint4 u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(x + (r + 16 * i) * n + cl * 8));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float f[8];
+          unpack8(u[i], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+      }
+      for (; r < r_end; r += 16) {
         float f[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * n + cl * 8)), f);
 #pragma unroll
@@ -333,8 +349,11 @@ int bf16_colsum_impl(const void* x, float* out, int64_t rows, int32_t cols, bool
   TMAE_CHECK_ARG(cols % 8 == 0, "cols must be a multiple of 8");
   if (zero) TMAE_CUDA(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), s));
   if (rows <= 0) return 0;
-  const int rpb = 1024;
-  dim3 grid((unsigned)cdiv(cols / 8, 16), (unsigned)cdiv(rows, rpb));
+  // rows per block: ~4 blocks per SM over the whole grid (134 blocks of 1024 rows left the 148 SMs under-filled: 1.5 TB/s)
+  const int64_t col_blocks = cdiv(cols / 8, 16);
+  int64_t want = cdiv(rows * col_blocks, (int64_t)kNumSMs * 4);
+  const int rpb = (int)(want < 128 ? 128 : (want > 1024 ? 1024 : align_up(want, 64)));
+  dim3 grid((unsigned)col_blocks, (unsigned)cdiv(rows, rpb));
   ProfScope prof("bf16_colsum", 0, 2.0 * rows * cols, s);
   colsum_bf16_kernel<false><<<grid, 256, 0, s>>>((const bf16*)x, nullptr, out, rows, cols, rpb);
   TMAE_CHECK_LAUNCH();

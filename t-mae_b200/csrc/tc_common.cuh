@@ -188,6 +188,11 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
                "f"(v[6]), "f"(v[7]) : "memory");
 }
+// Programmatic dependent launch (sm_90+).  pdl_trigger: the next kernel of the stream, IF it was launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, may start its set-up (barriers, TMEM, shared-memory clears) while this grid is still
+// running; it must call pdl_wait before it touches anything this grid reads or writes.  Both are no-ops otherwise.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void bar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory");
 }
