@@ -499,14 +499,18 @@ def roofline(ops, step, resident, args, step_ms):
         roof = {"kernel": name, "bound": "tensor", "achieved": round(tf, 3), "peak": pk["tensor"], "unit": "TFLOP/s", "frac": round(tf / pk["tensor"], 5)}
     else:
         roof = {"kernel": name, "bound": "hbm", "achieved": round(gb, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(gb / pk["hbm"], 5)}
-    traffic = None
+    traffic = traffic_req = None
     for tp in ("r02_traffic.json", "r01_traffic.json"):
         tp = os.path.join(ROOT, "profiles", tp)
         if os.path.exists(tp):  # dram__bytes_read + dram__bytes_write per launch of this kernel family from the committed ncu --set full capture
-            traffic = json.load(open(tp)).get(name, {}).get("traffic_bytes_per_launch")
+            rec = json.load(open(tp)).get(name, {})
+            traffic = rec.get("traffic_bytes_per_launch")
+            traffic_req = rec.get("l2_requested_bytes_per_launch")
             if traffic is not None:
                 break
-    roof.update(traffic=traffic, algorithmic_bytes_per_launch=round(r["bytes"] / r["calls"]) if r["calls"] else None, arithmetic_intensity_flop_per_byte=round(ai, 1) if r["bytes"] else None, ridge_flop_per_byte=round(ridge, 1),
+    roof.update(traffic=traffic, traffic_note=(f"ncu --set full, launches of this family captured inside the same program; those launches asked the L2 for {traffic_req} bytes each "
+                                               "(a family's launches differ in size: compare traffic with THIS figure, not with the family average below)") if traffic_req else None,
+                algorithmic_bytes_per_launch=round(r["bytes"] / r["calls"]) if r["calls"] else None, arithmetic_intensity_flop_per_byte=round(ai, 1) if r["bytes"] else None, ridge_flop_per_byte=round(ridge, 1),
                 tensor_tflops=round(tf, 2), peak_source=pk["src"], avg_launch_us=round(r["ms"] * 1e3 / r["calls"], 2),
                 launches_per_step=r["calls"] // n, share_of_library_time=round(r["ms"] / tot, 4))
     short = {k: {"ms_per_step": round(v["ms"] / n, 3), "launches_per_step": v["calls"] // n,

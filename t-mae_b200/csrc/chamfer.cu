@@ -89,15 +89,18 @@ __device__ __forceinline__ float sqdist(const float a[3], const float b[3]) {
 }
 
 // warp per pillar.  BWD = false: accumulate the weighted sums.  BWD = true: write dpred.
+// The forward is a grid-stride loop: a warp keeps its three partial sums in registers over all its pillars and a block adds ONE set
+// of three double atomics (41k warps x 3 atomics on the same three addresses were 2/3 of the forward kernel's 207 us).
 template <bool BWD>
 __global__ void chamfer_kernel(ChamferArgs a, GtArgs g) {
-  int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (v >= a.m) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double acc_x = 0.0, acc_y = 0.0, acc_w = 0.0;
+  for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < a.m; v += warps) {
   float w = a.w[v];
   if (w == 0.f) {
     if (BWD) for (int e = lane; e < a.P1 * 3; e += 32) a.dpred[v * a.P1 * 3 + e] = 0.f;
-    return;
+    continue;
   }
   float x[3] = {0.f, 0.f, 0.f};
   if (lane < a.P1) {
@@ -140,12 +143,8 @@ __global__ void chamfer_kernel(ChamferArgs a, GtArgs g) {
   }
   if (!BWD) {
     float sum_y = warp_sum((has0 ? best0 : 0.f) + (has1 ? best1 : 0.f));
-    if (lane == 0) {
-      atomicAdd(a.acc + 0, (double)(w * sum_x));
-      atomicAdd(a.acc + 1, (double)(w * sum_y));
-      atomicAdd(a.acc + 2, (double)w);
-    }
-    return;
+    acc_x += (double)(w * sum_x); acc_y += (double)(w * sum_y); acc_w += (double)w;   // identical in every lane
+    continue;
   }
   // y-direction: sum over gts whose nearest pred is i of (x_i - y_j)
   float gy[3] = {0.f, 0.f, 0.f};
@@ -164,6 +163,18 @@ __global__ void chamfer_kernel(ChamferArgs a, GtArgs g) {
     o[0] = sc * (cx * gx[0] + cy * gy[0]);
     o[1] = sc * (cx * gx[1] + cy * gy[1]);
     o[2] = sc * (cx * gx[2] + cy * gy[2]);
+  }
+  }  // pillar loop
+  if (!BWD) {
+    __shared__ double part[8][3];
+    const int wib = threadIdx.x >> 5;
+    if (lane == 0) { part[wib][0] = acc_x; part[wib][1] = acc_y; part[wib][2] = acc_w; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double t = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i][threadIdx.x];
+      if (t != 0.0) atomicAdd(a.acc + threadIdx.x, t);
+    }
   }
 }
 
@@ -214,7 +225,10 @@ int tmae_chamfer_fwd(const float* pred, const float* gt, const float* w, int64_t
   GtArgs g = make_gt(points_kept, point_stride, voxel_offset, pt_order, voxel_coords, range_lo, voxel, p2);
   ProfScope prof("chamfer_fwd", (double)n_voxels * p1 * p2 * 8, (double)n_voxels * (p1 * 12.0 + 4.0 + 24.0 * 5), s);
   TMAE_CUDA(cudaMemsetAsync(state, 0, 3 * sizeof(double), s));
-  if (n_voxels > 0) chamfer_kernel<false><<<cdiv(n_voxels * 32, 256), 256, 0, s>>>(a, g);
+  if (n_voxels > 0) {
+    const int64_t blocks = cdiv(n_voxels * 32, 256), cap = (int64_t)kNumSMs * 16;   // 8 warps per block; <= 16 blocks per SM in the grid
+    chamfer_kernel<false><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(a, g);
+  }
   chamfer_finalize_kernel<<<1, 1, 0, s>>>(a.acc, p1, p2, loss);
   TMAE_CHECK_LAUNCH();
   return 0;

@@ -207,8 +207,57 @@ def bev(batch=8):
         print("     " + "  ".join(f"{k} {v['ms'] / v['calls'] * 1e3:.0f}us x{v['calls'] // len(xs)} ({v['bytes'] / v['ms'] / 1e6:.0f} GB/s)" for k, v in tab.items() if v["ms"] > 0))
 
 
+def small():
+    """The kernels in front of and behind the encoder (voxelise, window partition, Chamfer) at the bench's size -- where a frame set is
+    5-10 MB and the multi-kernel calls are launch-latency-bound -- and at sizes where the bytes dominate: GB/s of the ALGORITHMIC bytes
+     from the library's own CUDA-event profiler, against the measured 6.45 TB/s copy peak."""
+    import numpy as np
+    from tmae_b200 import synth
+    shape = synth.SHAPES["once"]
+    grid = synth.grid_size(shape).tolist()
+    print("voxelize (points x 5 floats -> kept points, coords, inverse, CSR, voxel mean):")
+    for B, npts in ((4, 60000), (16, 120000), (64, 120000), (64, 500000)):
+        rng = np.random.default_rng(B)
+        n = B * npts
+        pts = np.empty((n, 5), np.float32)
+        pts[:, 0] = np.repeat(np.arange(B), npts)
+        r = np.abs(rng.normal(0, 30, n)) + 2
+        th = rng.uniform(0, 2 * np.pi, n)
+        pts[:, 1], pts[:, 2] = r * np.cos(th), r * np.sin(th)
+        pts[:, 3], pts[:, 4] = rng.normal(-1, 0.5, n), rng.uniform(0, 1, n)
+        p = torch.from_numpy(pts).to(DEV)
+        ops.voxelize(p, shape["range"], shape["voxel"], grid, B)
+        torch.cuda.synchronize()
+        tab = ops.lib_profile(lambda: [ops.voxelize(p, shape["range"], shape["voxel"], grid, B) for _ in range(5)])
+        v = tab["voxelize"]
+        print(f"   batch {B:3d} x {npts:7d} points ({n * 20 / 1e6:6.1f} MB in): {v['ms'] / v['calls'] * 1e3:8.1f} us  {v['bytes'] / v['ms'] / 1e6:7.0f} GB/s")
+    print("window_partition (both shifts, 3 levels):")
+    for M, g, B in ((70000, 468, 8), (560000, 468, 64), (2000000, 936, 64)):
+        coords, P = _lidar_partition(M, g, B)
+        lv = [(16, 0, 16), (32, 16, 32), (64, 32, 100000)]
+        torch.cuda.synchronize()
+        tab = ops.lib_profile(lambda: [ops.window_partition(coords, B, g, g, lv) for _ in range(5)])
+        v = tab["window_partition"]
+        print(f"   {coords.shape[0]:8d} voxels, grid {g}, batch {B:3d}: {v['ms'] / v['calls'] * 1e3:8.1f} us  {v['bytes'] / v['ms'] / 1e6:7.0f} GB/s")
+    print("chamfer (16 predictions vs <= 64 ground-truth points per pillar, dense (M, 64, 3) ground truth):")
+    for M in (55000, 500000, 4000000):
+        g = torch.Generator(device=DEV).manual_seed(M)
+        pred = torch.randn(M, 16, 3, device=DEV, generator=g)
+        gt = torch.randn(M, 64, 3, device=DEV, generator=g)
+        gt[:, 40:] = float("nan") if False else gt[:, 40:]
+        w = (torch.rand(M, device=DEV, generator=g) < 0.75).float()
+        ops.chamfer_fwd(pred, gt, w)
+        torch.cuda.synchronize()
+        tab = ops.lib_profile(lambda: [ops.chamfer_fwd(pred, gt, w) for _ in range(5)])
+        v = tab["chamfer_fwd"]
+        nb = M * (16 * 12 + 4) + 0.75 * M * 64 * 12
+        print(f"   {M:8d} pillars: {v['ms'] / v['calls'] * 1e3:8.1f} us  {nb / (v['ms'] / v['calls']) / 1e6:7.0f} GB/s (bytes actually needed: masked pillars skip their ground truth)")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "small":
+        small()
     if what in ("attn_bf16", "bf16"):
         attn_bf16()
     if what == "attn_bf16_one":

@@ -36,12 +36,22 @@ def main():
         d = dict(zip(hdr, r))
         if pat is not None and not pat.search(d["Kernel Name"]):
             continue
-        per.append({"kernel": d["Kernel Name"][:90], "us": round(to_us(d["gpu__time_duration.sum"], units["gpu__time_duration.sum"]), 3),
-                    "read": to_bytes(d["dram__bytes_read.sum"], units["dram__bytes_read.sum"]),
-                    "write": to_bytes(d["dram__bytes_write.sum"], units["dram__bytes_write.sum"])})
+        rec = {"kernel": d["Kernel Name"][:90], "us": round(to_us(d["gpu__time_duration.sum"], units["gpu__time_duration.sum"]), 3),
+               "read": to_bytes(d["dram__bytes_read.sum"], units["dram__bytes_read.sum"]),
+               "write": to_bytes(d["dram__bytes_write.sum"], units["dram__bytes_write.sum"])}
+        # what THIS launch asked of the L2 (sectors x 32 B): the yardstick for its own DRAM traffic -- a family's launches differ in size,
+        # and the captured ones need not be average
+        rk, wk = "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum"
+        if d.get(rk):
+            rec["l2_read_requested"] = 32 * float(d[rk].replace(",", ""))
+        if d.get(wk):
+            rec["l2_write_requested"] = 32 * float(d[wk].replace(",", ""))
+        per.append(rec)
     path = os.path.join(ROOT, "profiles", out_name)
     data = json.load(open(path)) if os.path.exists(path) else {}
+    req = [p.get("l2_read_requested", 0) + p.get("l2_write_requested", 0) for p in per]
     data[family] = {"traffic_bytes_per_launch": round(sum(p["read"] + p["write"] for p in per) / max(1, len(per))),
+                    "l2_requested_bytes_per_launch": round(sum(req) / max(1, len(per))) if any(req) else None,
                     "launches_captured": len(per), "per_launch": per, "how": how}
     json.dump(data, open(path, "w"), indent=1)
     print(json.dumps(data[family], indent=1))
