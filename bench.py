@@ -137,11 +137,34 @@ def aggregate_value(batch, steps, world, total_ms):
     return batch * steps * world / (total_ms / 1e3)
 
 
-def make_batches(w, n_batches, rank):
+def scan_cost(pair, shape):
+    """Cost proxy of a scan pair: occupied pillars of both frames (the encoder's row count)."""
+    lo, vs = np.asarray(shape["range"][:2]), np.asarray(shape["voxel"][:2])
+    n = 0
+    for pts in pair:
+        c = np.floor((pts[:, :2] - lo) / vs).astype(np.int64)
+        n += np.unique(c[:, 0] * 100000 + c[:, 1]).shape[0]
+    return n
+
+
+def make_batches(w, n_batches, rank, balanced=True):
+    """The rank's own scan pairs (shard_seeds: disjoint across ranks) as `n_batches` collated batches in pinned host memory.
+    balanced: the rank forms its batches from its scans SORTED by cost (occupied pillars), lightest batch first.  Data-parallel training
+    steps run in lockstep (the gradient exchange), so a step costs the slowest rank's batch; with every rank's i-th batch made of its
+    i-th cost quantile the ranks' steps line up (a length-grouped sampler, rank-local: no scan changes owner, nothing is exchanged).  The
+    mean cost per rank is unchanged -- the single-GPU number does not move."""
     from tmae_b200 import synth
+    shape = synth.SHAPES[w.get("shape", "once")]
+    seeds = [sd for b in shard_seeds(w, n_batches, rank) for sd in b]
+    pairs = [synth.scan_pair(sd, w["n_points"], w.get("shape", "once")) for sd in seeds]
+    if balanced:
+        order = np.argsort([scan_cost(p, shape) for p in pairs], kind="stable")
+        pairs = [pairs[i] for i in order]
     out = []
-    for seeds in shard_seeds(w, n_batches, rank):
-        pts, ptsp = synth.batch(seeds[0], w["batch"], w["n_points"], w.get("shape", "once"))
+    B = w["batch"]
+    for i in range(n_batches):
+        grp = pairs[i * B:(i + 1) * B]
+        pts, ptsp = synth.collate([p[0] for p in grp]), synth.collate([p[1] for p in grp])
         out.append((torch.from_numpy(pts).pin_memory(), torch.from_numpy(ptsp).pin_memory()))
     return out
 
@@ -228,7 +251,7 @@ def measure(w, args, c, steps, n_batches, full):
             torch.distributed.broadcast(p.data, 0)
     bb.mask_generator = torch.Generator(device=dev).manual_seed(2000 + rank)
 
-    host = make_batches(w, n_batches, rank + int(os.environ.get("TMAE_BENCH_RANK_OFFSET", "0")))   # debugging aid: another rank's scans on one GPU
+    host = make_batches(w, n_batches, rank + int(os.environ.get("TMAE_BENCH_RANK_OFFSET", "0")), balanced=not args.unbalanced)   # debugging aid: another rank's scans on one GPU
     resident = [(a.to(dev), b.to(dev)) for a, b in host]
     h2d = sum(t.numel() * 4 for t in host[0])
     side = ops.side_stream(dev) if args.side_stream else None
@@ -396,6 +419,7 @@ def run_ours(args):
             "config": {"workload": w["name"], "precision": f"encoder kernels {args.precision}; cuDNN decoder {args.decoder}",
                        "parallelism": f"dp{world} (scan-pair sharding" + ((", DistributedDataParallel NCCL gradient all-reduce)" if args.ddp else ", bucketed NCCL gradient all-reduce over one persistent flat buffer)") if w["train"] else ", no collective)"),
                        "l2": f"inputs cycle over {args.batches} distinct batches; per-step activation working set >> 126 MB L2",
+                       "batching": "seed order" if args.unbalanced else "each rank sorts its own scan pairs by occupied pillars and batches neighbours (rank-local length-grouped sampler: lockstep steps line up across ranks)",
                        "allocator": f"torch caching allocator over one pre-reserved {c.slab_gib} GiB slab"},
             "clocks": m["clocks"],
             "e2e": {"value": round(m["e_value"], 3), "unit": "scans/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
@@ -616,6 +640,7 @@ def main():
                          "not the luck of four scenes (measured: 21.1 .. 22.0 ms between ranks with 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-core and the stock-PyTorch-on-GPU baselines")
     ap.add_argument("--no-extra", dest="extra", action="store_false", help="skip the short finetune / Waymo-shaped lines (extra_workloads)")
+    ap.add_argument("--unbalanced", action="store_true", help="batches in seed order instead of the rank-local cost-sorted order (make_batches)")
     ap.add_argument("--profile-run", action="store_true", help="for runs under ncu: warm up exactly --warmup steps (no allocator-stationarity minimum)")
     ap.add_argument("--no-clock-sampler", dest="clock_sampler", action="store_false")
     ap.add_argument("--grad-sync", default="flat", choices=["flat", "overlap"],

@@ -77,6 +77,8 @@ class StatusLedger:
 
     def __init__(self):
         self.pending = []  # [(pinned host tensor, event, names, device buffer)], oldest first
+        self.free = []     # pinned buffers ready for reuse: a cudaHostAlloc per forward (the caching host allocator misses whenever the
+                           # host runs ahead) costs milliseconds and can stall the launch queue
 
     def begin(self, n, device):
         self.flush()
@@ -91,8 +93,10 @@ class StatusLedger:
         return self.dev[i:i + 1]
 
     def commit(self):
-        host = torch.empty(self.dev.shape, dtype=torch.int32, pin_memory=True)
-        host.copy_(self.dev, non_blocking=True)
+        n = self.dev.shape[0]
+        i = next((i for i, h in enumerate(self.free) if h.shape[0] >= n), None)
+        host = torch.empty(max(n, 32), dtype=torch.int32, pin_memory=True) if i is None else self.free.pop(i)
+        host[:n].copy_(self.dev, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         self.pending.append((host, ev, list(self.names), self.dev))
@@ -104,7 +108,10 @@ class StatusLedger:
                 return  # still in flight (the host ran ahead): keep it for the next call
             ev.synchronize()
             self.pending.pop(0)
-            for v, name in zip(host.tolist(), names):
+            vals = host[:len(names)].tolist()
+            if len(self.free) < 8:
+                self.free.append(host)
+            for v, name in zip(vals, names):
                 if v:
                     _raise_status(v, name + ", an earlier forward")
 
