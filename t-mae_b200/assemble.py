@@ -136,4 +136,8 @@ class FrameAssembler:
                 xforms.append((np.zeros((2, 3, 4)), np.zeros(2, np.uint8)))
         cur = self.assemble([s["points"] for s in samples], None, "points", sync)
         prev = self.assemble([s["points_prev"] for s in samples], xforms, "points_prev", sync)
-        return dict(points=cur, points_prev=prev, batch_size=len(samples))
+        # the stream these tensors were produced on and an event recorded behind them: a consumer that runs its first kernels on ANOTHER
+        # stream (the VFE / backbone pre-pass with batch_dict["side_stream"]) waits for the event and marks the tensors as used there
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return dict(points=cur, points_prev=prev, batch_size=len(samples), inputs_ready_event=ev)

@@ -88,7 +88,10 @@ def side_stream(device=None):
     """The library's high-priority side stream of a device: the coordinate-only pre-pass of a step (voxelisation, masks,
     geometry plans and their host reads of row counts) runs there when the caller opts in with
     batch_dict["side_stream"], so those reads wait for a few tiny kernels instead of draining the main stream's
-    backlog, and the host keeps running ahead of the GPU."""
+    backlog, and the host keeps running ahead of the GPU.
+    The inputs (`points`, `points_prev`) must be complete ON the side stream: either they were produced there (an input pipeline that
+    issues its H2D copies on it, as bench.py does), or batch_dict["inputs_ready_event"] holds an event recorded behind their producer
+    (FrameAssembler returns one) -- the pre-pass waits for it and marks the tensors as used by the side stream."""
     idx = torch.cuda.current_device() if device is None else torch.device(device).index
     if idx not in _side:
         _side[idx] = torch.cuda.Stream(device=idx, priority=-1)

@@ -226,13 +226,17 @@ class TemporalDynVFE(nn.Module):
             x = bn_relu(x, seq[i + 1], relu=True)
         return _SegMaxFn.apply(x, v["voxel_offset"], v["pt_order"], n_vox)
 
-    def _run(self, frames, batch_size, side=None):
+    def _run(self, frames, batch_size, side=None, ready=None):
         if side is None:
             vox = [self._voxelize(p, batch_size) for p in frames]
             counts = torch.stack([v["counts"] for v in vox]).cpu()  # the one host sync of the VFE
         else:
             # opt-in (batch_dict["side_stream"]): the inputs are ready on `side`; voxelise there and wait only for it
             main = torch.cuda.current_stream()
+            if ready is not None:
+                side.wait_event(ready)          # inputs produced on another stream (FrameAssembler, an H2D copy on main)
+            for p in frames:
+                p.record_stream(side)           # a no-op for tensors allocated on `side`
             with torch.cuda.stream(side):
                 vox = [self._voxelize(p, batch_size) for p in frames]
                 counts = torch.stack([v["counts"] for v in vox]).cpu()
@@ -256,7 +260,7 @@ class TemporalDynVFE(nn.Module):
 
     def forward(self, batch_dict, **kwargs):
         B = self._batch_size(batch_dict)
-        cur, prev = self._run([batch_dict["points"], batch_dict["points_prev"]], B, batch_dict.get("side_stream"))
+        cur, prev = self._run([batch_dict["points"], batch_dict["points_prev"]], B, batch_dict.get("side_stream"), batch_dict.get("inputs_ready_event"))
         for sfx, r in (("", cur), ("_prev", prev)):
             if self.finetuning:  # temporal_dyn_vfe.py:121-123,154-160
                 batch_dict.pop("points" + sfx, None)
@@ -281,7 +285,7 @@ class DynVFE(TemporalDynVFE):
         return num_point_features  # dyn_vfe.py:22: no group_id column
 
     def forward(self, batch_dict, **kwargs):
-        (r,) = self._run([batch_dict["points"]], self._batch_size(batch_dict), batch_dict.get("side_stream"))
+        (r,) = self._run([batch_dict["points"]], self._batch_size(batch_dict), batch_dict.get("side_stream"), batch_dict.get("inputs_ready_event"))
         batch_dict.update(points=r["points"], point_coords=r["point_coords"], point_inverse_indices=r["inverse"],
                           voxel_coords=r["voxel_coords"], pillar_features=r["voxel_features"],
                           voxel_features=r["voxel_features"], voxel_point_csr=r["csr"],

@@ -191,6 +191,37 @@ def test_no_sync_tail_is_dropped_by_the_voxeliser():
 
 
 @gpu
+def test_assembler_on_main_feeds_the_side_stream_prepass():
+    """The assembler produces its tensors on the CURRENT stream; the VFE's side-stream pre-pass must wait for them
+    (batch_dict["inputs_ready_event"]).  The main stream is kept busy in front of the assembler so that an unsynchronised side stream
+    would read the buffers before they are written."""
+    from tmae_b200 import ops
+    DEV = "cuda"
+    kind = "once"
+    S = synth.SHAPES[kind]
+    grid = [int(v) for v in synth.grid_size(S)]
+    vfe, _ = tmae_b200.build_model("pretrain", grid, S["voxel"], S["range"], num_point_features=5)
+    vfe.to(DEV).eval()
+    samples = [synth.raw_scan_pair(700 + i, 30000, kind) for i in range(2)]
+    asm = _assembler(kind)
+    with torch.no_grad():
+        ref = vfe(asm(samples, sync=False))
+        torch.cuda.synchronize()
+        side = ops.side_stream(DEV)
+        spin = torch.empty(64 << 20, device=DEV)
+        for _ in range(3):
+            for _ in range(20):
+                spin.add_(1.0)                 # ~10 ms of main-stream work in front of the assembler's kernels
+            bd = asm(samples, sync=False)
+            assert "inputs_ready_event" in bd
+            bd["side_stream"] = side
+            out = vfe(bd)
+            torch.cuda.synchronize()
+            assert torch.equal(out["voxel_coords"], ref["voxel_coords"]) and torch.equal(out["voxel_coords_prev"], ref["voxel_coords_prev"])
+            assert torch.equal(out["voxel_features"], ref["voxel_features"])
+
+
+@gpu
 def test_assembled_batch_through_the_vfe_matches_the_oracle_chain():
     """assemble -> TemporalDynVFE on the GPU against oracle assemble -> tier-2 VFE on the CPU."""
     from oracle import restated
