@@ -29,6 +29,7 @@ namespace tmae {
 namespace bfk {
 }  // namespace bfk
 extern int g_bf16_gemm_pdl;
+extern int g_bf16_tn_plain;
 namespace bfk {
 
 typedef __nv_bfloat16 bf16;
@@ -49,6 +50,7 @@ struct Args {
   bf16* P;                         // E_PLAIN: optional pre-activation copy (pitch ldc)
   const bf16* gelu_pre;            // E_PLAIN: optional, result *= gelu'(gelu_pre[m, n]) (pitch ldc)
   int act, accumulate;             // accumulate: C += (bf16 read-modify-write; fp32 vector atomics for E_F32)
+  int dbg_plain;                   // measurement only (tmae_set_option "tn_plain_store"): split-k partials overwrite instead of adding -> WRONG results
   int pre_deriv;                   // gelu_pre already holds gelu'(pre-activation) (written by a TMAE_ACT_GELU_DERIV forward)
   int64_t k_chunk;
   // TN only: B columns at n >= n_split come from a second tensor (map_b2, columns n - n_split) and land in C2 (pitch ldc2):
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(THREADS + (GATHER ? GATHER_WARPS * 32 : 0), OC
         }
         if (EPI == E_F32) {
           float* crow = (MODE == M_TN && col0 >= g.n_split) ? g.C2 + row * g.ldc2 + (col0 - g.n_split) : (float*)g.C + row * g.ldc + col0;
-          if (g.accumulate) {
+          if (g.accumulate && !g.dbg_plain) {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               if (col0 + 4 * c < g.N) atomicAdd(reinterpret_cast<float4*>(crow + 4 * c), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
@@ -536,6 +538,7 @@ static int launch(const bf16* A, const bf16* B, int64_t lda, int64_t ldb, Args g
   constexpr int STAGES = OCC == 2 ? (BN == 128 ? 3 : 4) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   if (g.M <= 0 || g.N <= 0) return 0;
   if (splits < 1) splits = 1;
+  g.dbg_plain = g_bf16_tn_plain;
   g.k_chunk = align_up((g.K + splits - 1) / splits, KB);
   int z = (int)((g.K + g.k_chunk - 1) / g.k_chunk);
   if (z < 1) z = 1;
@@ -593,6 +596,7 @@ static int launch(const bf16* A, const bf16* B, int64_t lda, int64_t ldb, Args g
 
 }  // namespace bfk
 int g_bf16_gemm_occ2 = 0;   // measurement switch (tmae_set_option "gemm_occ2")
+int g_bf16_tn_plain = 0;
 int g_bf16_gemm_pdl = 1;    // tmae_set_option "gemm_pdl": the bf16 GEMMs and the tcgen05 attention kernels are launched with programmatic stream serialization (measured: 20.46 -> 19.78 ms per step)
 namespace bfk {
 static int pick_bn(int64_t n) {
