@@ -215,7 +215,7 @@ def test_window_partition_rejects_unsorted_and_overflow():
 
 
 # ------------------------------------------------------------------------------------ dense algebra
-@pytest.mark.parametrize("m,n,k", [(1, 64, 10), (777, 64, 10), (1000, 128, 64), (333, 384, 128), (2049, 256, 512), (65, 48, 128)])
+@pytest.mark.parametrize("m,n,k", [(1, 64, 10), (777, 64, 10), (60001, 64, 10), (4099, 128, 11), (1000, 128, 64), (333, 384, 128), (2049, 256, 512), (65, 48, 128)])
 def test_linear_fwd_bwd(m, n, k):
     g = torch.Generator().manual_seed(m + n + k)
     x, w, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k ** .5, torch.randn(n, generator=g)
