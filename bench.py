@@ -65,29 +65,34 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region through NVML in a background thread (a looping
-    nvidia-smi process was measured to slow the timed region by ~15 %); falls back to nvidia-smi when NVML is absent."""
+    """SM clock and throttle reasons sampled DURING the timed region through NVML, inline at step boundaries (`sample`; a looping
+    nvidia-smi process was measured to slow the timed region by ~15 %); falls back to a nvidia-smi child when NVML is absent."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index, period=float(os.environ.get("TMAE_CLOCK_PERIOD", "0.25"))):
         self.index, self.period = index, period
         self.sm, self.mx, self.reasons, self.stop, self.t, self.proc, self.lines = [], 0, set(), False, None, None, []
+        self.nv = self.h = None
 
-    def _nvml_loop(self, nv, h):
+    def sample(self):
+        """One NVML sample, taken INLINE by the timing loop at a few step boundaries (two light queries, tens of microseconds).  A
+        sampling thread costs more than it looks: every wake-up has to take the GIL from the thread that enqueues the step (5 ms
+        switch interval), seen as 5-7 ms steps once or twice per timed region and, in lockstep, on every rank."""
+        if self.nv is None:
+            return
+        nv, h = self.nv, self.h
         bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-        while not self.stop:
-            try:
-                self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                for name, bit in bits.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(self.period)
+        try:
+            self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            for name, bit in bits.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def __enter__(self):
         try:
@@ -97,8 +102,7 @@ class ClockSampler:
             idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
             h = nv.nvmlDeviceGetHandleByIndex(idx)
             self.mx = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
-            self.t.start()
+            self.nv, self.h = nv, h
             return self
         except Exception:
             pass
@@ -249,10 +253,15 @@ def measure(w, args, c, steps, n_batches, full):
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[c.local], find_unused_parameters=False)
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True)
     params = [p for p in model.parameters() if p.requires_grad]
-    # gradient exchange: persistent flat buffer, buckets all-reduced on a communication stream WHILE backward runs (tmae_b200/dist.py)
+    # gradient exchange: persistent flat buffer, buckets all-reduced on a communication stream (tmae_b200/dist.py)
     flat = None
+    bucket_opts = None
     if w["train"] and world > 1 and not args.ddp:
-        flat = tdist.OverlappedGradients(params, world).attach() if args.grad_sync == "overlap" else tdist.FlatGradients(params, world)
+        flat = tdist.OverlappedGradients(params, world).attach() if args.grad_sync == "overlap" else tdist.FlatGradients(params, world, n_buckets=args.grad_buckets)
+        if args.grad_sync == "flat" and not args.single_optimizer:
+            # one fused AdamW per bucket (same hyper-parameters: the update of every parameter is what the single optimizer computes):
+            # bucket b is updated while bucket b+1 is still on the wire
+            bucket_opts = [torch.optim.AdamW(ps, lr=1e-4, weight_decay=0.01, fused=True) for ps in flat.bucket_params()]
     if world > 1:  # same initial weights on every rank (DDP broadcasts them; the flat all-reduce path does it here)
         for p in list(model.parameters()) + list(model.buffers()):
             torch.distributed.broadcast(p.data, 0)
@@ -278,6 +287,12 @@ def measure(w, args, c, steps, n_batches, full):
             chk("forward")
             loss.backward()
             chk("backward")
+            if flat is not None and module is None and bucket_opts is not None:
+                flat.reduce(step_fns=[o.step for o in bucket_opts])   # exchange and per-bucket updates pipelined
+                chk("finish+step")
+                for o in bucket_opts:
+                    o.zero_grad(set_to_none=True)
+                return loss
             if flat is not None and module is None:
                 # overlap: buckets whose gradients were complete have been in flight since, wait for the communication stream;
                 # flat: copy into the persistent flat buffer and all-reduce its buckets now
@@ -302,7 +317,7 @@ def measure(w, args, c, steps, n_batches, full):
     host_ms = []
     host_out = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(max(steps, 1))]
 
-    def timed(from_host, k):
+    def timed(from_host, k, sampler=None):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
         d2h = 0
         gc.collect()
@@ -311,7 +326,10 @@ def measure(w, args, c, steps, n_batches, full):
         c0 = ops.launch_count()
         host_t0 = time.perf_counter()
         ev[0].record()
+        marks = {k // 6, k // 3, k // 2, (2 * k) // 3, (5 * k) // 6} if sampler is not None else ()
         for i in range(k):
+            if i in marks:
+                sampler.sample()
             if i >= 2:
                 ev[i - 1].synchronize()  # bounded run-ahead: the host stays at most two steps in front of the GPU, so blocks
                                          # recorded on two streams return to the allocator pool before it has to grow
@@ -354,7 +372,7 @@ def measure(w, args, c, steps, n_batches, full):
     clocks = None
     if full and args.clock_sampler:
         with ClockSampler(c.local) as cs:
-            total, per, launches, _ = timed(False, steps)
+            total, per, launches, _ = timed(False, steps, cs)
         clocks = cs.summary()
     else:
         total, per, launches, _ = timed(False, steps)
@@ -647,6 +665,8 @@ def main():
                          "not the luck of four scenes (measured: 21.1 .. 22.0 ms between ranks with 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-core and the stock-PyTorch-on-GPU baselines")
     ap.add_argument("--no-extra", dest="extra", action="store_false", help="skip the short finetune / Waymo-shaped lines (extra_workloads)")
+    ap.add_argument("--grad-buckets", type=int, default=4, help="--grad-sync flat: slices of the flat gradient buffer all-reduced separately")
+    ap.add_argument("--single-optimizer", action="store_true", help="N > 1, --grad-sync flat: one optimizer step behind the whole exchange instead of one per bucket")
     ap.add_argument("--unbalanced", action="store_true", help="batches in seed order instead of the rank-local cost-sorted order (make_batches)")
     ap.add_argument("--profile-run", action="store_true", help="for runs under ncu: warm up exactly --warmup steps (no allocator-stationarity minimum)")
     ap.add_argument("--no-clock-sampler", dest="clock_sampler", action="store_false")

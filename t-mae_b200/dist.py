@@ -55,8 +55,18 @@ class FlatGradients:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         self.present = [bool(v) for v in t.tolist()]
 
-    def reduce(self):
-        """Averages the gradients of `params` over the group; afterwards every present `p.grad` is a view of `self.flat`."""
+    def bucket_params(self):
+        """The parameters of every bucket, in bucket order: a training loop that builds ONE OPTIMIZER PER BUCKET can hand their `step`s
+        to `reduce(step_fns=...)` and have bucket b's update run while bucket b+1 is still being all-reduced."""
+        if self.flat is None:
+            self._setup()
+        return [self.params[a:b] for a, b in self.bounds]
+
+    def reduce(self, step_fns=None):
+        """Averages the gradients of `params` over the group; afterwards every present `p.grad` is a view of `self.flat`.
+        step_fns (optional, one callable per bucket, e.g. the `step` of that bucket's optimizer): called on the compute stream as soon
+        as ITS bucket's all-reduce has completed -- the exchange of the later buckets overlaps the optimizer work of the earlier ones
+        instead of being exposed in front of one big optimizer step."""
         if not self.params:
             return None
         if self.flat is None:
@@ -67,6 +77,7 @@ class FlatGradients:
         elif any(h and not pr for h, pr in zip(has, self.present)):
             self._presence([h or pr for h, pr in zip(has, self.present)])
         main = torch.cuda.current_stream() if self.flat.is_cuda else None
+        done = []
         for a, b in self.bounds:
             src, dst, zero = [], [], []
             for i in range(a, b):
@@ -90,13 +101,26 @@ class FlatGradients:
                     self.comm.wait_stream(main)
                     with torch.cuda.stream(self.comm):
                         dist.all_reduce(sl, op=dist.ReduceOp.AVG, group=self.group)
+                        if step_fns is not None:
+                            ev = torch.cuda.Event()
+                            ev.record(self.comm)
+                            done.append(ev)
                 else:
                     dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=self.group)
                     sl.div_(self.world)
-        if self.comm is not None and self.world > 1:
-            main.wait_stream(self.comm)
-        for p, v, pr in zip(self.params, self.views, self.present):
-            p.grad = v if pr else None
+        if step_fns is None:
+            if self.comm is not None and self.world > 1:
+                main.wait_stream(self.comm)
+            for p, v, pr in zip(self.params, self.views, self.present):
+                p.grad = v if pr else None
+            return self.flat
+        assert len(step_fns) == len(self.bounds), "one step function per bucket (bucket_params())"
+        for bi, (a, b) in enumerate(self.bounds):
+            if done:
+                main.wait_event(done[bi])
+            for i in range(a, b):
+                self.params[i].grad = self.views[i] if self.present[i] else None
+            step_fns[bi]()
         return self.flat
 
 

@@ -120,3 +120,51 @@ def test_overlapped_gradients_gloo_world2():
             assert got[-1] is None
             for a, b in zip(got[:-1], ref):
                 assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+
+
+def _pipelined_worker(rank, world, port, out):
+    import importlib
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tdist = importlib.import_module("tmae_b200.dist")
+    res = {}
+    for mode in ("single", "per_bucket"):
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 4), torch.nn.ReLU(), torch.nn.Linear(4, 3))
+        params = list(net.parameters())
+        fg = tdist.FlatGradients(params, world, n_buckets=3)
+        if mode == "single":
+            opts = [torch.optim.AdamW(params, lr=0.05, weight_decay=0.01)]
+        else:
+            opts = [torch.optim.AdamW(ps, lr=0.05, weight_decay=0.01) for ps in fg.bucket_params()]
+            assert sum(len(ps) for ps in fg.bucket_params()) == len(params) and len(opts) == 3
+        for it in range(3):
+            net(torch.full((2, 6), float(rank + 1 + it))).sum().backward()
+            if mode == "single":
+                fg.reduce()
+                opts[0].step()
+            else:
+                fg.reduce(step_fns=[o.step for o in opts])
+            for o in opts:
+                o.zero_grad(set_to_none=True)
+        res[mode] = [p.detach().clone() for p in params]
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_per_bucket_optimizer_steps_equal_one_step_gloo_world2():
+    """FlatGradients.reduce(step_fns=...): one optimizer per bucket, stepped as its bucket's all-reduce completes, leaves the same
+    parameters as one optimizer stepped behind the whole exchange, on both ranks."""
+    import torch
+    import torch.multiprocessing as mp
+    import tmae_b200  # noqa: F401
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_pipelined_worker, args=(2, 29539, out), nprocs=2, join=True)
+    for a, b in zip(out[0]["single"], out[0]["per_bucket"]):
+        assert torch.equal(a, b)
+    for a, b in zip(out[0]["per_bucket"], out[1]["per_bucket"]):
+        assert torch.equal(a, b)
