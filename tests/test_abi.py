@@ -84,3 +84,47 @@ def test_ops_refuse_to_run_without_cuda():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.add_pos(torch.zeros(4, 128), torch.zeros(4, dtype=torch.uint8), torch.zeros(64, 128))
+
+
+def test_record_all_reaches_every_tensor_whatever_the_nesting():
+    """ops.record_all (side-stream tables -> main stream): no depth limit, cycles tolerated, modules and ctypes structs skipped.
+    Host logic only: tensors are stand-ins that claim to be CUDA tensors and log the call."""
+    import ctypes
+
+    import torch
+
+    from tmae_b200 import ops
+
+    seen = []
+
+    class Fake(torch.Tensor):
+        @property
+        def is_cuda(self):
+            return True
+
+        def record_stream(self, stream):
+            seen.append((id(self), stream))
+
+    def fake():
+        return torch.zeros(1).as_subclass(Fake)
+
+    class Slotted:
+        __slots__ = ("a", "b", "tcache")
+
+    class Plain:
+        pass
+
+    class Struct(ctypes.Structure):
+        _fields_ = [("p", ctypes.c_void_p)]
+
+    leaves = [fake() for _ in range(6)]
+    s = Slotted()
+    s.a, s.b, s.tcache = leaves[0], [leaves[1], (leaves[2],)], {"k": Struct()}
+    p = Plain()
+    p.part, p.self_ref, p.mod = s, p, torch.nn.Linear(2, 2)       # a cycle and a module: neither may be walked into
+    obj = leaves[3]
+    for _ in range(12):                                           # far below the old depth limit of 6
+        obj = {"x": [obj]}
+    ops.record_all((obj, [[[[[[[[p]]]]]]]], leaves[4], None, "text", 3), "STREAM")
+    assert {i for i, _ in seen} == {id(t) for t in leaves[:5]} and all(st == "STREAM" for _, st in seen)
+    assert id(leaves[5]) not in {i for i, _ in seen}
