@@ -5,6 +5,7 @@ plumbing) and enqueues the kernels on torch's current stream.  No arithmetic hap
 there is no fallback path: a tensor that is not on a CUDA device raises.
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -843,20 +844,21 @@ except ImportError:   # very old torch: training-mode forwards still refresh unc
 
 class WeightShadows:
     """bf16 copies of fp32 master weights (the tensor-core operands of the bf16 mode), refreshed when the master changes
-    (`Tensor._version` moves on every in-place optimizer update): ALL stale copies in one launch through a device-resident
-    segment table that is built once (the parameters and their shadows never move)."""
+    (`Tensor._version`, the optimizer epoch above, or `force`): ALL stale copies of a device in one launch through a device-resident
+    segment table that is built once (the parameters and their shadows never move).  Parameters are held by weak reference: the copies
+    of a model that was dropped go with it."""
 
     def __init__(self):
-        self.items = {}      # id(param) -> [param, shadow, version]
-        self.table = None    # (n, 3) int64 device: src ptr, dst ptr, numel
-        self.order = []
+        self.items = {}      # id(param) -> [weakref(param), shadow, version, data_ptr]
+        self.tables = {}     # device -> (tuple of item ids, (n, 3) int64 device table: src ptr, dst ptr, numel)
         self.epoch = -1      # _weights_epoch at the last full refresh
+        self._keep = []
 
     def _fresh(self, p):
         it = self.items.get(id(p))
-        if it is None or it[0] is not p or it[3] != p.data_ptr():   # new parameter, or its storage moved (module.to(...), p.data = ...)
-            it = self.items[id(p)] = [p, torch.empty(p.shape, dtype=BF16, device=p.device), -1, p.data_ptr()]
-            self.table = None
+        if it is None or it[0]() is not p or it[3] != p.data_ptr():   # new parameter, or its storage moved (module.to(...), p.data = ...)
+            it = self.items[id(p)] = [weakref.ref(p), torch.empty(p.shape, dtype=BF16, device=p.device), -1, p.data_ptr()]
+            self.tables.pop(p.device, None)
         return it
 
     def get(self, p):
@@ -871,26 +873,39 @@ class WeightShadows:
 
     def refresh(self, force=False):
         """force (or an optimizer step since the last refresh): every copy is stale, whatever the version counters say."""
-        for key in [k for k, it in self.items.items() if it[3] != it[0].data_ptr()]:   # storage moved: re-create
-            self._fresh(self.items[key][0])
+        live = []
+        for key, it in list(self.items.items()):
+            p = it[0]()
+            if p is None:                                   # the model is gone
+                del self.items[key]
+                self.tables.pop(it[1].device, None)
+                continue
+            if it[3] != p.data_ptr():                       # storage moved: re-create
+                it = self._fresh(p)
+            live.append((key, it, p))
         force = force or self.epoch != _weights_epoch[0]
         self.epoch = _weights_epoch[0]
-        stale = list(self.items.values()) if force else [it for it in self.items.values() if it[2] != it[0]._version]
-        if not stale:
-            return
-        dev = stale[0][0].device
-        if len(stale) == len(self.items):
-            if self.table is None or self.table.device != dev:
-                self.order = list(self.items.values())
-                self.table = torch.tensor([[it[0].data_ptr(), it[1].data_ptr(), it[0].numel()] for it in self.order], dtype=I64, device=dev)
-            table, n = self.table, len(self.order)
-        else:
-            table = torch.tensor([[it[0].data_ptr(), it[1].data_ptr(), it[0].numel()] for it in stale], dtype=I64, device=dev)
-            n = len(stale)
-        _call("cast_f32_bf16_multi", table.data_ptr(), n, _stream())
-        for it in stale:
-            it[2] = it[0]._version
-        self._keep = table   # alive until the next refresh (the launch reads it asynchronously)
+        self._keep = []
+        by_dev = {}
+        for key, it, p in live:
+            by_dev.setdefault(p.device, []).append((key, it, p))
+        for dev, group in by_dev.items():
+            stale = group if force else [g for g in group if g[1][2] != g[2]._version]
+            if not stale:
+                continue
+            keys = tuple(k for k, _, _ in stale)
+            cached = self.tables.get(dev) if len(stale) == len(group) else None
+            if cached is not None and cached[0] == keys:
+                table = cached[1]
+            else:
+                table = torch.tensor([[p.data_ptr(), it[1].data_ptr(), p.numel()] for _, it, p in stale], dtype=I64, device=dev)
+                if len(stale) == len(group):
+                    self.tables[dev] = (keys, table)
+            with torch.cuda.device(dev):
+                _call("cast_f32_bf16_multi", table.data_ptr(), len(stale), _stream())
+            for _, it, p in stale:
+                it[2] = p._version
+            self._keep.append(table)   # alive until the next refresh (the launch reads it asynchronously)
 
 
 shadows = WeightShadows()
@@ -1033,46 +1048,59 @@ class BF16Weights(ctypes.Structure):
 
 class QkvOperands:
     """Per attention layer the (3C, C + 64) bf16 operand [in_proj_weight | table^T] of the packed projection (tmae_bf16_qkv_wcat): it
-    depends on the weights only, so it is kept across calls and ALL stale ones are rebuilt by one launch when the masters changed
-    (`Tensor._version`, as WeightShadows); an inference loop never rebuilds it."""
+    depends on the weights only, so it is kept across calls and ALL stale ones of a device are rebuilt by one launch when the masters
+    changed (as WeightShadows: version counters, optimizer epoch, `force`); an inference loop never rebuilds it.  Weak references."""
 
     def __init__(self):
-        self.items = {}      # id(in_w) -> [in_w, in_b, lut, wcat, versions, pointers]
-        self.table = None
+        self.items = {}      # id(in_w) -> [weakref(in_w), weakref(in_b), weakref(lut), wcat, versions, pointers]
+        self.tables = {}     # device -> (item ids, record table)
         self.epoch = -1
+        self._keep = []
 
     def get(self, w, b, lut):
         it = self.items.get(id(w))
         ptrs = (w.data_ptr(), b.data_ptr(), lut.data_ptr())
-        if it is None or it[0] is not w or it[5] != ptrs:
+        if it is None or it[0]() is not w or it[5] != ptrs:
             n, c = w.shape
-            it = self.items[id(w)] = [w, b, lut, torch.empty(n, c + 64, dtype=BF16, device=w.device), None, ptrs]
-            self.table = None
+            it = self.items[id(w)] = [weakref.ref(w), weakref.ref(b), weakref.ref(lut), torch.empty(n, c + 64, dtype=BF16, device=w.device), None, ptrs]
+            self.tables.pop(w.device, None)
         if it[4] != (w._version, b._version) or self.epoch != _weights_epoch[0]:
             self.refresh()
         return it[3]
 
     def refresh(self, force=False):
+        live = []
+        for key, it in list(self.items.items()):
+            w, b, lut = it[0](), it[1](), it[2]()
+            if w is None or b is None or lut is None or it[5] != (w.data_ptr(), b.data_ptr(), lut.data_ptr()):
+                del self.items[key]                         # the layer is gone or was moved: get() re-creates the entry on its next call
+                self.tables.pop(it[3].device, None)
+                continue
+            live.append((key, it, w, b, lut))
         force = force or self.epoch != _weights_epoch[0]
         self.epoch = _weights_epoch[0]
-        stale = list(self.items.values()) if force else [it for it in self.items.values() if it[4] != (it[0]._version, it[1]._version)]
-        if not stale:
-            return
-        dev = stale[0][0].device
-
-        def recs(items):
-            return torch.tensor([[it[2].data_ptr(), it[0].data_ptr(), it[1].data_ptr(), it[3].data_ptr(), it[0].shape[0], 2 * it[0].shape[1], it[0].shape[1]]
-                                 for it in items], dtype=I64, device=dev)
-        if len(stale) == len(self.items):
-            if self.table is None or self.table.device != dev:
-                self.table = recs(stale)
-            table = self.table
-        else:
-            table = recs(stale)
-        _call("bf16_qkv_wcat_multi", table.data_ptr(), len(stale), max(it[0].shape[0] for it in stale), _stream())
-        for it in stale:
-            it[4] = (it[0]._version, it[1]._version)
-        self._keep = table   # alive until the next refresh (the launch reads it asynchronously)
+        self._keep = []
+        by_dev = {}
+        for rec in live:
+            by_dev.setdefault(rec[2].device, []).append(rec)
+        for dev, group in by_dev.items():
+            stale = group if force else [g for g in group if g[1][4] != (g[2]._version, g[3]._version)]
+            if not stale:
+                continue
+            keys = tuple(g[0] for g in stale)
+            cached = self.tables.get(dev) if len(stale) == len(group) else None
+            if cached is not None and cached[0] == keys:
+                table = cached[1]
+            else:
+                table = torch.tensor([[lut.data_ptr(), w.data_ptr(), b.data_ptr(), it[3].data_ptr(), w.shape[0], 2 * w.shape[1], w.shape[1]]
+                                      for _, it, w, b, lut in stale], dtype=I64, device=dev)
+                if len(stale) == len(group):
+                    self.tables[dev] = (keys, table)
+            with torch.cuda.device(dev):
+                _call("bf16_qkv_wcat_multi", table.data_ptr(), len(stale), max(w.shape[0] for _, _, w, _, _ in stale), _stream())
+            for _, it, w, b, _ in stale:
+                it[4] = (w._version, b._version)
+            self._keep.append(table)   # alive until the next refresh (the launch reads it asynchronously)
 
 
 qkv_operands = QkvOperands()

@@ -178,6 +178,24 @@ def test_shadows_follow_a_fused_optimizer_step():
     assert torch.equal(qo.get(w, b, lut), ops.bf16_qkv_wcat(lut, w.detach(), b.detach(), 256))
 
 
+def test_derived_weight_caches_drop_dead_models():
+    """The bf16 shadows and [W | table] operands hold their parameters by weak reference: a dropped model takes its copies with it and
+    is never refreshed again."""
+    import gc
+    sh, qo = ops.WeightShadows(), ops.QkvOperands()
+    keep_w = torch.nn.Parameter(torch.randn(64, 32, device=DEV))
+    w = torch.nn.Parameter(torch.randn(384, 128, device=DEV) / 11)
+    b = torch.nn.Parameter(torch.randn(384, device=DEV) * 0.1)
+    lut = torch.randn(64, 128, device=DEV)
+    sh.get(w), sh.get(keep_w), qo.get(w, b, lut)
+    assert len(sh.items) == 2 and len(qo.items) == 1
+    del w, b
+    gc.collect()
+    sh.refresh(force=True), qo.refresh(force=True)
+    assert len(sh.items) == 1 and len(qo.items) == 0
+    assert torch.equal(sh.get(keep_w), keep_w.detach().to(BF))
+
+
 def test_qkv_operands_cache_rebuilds_all_stale_in_one_launch():
     """ops.QkvOperands: the per-layer [W | table^T] operands equal the single-layer builder, are rebuilt when a master changes in place
     (an optimizer step) and not otherwise."""
