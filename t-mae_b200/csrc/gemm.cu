@@ -392,7 +392,7 @@ int tma_sparse_conv_bwd_weight(const float* dy, const float* x, const int* table
 
 using namespace tmae;
 
-namespace tmae { extern int g_bf16_tn_plain; extern int g_bf16_gemm_pdl; extern int g_bf16_gemm_occ2; extern int g_small_on_warps; extern bool g_wide_st; extern int g_attn_occ; extern int g_attn_occ_fwd; extern int g_bn_colsum_cap; extern int g_ln_bwd_cap; }  // gemm_tma.cu, attention_mma.cu, bn.cu, rowops.cu
+namespace tmae { extern int g_bf16_wgrad_stream; extern int g_bf16_tn_plain; extern int g_bf16_gemm_pdl; extern int g_bf16_gemm_occ2; extern int g_small_on_warps; extern bool g_wide_st; extern int g_attn_occ; extern int g_attn_occ_fwd; extern int g_bn_colsum_cap; extern int g_ln_bwd_cap; }  // gemm_tma.cu, attention_mma.cu, bn.cu, rowops.cu
 
 #define TMAE_CHECK_PREC(p) TMAE_CHECK_ARG((p) == TMAE_PREC_FP32 || (p) == TMAE_PREC_TF32, "precision must be TMAE_PREC_FP32 or TMAE_PREC_TF32 (the bf16-storage mode has its own entry points: tmae_bf16_*)")
 // Two kernels per GEMM shape and no third: the TMA-fed tcgen05 kernel in a tensor-core mode, the fp32 FFMA kernel in
@@ -407,6 +407,7 @@ int tmae_set_option(const char* name, int32_t value) {
   if (name && !strcmp(name, "ln_bwd_cap")) { g_ln_bwd_cap = value < 1 ? 1 : value; return 0; }
   if (name && !strcmp(name, "attn_occ_fwd")) { g_attn_occ_fwd = value; return 0; }
   if (name && !strcmp(name, "attn_occ")) { g_attn_occ = value; return 0; }   // 1: mma attention backward at one more CTA per SM
+  if (name && !strcmp(name, "wgrad_stream")) { g_bf16_wgrad_stream = value != 0; return 0; }   // layer backward: weight-gradient GEMMs on the auxiliary stream
   if (name && !strcmp(name, "tn_plain_store")) { g_bf16_tn_plain = value != 0; return 0; }  // measurement only: wrong results
   if (name && !strcmp(name, "gemm_pdl")) { g_bf16_gemm_pdl = value != 0; return 0; }     // bf16 GEMMs launched with programmatic stream serialization
   if (name && !strcmp(name, "gemm_occ2")) { g_bf16_gemm_occ2 = value != 0; return 0; }   // bf16 GEMMs with N <= 128: two 3-stage CTAs per SM

@@ -10,6 +10,9 @@
 // `attn_impl = 0` bridges to the fp32-I/O mma.sync kernels of attention.cu through cast passes (kept as the checker).
 #include <cuda_bf16.h>
 
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 using namespace tmae;
@@ -50,9 +53,36 @@ int attn_tc_bwd(const void* dout, const void* q, const void* k, const void* v, c
 bool attn_tc_available();
 }  // namespace tmae
 
+namespace tmae { int g_bf16_wgrad_stream = 1; }   // tmae_set_option "wgrad_stream": weight-gradient GEMMs of the layer backward on an auxiliary stream
+
 namespace {
 
 typedef __nv_bfloat16 bf16;
+
+// The weight-gradient GEMMs of a layer's backward are OFF its critical path (nothing in the layer reads dW) and, like every persistent
+// GEMM here, end with a tail in which the CTAs that drew 3 tiles idle next to those that drew 4.  They are therefore enqueued on an
+// auxiliary stream of the device (created on first use, kept for the life of the process; the only stream the library owns): their
+// CTAs fill the tails of the data-gradient kernels on the caller's stream and vice versa.  Events order the two streams inside one
+// call -- fork after the producer of an operand, join before the kernel that overwrites it and at the end of the call -- so nothing
+// of the auxiliary stream is in flight when the call returns to its stream's later work.
+struct Aux {
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t fork[6] = {}, done[4] = {};
+};
+std::mutex g_aux_mu;
+std::map<int, Aux> g_aux;
+Aux* aux_stream() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(g_aux_mu);
+  Aux& a = g_aux[dev];
+  if (!a.s2) {
+    if (cudaStreamCreateWithFlags(&a.s2, cudaStreamNonBlocking) != cudaSuccess) { a.s2 = nullptr; return nullptr; }
+    for (auto& e : a.fork) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& e : a.done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  }
+  return &a;
+}
 
 struct Carve {
   char* p;
@@ -272,16 +302,35 @@ int tmae_bf16_encoder_layer_bwd(const void* dy, const void* x, const void* x_kv,
   float* g_b1 = (float*)G->b1; float* g_w2 = (float*)G->w2; float* g_b2 = (float*)G->b2; float* g_ln2_g = (float*)G->ln2_g;
   float* g_ln2_b = (float*)G->ln2_b;
 
+  // the weight-gradient GEMMs go to the auxiliary stream (see Aux above); z (per-kernel clears) keeps everything on one stream
+  Aux* ax = (g_bf16_wgrad_stream && !z) ? aux_stream() : nullptr;
+  void* wstream = ax ? (void*)ax->s2 : stream;
+  auto fork = [&](int i) {        // the auxiliary stream continues behind what the caller's stream has enqueued so far
+    if (ax) { cudaEventRecord(ax->fork[i], st); cudaStreamWaitEvent(ax->s2, ax->fork[i], 0); }
+  };
+  auto mark = [&](int i) { if (ax) cudaEventRecord(ax->done[i], ax->s2); };          // a point of the auxiliary stream ...
+  auto await = [&](int i) { if (ax) cudaStreamWaitEvent(st, ax->done[i], 0); };     // ... the caller's stream waits for
+  struct Join {                   // whatever path leaves the call: nothing of the auxiliary stream outlives it
+    Aux* ax; cudaStream_t st;
+    ~Join() { if (ax) { cudaEventRecord(ax->done[3], ax->s2); cudaStreamWaitEvent(st, ax->done[3], 0); } }
+  } join_at_exit{ax, st};
+
   // LN2 -> FFN -> LN1 (the bias gradients of linear2 and out_proj are column sums of what the LayerNorm backward passes write)
   TRY(bf16_layernorm_bwd_impl(dy, s.v2, nullptr, P->ln2_g, s.m2, s.r2, dx1, nullptr, g_ln2_g, g_ln2_b, g_b2, m_q, c, z, stream));
-  TRY(bf16_linear_bwd_weight_impl(dx1, s.h, g_w2, nullptr, nullptr, m_q, c, ff, z, stream));
+  fork(0);
+  TRY(bf16_linear_bwd_weight_impl(dx1, s.h, g_w2, nullptr, nullptr, m_q, c, ff, z, wstream));
+  mark(0);                                                                                                    // dx1 has been read
   TRY(tmae_bf16_linear_bwd_data(dx1, W->w2, s.hpre, dh, m_q, c, ff, TMAE_BWD_PRE_IS_DERIVATIVE, stream));      // dh = (dx1 W2) * gelu'(hpre)
-  TRY(bf16_linear_bwd_weight_impl(dh, s.x1, g_w1, nullptr, nullptr, m_q, ff, c, z, stream));
+  fork(1);
+  TRY(bf16_linear_bwd_weight_impl(dh, s.x1, g_w1, nullptr, nullptr, m_q, ff, c, z, wstream));
   TRY(bf16_colsum_impl(dh, g_b1, m_q, ff, z, stream));
+  await(0);                                                                                                   // ... before it is overwritten
   TRY(tmae_bf16_linear_bwd_data(dh, W->w1, nullptr, dx1, m_q, ff, c, 1, stream));     // dx1 += dh W1: grad wrt x1 (both branches)
   TRY(bf16_layernorm_bwd_impl(dx1, s.v1, T->rowmask, P->ln1_g, s.m1, s.r1, dx, T->rowmask ? da : nullptr, g_ln1_g, g_ln1_b, g_out_b, m_q, c, z, stream));
   const bf16* dap = T->rowmask ? da : (const bf16*)dx;
-  TRY(bf16_linear_bwd_weight_impl(dap, s.o, g_out_w, nullptr, nullptr, m_q, c, c, z, stream));
+  fork(2);
+  TRY(bf16_linear_bwd_weight_impl(dap, s.o, g_out_w, nullptr, nullptr, m_q, c, c, z, wstream));
+  mark(1);                                                                                                    // dap (= dx without a row mask) has been read
   TRY(tmae_bf16_linear_bwd_data(dap, W->out_w, nullptr, dob, m_q, c, c, 0, stream));
   // attention core: gradients land in the packed layout of the projections, already taken back through the normalisation
   const int ldq = cross ? c : 3 * c, ldkv = cross ? 2 * c : 3 * c;
@@ -344,18 +393,21 @@ int tmae_bf16_encoder_layer_bwd(const void* dy, const void* x, const void* x_kv,
   auto in_proj_grads = [&](const bf16* dy_, const void* xin, const uint8_t* pidx, const float* onehot, int64_t rows, int n, int n_pos, float* gw,
                            float* gb, float* dtab_) -> int {
     if (onehot) {
-      TRY(bf16_linear_bwd_weight_impl(dy_, xin, gw, onehot, dtab_, rows, n, c, z, stream));
-      return tmae_pos_table_bwd(dtab_, 1, pos_lut, gw, gb, n, n_pos, c, stream);
+      TRY(bf16_linear_bwd_weight_impl(dy_, xin, gw, onehot, dtab_, rows, n, c, z, wstream));
+      return tmae_pos_table_bwd(dtab_, 1, pos_lut, gw, gb, n, n_pos, c, wstream);
     }
-    TRY(bf16_linear_bwd_weight_impl(dy_, xin, gw, nullptr, nullptr, rows, n, c, z, stream));
-    TRY(tmae_bf16_binned_colsum(dy_, pidx, dtab_, rows, n, stream));
-    return tmae_pos_table_bwd(dtab_, 0, pos_lut, gw, gb, n, n_pos, c, stream);
+    TRY(bf16_linear_bwd_weight_impl(dy_, xin, gw, nullptr, nullptr, rows, n, c, z, wstream));
+    TRY(tmae_bf16_binned_colsum(dy_, pidx, dtab_, rows, n, wstream));
+    return tmae_pos_table_bwd(dtab_, 0, pos_lut, gw, gb, n, n_pos, c, wstream);
   };
+  fork(3);          // behind the attention backward: dqkv / dkv are complete
   if (!cross) {
     TRY(in_proj_grads(dqkv, x, T->posidx_q, T->onehot_q, m_q, 3 * c, 2 * c, g_in_w, g_in_b, dtab));
+    await(1);       // the out_proj weight gradient has read dx (= dap) before dx += dqkv W
     TRY(tmae_bf16_linear_bwd_data(dqkv, in_w, nullptr, dx, m_q, 3 * c, c, 1, stream));
   } else {
     TRY(in_proj_grads(dqkv, x, T->posidx_q, T->onehot_q, m_q, c, c, g_in_w, g_in_b, dtab));
+    await(1);
     TRY(tmae_bf16_linear_bwd_data(dqkv, in_w, nullptr, dx, m_q, c, c, 1, stream));
     TRY(in_proj_grads(dkv, x_kv, T->posidx_kv, T->onehot_kv, m_kv, 2 * c, c, g_in_w + cc, g_in_b + c, dtab + 64 * c));
     if (dx_kv) TRY(tmae_bf16_linear_bwd_data(dkv, in_w + cc, nullptr, dx_kv, m_kv, 2 * c, c, 0, stream));
