@@ -460,7 +460,8 @@ TMAE_API int tmae_bf16_encoder_layer_bwd(const void* dy, const void* x, const vo
                                 int32_t heads, const void* saved, size_t saved_size, void* dx, void* dx_kv, const tmae_layer_params* G,
                                 void* g_base, size_t g_bytes, void* scratch, size_t scratch_size, void* stream);
 /* g_base / g_bytes (nullable): when the 13 gradient buffers of G are carved from ONE allocation, its extent -- the call then clears it with a
- * single memset; NULL: every kernel clears its own target. */
+ * single memset; NULL: every kernel clears its own target.  With g_base the weight-gradient GEMMs run on a per-device auxiliary stream owned
+ * by the library, forked from and joined to `stream` by events inside the call (tmae_set_option "wgrad_stream"). */
 /* which attention core the bf16 layers use: 1 = tcgen05 window kernel (attention_tc.cu), 0 = cast bridge to the fp32-I/O mma.sync
  * kernels (kept as the checker of the former; measurement switch, process-wide) */
 TMAE_API int tmae_bf16_set_attention_impl(int32_t impl);
