@@ -398,13 +398,18 @@ def measure(w, args, c, steps, n_batches, full):
     total, e_total = maxr(total), maxr(e_total)
     out = dict(value=aggregate_value(w["batch"], steps, world, total), e_value=aggregate_value(w["batch"], steps, world, e_total),
                ms_per_step=total / steps, e_ms_per_step=e_total / steps, per=per, launches=launches, host_ms=host_ms[0], h2d=h2d, d2h=d2h,
-               warmup=warmup, clocks=clocks, rank_ms_min_max=spread, roof=None, table=None, step_roof=None, counts=None, dispatch=ops.dispatch_counts())
+               warmup=warmup, clocks=clocks, rank_ms_min_max=spread, roof=None, table=None, step_roof=None, counts=None, attention_block=None,
+               dispatch=ops.dispatch_counts())
     if full and rank == 0:
         out["roof"], out["table"], out["step_roof"] = roofline(ops, step_local, resident, args, total / steps)
         try:
             out["counts"] = workload_counts(bb, resident)
         except Exception as e:  # diagnostics only: never lose the measurement over them
             out["counts"] = {"error": repr(e)}
+        try:
+            out["attention_block"] = attention_block(bb, out["table"], w["train"], peaks()["tensor"])
+        except Exception as e:
+            out["attention_block"] = {"error": repr(e)}
     if flat is not None and args.grad_sync == "overlap":
         flat.detach()
     del model, net, opt, params, flat, resident, host, vfe, bb
@@ -457,7 +462,7 @@ def run_ours(args):
             "rank_ms_per_step_min_max": [round(v, 3) for v in m["rank_ms_min_max"]],
             "roofline": m["roof"], "step_roofline": m["step_roof"], "cpu_baseline": cpu, "gpu_torch_baseline": gpu_torch, "extra_workloads": extras,
             "kernel_time_table": m["table"], "kernel_time_table_note": "per-kernel CUDA events inside the library over 2 extra steps with the weight-gradient GEMMs on the caller's stream (in the timed steps they run on the library's auxiliary stream and overlap the data-gradient kernels)",
-            "counts": m["counts"],
+            "counts": m["counts"], "attention_block": m["attention_block"],
         }
         emit(line)
     if world > 1:
@@ -524,6 +529,65 @@ def workload_counts(bb, resident):
             win[f"stage{s + 1}"] = {"windows_shift0": int(lb[0][-1]), "windows_shift1": int(lb[1][-1]), "windows_by_level_shift0":
                                     [int(lb[0][i + 1] - lb[0][i]) for i in range(len(lb[0]) - 1)], "level_max_tokens": list(st.part.tokens)}
     out["windows"] = win
+    return out
+
+
+def attention_block(bb, table, train, tensor_peak_tflops):
+    """Useful and executed tensor-core FLOPs of the window-attention core in one step, from the partition tables of the last plan
+    (token counts per window, both shifts) and the module structure, next to the time of its kernel families.
+    Per layer and window with q queries and k keys: S = QK^T and PV are 2 * 2 * q * k * C flops forward, five such products
+    backward.  The tcgen05 kernels run windows of 17..64 tokens as 128 x 128 tiles (4 / 2 windows per tile): executed = 128 * 128 per
+    tile and product whatever the occupancy; windows of <= 16 tokens run on warp kernels (SIMT, useful flops only)."""
+    plans, tparts = bb.last_plan
+    useful_tc = useful_simt = tiles_flops = 0.0
+
+    def part_sums(part, shift, cross):
+        lb = part.level_base[shift].cpu().tolist()
+        n = int(lb[-1])
+        cq = part.cnt_a[shift][:n].double().cpu()
+        ck = part.cnt_b[shift][:n].double().cpu() if cross else cq
+        prod = cq * ck
+        out = []
+        for li, tok in enumerate(part.tokens):
+            a, b = int(lb[li]), int(lb[li + 1])
+            out.append((tok, b - a, float(prod[a:b].sum())))
+        return out
+
+    passes = 14.0 if train else 4.0          # (2 products forward + 5 backward) x 2 flops per multiply-add
+    tile_passes = 14.0 if train else 4.0
+    stages = plans[-1].stages
+    for si, blk in enumerate(bb.sst_blocks):
+        C = blk.d_model
+        for sb in blk.encoder_blocks:
+            for shift, _ in enumerate(sb.encoder_list):
+                for tok, nwin, pq in part_sums(stages[si].part, shift, False):
+                    if tok <= 16:
+                        useful_simt += passes * pq * C
+                    else:
+                        useful_tc += passes * pq * C
+                        tiles_flops += tile_passes * (-(-nwin // (128 // tok))) * 128 * 128 * C
+    if tparts is not None:
+        for si, blk in enumerate(getattr(bb, "wca_blocks", [])):
+            C = blk.d_model
+            for shift, _ in enumerate(blk.encoder_blocks[0].encoder_list):
+                for tok, nwin, pq in part_sums(tparts[si], shift, True):
+                    if tok <= 16:
+                        useful_simt += passes * pq * C
+                    else:
+                        useful_tc += passes * pq * C
+                        tiles_flops += tile_passes * (-(-nwin // (128 // tok))) * 128 * 128 * C
+    fam = {k: v["ms_per_step"] for k, v in (table or {}).items() if k.startswith("attn_")}
+    ms_tc = sum(v for k, v in fam.items() if k.startswith("attn_tc"))
+    ms_all = sum(fam.values())
+    out = {"useful_gflop_per_step": round((useful_tc + useful_simt) / 1e9, 2), "useful_gflop_tcgen05_kernels": round(useful_tc / 1e9, 2),
+           "executed_tile_gflop_tcgen05_kernels": round(tiles_flops / 1e9, 2), "useful_gflop_warp_kernels": round(useful_simt / 1e9, 2),
+           "ms_per_step": round(ms_all, 3), "ms_per_step_tcgen05_kernels": round(ms_tc, 3), "kernel_families_ms": fam}
+    if ms_tc > 0:
+        out["tcgen05_kernels_useful_tflops"] = round(useful_tc / (ms_tc * 1e-3) / 1e12, 2)
+        out["tcgen05_kernels_executed_tflops"] = round(tiles_flops / (ms_tc * 1e-3) / 1e12, 2)
+        out["tcgen05_kernels_executed_frac_of_tensor_peak"] = round(tiles_flops / (ms_tc * 1e-3) / 1e12 / tensor_peak_tflops, 4)
+    out["note"] = ("windows hold <= 64 tokens and heads are 16 / 32 wide: the op is HBM- and latency-bound (17-30 useful flop per byte against a ridge "
+                   "of 220), see DESIGN.md section 6; ncu sm__pipe_tensor_cycles_active of the tcgen05 kernels: 5.1-5.3 % (profiles/r02_ncu_attn_in_bench.txt)")
     return out
 
 
