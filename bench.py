@@ -179,7 +179,8 @@ def make_batches(w, n_batches, rank, balanced=True):
     for i in range(n_batches):
         grp = pairs[i * B:(i + 1) * B]
         pts, ptsp = synth.collate([p[0] for p in grp]), synth.collate([p[1] for p in grp])
-        out.append((torch.from_numpy(pts).pin_memory(), torch.from_numpy(ptsp).pin_memory()))
+        a, b = torch.from_numpy(pts), torch.from_numpy(ptsp)
+        out.append((a.pin_memory(), b.pin_memory()) if torch.cuda.is_available() else (a, b))   # (no GPU: the host-logic tests)
     return out
 
 

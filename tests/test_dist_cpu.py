@@ -168,3 +168,29 @@ def test_per_bucket_optimizer_steps_equal_one_step_gloo_world2():
         assert torch.equal(a, b)
     for a, b in zip(out[0]["per_bucket"], out[1]["per_bucket"]):
         assert torch.equal(a, b)
+
+
+def test_balanced_batches_are_the_ranks_own_scans_sorted_by_cost():
+    """bench.make_batches(balanced=True): every rank keeps exactly its own scan pairs (nothing changes owner), batched in ascending
+    order of occupied pillars, so that lockstep steps line up across ranks."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from tmae_b200 import synth
+    w = dict(bench.WORKLOADS["pretrain"], n_points=4000)
+    shape = synth.SHAPES[w.get("shape", "once")]
+    for rank in (0, 1):
+        plain = bench.make_batches(w, 3, rank, balanced=False)
+        bal = bench.make_batches(w, 3, rank, balanced=True)
+
+        def scans(batches):
+            out = []
+            for pts, ptsp in batches:
+                for b in range(w["batch"]):
+                    out.append((pts[pts[:, 0] == b][:, 1:].numpy(), ptsp[ptsp[:, 0] == b][:, 1:].numpy()))
+            return out
+        a, b = scans(plain), scans(bal)
+        key = lambda pr: (pr[0].shape[0], float(pr[0].sum()))
+        assert sorted(map(key, a)) == sorted(map(key, b)), "the rank's scans changed"
+        costs = [bench.scan_cost(pr, shape) for pr in b]
+        assert costs == sorted(costs), "batches are not in ascending cost order"
