@@ -1,19 +1,24 @@
 // Window attention core of the bf16-storage mode on the 5th-generation tensor cores (replaces flat2window +
 // _scaled_cosine_attention + window2flat: pcdet/models/model_utils/cosine_msa.py:114-176, sst_basic_block.py:22-54,
 // wca_block.py:26-67).  Windows hold <= 64 tokens and heads are 16 / 32 wide, far below a UMMA tile, so windows are PACKED:
-// a 128-row tile holds 8 windows of the <= 16-token class, 4 of the <= 32 class or 2 of the <= 64 class (the partition sorts
-// windows by level), S = Q K^T is one M = N = 128 tcgen05.mma per head whose off-diagonal (cross-window) blocks are simply
-// never read, and P V runs over the tile's 128 keys with P block-diagonal (the off-diagonal part of the P tile is zeroed once:
-// block sizes only grow along a CTA's tile list).  The ragged key mask (tokens per window) is applied in the TMEM -> register
-// softmax.  One work item = (tile, 128-channel group = 8 heads of 16 or 4 heads of 32):
-//   warps 0..3   softmax + epilogue: thread = tile row = TMEM lane; S row block from TMEM, masked softmax (fp32), P (bf16) into
-//                the swizzled shared tile; at the end O (all heads, 128 columns) from TMEM, 1 / rowsum, one 256-byte row store
-//   warp  4      MMA issuer (one lane): S(h) = Qh Kh^T into a double-buffered TMEM slot, O[:, h] = P(h) Vh; tcgen05.commit -> mbarriers
-//   warps 5..7   gather producers: q / k / v rows of the tile's windows through the token tables, 16-byte cp.async (zero fill for
-//                empty slots) straight into the SWIZZLE_128B K-major layout, double-buffered per item
+// a 128-row tile holds 4 windows of the <= 32-token class or 2 of the <= 64 class (the partition sorts windows by level; the
+// <= 16-token class runs on the warp kernels at the end of this file, or as 8 windows per tile with attn_small_warps = 0),
+// S = Q K^T is one M = N = 128 tcgen05.mma per head whose off-diagonal (cross-window) blocks are simply never read, and P V runs
+// over the tile's 128 keys with P block-diagonal (the off-diagonal part of the P tile is zeroed once: block sizes only grow along a
+// CTA's tile list).  The ragged key mask (tokens per window) is applied in the TMEM -> register softmax.
+// One work item = (tile, 64-channel group = 4 heads of 16 or 2 heads of 32); 384 threads per CTA, one CTA per SM, persistent:
+//   warps 0..7   two softmax warpgroups (thread = tile row = TMEM lane).  Forward: alternate heads, each with its own S slot in TMEM
+//                and its own P tile; backward: the two halves of a row's key columns, partial D exchanged through shared memory;
+//                then the epilogue (O, or dQ / dK / dV taken back through the L2 normalisation) as 64-byte row pieces
+//   warp  8      MMA issuer (one lane): tcgen05.mma.kind::f16, tcgen05.commit -> mbarriers
+//   warps 9..11  gather producers: the tile's row indices are looked up once per item into shared memory, then q / k / v (and dO)
+//                rows arrive by 16-byte cp.async (zero fill for empty slots) straight into the SWIZZLE_128B K-major layout,
+//                double-buffered per item
 // q and k arrive L2-normalised per head (the projection epilogue, gemm_bf16.cu E_QKV); logits = q.k / max(tau, tau_min).
-// The backward kernel uses 64-channel groups (TMEM: S, dP, dQ, dK, dV accumulators) and recomputes P from the saved
-// log-sum-exp; D_i = sum_j P_ij dP_ij is taken from the registers that hold both, so O is never re-read.
+// The backward keeps S, dP, dQ, dK, dV accumulators in TMEM and recomputes P from the saved log-sum-exp; D_i = sum_j P_ij dP_ij is
+// taken from the registers that hold both, so O is never re-read by the tile kernel.
+// Both kernels are launched with programmatic stream serialization: set-up (barriers, zeroed P tiles, TMEM) overlaps the previous
+// kernel's tail, pdl_wait() stands in front of the first global access.
 #include <cuda_bf16.h>
 #include <cstring>
 
