@@ -10,15 +10,21 @@
 //        NN  C[m,n] = sum_k A[m,k] B[k,n]   (A K-major, B MN-major)   linear backward-data
 //        TN  C[m,n] = sum_k A[k,m] B[k,n]   (A, B MN-major)           weight gradients (fp32 out, split over k, vector atomics)
 // Epilogues (what the reference runs as separate ATen kernels, here folded into the pass that owns the accumulator):
-//   E_PLAIN  + bias, GELU / ReLU, optional pre-activation copy, optional * gelu'(pre) (FFN backward), optional C +=
-//   E_QKV    + (pos_lut W^T + b)[posidx[row]] (the window position embedding folded into a 64-row table, spt_backbone.py:186-231),
-//            then q and k are L2-normalised per head (cosine_msa.py:151-152) -> the attention kernel reads unit vectors;
-//            1 / max(|.|, 1e-12) per (row, head) is kept for the backward of the normalisation
+//   E_PLAIN  + bias, GELU / ReLU, optional pre-activation copy (or, TMAE_ACT_GELU_DERIV, GELU'(pre-activation) in its place: the
+//            backward then multiplies instead of re-deriving), optional * gelu'(pre) (FFN backward), optional C +=
+//   E_QKV    the window position embedding (spt_backbone.py:186-231) folded into a 64-row table (pos_lut W^T + b) that either rides the
+//            MMA as a one-hot second A operand, [x | onehot(cell)] [W | table^T]^T with K = C + 64 (tmae_bf16_qkv_fwd_onehot, what the
+//            fused layer uses), or is added per row in the epilogue (tmae_bf16_qkv_fwd); then q and k are L2-normalised per head
+//            (cosine_msa.py:151-152) -> the attention kernel reads unit vectors; 1 / max(|.|, 1e-12) per (row, head) is kept for the
+//            backward of the normalisation
 //   E_LN     + bias + residual, LayerNorm over the row (sst_basic_block.py:78,83; a CTA owns whole rows: N <= BN), writes the
 //            pre-norm sum v (for backward), y = LN(v), mean, rstd.  Row statistics are exchanged between the two warps that
 //            share a TMEM lane quarter through shared memory; v is parked in the accumulator's own TMEM columns between the
 //            statistics pass and the normalise pass (tcgen05.st).
-//   E_F32    fp32 output: plain store, or vector atomics when the reduction is split (weight gradients)
+//   E_F32    fp32 output: plain store, or vector atomics when the reduction is split (weight gradients); TN takes a second B operand
+//            (one-hot cell index): dy^T [x | onehot] = dW and the position-table gradient in one launch
+// Every launch carries cudaLaunchAttributeProgrammaticStreamSerialization (tmae_set_option "gemm_pdl"): the kernel triggers its
+// dependents at entry and waits (griddepcontrol.wait) after barrier / TMEM set-up, before its first global access.
 #include <cuda.h>
 #include <cuda_bf16.h>
 

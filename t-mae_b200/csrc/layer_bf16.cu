@@ -1,9 +1,12 @@
 // One encoder layer per ABI call in the bf16-STORAGE mode: the SST self-attention layer (pcdet/models/model_utils/
 // sst_basic_block.py:58-84) or the WCA cross-attention layer (wca_block.py:70-103), forward and backward.
-// Forward = 5 launches + the 64-row position table:
-//   pos_table -> [packed q/k/v GEMM + position-table add + per-head L2 normalisation] -> window attention
-//             -> [out_proj GEMM + bias + residual + LayerNorm1] -> [linear1 GEMM + bias + GELU (+ pre-activation copy)]
-//             -> [linear2 GEMM + bias + residual + LayerNorm2]
+// Forward = 6 launches (7 / 9 for a cross layer's second projection), the [W | table^T] operand of the projection coming from the
+// caller's per-step cache (tmae_bf16_weights.in_wcat) or, without it, from one more launch:
+//   [packed q/k/v GEMM with the position term as a one-hot second operand + per-head L2 normalisation] -> window attention (warp
+//   kernels for <= 16-token windows, tcgen05 tiles above) -> [out_proj GEMM + bias + residual + LayerNorm1]
+//   -> [linear1 GEMM + bias + GELU, GELU' saved for the backward] -> [linear2 GEMM + bias + residual + LayerNorm2]
+// Backward: LayerNorm-backward passes (with the bias gradients), data-gradient GEMMs on the caller's stream, weight-gradient GEMMs on the
+// library's auxiliary stream (fork / join by events inside the call).
 // The reference runs ~25 kernels per drop level per layer for the same arithmetic.  Activations (x, q/k/v, o, x1, h, y) and
 // their gradients are bf16 in HBM; row statistics, softmax log-sum-exp, normalisation factors, the position table, master
 // weights and every parameter gradient are fp32.  The attention core runs on the tcgen05 window kernel (attention_tc.cu);
